@@ -1,0 +1,207 @@
+"""ctypes bindings of the CPU oracle (oracle/liborb_oracle.so) and of the reference extractor
+compiled against the OpenCV stand-in (oracle/_ref/*.so). Test infrastructure only."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+def pattern():
+    txt = open(os.path.join(ROOT, "multiagent_orb_slam2_b200", "csrc", "orb_pattern_31.inc")).read()
+    txt = "\n".join(l for l in txt.splitlines() if not l.startswith("//"))
+    v = np.array([int(x) for x in re.findall(r"-?\d+", txt)], np.int32)
+    assert v.size == 1024
+    return v
+
+
+def lib():
+    global _lib
+    try:
+        return _lib
+    except NameError:
+        pass
+    L = C.CDLL(os.path.join(ROOT, "oracle", "liborb_oracle.so"))
+    L.orc_fast_atan2.restype = C.c_float
+    L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+    L.orc_round.argtypes = [C.c_float]
+    L.orc_extractor_create.restype = C.c_void_p
+    L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.orc_extractor_destroy.argtypes = [C.c_void_p]
+    L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+    L.orc_get_result.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    L.orc_level_dims.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
+    L.orc_level_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orc_level_has_blur.argtypes = [C.c_void_p, C.c_int]
+    L.orc_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_level_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_extract_mt.restype = C.c_long
+    _lib = L
+    return L
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(src.ctypes.data_as(C.c_void_p), src.shape[1], src.shape[0], C.c_size_t(src.strides[0]),
+                               dst.ctypes.data_as(C.c_void_p), dw, dh, C.c_size_t(dw))
+    return dst
+
+
+def gaussian(src):
+    src = np.ascontiguousarray(src)
+    dst = np.empty_like(src)
+    lib().orc_gaussian7x7_u8(src.ctypes.data_as(C.c_void_p), src.shape[1], src.shape[0], C.c_size_t(src.strides[0]),
+                             dst.ctypes.data_as(C.c_void_p), C.c_size_t(dst.strides[0]))
+    return dst
+
+
+def border(src, b=19):
+    src = np.ascontiguousarray(src)
+    dst = np.empty((src.shape[0] + 2 * b, src.shape[1] + 2 * b), np.uint8)
+    lib().orc_copy_make_border(src.ctypes.data_as(C.c_void_p), src.shape[1], src.shape[0], C.c_size_t(src.strides[0]),
+                               dst.ctypes.data_as(C.c_void_p), C.c_size_t(dst.strides[0]), b)
+    return dst
+
+
+def fast(img, th):
+    """img may be a (non-contiguous) view with unit column stride."""
+    assert img.strides[1] == 1
+    cap = img.size
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_fast9_nms(C.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]), th,
+                            out.ctypes.data_as(C.c_void_p), cap)
+    return out[:n]
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def quadtree(xs, ys, scores, minX, maxX, minY, maxY, N):
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+    sc = np.ascontiguousarray(scores, np.int32)
+    out = np.empty(max(len(xs), 1), np.int32)
+    n = lib().orc_quadtree(xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                           len(xs), minX, maxX, minY, maxY, N, out.ctypes.data_as(C.c_void_p), len(out))
+    return out[:n]
+
+
+class OracleExtractor:
+    """Mirror of ORB_SLAM2::ORBextractor over the oracle, with access to every intermediate."""
+
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7):
+        self.L = lib()
+        self.pat = pattern()
+        self.nlevels = nlevels
+        self.h = self.L.orc_extractor_create(nfeatures, scale, nlevels, ini, mn, self.pat.ctypes.data_as(C.c_void_p))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_extractor_destroy(self.h)
+            self.h = None
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img)
+        n = self.L.orc_extract(self.h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]))
+        kps = np.empty((n, 6), np.float32)
+        desc = np.empty((n, 32), np.uint8)
+        self.L.orc_get_result(self.h, kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p))
+        return kps, desc
+
+    def tables(self):
+        n = self.nlevels
+        t = [np.empty(n, np.float32) for _ in range(4)] + [np.empty(n, np.int32), np.empty(16, np.int32)]
+        self.L.orc_get_tables(self.h, *[a.ctypes.data_as(C.c_void_p) for a in t])
+        return dict(zip(["scale", "inv_scale", "sigma2", "inv_sigma2", "quota", "umax"], t))
+
+    def level(self, l):
+        w, h, nc, ns = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.L.orc_level_dims(self.h, l, C.byref(w), C.byref(h), C.byref(nc), C.byref(ns))
+        img = np.empty((h.value, w.value), np.uint8)
+        self.L.orc_level_image(self.h, l, img.ctypes.data_as(C.c_void_p), 0)
+        blur = None
+        if self.L.orc_level_has_blur(self.h, l):
+            blur = np.empty_like(img)
+            self.L.orc_level_image(self.h, l, blur.ctypes.data_as(C.c_void_p), 1)
+        cand = np.empty((nc.value, 3), np.int32)
+        self.L.orc_level_candidates(self.h, l, cand.ctypes.data_as(C.c_void_p))
+        sel = np.empty(ns.value, np.int32)
+        ang = np.empty(ns.value, np.float32)
+        self.L.orc_level_selected(self.h, l, sel.ctypes.data_as(C.c_void_p), ang.ctypes.data_as(C.c_void_p))
+        return dict(img=img, blur=blur, cand=cand, sel=sel, angle=ang)
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+
+
+def knn2(A, B, threads=1):
+    A = np.ascontiguousarray(A, np.uint8); B = np.ascontiguousarray(B, np.uint8)
+    idx = np.empty(len(A), np.int32); d1 = np.empty(len(A), np.int32); d2 = np.empty(len(A), np.int32)
+    lib().orc_knn2_mt(A.ctypes.data_as(C.c_void_p), len(A), B.ctypes.data_as(C.c_void_p), len(B),
+                      idx.ctypes.data_as(C.c_void_p), d1.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p), threads)
+    return idx, d1, d2
+
+
+def knn2_lists(A, B, offsets, cands):
+    A = np.ascontiguousarray(A, np.uint8); B = np.ascontiguousarray(B, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int32); cands = np.ascontiguousarray(cands, np.int32)
+    idx = np.empty(len(A), np.int32); d1 = np.empty(len(A), np.int32); d2 = np.empty(len(A), np.int32)
+    lib().orc_knn2_lists(A.ctypes.data_as(C.c_void_p), len(A), B.ctypes.data_as(C.c_void_p),
+                         offsets.ctypes.data_as(C.c_void_p), cands.ctypes.data_as(C.c_void_p),
+                         idx.ctypes.data_as(C.c_void_p), d1.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+    return idx, d1, d2
+
+
+# ---- the reference's own extractor (oracle/_ref), when it was built ------------------------
+def ref_available(kind="canonical"):
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_orb_%s.so" % kind))
+
+
+class RefExtractor:
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, kind="canonical"):
+        self.L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_orb_%s.so" % kind))
+        self.L.ref_extractor_create.restype = C.c_void_p
+        self.L.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        self.L.ref_extractor_destroy.argtypes = [C.c_void_p]
+        self.L.ref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        self.L.ref_get_tables.argtypes = [C.c_void_p] * 5
+        self.L.ref_level_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self.L.ref_level_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self.nlevels = nlevels
+        self.cap = nfeatures + 4 * nlevels + 64
+        self.h = self.L.ref_extractor_create(nfeatures, scale, nlevels, ini, mn)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_extractor_destroy(self.h)
+            self.h = None
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img)
+        kps = np.empty((self.cap, 6), np.float32)
+        desc = np.empty((self.cap, 32), np.uint8)
+        n = self.L.ref_extract(self.h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]),
+                               kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), self.cap)
+        assert n <= self.cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def tables(self):
+        t = [np.empty(self.nlevels, np.float32) for _ in range(4)]
+        self.L.ref_get_tables(self.h, *[a.ctypes.data_as(C.c_void_p) for a in t])
+        return dict(zip(["scale", "inv_scale", "sigma2", "inv_sigma2"], t))
+
+    def level_image(self, l, border=0):
+        w, h = C.c_int(), C.c_int()
+        self.L.ref_level_dims(self.h, l, C.byref(w), C.byref(h))
+        out = np.empty((h.value + 2 * border, w.value + 2 * border), np.uint8)
+        self.L.ref_level_image(self.h, l, out.ctypes.data_as(C.c_void_p), border)
+        return out
