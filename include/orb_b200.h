@@ -1,0 +1,161 @@
+/* orb_b200.h - C ABI of the B200-native ORB frontend (extraction + binary descriptor matching).
+ *
+ * Drop-in boundary for the data-parallel hot path of andresenwc/MultiAgent_ORB_SLAM2:
+ *   ORB_SLAM2::ORBextractor   include/ORBextractor.h:45-111, src/ORBextractor.cc:410-1132
+ *   ORB_SLAM2::ORBmatcher     include/ORBmatcher.h:37-102,   src/ORBmatcher.cc:37-1665
+ *   Frame::ComputeStereoMatches                               src/Frame.cc:466-640
+ * The C++ facade classes with the reference's own signatures live in include/orbslam2_b200/ and call
+ * only the functions below. Plain pointers and sizes; no C++/torch types; never throws.
+ *
+ * All entry points return ORB_OK (0) or a negative ORB_E* code. There is no CPU fallback: without a
+ * CUDA device every compute call returns ORB_ECUDA.
+ *
+ * Streams: `stream` arguments are cudaStream_t values passed as void* (NULL = the legacy default
+ * stream). "_device" functions take device pointers and only enqueue work on `stream`;
+ * functions without the suffix take HOST pointers, copy in/out and synchronise before returning.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    ORB_OK = 0,
+    ORB_EINVAL = -1,   /* bad argument (null pointer, size out of range, image too small/large) */
+    ORB_ECUDA = -2,    /* CUDA runtime error; orb_last_error() has the text */
+    ORB_ECAPACITY = -3 /* result does not fit the caller's buffer / handle capacity */
+};
+
+const char* orb_last_error(void);          /* thread-local text of the last failure */
+int orb_device_count(void);                /* number of visible CUDA devices (0 = none) */
+const char* orb_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Extractor. Replaces ORBextractor::ORBextractor (src/ORBextractor.cc:410-470) and
+ * ORBextractor::operator() (1043-1105) incl. ComputePyramid (1107-1132),
+ * ComputeKeyPointsOctTree (765-853), DistributeOctTree (539-763), IC_Angle (77-104) and
+ * computeOrbDescriptor (108-147).
+ * One handle == one reference ORBextractor instance: not re-entrant, distinct handles may run
+ * concurrently (src/Frame.cc:78-81). A handle is pinned to one device (one agent per GPU). */
+typedef struct orbx_extractor* orbx_handle;
+
+typedef struct {
+    int nfeatures;      /* ORBextractor.nFeatures   */
+    float scale_factor; /* ORBextractor.scaleFactor */
+    int nlevels;        /* ORBextractor.nLevels (1..16) */
+    int ini_th_fast;    /* ORBextractor.iniThFAST   */
+    int min_th_fast;    /* ORBextractor.minThFAST   */
+} orbx_config;
+
+/* One keypoint = cv::KeyPoint minus class_id (always -1 in the reference). 24 bytes. */
+typedef struct {
+    float x, y;     /* pt, already multiplied by the level scale (src/ORBextractor.cc:1095-1101) */
+    float size;     /* int(31 * scale[octave])  (837-846) */
+    float angle;    /* degrees [0,360), cv::fastAtan2 of the intensity centroid */
+    float response; /* FAST score */
+    int32_t octave; /* pyramid level */
+} orbx_keypoint;
+
+/* Image geometry is fixed per handle (all frames of an agent share a camera). max_batch frames can
+ * be extracted per call. */
+int orbx_create(const orbx_config* cfg, int device, int width, int height, int max_batch, orbx_handle* out);
+void orbx_destroy(orbx_handle h);
+
+/* Tables of the ctor, for the getters of the facade (GetScaleFactors() etc., ORBextractor.h:63-83).
+ * Each array has nlevels entries; any pointer may be NULL. */
+int orbx_get_tables(orbx_handle h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int32_t* features_per_level);
+/* Upper bound of keypoints per frame (nfeatures + per-level overshoot, src/ORBextractor.cc:669-737). */
+int orbx_max_keypoints(orbx_handle h);
+int orbx_level_size(orbx_handle h, int level, int* width, int* height);
+
+/* operator(): one frame from host memory. Writes min(n, cap) keypoints + 32-byte descriptors in the
+ * reference's output order (levels 0..n-1, final node-list order inside a level) and the true count
+ * to *n_out. Returns ORB_ECAPACITY (after filling cap entries) when n > cap. An empty image
+ * (NULL / zero size) is the reference's silent no-op: ORB_OK with *n_out = 0. */
+int orbx_extract(orbx_handle h, const uint8_t* image, size_t stride, orbx_keypoint* kps, uint8_t* desc,
+                 int cap, int* n_out);
+
+/* Batched operator() over `n` host frames (n <= max_batch), frame i at images + i*frame_stride.
+ * Outputs are [n][cap] arrays; counts[n]. */
+int orbx_extract_batch(orbx_handle h, const uint8_t* images, size_t stride, size_t frame_stride, int n,
+                       orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts);
+
+/* Device-resident variant: frames already in device memory; only enqueues on `stream`. Results stay
+ * on the device: d_kps[n][cap_dev], d_desc[n][cap_dev][32], d_counts[n] with cap_dev = orbx_max_keypoints(). */
+int orbx_extract_device(orbx_handle h, const uint8_t* d_images, size_t stride, size_t frame_stride, int n,
+                        void* stream);
+int orbx_device_results(orbx_handle h, const orbx_keypoint** d_kps, const uint8_t** d_desc,
+                        const int32_t** d_counts, int* cap_dev);
+
+/* mvImagePyramid (ORBextractor.h:85): level `level` of frame `frame` of the last call. Device view
+ * (pointer + pitch) or a copy to host (dst_stride >= width). */
+int orbx_pyramid_level_device(orbx_handle h, int frame, int level, const uint8_t** d_ptr, size_t* pitch);
+int orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride);
+
+/* Stage taps used by the parity tests (not needed by a SLAM caller): the blurred level
+ * (src/ORBextractor.cc:1085-1086) and the FAST candidates of a level in the reference's order
+ * (cell row-major, then row-major inside the cell; x,y in level coordinates; 789-829). */
+int orbx_debug_blurred_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride);
+int orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xys /* [cap][3] */, int cap, int* n_out);
+
+/* Measurement hooks (bench.py): with stage timing on, the pipeline runs its stages back to back on
+ * ONE stream with CUDA events in between; orbx_stage_times returns the device milliseconds of
+ * {resize chain, blur, FAST, quadtree, orient+describe} of the last call, orbx_algorithmic_bytes the
+ * per-frame algorithmic HBM bytes of the same stages. */
+#define ORBX_NUM_STAGES 5
+int orbx_set_stage_timing(orbx_handle h, int enable);
+int orbx_stage_times(orbx_handle h, float* ms /* [ORBX_NUM_STAGES] */);
+int orbx_algorithmic_bytes(orbx_handle h, double* bytes /* [ORBX_NUM_STAGES] */);
+
+/* Stand-alone stages on host buffers (parity tests / micro-benchmarks). */
+int orbx_debug_quadtree(int device, const int32_t* xs, const int32_t* ys, const int32_t* scores, int n,
+                        int minX, int maxX, int minY, int maxY, int N, int32_t* out_idx, int cap, int* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Matcher primitives. Replace the DescriptorDistance loops of ORBmatcher (src/ORBmatcher.cc:1649-1665
+ * called from 102, 216, 387, 444, 586, 738, 944, 1074, 1214, 1294, 1419, 1548; src/Frame.cc:541).
+ * Descriptors are 32 bytes, rows contiguous. Selection rule of every reference search: strict '<'
+ * updates in iteration order => (two smallest distances, index of the FIRST minimum); both
+ * distances start at 256; idx = -1 when no candidate is closer than 256. */
+
+/* Brute force: every row of A against every row of B (SearchByBoW inner loop with the gate removed,
+ * src/ORBmatcher.cc:566-598; BASELINE configs 3 and 5). */
+int orbm_knn2_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best,
+                     int32_t* d_second, void* stream);
+int orbm_knn2(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int32_t* idx, int32_t* best,
+              int32_t* second);
+
+/* Batched brute force: pair p matches A[p] (nA[p] rows at dA + p*strideA_rows*32) against B[p].
+ * d_nA / d_nB are device int arrays (e.g. the d_counts of two extractor runs). Outputs [pairs][strideA_rows]. */
+int orbm_knn2_batched_device(const uint8_t* dA, const int32_t* d_nA, int strideA_rows, const uint8_t* dB,
+                             const int32_t* d_nB, int strideB_rows, int pairs, int32_t* d_idx, int32_t* d_best,
+                             int32_t* d_second, void* stream);
+
+/* Candidate-list search: query i is compared with B[cands[offsets[i] .. offsets[i+1])] in list order
+ * (the GetFeaturesInArea / BoW-node gated loops, e.g. src/ORBmatcher.cc:427-459, 1385-1426). */
+int orbm_knn2_lists_device(const uint8_t* dA, int nA, const uint8_t* dB, const int32_t* d_offsets,
+                           const int32_t* d_cands, int32_t* d_idx, int32_t* d_best, int32_t* d_second, void* stream);
+int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* offsets,
+                    const int32_t* cands, int32_t* idx, int32_t* best, int32_t* second);
+
+/* Acceptance test of SearchByBoW(KF,KF) (src/ORBmatcher.cc:600-603): match[i] = idx[i] if
+ * best < th_strict_upper && (float)best < ratio*(float)second, else -1. With inclusive != 0 the
+ * threshold test is best <= th (SearchForInitialization / SearchByBoW(KF,F), 229-232, 461-463). */
+int orbm_ratio_filter_device(const int32_t* d_idx, const int32_t* d_best, const int32_t* d_second, int n,
+                             int th, int inclusive, float ratio, int32_t* d_match, void* stream);
+
+/* Full distance matrix (nA x nB, int16) for the ordered greedy resolve of the stateful searches and for
+ * MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:246-311). */
+int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int16_t* d_out, void* stream);
+int orbm_distance_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int16_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H */

@@ -1,0 +1,85 @@
+"""ctypes binding of the C ABI (include/orb_b200.h). There is no CPU fallback: a missing or
+unloadable liborb_b200.so is a hard error, and every compute call fails without a CUDA device."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "liborb_b200.so")
+
+ORB_OK, ORB_EINVAL, ORB_ECUDA, ORB_ECAPACITY = 0, -1, -2, -3
+
+
+class OrbError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("orb_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrbError(ORB_ECUDA, "CUDA extension %s is missing - run `python -m multiagent_orb_slam2_b200.build` "
+                                  "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz, f32 = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+    L.orb_last_error.restype = C.c_char_p
+    L.orb_version.restype = C.c_char_p
+    sigs = {
+        "orb_device_count": [],
+        "orbx_create": [C.POINTER(Config), i32, i32, i32, i32, C.POINTER(vp)],
+        "orbx_get_tables": [vp, vp, vp, vp, vp, vp],
+        "orbx_max_keypoints": [vp],
+        "orbx_set_stage_timing": [vp, i32],
+        "orbx_stage_times": [vp, vp],
+        "orbx_algorithmic_bytes": [vp, vp],
+        "orbx_level_size": [vp, i32, C.POINTER(i32), C.POINTER(i32)],
+        "orbx_extract": [vp, vp, sz, vp, vp, i32, C.POINTER(i32)],
+        "orbx_extract_batch": [vp, vp, sz, sz, i32, vp, vp, i32, vp],
+        "orbx_extract_device": [vp, vp, sz, sz, i32, vp],
+        "orbx_device_results": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)],
+        "orbx_pyramid_level_device": [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)],
+        "orbx_pyramid_level": [vp, i32, i32, vp, sz],
+        "orbx_debug_blurred_level": [vp, i32, i32, vp, sz],
+        "orbx_debug_candidates": [vp, i32, i32, vp, i32, C.POINTER(i32)],
+        "orbx_debug_quadtree": [i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32)],
+        "orbm_knn2_device": [vp, i32, vp, i32, vp, vp, vp, vp],
+        "orbm_knn2": [i32, vp, i32, vp, i32, vp, vp, vp],
+        "orbm_knn2_batched_device": [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp],
+        "orbm_knn2_lists_device": [vp, i32, vp, vp, vp, vp, vp, vp, vp],
+        "orbm_knn2_lists": [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp],
+        "orbm_ratio_filter_device": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
+        "orbm_distance_matrix_device": [vp, i32, vp, i32, vp, vp],
+        "orbm_distance_matrix": [i32, vp, i32, vp, i32, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_destroy.restype = None
+    _lib = L
+    return L
+
+
+def check(rc, allow=()):
+    if rc != ORB_OK and rc not in allow:
+        raise OrbError(rc, lib().orb_last_error().decode())
+    return rc
+
+
+def exported_symbols():
+    """Names declared in include/orb_b200.h (parsed), for the load/export test."""
+    import re
+    hdr = open(os.path.join(HERE, "..", "include", "orb_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(orb[xm]?_[a-z0-9_]+)\s*\(", hdr)))

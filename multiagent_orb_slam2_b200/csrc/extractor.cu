@@ -1,0 +1,481 @@
+// Extractor handle: geometry tables (the reference ctor, /root/reference/src/ORBextractor.cc:410-470,
+// plus the per-level cell grid of ComputeKeyPointsOctTree 771-787), HBM buffers, kernel
+// orchestration (operator(), 1043-1105) and the orbx_* C ABI.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "extract_kernels.cuh"
+
+namespace orb {
+
+static const int kPatternInts[1024] = {
+#include "orb_pattern_31.inc"
+};
+
+// cvRound / cvFloor / cvCeil of the ctor
+static inline int round_half_even(float v) { return (int)nearbyintf(v); }
+static inline int round_half_even_d(double v) { return (int)nearbyint(v); }
+static inline int ifloor(double v) { int i = (int)v; return i - (i > v); }
+static inline int iceil(double v) { int i = (int)v; return i + (i < v); }
+
+static std::vector<LinTap> linear_taps(int src_n, int dst_n) {
+    std::vector<LinTap> t(dst_n);
+    const double scale = (double)src_n / dst_n;
+    for (int d = 0; d < dst_n; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = ifloor(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src_n - 1) { s = src_n - 1; f = 0.f; }
+        t[d].ofs = s;
+        t[d].c0 = (short)round_half_even((1.f - f) * 2048.f);
+        t[d].c1 = (short)round_half_even(f * 2048.f);
+    }
+    return t;
+}
+
+}  // namespace orb
+
+using namespace orb;
+
+struct orbx_extractor {
+    orbx_config cfg;
+    int device = 0, width = 0, height = 0, max_batch = 0;
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    Geometry hg;  // host copy
+    DeviceBuffers db{};
+    void* d_geom = nullptr; void* d_cells = nullptr; void* d_taps = nullptr; void* d_tiles = nullptr; void* d_pattern = nullptr;
+    uint8_t* d_input = nullptr;  // staging for host frames: [max_batch][height][pitch0]
+    size_t in_pitch = 0;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    FrameSet last{};  // frames of the last call (for mvImagePyramid level 0)
+    int last_n = 0;
+    // optional per-stage device timing (bench roofline): events around each stage of the pipeline
+    bool stage_timing = false;
+    cudaEvent_t ev_stage[ORBX_NUM_STAGES + 1] = {};
+    cudaEvent_t ev_blur_begin = nullptr, ev_blur_end = nullptr;
+};
+
+namespace {
+
+int build_geometry(orbx_extractor* h) {
+    const orbx_config& c = h->cfg;
+    const int nl = c.nlevels;
+    // ---- ctor tables (410-446): float chain with a double scaleFactor member ----------------
+    const double sf = (double)c.scale_factor;
+    h->scale.assign(nl, 1.f); h->sigma2.assign(nl, 1.f); h->inv_scale.resize(nl); h->inv_sigma2.resize(nl);
+    for (int i = 1; i < nl; ++i) { h->scale[i] = (float)(h->scale[i - 1] * sf); h->sigma2[i] = h->scale[i] * h->scale[i]; }
+    for (int i = 0; i < nl; ++i) { h->inv_scale[i] = 1.0f / h->scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+    h->quota.resize(nl);
+    {
+        const float factor = (float)(1.0f / sf);
+        float per = c.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; ++l) { h->quota[l] = round_half_even(per); sum += h->quota[l]; per *= factor; }
+        h->quota[nl - 1] = std::max(c.nfeatures - sum, 0);
+    }
+    Geometry& g = h->hg;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = nl; g.iniTh = c.ini_th_fast; g.minTh = c.min_th_fast;
+    {   // umax (452-469)
+        int v, v0;
+        const int vmax = ifloor(kHalfPatch * sqrt(2.f) / 2 + 1), vmin = iceil(kHalfPatch * sqrt(2.f) / 2);
+        const double hp2 = kHalfPatch * kHalfPatch;
+        for (v = 0; v <= vmax; ++v) g.umax[v] = round_half_even_d(sqrt(hp2 - v * v));
+        for (v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+            while (g.umax[v0] == g.umax[v0 + 1]) ++v0;
+            g.umax[v] = v0;
+            ++v0;
+        }
+    }
+    std::vector<CellDesc> cells;
+    std::vector<LinTap> taps;
+    std::vector<BlurTile> tiles;
+    size_t pyr = 0, blur = 0, slot = 0;
+    int sel = 0;
+    for (int l = 0; l < nl; ++l) {
+        LevelGeom& L = g.lv[l];
+        L.w = round_half_even((float)h->width * h->inv_scale[l]);   // 1111-1112
+        L.h = round_half_even((float)h->height * h->inv_scale[l]);
+        L.pitch = (int)align_up((size_t)L.w, 128);
+        L.scale = h->scale[l];
+        L.patch_size = (int)(31 * h->scale[l]);  // 837
+        L.quota = h->quota[l];
+        const int minB = kMinBorder, maxBX = L.w - kEdgeThreshold + 3, maxBY = L.h - kEdgeThreshold + 3;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        L.nCols = (int)(width / 30.f); L.nRows = (int)(height / 30.f);  // 784-785
+        if (L.nCols < 1 || L.nRows < 1) { set_error("pyramid level %d (%dx%d) is smaller than one 30 px cell", l, L.w, L.h); return ORB_EINVAL; }
+        L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows);
+        L.nRoots = (int)roundf(width / (float)(maxBY - minB));  // 543
+        if (L.nRoots < 1) { set_error("level %d: aspect ratio below 0.5 is not supported by the reference quadtree", l); return ORB_EINVAL; }
+        L.rootW = width / L.nRoots;  // 545
+        int root_bits = 0;
+        while ((1 << root_bits) < L.nRoots) ++root_bits;
+        const int span = std::max((int)ceilf(L.rootW) + 1, maxBY - minB);
+        int depth = 1;
+        while ((1 << depth) < span) ++depth;
+        L.key_depth = std::min(depth + 1, kQtMaxDepth);
+        if (span > 4096 || 2 * L.key_depth + root_bits > 31) { set_error("level %d too large for the 32-bit quadtree key", l); return ORB_EINVAL; }
+        L.slot_cap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);  // one NMS survivor per 2x2 block at most
+        L.cell_begin = (int)cells.size();
+        int ord = 0;
+        for (int i = 0; i < L.nRows; ++i) {  // 789-806
+            const int y0 = minB + i * L.hCell;
+            int y1 = y0 + L.hCell + 6;
+            if (y0 >= maxBY - 3) continue;
+            if (y1 > maxBY) y1 = maxBY;
+            for (int j = 0; j < L.nCols; ++j) {
+                const int x0 = minB + j * L.wCell;
+                int x1 = x0 + L.wCell + 6;
+                if (x0 >= maxBX - 6) continue;
+                if (x1 > maxBX) x1 = maxBX;
+                CellDesc cd{};
+                cd.level = (int16_t)l; cd.x0 = (int16_t)x0; cd.y0 = (int16_t)y0; cd.tw = (int16_t)(x1 - x0); cd.th = (int16_t)(y1 - y0);
+                cd.offx = (int16_t)(j * L.wCell); cd.offy = (int16_t)(i * L.hCell); cd.ordinal = ord++;
+                cells.push_back(cd);
+                g.max_tw = std::max(g.max_tw, (int)cd.tw); g.max_th = std::max(g.max_th, (int)cd.th);
+            }
+        }
+        L.cell_count = ord;
+        L.cand_cap = ord * L.slot_cap;
+        L.slot_off = slot; L.cand_off = slot;
+        slot += (size_t)L.cand_cap;
+        L.sel_cap = std::max(L.quota, 4 * L.nRoots) + 3;
+        L.sel_off = sel; sel += L.sel_cap;
+        L.blur_off = blur; blur += align_up((size_t)L.pitch * L.h, 256);
+        if (l > 0) {
+            L.img_off = pyr; pyr += align_up((size_t)L.pitch * L.h, 256);
+            std::vector<LinTap> tx = linear_taps(g.lv[l - 1].w, L.w), ty = linear_taps(g.lv[l - 1].h, L.h);
+            L.tab_x_off = (int)taps.size(); taps.insert(taps.end(), tx.begin(), tx.end());
+            L.tab_y_off = (int)taps.size(); taps.insert(taps.end(), ty.begin(), ty.end());
+        }
+        for (int ty = 0; ty < ceil_div(L.h, 16); ++ty)
+            for (int tx = 0; tx < ceil_div(L.w, 128); ++tx) tiles.push_back(BlurTile{(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
+    }
+    g.ncells = (int)cells.size(); g.ntiles = (int)tiles.size();
+    g.pyr_bytes = std::max<size_t>(pyr, 256); g.blur_bytes = blur; g.slot_words = slot; g.cand_words = slot;
+    g.sel_words = sel; g.out_cap = sel;
+    if (taps.empty()) taps.push_back(LinTap{0, 0, 0});
+
+    const int B = h->max_batch;
+    auto dalloc = [&](void** p, size_t bytes) -> int { ORB_CUDA_TRY(cudaMalloc(p, std::max<size_t>(bytes, 256))); return ORB_OK; };
+    int rc;
+    if ((rc = dalloc(&h->d_geom, sizeof(Geometry))) || (rc = dalloc(&h->d_cells, cells.size() * sizeof(CellDesc))) ||
+        (rc = dalloc(&h->d_taps, taps.size() * sizeof(LinTap))) || (rc = dalloc(&h->d_tiles, tiles.size() * sizeof(BlurTile))) ||
+        (rc = dalloc(&h->d_pattern, 1024)))
+        return rc;
+    int8_t pat8[1024];
+    for (int i = 0; i < 1024; ++i) pat8[i] = (int8_t)kPatternInts[i];
+    ORB_CUDA_TRY(cudaMemcpy(h->d_geom, &g, sizeof(Geometry), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_taps, taps.data(), taps.size() * sizeof(LinTap), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_pattern, pat8, 1024, cudaMemcpyHostToDevice));
+    DeviceBuffers& db = h->db;
+    db.geom = (const Geometry*)h->d_geom; db.cells = (const CellDesc*)h->d_cells; db.taps = (const LinTap*)h->d_taps;
+    db.tiles = (const BlurTile*)h->d_tiles; db.pattern = (const int8_t*)h->d_pattern;
+    h->in_pitch = align_up((size_t)h->width, 128);
+    if ((rc = dalloc((void**)&db.pyr, (size_t)B * g.pyr_bytes)) || (rc = dalloc((void**)&db.blur, (size_t)B * g.blur_bytes)) ||
+        (rc = dalloc((void**)&db.slots, (size_t)B * g.slot_words * 4)) || (rc = dalloc((void**)&db.cell_counts, (size_t)B * g.ncells * 4)) ||
+        (rc = dalloc((void**)&db.sortbuf, (size_t)B * 5 * g.cand_words * 4)) || (rc = dalloc((void**)&db.selected, (size_t)B * g.sel_words * 4)) ||
+        (rc = dalloc((void**)&db.sel_counts, (size_t)B * nl * 4)) || (rc = dalloc((void**)&db.kps, (size_t)B * g.out_cap * sizeof(orbx_keypoint))) ||
+        (rc = dalloc((void**)&db.desc, (size_t)B * g.out_cap * 32)) || (rc = dalloc((void**)&db.counts, (size_t)B * 4)) ||
+        (rc = dalloc((void**)&h->d_input, (size_t)B * h->in_pitch * h->height)))
+        return rc;
+    ORB_CUDA_TRY(cudaMemset(db.counts, 0, (size_t)B * 4));
+    ORB_CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    ORB_CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    ORB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming));
+    ORB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming));
+    return ORB_OK;
+}
+
+// the whole of operator() for n frames, enqueued on st (blur runs on the side stream)
+int enqueue_pipeline(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t st) {
+    const Geometry& g = h->hg;
+    int rc;
+    if (h->stage_timing) {  // serialised on one stream so that every stage is timed alone
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[0], st));
+        for (int l = 1; l < g.nlevels; ++l)
+            if ((rc = launch_resize_level(g, h->db, fs, l, n, st))) return rc;
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[1], st));
+        if ((rc = launch_blur(g, h->db, fs, n, st))) return rc;
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[2], st));
+        if ((rc = launch_fast(g, h->db, fs, n, st))) return rc;
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[3], st));
+        if ((rc = launch_quadtree(g, h->db, n, st))) return rc;
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[4], st));
+        if ((rc = launch_describe(g, h->db, fs, n, st))) return rc;
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[5], st));
+        h->last = fs; h->last_n = n;
+        return ORB_OK;
+    }
+    for (int l = 1; l < g.nlevels; ++l)
+        if ((rc = launch_resize_level(g, h->db, fs, l, n, st))) return rc;
+    // fork: the Gaussian blur (1085-1086) only depends on the pyramid
+    ORB_CUDA_TRY(cudaEventRecord(h->ev_pyr, st));
+    ORB_CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_pyr, 0));
+    if ((rc = launch_blur(g, h->db, fs, n, h->stream2))) return rc;
+    ORB_CUDA_TRY(cudaEventRecord(h->ev_blur, h->stream2));
+    if ((rc = launch_fast(g, h->db, fs, n, st))) return rc;
+    if ((rc = launch_quadtree(g, h->db, n, st))) return rc;
+    ORB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_blur, 0));
+    if ((rc = launch_describe(g, h->db, fs, n, st))) return rc;
+    h->last = fs; h->last_n = n;
+    return ORB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbx_create(const orbx_config* cfg, int device, int width, int height, int max_batch, orbx_handle* out) {
+    ORB_REQUIRE(cfg && out, "null pointer");
+    ORB_REQUIRE(cfg->nlevels >= 1 && cfg->nlevels <= kMaxLevels, "nlevels out of range (1..16)");
+    ORB_REQUIRE(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f, "nfeatures >= 1 and scale_factor > 1 required");
+    ORB_REQUIRE(cfg->min_th_fast >= 1 && cfg->ini_th_fast >= cfg->min_th_fast && cfg->ini_th_fast < 255, "FAST thresholds: 1 <= min <= ini < 255");
+    ORB_REQUIRE(width > 0 && height > 0 && max_batch >= 1, "image size / batch must be positive");
+    *out = nullptr;
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    orbx_extractor* h = new (std::nothrow) orbx_extractor();
+    ORB_REQUIRE(h, "out of host memory");
+    h->cfg = *cfg; h->device = device; h->width = width; h->height = height; h->max_batch = max_batch;
+    const int rc = build_geometry(h);
+    if (rc != ORB_OK) { orbx_destroy(h); return rc; }
+    *out = h;
+    return ORB_OK;
+}
+
+void orbx_destroy(orbx_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
+    void* ptrs[] = {h->d_geom, h->d_cells, h->d_taps, h->d_tiles, h->d_pattern, h->db.pyr, h->db.blur, h->db.slots, h->db.cell_counts,
+                    h->db.sortbuf, h->db.selected, h->db.sel_counts, h->db.kps, h->db.desc, h->db.counts, h->d_input};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : h->ev_stage) if (e) cudaEventDestroy(e);
+    if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
+    if (h->ev_blur) cudaEventDestroy(h->ev_blur);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    delete h;
+}
+
+int orbx_get_tables(orbx_handle h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* fpl) {
+    ORB_REQUIRE(h, "null handle");
+    for (int i = 0; i < h->cfg.nlevels; ++i) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->inv_scale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+        if (fpl) fpl[i] = h->quota[i];
+    }
+    return ORB_OK;
+}
+
+int orbx_set_stage_timing(orbx_handle h, int enable) {
+    ORB_REQUIRE(h, "null handle");
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    if (enable && !h->ev_stage[0])
+        for (int i = 0; i <= ORBX_NUM_STAGES; ++i) ORB_CUDA_TRY(cudaEventCreate(&h->ev_stage[i]));
+    h->stage_timing = enable != 0;
+    return ORB_OK;
+}
+
+int orbx_stage_times(orbx_handle h, float* ms) {
+    ORB_REQUIRE(h && ms && h->ev_stage[0], "stage timing was never enabled");
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    ORB_CUDA_TRY(cudaEventSynchronize(h->ev_stage[ORBX_NUM_STAGES]));
+    for (int i = 0; i < ORBX_NUM_STAGES; ++i) ORB_CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev_stage[i], h->ev_stage[i + 1]));
+    return ORB_OK;
+}
+
+int orbx_algorithmic_bytes(orbx_handle h, double* bytes) {
+    ORB_REQUIRE(h && bytes, "null pointer");
+    const Geometry& g = h->hg;
+    double px = 0, pyr_rw = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        px += (double)g.lv[l].w * g.lv[l].h;
+        if (l) pyr_rw += (double)g.lv[l - 1].w * g.lv[l - 1].h + (double)g.lv[l].w * g.lv[l].h;
+    }
+    bytes[0] = pyr_rw;                                  /* resize: read level l-1, write level l */
+    bytes[1] = 2 * px;                                  /* blur: read + write every level */
+    bytes[2] = px;                                      /* FAST: read every level once */
+    bytes[3] = 0;                                       /* quadtree: latency bound, no streaming */
+    bytes[4] = (double)g.out_cap * 56;                  /* describe: result records */
+    return ORB_OK;
+}
+
+int orbx_max_keypoints(orbx_handle h) { return h ? h->hg.out_cap : ORB_EINVAL; }
+
+int orbx_level_size(orbx_handle h, int level, int* width, int* height) {
+    ORB_REQUIRE(h && level >= 0 && level < h->cfg.nlevels, "bad handle / level");
+    if (width) *width = h->hg.lv[level].w;
+    if (height) *height = h->hg.lv[level].h;
+    return ORB_OK;
+}
+
+int orbx_extract_device(orbx_handle h, const uint8_t* d_images, size_t stride, size_t frame_stride, int n, void* stream) {
+    ORB_REQUIRE(h, "null handle");
+    ORB_REQUIRE(n >= 0 && n <= h->max_batch, "batch larger than max_batch");
+    if (n == 0) return ORB_OK;
+    ORB_REQUIRE(d_images && stride >= (size_t)h->width && frame_stride >= stride * (size_t)(h->height - 1) + h->width, "bad frame layout");
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    FrameSet fs{d_images, stride, frame_stride};
+    return enqueue_pipeline(h, fs, n, (cudaStream_t)stream);
+}
+
+int orbx_device_results(orbx_handle h, const orbx_keypoint** d_kps, const uint8_t** d_desc, const int32_t** d_counts, int* cap_dev) {
+    ORB_REQUIRE(h, "null handle");
+    if (d_kps) *d_kps = h->db.kps;
+    if (d_desc) *d_desc = h->db.desc;
+    if (d_counts) *d_counts = h->db.counts;
+    if (cap_dev) *cap_dev = h->hg.out_cap;
+    return ORB_OK;
+}
+
+int orbx_extract_batch(orbx_handle h, const uint8_t* images, size_t stride, size_t frame_stride, int n, orbx_keypoint* kps,
+                       uint8_t* desc, int cap, int32_t* counts) {
+    ORB_REQUIRE(h, "null handle");
+    ORB_REQUIRE(n >= 0 && n <= h->max_batch, "batch larger than max_batch");
+    if (n == 0) return ORB_OK;
+    ORB_REQUIRE(counts, "null counts");
+    if (!images) {  // empty image: the reference returns without touching the outputs (1046-1047)
+        for (int i = 0; i < n; ++i) counts[i] = 0;
+        return ORB_OK;
+    }
+    ORB_REQUIRE(stride >= (size_t)h->width && cap >= 0 && (cap == 0 || (kps && desc)), "bad stride / output buffers");
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t dev_frame = h->in_pitch * h->height;
+    if (frame_stride == stride * (size_t)h->height || n == 1) {
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input, h->in_pitch, images, stride, h->width, (size_t)h->height * n, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int i = 0; i < n; ++i)
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input + i * dev_frame, h->in_pitch, images + i * frame_stride, stride, h->width, h->height,
+                                           cudaMemcpyHostToDevice, st));
+    }
+    FrameSet fs{h->d_input, h->in_pitch, dev_frame};
+    int rc = enqueue_pipeline(h, fs, n, st);
+    if (rc) return rc;
+    const int oc = h->hg.out_cap, take = std::min(cap, oc);
+    ORB_CUDA_TRY(cudaMemcpyAsync(counts, h->db.counts, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (take > 0) {
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_keypoint), h->db.kps, (size_t)oc * sizeof(orbx_keypoint),
+                                       (size_t)take * sizeof(orbx_keypoint), n, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->db.desc, (size_t)oc * 32, (size_t)take * 32, n, cudaMemcpyDeviceToHost, st));
+    }
+    ORB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i)
+        if (counts[i] > cap) { set_error("frame %d has %d keypoints, buffer holds %d", i, counts[i], cap); rc = ORB_ECAPACITY; }
+    return rc;
+}
+
+int orbx_extract(orbx_handle h, const uint8_t* image, size_t stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+    ORB_REQUIRE(h && n_out, "null pointer");
+    int32_t cnt = 0;
+    const int rc = orbx_extract_batch(h, image, stride, stride * (size_t)h->height, 1, kps, desc, cap, &cnt);
+    *n_out = cnt;
+    return rc;
+}
+
+int orbx_pyramid_level_device(orbx_handle h, int frame, int level, const uint8_t** d_ptr, size_t* pitch) {
+    ORB_REQUIRE(h && level >= 0 && level < h->cfg.nlevels && frame >= 0 && frame < h->last_n, "bad handle / level / frame");
+    int p;
+    const uint8_t* ptr = level_ptr(h->hg, h->last, h->db.pyr, frame, level, &p);
+    if (d_ptr) *d_ptr = ptr;
+    if (pitch) *pitch = (size_t)p;
+    return ORB_OK;
+}
+
+int orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    const uint8_t* p; size_t pitch;
+    const int rc = orbx_pyramid_level_device(h, frame, level, &p, &pitch);
+    if (rc) return rc;
+    const LevelGeom& L = h->hg.lv[level];
+    ORB_REQUIRE(dst && dst_stride >= (size_t)L.w, "bad destination");
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, p, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbx_debug_blurred_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    ORB_REQUIRE(h && level >= 0 && level < h->cfg.nlevels && frame >= 0 && frame < h->last_n, "bad handle / level / frame");
+    const LevelGeom& L = h->hg.lv[level];
+    ORB_REQUIRE(dst && dst_stride >= (size_t)L.w, "bad destination");
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, h->db.blur + (size_t)frame * h->hg.blur_bytes + L.blur_off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xys, int cap, int* n_out) {
+    ORB_REQUIRE(h && n_out && level >= 0 && level < h->cfg.nlevels && frame >= 0 && frame < h->last_n, "bad handle / level / frame");
+    const Geometry& g = h->hg;
+    const LevelGeom& L = g.lv[level];
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<int> cnt(L.cell_count);
+    std::vector<uint32_t> sl((size_t)L.cand_cap);
+    ORB_CUDA_TRY(cudaMemcpy(cnt.data(), h->db.cell_counts + (size_t)frame * g.ncells + L.cell_begin, cnt.size() * 4, cudaMemcpyDeviceToHost));
+    ORB_CUDA_TRY(cudaMemcpy(sl.data(), h->db.slots + (size_t)frame * g.slot_words + L.slot_off, sl.size() * 4, cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int c = 0; c < L.cell_count; ++c)
+        for (int k = 0; k < cnt[c]; ++k, ++n) {
+            if (n >= cap) continue;
+            const uint32_t p = sl[(size_t)c * L.slot_cap + k];
+            xys[3 * n] = (int)(p & 0xfff) + kMinBorder; xys[3 * n + 1] = (int)((p >> 12) & 0xfff) + kMinBorder; xys[3 * n + 2] = (int)(p >> 24);
+        }
+    *n_out = n;
+    return n > cap ? ORB_ECAPACITY : ORB_OK;
+}
+
+int orbx_debug_quadtree(int device, const int32_t* xs, const int32_t* ys, const int32_t* scores, int n, int minX, int maxX,
+                        int minY, int maxY, int N, int32_t* out_idx, int cap, int* n_out) {
+    ORB_REQUIRE(n >= 0 && n_out && (n == 0 || (xs && ys && scores)), "bad arguments");
+    *n_out = 0;
+    if (n == 0) return ORB_OK;
+    const int W = maxX - minX, H = maxY - minY;
+    ORB_REQUIRE(W > 0 && H > 0 && W <= 4096 && H <= 4096, "bad bounds");
+    const int nRoots = (int)roundf((float)W / (float)H);
+    ORB_REQUIRE(nRoots >= 1, "aspect ratio below 0.5");
+    const float rootW = (float)W / nRoots;
+    const int span = std::max((int)ceilf(rootW) + 1, H);
+    int depth = 1;
+    while ((1 << depth) < span) ++depth;
+    depth = std::min(depth + 1, kQtMaxDepth);
+    const int sel_cap = std::max(N, 4 * nRoots) + 3;
+    std::vector<uint32_t> packed(n);
+    for (int i = 0; i < n; ++i) {
+        ORB_REQUIRE(xs[i] >= 0 && xs[i] < 4096 && ys[i] >= 0 && ys[i] < 4096 && scores[i] >= 0 && scores[i] < 256, "candidate out of range");
+        packed[i] = (uint32_t)xs[i] | (uint32_t)ys[i] << 12 | (uint32_t)scores[i] << 24;
+    }
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    uint32_t *d_cand = nullptr, *d_scr = nullptr, *d_sel = nullptr; int* d_cnt = nullptr;
+    ORB_CUDA_TRY(cudaMalloc(&d_cand, (size_t)n * 4)); ORB_CUDA_TRY(cudaMalloc(&d_scr, (size_t)n * 16));
+    ORB_CUDA_TRY(cudaMalloc(&d_sel, (size_t)sel_cap * 4)); ORB_CUDA_TRY(cudaMalloc(&d_cnt, 4));
+    ORB_CUDA_TRY(cudaMemcpy(d_cand, packed.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    int rc = launch_quadtree_standalone(d_cand, n, N, nRoots, rootW, H, depth, d_scr, d_sel, sel_cap, d_cnt, 0);
+    int cnt = 0;
+    std::vector<uint32_t> sel(sel_cap);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(sel.data(), d_sel, (size_t)sel_cap * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("quadtree kernel failed: %s", cudaGetErrorString(e)); rc = ORB_ECUDA; }
+    }
+    cudaFree(d_cand); cudaFree(d_scr); cudaFree(d_sel); cudaFree(d_cnt);
+    if (rc) return rc;
+    // map the packed survivors back to candidate indices (pixels are unique per level)
+    for (int k = 0; k < cnt && k < cap; ++k) {
+        int found = -1;
+        for (int i = 0; i < n; ++i) if (packed[i] == sel[k]) { found = i; break; }
+        out_idx[k] = found;
+    }
+    *n_out = cnt;
+    return cnt > cap ? ORB_ECAPACITY : ORB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// Hamming matching kernels (K7 brute-force kNN-2, K8 candidate lists, distance matrix, ratio test).
+//
+// Replaces the DescriptorDistance loops of the reference matcher:
+//   ORBmatcher::DescriptorDistance          /root/reference/src/ORBmatcher.cc:1649-1665
+//   best/second selection rule              src/ORBmatcher.cc:104-116, 218-227, 449-458, 588-597
+//   acceptance (threshold + ratio)          src/ORBmatcher.cc:229-232, 461-463, 600-603
+//
+// The selection rule "strict '<' updates in iteration order" is equivalent to
+//   (best, second) = the two smallest values of the multiset {dist_j} U {256, 256},
+//   idx            = first position attaining best,
+// which is associative, so the database can be tiled / split freely and partial triples merged
+// in position order (merge()). All arithmetic is integer: bit-exact by construction.
+//
+// Roofline: POPC pipe. 8 x POPC.b32 per comparison; memory traffic is (nA + nB) * 32 B per
+// pass plus L2-resident tile re-reads, i.e. irrelevant next to the popcount work.
+#include "common.cuh"
+
+namespace orb {
+
+struct Top2 {
+    int b1, b2, pos;  // pos: iteration position of the first minimum (-1: none)
+};
+
+__device__ __forceinline__ void top2_update(Top2& t, int d, int pos) {
+    t.b2 = min(t.b2, max(d, t.b1));
+    t.pos = d < t.b1 ? pos : t.pos;
+    t.b1 = min(t.b1, d);
+}
+// a precedes b in iteration order
+__device__ __forceinline__ Top2 top2_merge(const Top2& a, const Top2& b) {
+    Top2 r;
+    r.b1 = min(a.b1, b.b1);
+    r.pos = b.b1 < a.b1 ? b.pos : a.pos;
+    r.b2 = min(max(a.b1, b.b1), min(a.b2, b.b2));
+    return r;
+}
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+constexpr int kQueriesPerBlock = 256;  // one query per thread, held in 8 registers
+constexpr int kTileRows = 256;         // database rows per shared-memory stage (8 KB)
+constexpr int kStages = 2;
+
+// grid: (query blocks, database splits, pairs)
+__global__ void __launch_bounds__(kQueriesPerBlock)
+knn2_kernel(const uint4* __restrict__ A, const int* __restrict__ nA_dev, int nA_const, int strideA_rows,
+            const uint4* __restrict__ B, const int* __restrict__ nB_dev, int nB_const, int strideB_rows,
+            int rows_per_split, int nsplit, int out_stride,
+            int* __restrict__ o_idx, int* __restrict__ o_b1, int* __restrict__ o_b2) {
+    __shared__ __align__(128) uint4 tile[kStages][kTileRows * 2];
+    __shared__ __align__(8) uint64_t full[kStages];
+
+    const int pair = blockIdx.z, split = blockIdx.y;
+    const int nA = nA_dev ? nA_dev[pair] : nA_const;
+    const int nB = nB_dev ? nB_dev[pair] : nB_const;
+    const int q0 = blockIdx.x * kQueriesPerBlock;
+    if (q0 >= nA) return;  // whole block exits together
+    const int q = q0 + threadIdx.x;
+    const uint4* Ap = A + (size_t)pair * strideA_rows * 2;
+    const uint4* Bp = B + (size_t)pair * strideB_rows * 2;
+
+    const int lo = min(split * rows_per_split, nB), hi = min(lo + rows_per_split, nB);
+    const int ntiles = ceil_div(hi - lo, kTileRows);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int r0 = lo + t * kTileRows;
+        const uint32_t bytes = (uint32_t)min(kTileRows, hi - r0) * 32u;
+        mbar_expect_tx(&full[t % kStages], bytes);
+        bulk_g2s(tile[t % kStages], Bp + (size_t)r0 * 2, bytes, &full[t % kStages]);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
+
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (q < nA) { a0 = __ldg(Ap + (size_t)q * 2); a1 = __ldg(Ap + (size_t)q * 2 + 1); }
+    Top2 best{256, 256, -1};
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kStages;
+        mbar_wait(&full[s], (t / kStages) & 1);
+        const int r0 = lo + t * kTileRows;
+        const int rows = min(kTileRows, hi - r0);
+        const uint4* tp = tile[s];
+        int j = 0;
+#pragma unroll 4
+        for (; j + 1 <= rows; ++j) {
+            const uint4 b0 = tp[2 * j], b1 = tp[2 * j + 1];
+            top2_update(best, hamming256(a0, a1, b0, b1), r0 + j);
+        }
+        __syncthreads();  // every thread is done with stage s
+        if (threadIdx.x == 0 && t + kStages < ntiles) issue(t + kStages);
+    }
+    if (q < nA) {
+        const size_t o = ((size_t)pair * nsplit + split) * out_stride + q;
+        o_idx[o] = best.pos; o_b1[o] = best.b1; o_b2[o] = best.b2;
+    }
+}
+
+// merges the nsplit partial triples of each query in split (= position) order
+__global__ void knn2_merge_kernel(const int* __restrict__ p_idx, const int* __restrict__ p_b1,
+                                  const int* __restrict__ p_b2, const int* __restrict__ nA_dev, int nA_const,
+                                  int nsplit, int part_stride, int out_stride, int* __restrict__ o_idx,
+                                  int* __restrict__ o_b1, int* __restrict__ o_b2) {
+    const int pair = blockIdx.y;
+    const int nA = nA_dev ? nA_dev[pair] : nA_const;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nA) return;
+    Top2 acc{256, 256, -1};
+    for (int s = 0; s < nsplit; ++s) {
+        const size_t o = ((size_t)pair * nsplit + s) * part_stride + q;
+        acc = top2_merge(acc, Top2{p_b1[o], p_b2[o], p_idx[o]});
+    }
+    const size_t o = (size_t)pair * out_stride + q;
+    o_idx[o] = acc.pos; o_b1[o] = acc.b1; o_b2[o] = acc.b2;
+}
+
+// One warp per query; lanes stride over the candidate list; positions (not row ids) break ties.
+__global__ void knn2_lists_kernel(const uint4* __restrict__ A, int nA, const uint4* __restrict__ B,
+                                  const int* __restrict__ offsets, const int* __restrict__ cands,
+                                  int* __restrict__ o_idx, int* __restrict__ o_b1, int* __restrict__ o_b2) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nA) return;
+    const uint4 a0 = __ldg(A + (size_t)q * 2), a1 = __ldg(A + (size_t)q * 2 + 1);
+    const int lo = offsets[q], hi = offsets[q + 1];
+    Top2 t{256, 256, -1};
+    for (int k = lo + lane; k < hi; k += 32) {
+        const int j = cands[k];
+        top2_update(t, hamming256(a0, a1, __ldg(B + (size_t)j * 2), __ldg(B + (size_t)j * 2 + 1)), k);
+    }
+    // lanes hold interleaved subsequences: order by position explicitly
+    for (int off = 16; off; off >>= 1) {
+        Top2 o{__shfl_xor_sync(0xffffffffu, t.b1, off), __shfl_xor_sync(0xffffffffu, t.b2, off),
+               __shfl_xor_sync(0xffffffffu, t.pos, off)};
+        Top2 r;
+        r.b1 = min(t.b1, o.b1);
+        const bool take_o = o.b1 < t.b1 || (o.b1 == t.b1 && o.pos >= 0 && (t.pos < 0 || o.pos < t.pos));
+        r.pos = take_o ? o.pos : t.pos;
+        r.b2 = min(max(t.b1, o.b1), min(t.b2, o.b2));
+        t = r;
+    }
+    if (lane == 0) { o_idx[q] = t.pos >= 0 ? cands[t.pos] : -1; o_b1[q] = t.b1; o_b2[q] = t.b2; }
+}
+
+__global__ void ratio_filter_kernel(const int* __restrict__ idx, const int* __restrict__ b1, const int* __restrict__ b2,
+                                    int n, int th, int inclusive, float ratio, int* __restrict__ match) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d1 = b1[i], d2 = b2[i];
+    const bool th_ok = inclusive ? d1 <= th : d1 < th;
+    const bool ok = th_ok && idx[i] >= 0 && (float)d1 < __fmul_rn(ratio, (float)d2);
+    match[i] = ok ? idx[i] : -1;
+}
+
+// 16x16 output tile per block; both operand tiles staged in shared memory
+__global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, const uint4* __restrict__ B, int nB,
+                                       int16_t* __restrict__ out) {
+    __shared__ uint4 sa[16][2], sb[16][2];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+    const int t = ty * 16 + tx;
+    if (t < 32) { const int r = blockIdx.y * 16 + (t >> 1); sa[t >> 1][t & 1] = r < nA ? __ldg(A + (size_t)r * 2 + (t & 1)) : make_uint4(0, 0, 0, 0); }
+    else if (t < 64) { const int u = t - 32, r = blockIdx.x * 16 + (u >> 1); sb[u >> 1][u & 1] = r < nB ? __ldg(B + (size_t)r * 2 + (u & 1)) : make_uint4(0, 0, 0, 0); }
+    __syncthreads();
+    if (i < nA && j < nB) out[(size_t)i * nB + j] = (int16_t)hamming256(sa[ty][0], sa[ty][1], sb[tx][0], sb[tx][1]);
+}
+
+// ---- host launchers --------------------------------------------------------------------------
+static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB,
+                       const int* d_nB, int nB_max, int strideB_rows, int pairs, int* d_idx, int* d_b1, int* d_b2,
+                       cudaStream_t st) {
+    if (pairs <= 0 || nA_max <= 0) return ORB_OK;
+    const int qblocks = ceil_div(nA_max, kQueriesPerBlock);
+    const int ctas = qblocks * pairs;
+    int nsplit = 1;
+    if (ctas < 2 * kNumSMs) {
+        nsplit = ceil_div(2 * kNumSMs, ctas);
+        const int max_split = max(1, nB_max / (2 * kTileRows));
+        nsplit = min(nsplit, max_split);
+    }
+    int rows_per_split = ceil_div(ceil_div(max(nB_max, 1), nsplit), kTileRows) * kTileRows;
+    nsplit = max(1, ceil_div(max(nB_max, 1), rows_per_split));
+    dim3 grid(qblocks, nsplit, pairs);
+    if (nsplit == 1) {
+        knn2_kernel<<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)dA, d_nA, nA_max, strideA_rows, (const uint4*)dB,
+                                                       d_nB, nB_max, strideB_rows, rows_per_split, 1, strideA_rows,
+                                                       d_idx, d_b1, d_b2);
+        ORB_CUDA_TRY(cudaGetLastError());
+        return ORB_OK;
+    }
+    int* part = nullptr;
+    const size_t per = (size_t)pairs * nsplit * nA_max;
+    ORB_CUDA_TRY(cudaMallocAsync(&part, 3 * per * sizeof(int), st));
+    knn2_kernel<<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)dA, d_nA, nA_max, strideA_rows, (const uint4*)dB, d_nB,
+                                                   nB_max, strideB_rows, rows_per_split, nsplit, nA_max, part,
+                                                   part + per, part + 2 * per);
+    ORB_CUDA_TRY(cudaGetLastError());
+    knn2_merge_kernel<<<dim3(ceil_div(nA_max, 256), pairs), 256, 0, st>>>(part, part + per, part + 2 * per, d_nA, nA_max,
+                                                                          nsplit, nA_max, strideA_rows, d_idx, d_b1, d_b2);
+    ORB_CUDA_TRY(cudaGetLastError());
+    ORB_CUDA_TRY(cudaFreeAsync(part, st));
+    return ORB_OK;
+}
+
+}  // namespace orb
+
+using namespace orb;
+
+extern "C" {
+
+int orbm_knn2_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best,
+                     int32_t* d_second, void* stream) {
+    ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
+    ORB_REQUIRE(nA == 0 || (dA && d_idx && d_best && d_second), "null pointer");
+    ORB_REQUIRE(nB == 0 || dB, "null database");
+    ORB_REQUIRE(((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0, "descriptor arrays must be 16-byte aligned");
+    return launch_knn2(dA, nullptr, nA, nA, dB, nullptr, nB, nB, 1, d_idx, d_best, d_second, (cudaStream_t)stream);
+}
+
+int orbm_knn2_batched_device(const uint8_t* dA, const int32_t* d_nA, int strideA_rows, const uint8_t* dB,
+                             const int32_t* d_nB, int strideB_rows, int pairs, int32_t* d_idx, int32_t* d_best,
+                             int32_t* d_second, void* stream) {
+    ORB_REQUIRE(pairs >= 0 && strideA_rows >= 0 && strideB_rows >= 0, "negative size");
+    ORB_REQUIRE(dA && dB && d_idx && d_best && d_second, "null pointer");
+    ORB_REQUIRE(((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0, "descriptor arrays must be 16-byte aligned");
+    return launch_knn2(dA, d_nA, strideA_rows, strideA_rows, dB, d_nB, strideB_rows, strideB_rows, pairs, d_idx, d_best,
+                       d_second, (cudaStream_t)stream);
+}
+
+int orbm_knn2_lists_device(const uint8_t* dA, int nA, const uint8_t* dB, const int32_t* d_offsets,
+                           const int32_t* d_cands, int32_t* d_idx, int32_t* d_best, int32_t* d_second, void* stream) {
+    ORB_REQUIRE(nA >= 0, "negative row count");
+    if (nA == 0) return ORB_OK;
+    ORB_REQUIRE(dA && dB && d_offsets && d_cands && d_idx && d_best && d_second, "null pointer");
+    knn2_lists_kernel<<<ceil_div(nA * 32, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dA, nA, (const uint4*)dB, d_offsets,
+                                                                                d_cands, d_idx, d_best, d_second);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbm_ratio_filter_device(const int32_t* d_idx, const int32_t* d_best, const int32_t* d_second, int n, int th,
+                             int inclusive, float ratio, int32_t* d_match, void* stream) {
+    ORB_REQUIRE(n >= 0, "negative count");
+    if (n == 0) return ORB_OK;
+    ORB_REQUIRE(d_idx && d_best && d_second && d_match, "null pointer");
+    ratio_filter_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d_idx, d_best, d_second, n, th, inclusive, ratio, d_match);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int16_t* d_out, void* stream) {
+    ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
+    if (nA == 0 || nB == 0) return ORB_OK;
+    ORB_REQUIRE(dA && dB && d_out, "null pointer");
+    distance_matrix_kernel<<<dim3(ceil_div(nB, 16), ceil_div(nA, 16)), dim3(16, 16), 0, (cudaStream_t)stream>>>(
+        (const uint4*)dA, nA, (const uint4*)dB, nB, d_out);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+// ---- host-buffer wrappers: H2D, kernel, D2H, synchronise --------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        ORB_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16));
+        return ORB_OK;
+    }
+};
+}  // namespace
+
+int orbm_knn2(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int32_t* idx, int32_t* best, int32_t* second) {
+    ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
+    if (nA == 0) return ORB_OK;
+    ORB_REQUIRE(A && idx && best && second && (nB == 0 || B), "null pointer");
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    DevBuf dA, dB, dO;
+    int rc;
+    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dO.alloc((size_t)nA * 12))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
+    if (nB) ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
+    int* o = (int*)dO.p;
+    if ((rc = orbm_knn2_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, nB, o, o + nA, o + 2 * (size_t)nA, 0))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    return ORB_OK;
+}
+
+int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* offsets,
+                    const int32_t* cands, int32_t* idx, int32_t* best, int32_t* second) {
+    ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
+    if (nA == 0) return ORB_OK;
+    ORB_REQUIRE(A && B && offsets && cands && idx && best && second, "null pointer");
+    const int total = offsets[nA];
+    ORB_REQUIRE(total >= 0, "bad offsets");
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    DevBuf dA, dB, dOf, dC, dO;
+    int rc;
+    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dOf.alloc((size_t)(nA + 1) * 4)) ||
+        (rc = dC.alloc((size_t)total * 4)) || (rc = dO.alloc((size_t)nA * 12)))
+        return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dOf.p, offsets, (size_t)(nA + 1) * 4, cudaMemcpyHostToDevice, 0));
+    if (total) ORB_CUDA_TRY(cudaMemcpyAsync(dC.p, cands, (size_t)total * 4, cudaMemcpyHostToDevice, 0));
+    int* o = (int*)dO.p;
+    if ((rc = orbm_knn2_lists_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, (const int*)dOf.p, (const int*)dC.p, o,
+                                     o + nA, o + 2 * (size_t)nA, 0)))
+        return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    return ORB_OK;
+}
+
+int orbm_distance_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int16_t* out) {
+    ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
+    if (nA == 0 || nB == 0) return ORB_OK;
+    ORB_REQUIRE(A && B && out, "null pointer");
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    DevBuf dA, dB, dO;
+    int rc;
+    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dO.alloc((size_t)nA * nB * 2))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
+    if ((rc = orbm_distance_matrix_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, nB, (int16_t*)dO.p, 0))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(out, dO.p, (size_t)nA * nB * 2, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    return ORB_OK;
+}
+
+}  // extern "C"

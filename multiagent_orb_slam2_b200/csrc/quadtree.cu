@@ -1,0 +1,391 @@
+// K4: quadtree keypoint distribution, one thread block per (level, frame).
+//
+// Replaces ORBextractor::DistributeOctTree + ExtractorNode::DivideNode,
+// /root/reference/src/ORBextractor.cc:481-763, which walk a std::list of nodes one at a time. The
+// same result (same keypoints, same output order, canonical tie-break) is produced here by:
+//   1. path keys: root index, then 2 bits per depth (bit0 right half, bit1 bottom half) from the
+//      recursive ceil-halving of DivideNode (483-509) - independent per candidate;
+//   2. a block radix sort by key, after which every tree node is a contiguous range + a depth;
+//   3. a node-parallel simulation of the list: one step processes the expandable nodes in a given
+//      order (list order for a full pass 606-665; (size desc, list position asc) in the final phase
+//      676-737, the canonical form of the reference's sort of pair<int,Node*> at 684), pushes the
+//      children of each to the front and stops once the list holds >= N nodes (730-731);
+//   4. per surviving node the candidate with the highest response, earliest candidate on ties
+//      (744-760).
+// The CPU statement of exactly this formulation is oracle/quadtree_arrayform.cc (checked against the
+// direct std::list restatement); integer only, so results are bit-exact.
+#include "extract_kernels.cuh"
+
+namespace orb {
+
+constexpr int kQtThreads = 1024;
+constexpr int kQtWarps = kQtThreads / 32;
+
+struct QtShared {
+    int warp_tmp[kQtWarps];
+    int carry;
+    int bcast[4];
+    int hist[256];
+    int wcount[kQtWarps][256];
+};
+
+// exclusive scan of in[0..len) into out[0..len) (may alias); returns the total to every thread
+__device__ int block_exclusive_scan(const int* in, int* out, int len, QtShared& sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sh.carry = 0;
+    __syncthreads();
+    for (int base = 0; base < len; base += kQtThreads) {
+        const int i = base + threadIdx.x;
+        const int v = i < len ? in[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sh.warp_tmp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = sh.warp_tmp[lane];
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+            sh.warp_tmp[lane] = winc - w;  // exclusive warp offsets
+            if (lane == 31) sh.bcast[0] = winc;  // chunk total
+        }
+        __syncthreads();
+        const int carry = sh.carry;
+        if (i < len) out[i] = carry + sh.warp_tmp[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) sh.carry = carry + sh.bcast[0];
+        __syncthreads();
+    }
+    const int total = sh.carry;
+    __syncthreads();  // nobody may still be reading carry when the next scan resets it
+    return total;
+}
+
+__device__ __forceinline__ uint32_t qt_path_key(int x, int y, int H, float rootW, int depth) {
+    const int r = (int)__fdiv_rn((float)x, rootW);
+    int x0 = (int)__fmul_rn(rootW, (float)r), x1 = (int)__fmul_rn(rootW, (float)(r + 1));
+    int y0 = 0, y1 = H;
+    uint32_t key = (uint32_t)r;
+    for (int d = 0; d < depth; ++d) {
+        const int xm = x0 + ((x1 - x0 + 1) >> 1), ym = y0 + ((y1 - y0 + 1) >> 1);
+        const uint32_t xb = x >= xm, yb = y >= ym;
+        x0 = xb ? xm : x0; x1 = xb ? x1 : xm;
+        y0 = yb ? ym : y0; y1 = yb ? y1 : ym;
+        key = (key << 2) | (yb << 1) | xb;
+    }
+    return key;
+}
+
+// LSD radix sort of (key, val) pairs, 8 bits per pass; result ends in (kA, vA) or (kB, vB): returns
+// 0 / 1 accordingly. Buffers are global (L2 resident) so any candidate count fits.
+__device__ int block_radix_sort(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32_t* vB, int n, int key_bits, QtShared& sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kQtWarps * 256; i += kQtThreads) (&sh.wcount[0][0])[i] = 0;
+    int flip = 0;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        const uint32_t* ki = flip ? kB : kA; const uint32_t* vi = flip ? vB : vA;
+        uint32_t* ko = flip ? kA : kB;       uint32_t* vo = flip ? vA : vB;
+        if (threadIdx.x < 256) sh.hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kQtThreads) atomicAdd(&sh.hist[(ki[i] >> shift) & 255], 1);
+        __syncthreads();
+        // exclusive scan of the 256 bins (warps 0..7), result back into hist
+        {
+            int v = 0, inc = 0;
+            if (threadIdx.x < 256) {
+                v = sh.hist[threadIdx.x];
+                inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (lane == 31) sh.warp_tmp[warp] = inc;
+            }
+            __syncthreads();
+            if (threadIdx.x < 256) {
+                int off = 0;
+                for (int w = 0; w < warp; ++w) off += sh.warp_tmp[w];
+                sh.hist[threadIdx.x] = off + inc - v;
+            }
+            __syncthreads();
+        }
+        for (int base = 0; base < n; base += kQtThreads) {
+            const int i = base + threadIdx.x;
+            const bool valid = i < n;
+            uint32_t k = 0, v = 0;
+            if (valid) { k = ki[i]; v = vi[i]; }
+            const uint32_t digit = valid ? (k >> shift) & 255u : 0x100u + lane;  // invalid lanes never group
+            const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            const bool leader = valid && rank == 0;
+            if (leader) sh.wcount[warp][digit] = __popc(peers);
+            __syncthreads();
+            if (threadIdx.x < 256) {  // per digit: offsets of the warps of this tile, advance the bin base
+                int run = sh.hist[threadIdx.x];
+#pragma unroll 8
+                for (int w = 0; w < kQtWarps; ++w) {
+                    const int c = sh.wcount[w][threadIdx.x];
+                    if (c) { sh.wcount[w][threadIdx.x] = run; run += c; }  // untouched entries stay 0
+                }
+                sh.hist[threadIdx.x] = run;
+            }
+            __syncthreads();
+            if (valid) { const int pos = sh.wcount[warp][digit] + rank; ko[pos] = k; vo[pos] = v; }
+            __syncwarp();
+            if (leader) sh.wcount[warp][digit] = 0;
+            __syncwarp();
+        }
+        flip ^= 1;
+        __syncthreads();
+    }
+    return flip;
+}
+
+// The node list simulation. Node arrays live in shared memory (cap entries each).
+struct QtNodes {
+    int* lo[2]; int* hi[2]; int* dep[2];  // double-buffered list
+    int* b1; int* b2; int* b3;            // inner child boundaries of expandable nodes
+    int* cc;                              // non-empty children (0 for non-expandable)
+    int* flag; int* scan;                 // scratch
+    int* P;                               // processing order (node indices)
+    int* inc;                             // per P-slot: children counts, then prefix sums
+};
+
+// core: candidates packed (x | y<<12 | score<<24) in cand[0..n); scratch = 4 arrays of n words.
+// Writes the survivors (packed) in list order to sel[] and their number to *count_out.
+// (no __restrict__ / read-only-cache hints: cand and scratch are written earlier in the same kernel)
+__device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, float rootW, int H, int depth,
+                                uint32_t* scratch, uint32_t* sel, int sel_cap, int* count_out,
+                                QtShared& sh, int* nodemem) {
+    if (n <= 0 || nRoots <= 0) {
+        if (threadIdx.x == 0) *count_out = 0;
+        return;
+    }
+    uint32_t *kA = scratch, *vA = scratch + n, *kB = scratch + 2 * (size_t)n, *vB = scratch + 3 * (size_t)n;
+    for (int i = threadIdx.x; i < n; i += kQtThreads) {
+        const uint32_t p = cand[i];
+        kA[i] = qt_path_key(p & 0xfff, (p >> 12) & 0xfff, H, rootW, depth);
+        vA[i] = i;
+    }
+    __syncthreads();
+    int root_bits = 0;
+    while ((1 << root_bits) < nRoots) ++root_bits;
+    const int flip = block_radix_sort(kA, vA, kB, vB, n, 2 * depth + root_bits, sh);
+    const uint32_t* sk = flip ? kB : kA;
+    const uint32_t* sv = flip ? vB : vA;
+
+    const int cap = sel_cap;
+    QtNodes q;
+    {
+        int* p = nodemem;
+        for (int s = 0; s < 2; ++s) { q.lo[s] = p; p += cap; q.hi[s] = p; p += cap; q.dep[s] = p; p += cap; }
+        q.b1 = p; p += cap; q.b2 = p; p += cap; q.b3 = p; p += cap; q.cc = p; p += cap;
+        q.flag = p; p += cap; q.scan = p; p += cap; q.P = p; p += cap; q.inc = p; p += cap;
+    }
+    auto lower_bound_key = [&](uint32_t key) {
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sk[mid] >= key) hi = mid; else lo = mid + 1; }
+        return lo;
+    };
+
+    // roots (539-585): non-empty ones, in order
+    int cur = 0;
+    for (int r = threadIdx.x; r < nRoots; r += kQtThreads) {
+        const int lo = lower_bound_key((uint32_t)r << (2 * depth));
+        const int hi = r + 1 == nRoots ? n : lower_bound_key((uint32_t)(r + 1) << (2 * depth));
+        q.b1[r] = lo; q.b2[r] = hi; q.flag[r] = hi > lo;
+    }
+    __syncthreads();
+    int count = block_exclusive_scan(q.flag, q.scan, nRoots, sh);
+    for (int r = threadIdx.x; r < nRoots; r += kQtThreads)
+        if (q.flag[r]) { const int p = q.scan[r]; q.lo[0][p] = q.b1[r]; q.hi[0][p] = q.b2[r]; q.dep[0][p] = 0; }
+    __syncthreads();
+
+    bool final_phase = false;
+    for (;;) {
+        const int before = count;
+        int *lo = q.lo[cur], *hi = q.hi[cur], *dep = q.dep[cur];
+        int *nlo = q.lo[cur ^ 1], *nhi = q.hi[cur ^ 1], *ndep = q.dep[cur ^ 1];
+        // children of every expandable node
+        for (int i = threadIdx.x; i < before; i += kQtThreads) {
+            const int l = lo[i], h = hi[i], d = dep[i];
+            int c = 0;
+            if (h - l >= 2 && d < depth) {
+                const int sft = 2 * (depth - d - 1);
+                int bnd[3];
+#pragma unroll
+                for (int t = 1; t < 4; ++t) {
+                    int a = l, b = h;
+                    while (a < b) { const int mid = (a + b) >> 1; if (((sk[mid] >> sft) & 3u) >= (uint32_t)t) b = mid; else a = mid + 1; }
+                    bnd[t - 1] = a;
+                }
+                q.b1[i] = bnd[0]; q.b2[i] = bnd[1]; q.b3[i] = bnd[2];
+                c = (bnd[0] > l) + (bnd[1] > bnd[0]) + (bnd[2] > bnd[1]) + (h > bnd[2]);
+            }
+            q.cc[i] = c;
+            q.flag[i] = c > 0;
+        }
+        __syncthreads();
+        const int m = block_exclusive_scan(q.flag, q.scan, before, sh);
+        // processing order P
+        if (!final_phase) {
+            for (int i = threadIdx.x; i < before; i += kQtThreads) if (q.flag[i]) q.P[q.scan[i]] = i;
+        } else {
+            // compact list-ordered expandable nodes into inc[] (temporarily), then rank by
+            // (size desc, list position asc)
+            for (int i = threadIdx.x; i < before; i += kQtThreads) if (q.flag[i]) q.inc[q.scan[i]] = i;
+            __syncthreads();
+            for (int a = threadIdx.x; a < m; a += kQtThreads) {
+                const int na = q.inc[a], sa = hi[na] - lo[na];
+                int rank = 0;
+                for (int b = 0; b < m; ++b) {
+                    const int nb = q.inc[b], sb = hi[nb] - lo[nb];
+                    rank += (sb > sa) || (sb == sa && b < a);
+                }
+                q.P[rank] = na;
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < m; k += kQtThreads) q.inc[k] = q.cc[q.P[k]];
+        __syncthreads();
+        const int all_children = block_exclusive_scan(q.inc, q.inc, m, sh);  // inc[k] = children before slot k
+        // how many slots get processed (730-731)
+        int processed = m;
+        if (final_phase) {
+            if (threadIdx.x == 0) sh.bcast[1] = m;
+            __syncthreads();
+            for (int k = threadIdx.x; k < m; k += kQtThreads) {
+                // list size after processing slots 0..k
+                const int after_k = before + q.inc[k] + q.cc[q.P[k]] - (k + 1);
+                if (after_k >= N) atomicMin(&sh.bcast[1], k + 1);
+            }
+            __syncthreads();
+            processed = sh.bcast[1];
+        }
+        const int children = processed < m ? q.inc[processed] : all_children;
+        __syncthreads();
+        // new list: children of slot processed-1 (q=3..0), ..., of slot 0; then untouched nodes in order
+        for (int i = threadIdx.x; i < before; i += kQtThreads) q.flag[i] = 1;  // 1 = untouched
+        if (threadIdx.x == 0) sh.bcast[2] = 0;
+        __syncthreads();
+        int my_expand = 0;
+        for (int k = threadIdx.x; k < processed; k += kQtThreads) {
+            const int i = q.P[k];
+            q.flag[i] = 0;
+            const int bnd[5] = {lo[i], q.b1[i], q.b2[i], q.b3[i], hi[i]};
+            int pos = children - q.inc[k] - q.cc[i];
+            const int d = dep[i] + 1;
+#pragma unroll
+            for (int t = 3; t >= 0; --t)
+                if (bnd[t + 1] > bnd[t]) {
+                    nlo[pos] = bnd[t]; nhi[pos] = bnd[t + 1]; ndep[pos] = d; ++pos;
+                    my_expand += (bnd[t + 1] - bnd[t]) >= 2;
+                }
+        }
+        if (my_expand) atomicAdd(&sh.bcast[2], my_expand);
+        __syncthreads();
+        block_exclusive_scan(q.flag, q.scan, before, sh);
+        for (int i = threadIdx.x; i < before; i += kQtThreads)
+            if (q.flag[i]) { const int p = children + q.scan[i]; nlo[p] = lo[i]; nhi[p] = hi[i]; ndep[p] = dep[i]; }
+        __syncthreads();
+        const int n_expand = sh.bcast[2];
+        count = children + (before - processed);
+        cur ^= 1;
+        if (count >= N || count == before) break;
+        if (!final_phase && count + 3 * n_expand > N) final_phase = true;
+        __syncthreads();
+    }
+
+    // best candidate per node: max response, earliest candidate on ties; one warp per node
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int* lo = q.lo[cur]; const int* hi = q.hi[cur];
+    for (int p = warp; p < count; p += kQtWarps) {
+        uint32_t best = 0;
+        for (int i = lo[p] + lane; i < hi[p]; i += 32) {
+            const uint32_t c = sv[i];
+            best = max(best, (cand[c] >> 24) << 24 | (0xffffffu - c));
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (lane == 0 && p < sel_cap) sel[p] = cand[0xffffffu - (best & 0xffffffu)];
+    }
+    if (threadIdx.x == 0) *count_out = min(count, sel_cap);
+}
+
+static size_t qt_smem_bytes(int sel_cap) { return (size_t)sel_cap * 14 * sizeof(int); }
+
+// grid (levels, frames)
+__global__ void __launch_bounds__(kQtThreads)
+quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slots, const int* __restrict__ cell_counts,
+                uint32_t* sortbuf, uint32_t* selected, int* sel_counts) {
+    extern __shared__ __align__(16) int nodemem[];
+    __shared__ QtShared sh;
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const LevelGeom& L = g->lv[level];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* fb = sortbuf + (size_t)frame * 5 * g->cand_words;
+    uint32_t* cand = fb + L.cand_off;
+    uint32_t* scratch = fb + g->cand_words + 4 * L.cand_off;
+    const int* counts = cell_counts + (size_t)frame * g->ncells + L.cell_begin;
+    const uint32_t* lslots = slots + (size_t)frame * g->slot_words + L.slot_off;
+
+    // stitch the cells' lists in row-major cell order (789-829): offsets = scan of counts.
+    // nodemem is free until quadtree_select: use it for the offsets when it is large enough,
+    // else fall back to a serial prefix inside each warp's walk.
+    int* offs = nodemem;  // sel_cap*14 ints >= cell_count always holds for sane settings (checked on host)
+    const int total = block_exclusive_scan(counts, offs, L.cell_count, sh);
+    __syncthreads();
+    for (int c = warp; c < L.cell_count; c += kQtWarps) {
+        const int n = counts[c], o = offs[c];
+        const uint32_t* s = lslots + (size_t)c * L.slot_cap;
+        for (int k = lane; k < n; k += 32) cand[o + k] = s[k];
+    }
+    __syncthreads();
+    quadtree_select(cand, total, L.quota, L.nRoots, L.rootW, L.h - 2 * kMinBorder, L.key_depth, scratch,
+                    selected + (size_t)frame * g->sel_words + L.sel_off, L.sel_cap,
+                    sel_counts + (size_t)frame * g->nlevels + level, sh, nodemem);
+}
+
+__global__ void __launch_bounds__(kQtThreads)
+quadtree_standalone_kernel(const uint32_t* cand, int n, int N, int nRoots, float rootW, int H, int depth,
+                           uint32_t* scratch, uint32_t* sel, int sel_cap, int* count) {
+    extern __shared__ __align__(16) int nodemem[];
+    __shared__ QtShared sh;
+    quadtree_select(cand, n, N, nRoots, rootW, H, depth, scratch, sel, sel_cap, count, sh, nodemem);
+}
+
+// opt in once per device to the large dynamic shared memory carve-out
+constexpr size_t kQtMaxDynSmem = 160 * 1024;
+static int qt_configure(size_t need) {
+    static bool done[64] = {};
+    if (need > kQtMaxDynSmem) { set_error("nfeatures too large for the quadtree kernel's shared memory"); return ORB_EINVAL; }
+    int dev = 0;
+    ORB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return ORB_OK;
+    ORB_CUDA_TRY(cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQtMaxDynSmem));
+    ORB_CUDA_TRY(cudaFuncSetAttribute(quadtree_standalone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQtMaxDynSmem));
+    if (dev < 64) done[dev] = true;
+    return ORB_OK;
+}
+
+int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStream_t st) {
+    int max_cap = 0;
+    for (int l = 0; l < hg.nlevels; ++l) max_cap = max(max_cap, max(hg.lv[l].sel_cap, ceil_div(hg.lv[l].cell_count, 14) + 1));
+    const size_t smem = qt_smem_bytes(max_cap);
+    int rc = qt_configure(smem);
+    if (rc) return rc;
+    quadtree_kernel<<<dim3(hg.nlevels, n), kQtThreads, smem, st>>>(db.geom, db.slots, db.cell_counts, db.sortbuf, db.selected, db.sel_counts);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int launch_quadtree_standalone(const uint32_t* d_cand, int n, int N, int nRoots, float rootW, int H, int depth,
+                               uint32_t* d_scratch4n, uint32_t* d_sel, int sel_cap, int* d_count, cudaStream_t st) {
+    const size_t smem = qt_smem_bytes(sel_cap);
+    int rc = qt_configure(smem);
+    if (rc) return rc;
+    quadtree_standalone_kernel<<<1, kQtThreads, smem, st>>>(d_cand, n, N, nRoots, rootW, H, depth, d_scratch4n, d_sel, sel_cap, d_count);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+}  // namespace orb

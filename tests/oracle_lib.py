@@ -205,3 +205,13 @@ class RefExtractor:
         out = np.empty((h.value + 2 * border, w.value + 2 * border), np.uint8)
         self.L.ref_level_image(self.h, l, out.ctypes.data_as(C.c_void_p), border)
         return out
+
+
+def quadtree_arrayform(xs, ys, scores, minX, maxX, minY, maxY, N):
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+    sc = np.ascontiguousarray(scores, np.int32)
+    out = np.empty(max(len(xs), 1), np.int32)
+    n = lib().orc_quadtree_arrayform(xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p),
+                                     sc.ctypes.data_as(C.c_void_p), len(xs), minX, maxX, minY, maxY, N,
+                                     out.ctypes.data_as(C.c_void_p), len(out))
+    return out[:n]

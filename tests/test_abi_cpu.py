@@ -1,0 +1,68 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol that
+include/orb_b200.h declares; without a GPU every compute call fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from multiagent_orb_slam2_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _lib.exported_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), n
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not out:
+        pytest.skip("cuobjdump not available")
+    archs = {l.split(".")[-2] for l in out.splitlines() if ".cubin" in l}
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_validation_needs_no_gpu():
+    L = _lib.lib()
+    h = C.c_void_p()
+    cfg = _lib.Config(1000, 1.2, 99, 20, 7)
+    assert L.orbx_create(C.byref(cfg), 0, 640, 480, 1, C.byref(h)) == _lib.ORB_EINVAL
+    assert b"nlevels" in L.orb_last_error()
+    cfg = _lib.Config(1000, 1.2, 8, 5, 7)
+    assert L.orbx_create(C.byref(cfg), 0, 640, 480, 1, C.byref(h)) == _lib.ORB_EINVAL
+    assert L.orbm_knn2_device(None, -1, None, 0, None, None, None, None) == _lib.ORB_EINVAL
+
+
+def test_no_cpu_fallback_without_device():
+    L = _lib.lib()
+    if L.orb_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    h = C.c_void_p()
+    cfg = _lib.Config(1000, 1.2, 8, 20, 7)
+    assert L.orbx_create(C.byref(cfg), 0, 640, 480, 1, C.byref(h)) == _lib.ORB_ECUDA
+    a = np.zeros((4, 32), np.uint8)
+    o = np.zeros(4, np.int32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    assert L.orbm_knn2(0, p(a), 4, p(a), 4, p(o), p(o), p(o)) == _lib.ORB_ECUDA
+    from multiagent_orb_slam2_b200 import ORBmatcher, OrbError
+    with pytest.raises(OrbError):
+        ORBmatcher().knn2(a, a)
+
+
+def test_three_maxima_and_descriptor_distance_host_helpers():
+    from multiagent_orb_slam2_b200 import ORBmatcher
+    import oracle_lib as O
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        a, b = rng.integers(0, 256, (2, 32), dtype=np.uint8)
+        assert ORBmatcher.DescriptorDistance(a, b) == O.hamming(a, b)
+    assert ORBmatcher.ComputeThreeMaxima([0, 30, 3, 2] + [0] * 26) == (1, 2, -1)
+    assert ORBmatcher.ComputeThreeMaxima([5, 30, 3, 2] + [0] * 26) == (1, 0, 2)
+    assert ORBmatcher.ComputeThreeMaxima([0] * 30) == (-1, -1, -1)

@@ -1,0 +1,145 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs. Integer / byte / index results must be bit-exact; angles are compared as bit patterns."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from multiagent_orb_slam2_b200 import ORBextractor, ORBmatcher, synth
+from multiagent_orb_slam2_b200.extractor import quadtree as gpu_quadtree
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {  # name: (w, h, nfeatures, iniTh)   SURVEY.md section 5 / BASELINE.json configs
+    "tum": (640, 480, 1000, 20),
+    "kitti": (1241, 376, 2000, 20),
+    "euroc": (752, 480, 1200, 20),
+}
+
+
+def run_both(w, h, nf, ini, kind, seed, nlevels=8, scale=1.2, mn=7):
+    img = synth.image(kind, w, h, seed)
+    o = O.OracleExtractor(nf, scale, nlevels, ini, mn)
+    ok, od = o(img)
+    g = ORBextractor(nf, scale, nlevels, ini, mn)
+    gk, gd = g(img)
+    return img, o, ok, od, g, gk, gd
+
+
+def kp_matrix(gk):
+    return np.stack([gk["x"], gk["y"], gk["size"], gk["angle"], gk["response"], gk["octave"].astype(np.float32)], 1)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("kind,seed", [("blocks", 0), ("blurnoise", 1), ("noise", 2)])
+def test_stages_bit_exact(cfg, kind, seed):
+    w, h, nf, ini = CONFIGS[cfg]
+    img, o, ok, od, g, gk, gd = run_both(w, h, nf, ini, kind, seed)
+    for l in range(8):
+        L = o.level(l)
+        assert np.array_equal(g.pyramid_level(l), L["img"]), "pyramid level %d" % l
+        if L["blur"] is not None:
+            assert np.array_equal(g.blurred_level(l), L["blur"]), "blurred level %d" % l
+        assert np.array_equal(g.candidates(l), L["cand"]), "FAST candidates level %d" % l
+    assert len(gk) == len(ok)
+    assert np.array_equal(kp_matrix(gk).view(np.uint32), ok.view(np.uint32)), "keypoints (incl. angle bits)"
+    mism = np.flatnonzero((gd != od).any(1))
+    assert len(mism) == 0, "descriptor rows differ: %d of %d" % (len(mism), len(od))
+
+
+def test_tables_match_oracle():
+    g = ORBextractor(1200, 1.2, 8, 20, 7, width=752, height=480)
+    t = O.OracleExtractor(1200, 1.2, 8).tables()
+    assert np.array_equal(g.GetScaleFactors().view(np.uint32), t["scale"].view(np.uint32))
+    assert np.array_equal(g.GetInverseScaleFactors().view(np.uint32), t["inv_scale"].view(np.uint32))
+    assert np.array_equal(g.GetScaleSigmaSquares().view(np.uint32), t["sigma2"].view(np.uint32))
+    assert np.array_equal(g.GetInverseScaleSigmaSquares().view(np.uint32), t["inv_sigma2"].view(np.uint32))
+    assert g.features_per_level().tolist() == t["quota"].tolist()
+    assert g.GetLevels() == 8
+
+
+@pytest.mark.parametrize("nf,s,nl,ini,mn", [(500, 1.2, 8, 20, 7), (1500, 1.1, 5, 15, 5), (300, 1.5, 4, 30, 10), (3000, 1.2, 8, 12, 7)])
+def test_other_settings(nf, s, nl, ini, mn):
+    img, o, ok, od, g, gk, gd = run_both(640, 480, nf, ini, "blocks", 3, nlevels=nl, scale=s, mn=mn)
+    assert np.array_equal(kp_matrix(gk).view(np.uint32), ok.view(np.uint32))
+    assert np.array_equal(gd, od)
+
+
+def test_flat_and_empty_images():
+    g = ORBextractor(1000, 1.2, 8, 20, 7)
+    k, d = g(synth.image("flat", 640, 480, 0))
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = g(np.empty((0, 0), np.uint8))
+    assert len(k) == 0
+
+
+def test_batch_equals_single_frames():
+    imgs = np.stack([synth.image(k, 640, 480, s) for k, s in [("blocks", 0), ("blurnoise", 1), ("blocks", 2), ("noise", 3), ("flat", 0)]])
+    g = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=8)
+    kps, desc, counts = g.extract_batch(imgs)
+    o = O.OracleExtractor()
+    for i in range(len(imgs)):
+        ok, od = o(imgs[i])
+        assert counts[i] == len(ok)
+        assert np.array_equal(kp_matrix(kps[i, :counts[i]]).view(np.uint32), ok.view(np.uint32)), i
+        assert np.array_equal(desc[i, :counts[i]], od), i
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_quadtree_kernel_on_random_candidate_sets(seed):
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(25):
+        W, H = [(608, 448), (1209, 344), (720, 448), (147, 102), (314, 73), (1000, 333)][rng.integers(0, 6)]
+        n = int(rng.choice([1, 2, 3, 7, 50, 300, 1500, 6000, 30000]))
+        N = int(rng.choice([1, 5, 60, 217, 434, 1000]))
+        x = rng.integers(0, W - 6, n); y = rng.integers(0, H - 6, n)
+        if rng.random() < 0.5:
+            x = np.clip(rng.normal(W / 3, 25, n), 0, W - 7).astype(np.int64); y = np.clip(rng.normal(H / 2, 25, n), 0, H - 7).astype(np.int64)
+        _, first = np.unique(x * 8192 + y, return_index=True)
+        first = np.sort(first)
+        x, y = x[first].astype(np.int32), y[first].astype(np.int32)
+        sc = rng.integers(7, 255, len(x)).astype(np.int32)
+        a = O.quadtree(x, y, sc, 16, 16 + W, 16, 16 + H, N)
+        b = gpu_quadtree(x, y, sc, 16, 16 + W, 16, 16 + H, N)
+        assert np.array_equal(a, b), (W, H, n, N)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nA,nB", [(1000, 1000), (2013, 2013), (1, 1), (7, 5000), (3000, 33), (257, 513), (5, 0)])
+def test_knn2_bit_exact(nA, nB):
+    B = synth.descriptors(nB, 1)
+    A = synth.descriptors(nA, 2, dup_from=B) if nB else synth.descriptors(nA, 2)
+    if nB > 10:  # exact duplicates: ties between best and second, first index must win
+        B[nB // 2] = B[3]
+    m = ORBmatcher(0.75)
+    gi, g1, g2 = m.knn2(A, B)
+    oi, o1, o2 = O.knn2(A, B)
+    assert np.array_equal(gi, oi) and np.array_equal(g1, o1) and np.array_equal(g2, o2)
+
+
+def test_knn2_large_split_database():
+    B = synth.descriptors(60000, 3)
+    A = synth.descriptors_fast(4000, 4, B)
+    m = ORBmatcher(0.75)
+    gi, g1, g2 = m.knn2(A, B)
+    oi, o1, o2 = O.knn2(A, B, threads=8)
+    assert np.array_equal(gi, oi) and np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    acc = m.accept(gi, g1, g2)
+    assert (acc >= 0).sum() > 1000
+
+
+def test_knn2_lists_and_distance_matrix():
+    rng = np.random.default_rng(5)
+    B = synth.descriptors(1500, 6)
+    A = synth.descriptors(800, 7, dup_from=B)
+    lens = rng.integers(0, 60, len(A))
+    lens[:5] = [0, 1, 2, 33, 64]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cands = rng.integers(0, len(B), offsets[-1]).astype(np.int32)
+    m = ORBmatcher()
+    gi, g1, g2 = m.knn2_lists(A, B, offsets, cands)
+    oi, o1, o2 = O.knn2_lists(A, B, offsets, cands)
+    assert np.array_equal(g1, o1) and np.array_equal(g2, o2) and np.array_equal(gi, oi)
+    D = m.distance_matrix(A[:100], B[:77])
+    ref = np.array([[O.hamming(a, b) for b in B[:77]] for a in A[:100]], np.int16)
+    assert np.array_equal(D, ref)
