@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/s of ORB extract + frame-to-frame match at 640x480 / 1000 keypoints
+(BASELINE.json metric; TUM mono settings, 8 levels, scale 1.2) on N GPUs of one node, one agent
+stream per GPU (no data-path collective: "weak" scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+A step = one pass of the hot path over a batch of B synthetic frames per GPU:
+  pyramid -> per-cell FAST -> quadtree distribution -> orientation -> blur -> rBRIEF, then
+  brute-force Hamming kNN-2 + ratio test of every frame against the next one.
+`value`  : frames already resident in HBM (B * 307 KB > L2 so every step streams from HBM).
+`e2e`    : the same work through the host-buffer API: pinned host frames -> H2D -> kernels -> D2H of
+           keypoints, descriptors, counts and matches, every step, copies inside the timed region.
+`--impl reference` times the reference's own CPU extractor (oracle/_ref, its ORBextractor.cc
+compiled unmodified) + the oracle's Hamming loop on the host cores, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
+NNRATIO, TH = 0.9, 50
+METRIC = "frames/s ORB extract+match @640x480,1000kp"
+STAGES = ["pyramid_resize", "gaussian_blur", "fast_cells", "quadtree", "orient_describe"]
+
+
+def make_frames(n, seed0):
+    """n synthetic 640x480 frames: consecutive frames are shifted/re-noised copies (real matches)."""
+    from multiagent_orb_slam2_b200 import synth
+    base = []
+    for s in range(8):  # 8 distinct scenes x 2 views, tiled to n frames (generation is CPU heavy)
+        a, b, _ = synth.shifted_pair("blocks", W, H, seed0 + s)
+        base += [a, b]
+    reps = (n + len(base) - 1) // len(base)
+    return np.ascontiguousarray(np.stack((base * reps)[:n]))
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.path = gpu, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(frames, threads):
+    """Reference CPU path on `frames`: extraction with the reference's own ORBextractor.cc
+    (oracle/_ref) when present, else the oracle port; matching with the oracle's Hamming loop.
+    Returns (seconds, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib as O
+    from concurrent.futures import ThreadPoolExecutor
+    kind = "reference" if O.ref_available("canonical") else "port"
+    n = len(frames)
+    local = threading.local()
+
+    def extract(i):
+        ex = getattr(local, "ex", None)
+        if ex is None:
+            ex = local.ex = (O.RefExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) if kind == "reference"
+                             else O.OracleExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH))
+        return ex(frames[i])[1]
+
+    def match(i):
+        return O.knn2(descs[i], descs[(i + 1) % n])
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as pool:
+        descs = list(pool.map(extract, range(n)))
+        list(pool.map(match, range(n)))
+    return time.perf_counter() - t0, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(cores * 4, 32)
+    frames = make_frames(sample, 0)
+    for _ in range(args.warmup):
+        cpu_reference_run(frames[:cores], cores)
+    t = []
+    kind = "port"
+    for _ in range(args.steps):
+        dt, kind = cpu_reference_run(frames, cores)
+        t.append(dt)
+    total = sum(t)
+    v = sample * args.steps / total
+    what = "%d frames per step, %d host threads, one extractor per thread" % (sample, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "640x480 gray, 1000 kp, 8 levels, scale 1.2, FAST 20/7; frame-to-frame brute-force match", "sample": what},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from multiagent_orb_slam2_b200 import _lib
+    from multiagent_orb_slam2_b200.frontend import AgentFrontend
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    L = _lib.lib()
+
+    frames = make_frames(B, 1000 * rank)
+    fe = AgentFrontend(W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B, nnratio=NNRATIO, th=TH)
+    d_frames = torch.from_numpy(frames).to(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") -----------------------------------------------------
+    for _ in range(args.warmup):
+        fe.process_device(d_frames)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.orb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fe.process_device(d_frames)
+    e1.record()
+    barrier()
+    launches = L.orb_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+    import ctypes as C
+    # counts live in handle-owned memory: read them through the ABI download
+    pin = fe.pinned_outputs()
+    _lib.check(L.orbx_download_results(fe.ex._h, B, C.c_void_p(pin["kps"].data_ptr()), C.c_void_p(pin["desc"].data_ptr()), fe.cap,
+                                       C.c_void_p(pin["counts"].data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    torch.cuda.synchronize(dev)
+    kp_per_frame = float(pin["counts"].numpy()[:B].mean())
+    matches_per_frame = float((fe.match[:B].cpu().numpy() >= 0).sum() / B)
+
+    # ---- end to end through the host-buffer API ("e2e"): two agents' worth of buffers in flight ----
+    h_frames = torch.from_numpy(frames).pin_memory()
+    fes = [fe, AgentFrontend(W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B, nnratio=NNRATIO, th=TH)]
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    outs = [f.pinned_outputs() for f in fes]
+
+    def e2e_step(i):
+        k = i & 1
+        with torch.cuda.stream(streams[k]):
+            fes[k].process_async(h_frames, outs[k])
+
+    for i in range(max(args.warmup, 2)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+        if i >= 1:
+            streams[(i - 1) & 1].synchronize()  # the host consumes step i-1's results while step i runs
+            _ = int(outs[(i - 1) & 1]["counts"][0])
+    for s in streams:
+        s.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    # ---- per-stage device time of the dominant kernels (roofline), rank 0 -----------------------------
+    roof = None
+    stage_ms = None
+    if rank == 0:
+        _lib.check(L.orbx_set_stage_timing(fe.ex._h, 1))
+        acc = np.zeros(len(STAGES))
+        reps = max(3, min(args.steps, 10))
+        ms = (C.c_float * len(STAGES))()
+        for _ in range(reps):
+            fe.ex.extract_device(d_frames.data_ptr(), d_frames.stride(1), d_frames.stride(0), B, torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(L.orbx_stage_times(fe.ex._h, ms))
+            acc += np.array(list(ms))
+        _lib.check(L.orbx_set_stage_timing(fe.ex._h, 0))
+        stage_ms = (acc / reps).tolist()
+        alg = (C.c_double * len(STAGES))()
+        _lib.check(L.orbx_algorithmic_bytes(fe.ex._h, alg))
+        # matching stage, timed alone
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(reps):
+            fe.match_consecutive(B)
+        m1.record()
+        torch.cuda.synchronize(dev)
+        match_ms = m0.elapsed_time(m1) / reps
+        pk, pk_src = peaks()
+        dom = int(np.argmax(stage_ms))
+        per_stage = {}
+        for i, name in enumerate(STAGES):
+            gbs = alg[i] * B / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else 0.0
+            per_stage[name] = {"ms": stage_ms[i], "alg_bytes_per_frame": alg[i], "gbs": gbs, "frac_hbm": gbs / pk["hbm_gbs"]}
+        cmp_per_step = float((pin["counts"].numpy()[:B].astype(np.float64) * np.roll(pin["counts"].numpy()[:B], -1)).sum())
+        per_stage["hamming_knn2"] = {"ms": match_ms, "gcmp_per_s": cmp_per_step / (match_ms * 1e-3) / 1e9}
+        a = per_stage[STAGES[dom]]
+        roof = {"kernel": STAGES[dom], "bound": "hbm", "achieved": a["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": a["frac_hbm"], "traffic": None, "peak_source": pk_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "stages": per_stage}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample = max(cores * 8, 64)
+        cf = make_frames(sample, 0)
+        cpu_reference_run(cf[:cores], cores)
+        dt, kind = cpu_reference_run(cf, cores)
+        cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": "%d frames extract+match on %d host threads (%.1f s)" % (sample, cores, dt)}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "640x480 gray, 1000 kp, 8 levels, scale 1.2, FAST 20/7; frame-to-frame brute-force match (ratio 0.9, TH_LOW 50)",
+                       "frames_per_step_per_gpu": B, "agents": world, "parallelism": "one agent stream per GPU, no collective",
+                       "l2": "inputs larger than L2 (%d MB of frames per step)" % (B * W * H // 2**20),
+                       "keypoints_per_frame": kp_per_frame, "matches_per_frame": matches_per_frame},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * fe.h2d_bytes_per_frame(),
+                    "d2h_bytes_per_step": B * fe.d2h_bytes_per_frame(), "ms_per_step": e2e_ms / args.steps,
+                    "how": "pinned host frames -> orbx_upload_frames/extract_staged/orbm_knn2_batched/download, 2 buffers in flight"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,7 @@ enum {
 const char* orb_last_error(void);          /* thread-local text of the last failure */
 int orb_device_count(void);                /* number of visible CUDA devices (0 = none) */
 const char* orb_version(void);
+long long orb_launch_count(void);          /* kernels this library has launched so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------
  * Extractor. Replaces ORBextractor::ORBextractor (src/ORBextractor.cc:410-470) and
@@ -92,6 +93,15 @@ int orbx_extract_device(orbx_handle h, const uint8_t* d_images, size_t stride, s
                         void* stream);
 int orbx_device_results(orbx_handle h, const orbx_keypoint** d_kps, const uint8_t** d_desc,
                         const int32_t** d_counts, int* cap_dev);
+
+/* Asynchronous building blocks of orbx_extract_batch for callers that pipeline copies and compute
+ * themselves (pinned host memory recommended). All three only enqueue on `stream`:
+ *   upload   : host frames -> the handle's device staging area
+ *   staged   : operator() over the n staged frames
+ *   download : counts[n], kps[n][cap], desc[n][cap][32] -> host (cap <= orbx_max_keypoints()) */
+int orbx_upload_frames(orbx_handle h, const uint8_t* images, size_t stride, size_t frame_stride, int n, void* stream);
+int orbx_extract_staged(orbx_handle h, int n, void* stream);
+int orbx_download_results(orbx_handle h, int n, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts, void* stream);
 
 /* mvImagePyramid (ORBextractor.h:85): level `level` of frame `frame` of the last call. Device view
  * (pointer + pitch) or a copy to host (dst_stride >= width). */

@@ -46,6 +46,9 @@ def lib():
         "orbx_extract": [vp, vp, sz, vp, vp, i32, C.POINTER(i32)],
         "orbx_extract_batch": [vp, vp, sz, sz, i32, vp, vp, i32, vp],
         "orbx_extract_device": [vp, vp, sz, sz, i32, vp],
+        "orbx_upload_frames": [vp, vp, sz, sz, i32, vp],
+        "orbx_extract_staged": [vp, i32, vp],
+        "orbx_download_results": [vp, i32, vp, vp, i32, vp, vp],
         "orbx_device_results": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)],
         "orbx_pyramid_level_device": [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)],
         "orbx_pyramid_level": [vp, i32, i32, vp, sz],
@@ -65,6 +68,8 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    L.orb_launch_count.argtypes = []
+    L.orb_launch_count.restype = C.c_longlong
     L.orbx_destroy.argtypes = [vp]
     L.orbx_destroy.restype = None
     _lib = L

@@ -133,6 +133,7 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
 int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
     orient_describe_kernel<<<dim3(ceil_div(hg.sel_words, kDescWarps), n), kDescWarps * 32, 0, st>>>(
         db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.kps, db.desc, db.counts);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }

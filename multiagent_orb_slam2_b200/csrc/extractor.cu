@@ -339,6 +339,48 @@ int orbx_device_results(orbx_handle h, const orbx_keypoint** d_kps, const uint8_
     return ORB_OK;
 }
 
+int orbx_upload_frames(orbx_handle h, const uint8_t* images, size_t stride, size_t frame_stride, int n, void* stream) {
+    ORB_REQUIRE(h && images, "null pointer");
+    ORB_REQUIRE(n >= 0 && n <= h->max_batch && stride >= (size_t)h->width, "bad batch / stride");
+    if (n == 0) return ORB_OK;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t dev_frame = h->in_pitch * h->height;
+    if (frame_stride == stride * (size_t)h->height || n == 1) {
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input, h->in_pitch, images, stride, h->width, (size_t)h->height * n, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int i = 0; i < n; ++i)
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input + i * dev_frame, h->in_pitch, images + i * frame_stride, stride, h->width, h->height,
+                                           cudaMemcpyHostToDevice, st));
+    }
+    return ORB_OK;
+}
+
+int orbx_extract_staged(orbx_handle h, int n, void* stream) {
+    ORB_REQUIRE(h, "null handle");
+    ORB_REQUIRE(n >= 0 && n <= h->max_batch, "batch larger than max_batch");
+    if (n == 0) return ORB_OK;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    FrameSet fs{h->d_input, h->in_pitch, h->in_pitch * h->height};
+    return enqueue_pipeline(h, fs, n, (cudaStream_t)stream);
+}
+
+int orbx_download_results(orbx_handle h, int n, orbx_keypoint* kps, uint8_t* desc, int cap, int32_t* counts, void* stream) {
+    ORB_REQUIRE(h && counts, "null pointer");
+    ORB_REQUIRE(n >= 0 && n <= h->max_batch && cap >= 0 && (cap == 0 || (kps && desc)), "bad batch / buffers");
+    if (n == 0) return ORB_OK;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int oc = h->hg.out_cap, take = std::min(cap, oc);
+    ORB_CUDA_TRY(cudaMemcpyAsync(counts, h->db.counts, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (take > 0) {
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_keypoint), h->db.kps, (size_t)oc * sizeof(orbx_keypoint),
+                                       (size_t)take * sizeof(orbx_keypoint), n, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->db.desc, (size_t)oc * 32, (size_t)take * 32, n, cudaMemcpyDeviceToHost, st));
+    }
+    return ORB_OK;
+}
+
 int orbx_extract_batch(orbx_handle h, const uint8_t* images, size_t stride, size_t frame_stride, int n, orbx_keypoint* kps,
                        uint8_t* desc, int cap, int32_t* counts) {
     ORB_REQUIRE(h, "null handle");
@@ -352,24 +394,10 @@ int orbx_extract_batch(orbx_handle h, const uint8_t* images, size_t stride, size
     ORB_REQUIRE(stride >= (size_t)h->width && cap >= 0 && (cap == 0 || (kps && desc)), "bad stride / output buffers");
     ORB_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    const size_t dev_frame = h->in_pitch * h->height;
-    if (frame_stride == stride * (size_t)h->height || n == 1) {
-        ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input, h->in_pitch, images, stride, h->width, (size_t)h->height * n, cudaMemcpyHostToDevice, st));
-    } else {
-        for (int i = 0; i < n; ++i)
-            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input + i * dev_frame, h->in_pitch, images + i * frame_stride, stride, h->width, h->height,
-                                           cudaMemcpyHostToDevice, st));
-    }
-    FrameSet fs{h->d_input, h->in_pitch, dev_frame};
-    int rc = enqueue_pipeline(h, fs, n, st);
-    if (rc) return rc;
-    const int oc = h->hg.out_cap, take = std::min(cap, oc);
-    ORB_CUDA_TRY(cudaMemcpyAsync(counts, h->db.counts, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (take > 0) {
-        ORB_CUDA_TRY(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_keypoint), h->db.kps, (size_t)oc * sizeof(orbx_keypoint),
-                                       (size_t)take * sizeof(orbx_keypoint), n, cudaMemcpyDeviceToHost, st));
-        ORB_CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->db.desc, (size_t)oc * 32, (size_t)take * 32, n, cudaMemcpyDeviceToHost, st));
-    }
+    int rc;
+    if ((rc = orbx_upload_frames(h, images, stride, frame_stride, n, st)) || (rc = orbx_extract_staged(h, n, st)) ||
+        (rc = orbx_download_results(h, n, kps, desc, cap, counts, st)))
+        return rc;
     ORB_CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < n; ++i)
         if (counts[i] > cap) { set_error("frame %d has %d keypoints, buffer holds %d", i, counts[i], cap); rc = ORB_ECAPACITY; }

@@ -176,6 +176,7 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs,
     const int tp = (hg.max_tw + 3) & ~3;
     const size_t smem = 2 * (size_t)hg.max_th * tp + (size_t)hg.max_th * 4 * sizeof(uint32_t) + (2 * (size_t)hg.max_th + 1) * sizeof(int);
     fast_cells_kernel<<<dim3(hg.ncells, n), kFastThreads, smem, st>>>(db.geom, db.cells, fs, db.pyr, db.slots, db.cell_counts, tp);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }

@@ -192,6 +192,7 @@ static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strid
         knn2_kernel<<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)dA, d_nA, nA_max, strideA_rows, (const uint4*)dB,
                                                        d_nB, nB_max, strideB_rows, rows_per_split, 1, strideA_rows,
                                                        d_idx, d_b1, d_b2);
+        count_launch();
         ORB_CUDA_TRY(cudaGetLastError());
         return ORB_OK;
     }
@@ -201,9 +202,11 @@ static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strid
     knn2_kernel<<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)dA, d_nA, nA_max, strideA_rows, (const uint4*)dB, d_nB,
                                                    nB_max, strideB_rows, rows_per_split, nsplit, nA_max, part,
                                                    part + per, part + 2 * per);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     knn2_merge_kernel<<<dim3(ceil_div(nA_max, 256), pairs), 256, 0, st>>>(part, part + per, part + 2 * per, d_nA, nA_max,
                                                                           nsplit, nA_max, strideA_rows, d_idx, d_b1, d_b2);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     ORB_CUDA_TRY(cudaFreeAsync(part, st));
     return ORB_OK;
@@ -241,6 +244,7 @@ int orbm_knn2_lists_device(const uint8_t* dA, int nA, const uint8_t* dB, const i
     ORB_REQUIRE(dA && dB && d_offsets && d_cands && d_idx && d_best && d_second, "null pointer");
     knn2_lists_kernel<<<ceil_div(nA * 32, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dA, nA, (const uint4*)dB, d_offsets,
                                                                                 d_cands, d_idx, d_best, d_second);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }
@@ -251,6 +255,7 @@ int orbm_ratio_filter_device(const int32_t* d_idx, const int32_t* d_best, const 
     if (n == 0) return ORB_OK;
     ORB_REQUIRE(d_idx && d_best && d_second && d_match, "null pointer");
     ratio_filter_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d_idx, d_best, d_second, n, th, inclusive, ratio, d_match);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }
@@ -261,6 +266,7 @@ int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, in
     ORB_REQUIRE(dA && dB && d_out, "null pointer");
     distance_matrix_kernel<<<dim3(ceil_div(nB, 16), ceil_div(nA, 16)), dim3(16, 16), 0, (cudaStream_t)stream>>>(
         (const uint4*)dA, nA, (const uint4*)dB, nB, d_out);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }

@@ -50,6 +50,7 @@ int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const Frame
     const LevelGeom& L = hg.lv[level];
     dim3 grid(ceil_div(L.w, 128), ceil_div(L.h, 8), n);
     resize_kernel<<<grid, dim3(32, 8), 0, st>>>(db.geom, db.taps, fs, db.pyr, level);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }
@@ -111,6 +112,7 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
 
 int launch_blur(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
     blur_kernel<<<dim3(hg.ntiles, n), 256, 0, st>>>(db.geom, db.tiles, fs, db.pyr, db.blur);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }

@@ -374,6 +374,7 @@ int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStre
     int rc = qt_configure(smem);
     if (rc) return rc;
     quadtree_kernel<<<dim3(hg.nlevels, n), kQtThreads, smem, st>>>(db.geom, db.slots, db.cell_counts, db.sortbuf, db.selected, db.sel_counts);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }
@@ -384,6 +385,7 @@ int launch_quadtree_standalone(const uint32_t* d_cand, int n, int N, int nRoots,
     int rc = qt_configure(smem);
     if (rc) return rc;
     quadtree_standalone_kernel<<<1, kQtThreads, smem, st>>>(d_cand, n, N, nRoots, rootW, H, depth, d_scratch4n, d_sel, sel_cap, d_count);
+    count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }

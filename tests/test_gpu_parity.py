@@ -143,3 +143,33 @@ def test_knn2_lists_and_distance_matrix():
     D = m.distance_matrix(A[:100], B[:77])
     ref = np.array([[O.hamming(a, b) for b in B[:77]] for a in A[:100]], np.int16)
     assert np.array_equal(D, ref)
+
+
+def test_agent_frontend_extract_and_match_consecutive():
+    import torch
+    from multiagent_orb_slam2_b200.frontend import AgentFrontend
+    frames = []
+    for s in range(3):
+        a, b, _ = synth.shifted_pair("blocks", 640, 480, s)
+        frames += [a, b]
+    imgs = np.stack(frames)
+    fe = AgentFrontend(640, 480, max_batch=8)
+    kps, desc, counts, match = fe.process(imgs)
+    o = O.OracleExtractor()
+    od = []
+    for i in range(len(imgs)):
+        ok, d = o(imgs[i])
+        assert counts[i] == len(ok) and np.array_equal(desc[i, :counts[i]], d)
+        od.append(d)
+    m = ORBmatcher(0.9)
+    n = len(imgs)
+    for i in range(n):
+        oi, o1, o2 = O.knn2(od[i], od[(i + 1) % n])
+        ref = m.accept(oi, o1, o2, th=50, inclusive=True)
+        assert np.array_equal(match[i, :counts[i]], ref), i
+    assert (match[0, :counts[0]] >= 0).sum() > 200  # shifted copy: plenty of true matches
+    # device-resident path gives the same matches
+    d_imgs = torch.from_numpy(imgs).cuda()
+    fe.process_device(d_imgs)
+    torch.cuda.synchronize()
+    assert np.array_equal(fe.match[:n].cpu().numpy()[0, :counts[0]], match[0, :counts[0]])
