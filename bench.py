@@ -46,7 +46,7 @@ def make_frames(n, seed0):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("utilization.gpu,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
@@ -57,7 +57,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -70,21 +70,25 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                rows.append((float(f[0]), float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+        os.unlink(self.path)
+        loaded = [r for r in rows if r[0] >= 20.0] or rows  # samples taken while the GPU was busy
+        reasons = set()
+        for r in loaded:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if loaded:
+            out = {"sm_mhz": float(np.median([r[1] for r in loaded])), "sm_max_mhz": float(max(r[2] for r in loaded)),
+                   "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len([r for r in rows if r[0] >= 20.0])}
         return out
 
 
@@ -188,12 +192,12 @@ def run_b200(args):
         return float(t.item())
 
     # ---- device-resident throughput ("value") -----------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # sampled through the value, e2e and stage-timing legs; idle samples are dropped
     for _ in range(args.warmup):
         fe.process_device(d_frames)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = L.orb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -203,7 +207,6 @@ def run_b200(args):
     barrier()
     launches = L.orb_launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
     import ctypes as C
     # counts live in handle-owned memory: read them through the ABI download
@@ -276,6 +279,8 @@ def run_b200(args):
         roof = {"kernel": STAGES[dom], "bound": "hbm", "achieved": a["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": a["frac_hbm"], "traffic": None, "peak_source": pk_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "stages": per_stage}
+
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None

@@ -147,6 +147,12 @@ int orbm_knn2_batched_device(const uint8_t* dA, const int32_t* d_nA, int strideA
                              const int32_t* d_nB, int strideB_rows, int pairs, int32_t* d_idx, int32_t* d_best,
                              int32_t* d_second, void* stream);
 
+/* Same over a list of (query set, database set) index pairs into ONE array of descriptor sets
+ * (set k at d_sets + k*stride_rows*32, d_counts[k] rows): frame-to-frame matching of a batch of frames,
+ * or every map against every other map (MapFusion). d_pairs = int32 [pairs][2] on the device. */
+int orbm_knn2_pairs_device(const uint8_t* d_sets, const int32_t* d_counts, int stride_rows, const int32_t* d_pairs,
+                           int pairs, int32_t* d_idx, int32_t* d_best, int32_t* d_second, void* stream);
+
 /* Candidate-list search: query i is compared with B[cands[offsets[i] .. offsets[i+1])] in list order
  * (the GetFeaturesInArea / BoW-node gated loops, e.g. src/ORBmatcher.cc:427-459, 1385-1426). */
 int orbm_knn2_lists_device(const uint8_t* dA, int nA, const uint8_t* dB, const int32_t* d_offsets,

@@ -153,7 +153,7 @@ int build_geometry(orbx_extractor* h) {
             L.tab_x_off = (int)taps.size(); taps.insert(taps.end(), tx.begin(), tx.end());
             L.tab_y_off = (int)taps.size(); taps.insert(taps.end(), ty.begin(), ty.end());
         }
-        for (int ty = 0; ty < ceil_div(L.h, 16); ++ty)
+        for (int ty = 0; ty < ceil_div(L.h, 58); ++ty)  // kBlurTH x kBlurTW output tiles (pyramid.cu)
             for (int tx = 0; tx < ceil_div(L.w, 128); ++tx) tiles.push_back(BlurTile{(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
     }
     g.ncells = (int)cells.size(); g.ntiles = (int)tiles.size();

@@ -10,9 +10,15 @@
 //     thresholded score map of THIS cell (0 outside), strict '>' on all 8 neighbours.
 // Since the NMS test for a pixel with score s >= t reduces to "all neighbours < s", the local-maximum
 // flag is threshold independent; the ini/min decision is a block-wide count.
-// Keypoints leave the kernel in the reference's order (row-major inside the cell) through a
-// ballot + prefix-sum compaction into the cell's slot list; cells are stitched in row-major order
-// by the quadtree kernel.
+//
+// Work is compacted between phases so that the expensive paths run on dense thread sets instead of
+// diverged warps (the first version spent ~310 instructions per pixel, 2/3 of them in diverged
+// slow paths):
+//   1. every interior pixel: 4-point rejection test (any arc of 9 contains ring pixel 0 or 8 and 4
+//      or 12)                                     -> survivors appended to a shared-memory list
+//   2. list entries: full 16-pixel arc test + exact score        -> score map, corner list
+//   3. corner list: 3x3 maximum test                              -> per-row bit masks
+//   4. masks -> row-major ordered slot list (reference order inside the cell).
 #include "extract_kernels.cuh"
 
 namespace orb {
@@ -28,15 +34,9 @@ __device__ __forceinline__ int ring_offset(int k, int tp) {
 }
 
 // exact FAST score if the pixel is a corner at threshold th (th >= 1), else 0
-__device__ __forceinline__ int fast_score_px(const uint8_t* __restrict__ p, int tp, int th) {
+__device__ __forceinline__ int fast_score_full(const uint8_t* __restrict__ p, int tp, int th) {
     const int v = p[0];
     const int lo = v - th, hi = v + th;
-    // any arc of 9 contains ring pixel 0 or 8, and 4 or 12: cheap exact rejection
-    const int r0 = p[ring_offset(0, tp)], r8 = p[ring_offset(8, tp)];
-    const int r4 = p[ring_offset(4, tp)], r12 = p[ring_offset(12, tp)];
-    const bool brightish = (r0 < lo || r8 < lo) && (r4 < lo || r12 < lo);
-    const bool darkish = (r0 > hi || r8 > hi) && (r4 > hi || r12 > hi);
-    if (!brightish && !darkish) return 0;
     int r[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) r[k] = p[ring_offset(k, tp)];
@@ -70,7 +70,9 @@ __device__ __forceinline__ int fast_score_px(const uint8_t* __restrict__ p, int 
     return best - 1;  // >= th by construction
 }
 
-// dynamic shared memory: tile[max_th][tp] | score[max_th][tp] | masks
+// Shared memory (dynamic): tile | score | masks | offsets | two index lists.
+// The tile keeps the 4-byte phase of global memory (column c of the tile sits at byte c + phase)
+// so that rows can be fetched with aligned 32-bit loads.
 __global__ void __launch_bounds__(kFastThreads)
 fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, FrameSet fs,
                   const uint8_t* __restrict__ pyr, uint32_t* __restrict__ slots, int* __restrict__ cell_counts, int tp) {
@@ -81,7 +83,9 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     uint32_t* mask_ini = reinterpret_cast<uint32_t*>(score + (size_t)max_th * tp);  // [max_th][2]
     uint32_t* mask_all = mask_ini + 2 * max_th;
     int* offs = reinterpret_cast<int*>(mask_all + 2 * max_th);                      // [2*max_th + 1]
-    __shared__ int s_total_ini;
+    uint16_t* list1 = reinterpret_cast<uint16_t*>(offs + 2 * max_th + 2);           // survivors of the 4-point test
+    uint16_t* list2 = list1 + (size_t)max_th * tp;                                  // corners
+    __shared__ int s_n1, s_n2, s_total_ini;
 
     const CellDesc c = cells[blockIdx.x];
     const int frame = blockIdx.y;
@@ -95,87 +99,140 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         return;
     }
     int spitch;
-    const uint8_t* src = level_ptr(*g, fs, pyr, frame, c.level, &spitch);
-    src += (size_t)c.y0 * spitch + c.x0;
+    const uint8_t* img = level_ptr(*g, fs, pyr, frame, c.level, &spitch);
+    const uint8_t* src = img + (size_t)c.y0 * spitch + c.x0;
+    // rows can be fetched as aligned words when every row of the level starts 4-byte aligned (always
+    // true for pyramid levels >= 1; for level 0 it depends on the caller's frame pitch)
+    const bool word_rows = ((spitch & 3) == 0) && (((uintptr_t)img & 3) == 0);
+    const int phase = word_rows ? (int)((uintptr_t)src & 3) : 0;
+    const int nwords = (phase + tw + 3) >> 2;  // aligned words per tile row
 
-    if (threadIdx.x == 0) s_total_ini = 0;
-    for (int y = warp; y < th; y += kFastWarps)
-        for (int x = lane; x < tp; x += 32) {
-            tile[y * tp + x] = x < tw ? src[(size_t)y * spitch + x] : 0;
-            score[y * tp + x] = 0;
+    if (threadIdx.x == 0) { s_n1 = 0; s_n2 = 0; s_total_ini = 0; }
+    {
+        uint32_t* tilew = reinterpret_cast<uint32_t*>(tile);
+        uint32_t* scorew = reinterpret_cast<uint32_t*>(score);
+        const int tpw = tp >> 2;
+        if (word_rows) {  // the row's own tail (x < level width) keeps the last word inside the row
+            const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src - phase);
+            const int spw = spitch >> 2;
+            for (int i = threadIdx.x; i < th * tpw; i += kFastThreads) {
+                const int y = i / tpw, xw = i - y * tpw;
+                tilew[i] = xw < nwords ? __ldg(srcw + (size_t)y * spw + xw) : 0u;
+                scorew[i] = 0u;
+            }
+        } else {
+            for (int i = threadIdx.x; i < th * tpw; i += kFastThreads) scorew[i] = 0u;
+            for (int y = warp; y < th; y += kFastWarps)
+                for (int x = lane; x < tp; x += 32) tile[y * tp + x] = x < tw ? src[(size_t)y * spitch + x] : 0;
         }
+        for (int i = threadIdx.x; i < 4 * max_th; i += kFastThreads) mask_ini[i] = 0u;  // mask_ini + mask_all
+    }
     __syncthreads();
 
     const int minTh = g->minTh, iniTh = g->iniTh;
-    for (int y = 3 + warp; y < th - 3; y += kFastWarps)
-        for (int x = 3 + lane; x < tw - 3; x += 32)
-            score[y * tp + x] = (uint8_t)fast_score_px(tile + y * tp + x, tp, minTh);
-    __syncthreads();
+    const uint8_t* t0 = tile + phase;  // pixel (x, y) of the cell tile at t0[y * tp + x]
+    uint8_t* sc0 = score + phase;
 
-    // local maxima + per-(row, 32-column chunk) ballots
-    const int nchunk = (dw + 31) >> 5;  // 1 or 2
-    int my_ini = 0;
+    // ---- phase 1: 4-point rejection on every interior pixel ----------------------------------------
     for (int y = 3 + warp; y < th - 3; y += kFastWarps)
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const int x = 3 + ch * 32 + lane;
-            bool ismax = false;
-            int s = 0;
+        for (int x0 = 3; x0 < tw - 3; x0 += 32) {
+            const int x = x0 + lane;
+            bool keep = false;
             if (x < tw - 3) {
-                const uint8_t* q = score + y * tp + x;
-                s = q[0];
-                if (s > 0) {
-                    const int m = max(max(max(q[-tp - 1], q[-tp]), max(q[-tp + 1], q[-1])),
-                                      max(max(q[1], q[tp - 1]), max(q[tp], q[tp + 1])));
-                    ismax = m < s;
-                }
+                const uint8_t* p = t0 + y * tp + x;
+                const int v = p[0], lo = v - minTh, hi = v + minTh;
+                const int r0 = p[3 * tp], r8 = p[-3 * tp], r4 = p[3], r12 = p[-3];
+                keep = ((r0 < lo || r8 < lo) && (r4 < lo || r12 < lo)) || ((r0 > hi || r8 > hi) && (r4 > hi || r12 > hi));
             }
-            const uint32_t ball = __ballot_sync(0xffffffffu, ismax);
-            const uint32_t bini = __ballot_sync(0xffffffffu, ismax && s >= iniTh);
-            if (lane == 0) {
-                mask_all[(y - 3) * 2 + ch] = ball;
-                mask_ini[(y - 3) * 2 + ch] = bini;
-                my_ini += __popc(bini);
+            const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+            if (ball) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_n1, __popc(ball));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) list1[base + __popc(ball & ((1u << lane) - 1))] = (uint16_t)(y * tp + x);
             }
         }
-    if (lane == 0 && my_ini) atomicAdd(&s_total_ini, my_ini);
+    __syncthreads();
+
+    // ---- phase 2: full arc test + exact score on the survivors -------------------------------------
+    const int n1 = s_n1;
+    for (int i0 = 0; i0 < n1; i0 += kFastThreads) {
+        const int i = i0 + threadIdx.x;
+        int s = 0, at = 0;
+        if (i < n1) { at = list1[i]; s = fast_score_full(t0 + at, tp, minTh); }
+        if (s > 0) sc0[at] = (uint8_t)s;
+        const uint32_t ball = __ballot_sync(0xffffffffu, s > 0);
+        if (ball) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_n2, __popc(ball));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (s > 0) list2[base + __popc(ball & ((1u << lane) - 1))] = (uint16_t)at;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: 3x3 strict maximum on the corners -> bit masks per (row, 32-column chunk) --------
+    const int n2 = s_n2;
+    int my_ini = 0;
+    for (int i = threadIdx.x; i < n2; i += kFastThreads) {
+        const int at = list2[i];
+        const uint8_t* q = sc0 + at;
+        const int s = q[0];
+        const int m = max(max(max(q[-tp - 1], q[-tp]), max(q[-tp + 1], q[-1])), max(max(q[1], q[tp - 1]), max(q[tp], q[tp + 1])));
+        if (m < s) {
+            const int y = at / tp, x = at - y * tp;
+            const int e = (y - 3) * 2 + ((x - 3) >> 5);
+            const uint32_t bit = 1u << ((x - 3) & 31);
+            atomicOr(&mask_all[e], bit);
+            if (s >= iniTh) { atomicOr(&mask_ini[e], bit); ++my_ini; }
+        }
+    }
+    if (my_ini) atomicAdd(&s_total_ini, my_ini);
     __syncthreads();
     const uint32_t* mask = s_total_ini > 0 ? mask_ini : mask_all;  // minThFAST retry of an empty cell
 
-    // exclusive prefix over (row, chunk) entries in row-major order: warp 0
+    // ---- phase 4: exclusive prefix over the entries in row-major order (warp 0), ordered write ------
     const int nent = dh * 2;
     if (warp == 0) {
         int carry = 0;
         for (int e0 = 0; e0 < nent; e0 += 32) {
             const int e = e0 + lane;
-            const int cnt = (e < nent && (e & 1) < nchunk) ? __popc(mask[e]) : 0;
+            const int cnt = e < nent ? __popc(mask[e]) : 0;
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
             if (e < nent) offs[e] = carry + inc - cnt;
             carry += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (lane == 0) { offs[nent] = carry; *count_out = min(carry, L.slot_cap); }
+        if (lane == 0) *count_out = min(carry, L.slot_cap);
     }
     __syncthreads();
 
     uint32_t* out = slots + (size_t)frame * g->slot_words + L.slot_off + (size_t)c.ordinal * L.slot_cap;
-    for (int y = 3 + warp; y < th - 3; y += kFastWarps)
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const int e = (y - 3) * 2 + ch;
-            const uint32_t m = mask[e];
-            if (m >> lane & 1) {
-                const int x = 3 + ch * 32 + lane;
-                const int rank = offs[e] + __popc(m & ((1u << lane) - 1));
-                if (rank < L.slot_cap)
-                    out[rank] = (uint32_t)(x + c.offx) | (uint32_t)(y + c.offy) << 12 | (uint32_t)score[y * tp + x] << 24;
-            }
+    for (int e = threadIdx.x; e < nent; e += kFastThreads) {
+        uint32_t m = mask[e];
+        int rank = offs[e];
+        const int y = 3 + (e >> 1), xb = 3 + (e & 1) * 32;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int x = xb + b;
+            if (rank < L.slot_cap)
+                out[rank] = (uint32_t)(x + c.offx) | (uint32_t)(y + c.offy) << 12 | (uint32_t)sc0[y * tp + x] << 24;
+            ++rank;
         }
+    }
+}
+
+static size_t fast_smem_bytes(const Geometry& hg, int tp) {
+    const size_t px = (size_t)hg.max_th * tp;
+    return 2 * px + (size_t)hg.max_th * 4 * sizeof(uint32_t) + (2 * (size_t)hg.max_th + 2) * sizeof(int) + 2 * px * sizeof(uint16_t);
 }
 
 int launch_fast(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
-    const int tp = (hg.max_tw + 3) & ~3;
-    const size_t smem = 2 * (size_t)hg.max_th * tp + (size_t)hg.max_th * 4 * sizeof(uint32_t) + (2 * (size_t)hg.max_th + 1) * sizeof(int);
-    fast_cells_kernel<<<dim3(hg.ncells, n), kFastThreads, smem, st>>>(db.geom, db.cells, fs, db.pyr, db.slots, db.cell_counts, tp);
+    const int tp = (hg.max_tw + 3 + 3) & ~3;  // + up to 3 bytes of alignment phase
+    fast_cells_kernel<<<dim3(hg.ncells, n), kFastThreads, fast_smem_bytes(hg, tp), st>>>(db.geom, db.cells, fs, db.pyr, db.slots,
+                                                                                       db.cell_counts, tp);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

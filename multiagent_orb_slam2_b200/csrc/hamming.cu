@@ -40,30 +40,72 @@ __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, cons
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-constexpr int kQueriesPerBlock = 256;  // one query per thread, held in 8 registers
-constexpr int kTileRows = 256;         // database rows per shared-memory stage (8 KB)
+// 256-bit Hamming distance with a carry-save adder tree: 4 full adders (2 LOP3 each) fold the 8
+// XOR words into {2 x ones, twos, fours}, so only 4 POPC (XU pipe, 16 lanes/clk/SM) are needed per
+// comparison instead of 8; the extra LOP3s run on the 64-lane ALU pipe
+// (tools/microbench/popc_bench.cu measures both forms).
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int hamming256_csa(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+    const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    const uint32_t s0 = lop3_xor3(x0, x1, x2), c0 = lop3_maj(x0, x1, x2);
+    const uint32_t s1 = lop3_xor3(x3, x4, x5), c1 = lop3_maj(x3, x4, x5);
+    const uint32_t s2 = lop3_xor3(s0, s1, x6), c2 = lop3_maj(s0, s1, x6);
+    const uint32_t t0 = lop3_xor3(c0, c1, c2), f0 = lop3_maj(c0, c1, c2);
+    return __popc(s2) + __popc(x7) + 2 * __popc(t0) + 4 * __popc(f0);
+}
+
+constexpr int kKnnThreads = 256;
+constexpr int kTileRows = 256;  // database rows per shared-memory stage (8 KB)
 constexpr int kStages = 2;
 
-// grid: (query blocks, database splits, pairs)
-__global__ void __launch_bounds__(kQueriesPerBlock)
+// position-explicit merge (partials may come in any order)
+__device__ __forceinline__ Top2 top2_merge_any(const Top2& a, const Top2& b) {
+    Top2 r;
+    r.b1 = min(a.b1, b.b1);
+    const bool take_b = b.b1 < a.b1 || (b.b1 == a.b1 && b.pos >= 0 && (a.pos < 0 || b.pos < a.pos));
+    r.pos = take_b ? b.pos : a.pos;
+    r.b2 = min(max(a.b1, b.b1), min(a.b2, b.b2));
+    return r;
+}
+
+// grid: (query blocks, 1, pairs). A block of 256 threads serves 256/S queries; the S thread groups
+// ("slices", warp-uniform) each scan 1/S of every database tile and are merged through shared
+// memory, so that small problems still fill the machine (S=8: 32 queries per block).
+// Pair p matches set pairs[2p] (queries) against set pairs[2p+1] (database); without a pair list
+// both are set p. Set k lives at base + k*stride_rows*32 with count n_dev[k] (or n_const).
+template <int S>
+__global__ void __launch_bounds__(kKnnThreads)
 knn2_kernel(const uint4* __restrict__ A, const int* __restrict__ nA_dev, int nA_const, int strideA_rows,
             const uint4* __restrict__ B, const int* __restrict__ nB_dev, int nB_const, int strideB_rows,
-            int rows_per_split, int nsplit, int out_stride,
+            const int* __restrict__ pairs, int out_stride,
             int* __restrict__ o_idx, int* __restrict__ o_b1, int* __restrict__ o_b2) {
+    constexpr int QB = kKnnThreads / S;   // queries per block
+    constexpr int R = kTileRows / S;      // rows of a tile per slice
     __shared__ __align__(128) uint4 tile[kStages][kTileRows * 2];
     __shared__ __align__(8) uint64_t full[kStages];
+    __shared__ int m_b1[S > 1 ? S : 1][QB], m_b2[S > 1 ? S : 1][QB], m_pos[S > 1 ? S : 1][QB];
 
-    const int pair = blockIdx.z, split = blockIdx.y;
-    const int nA = nA_dev ? nA_dev[pair] : nA_const;
-    const int nB = nB_dev ? nB_dev[pair] : nB_const;
-    const int q0 = blockIdx.x * kQueriesPerBlock;
+    const int pair = blockIdx.z;
+    const int ia = pairs ? pairs[2 * pair] : pair, ib = pairs ? pairs[2 * pair + 1] : pair;
+    const int nA = nA_dev ? nA_dev[ia] : nA_const;
+    const int nB = nB_dev ? nB_dev[ib] : nB_const;
+    const int q0 = blockIdx.x * QB;
     if (q0 >= nA) return;  // whole block exits together
-    const int q = q0 + threadIdx.x;
-    const uint4* Ap = A + (size_t)pair * strideA_rows * 2;
-    const uint4* Bp = B + (size_t)pair * strideB_rows * 2;
-
-    const int lo = min(split * rows_per_split, nB), hi = min(lo + rows_per_split, nB);
-    const int ntiles = ceil_div(hi - lo, kTileRows);
+    const int slice = threadIdx.x / QB, qi = threadIdx.x % QB;
+    const int q = q0 + qi;
+    const uint4* Ap = A + (size_t)ia * strideA_rows * 2;
+    const uint4* Bp = B + (size_t)ib * strideB_rows * 2;
+    const int ntiles = ceil_div(nB, kTileRows);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
@@ -71,8 +113,8 @@ knn2_kernel(const uint4* __restrict__ A, const int* __restrict__ nA_dev, int nA_
     }
     __syncthreads();
     auto issue = [&](int t) {
-        const int r0 = lo + t * kTileRows;
-        const uint32_t bytes = (uint32_t)min(kTileRows, hi - r0) * 32u;
+        const int r0 = t * kTileRows;
+        const uint32_t bytes = (uint32_t)min(kTileRows, nB - r0) * 32u;
         mbar_expect_tx(&full[t % kStages], bytes);
         bulk_g2s(tile[t % kStages], Bp + (size_t)r0 * 2, bytes, &full[t % kStages]);
     };
@@ -86,40 +128,30 @@ knn2_kernel(const uint4* __restrict__ A, const int* __restrict__ nA_dev, int nA_
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % kStages;
         mbar_wait(&full[s], (t / kStages) & 1);
-        const int r0 = lo + t * kTileRows;
-        const int rows = min(kTileRows, hi - r0);
+        const int r0 = t * kTileRows;
+        const int rows = min(kTileRows, nB - r0);
+        const int jlo = slice * R, jhi = min(jlo + R, rows);
         const uint4* tp = tile[s];
-        int j = 0;
 #pragma unroll 4
-        for (; j + 1 <= rows; ++j) {
-            const uint4 b0 = tp[2 * j], b1 = tp[2 * j + 1];
-            top2_update(best, hamming256(a0, a1, b0, b1), r0 + j);
+        for (int j = jlo; j < jhi; ++j) {
+            const int d = hamming256_csa(a0, a1, tp[2 * j], tp[2 * j + 1]);
+            if (d < best.b2) top2_update(best, d, r0 + j);  // rare once the running second-best is small
         }
         __syncthreads();  // every thread is done with stage s
         if (threadIdx.x == 0 && t + kStages < ntiles) issue(t + kStages);
     }
-    if (q < nA) {
-        const size_t o = ((size_t)pair * nsplit + split) * out_stride + q;
+    if (S > 1) {
+        m_b1[slice][qi] = best.b1; m_b2[slice][qi] = best.b2; m_pos[slice][qi] = best.pos;
+        __syncthreads();
+        if (slice == 0) {
+#pragma unroll
+            for (int k = 1; k < S; ++k) best = top2_merge_any(best, Top2{m_b1[k][qi], m_b2[k][qi], m_pos[k][qi]});
+        }
+    }
+    if (slice == 0 && q < nA) {
+        const size_t o = (size_t)pair * out_stride + q;
         o_idx[o] = best.pos; o_b1[o] = best.b1; o_b2[o] = best.b2;
     }
-}
-
-// merges the nsplit partial triples of each query in split (= position) order
-__global__ void knn2_merge_kernel(const int* __restrict__ p_idx, const int* __restrict__ p_b1,
-                                  const int* __restrict__ p_b2, const int* __restrict__ nA_dev, int nA_const,
-                                  int nsplit, int part_stride, int out_stride, int* __restrict__ o_idx,
-                                  int* __restrict__ o_b1, int* __restrict__ o_b2) {
-    const int pair = blockIdx.y;
-    const int nA = nA_dev ? nA_dev[pair] : nA_const;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nA) return;
-    Top2 acc{256, 256, -1};
-    for (int s = 0; s < nsplit; ++s) {
-        const size_t o = ((size_t)pair * nsplit + s) * part_stride + q;
-        acc = top2_merge(acc, Top2{p_b1[o], p_b2[o], p_idx[o]});
-    }
-    const size_t o = (size_t)pair * out_stride + q;
-    o_idx[o] = acc.pos; o_b1[o] = acc.b1; o_b2[o] = acc.b2;
 }
 
 // One warp per query; lanes stride over the candidate list; positions (not row ids) break ties.
@@ -172,43 +204,27 @@ __global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, cons
     if (i < nA && j < nB) out[(size_t)i * nB + j] = (int16_t)hamming256(sa[ty][0], sa[ty][1], sb[tx][0], sb[tx][1]);
 }
 
-// ---- host launchers --------------------------------------------------------------------------
+// ---- host launcher ----------------------------------------------------------------------------
 static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB,
-                       const int* d_nB, int nB_max, int strideB_rows, int pairs, int* d_idx, int* d_b1, int* d_b2,
-                       cudaStream_t st) {
+                       const int* d_nB, int nB_max, int strideB_rows, const int* d_pairs, int pairs, int* d_idx, int* d_b1,
+                       int* d_b2, cudaStream_t st) {
     if (pairs <= 0 || nA_max <= 0) return ORB_OK;
-    const int qblocks = ceil_div(nA_max, kQueriesPerBlock);
-    const int ctas = qblocks * pairs;
-    int nsplit = 1;
-    if (ctas < 2 * kNumSMs) {
-        nsplit = ceil_div(2 * kNumSMs, ctas);
-        const int max_split = max(1, nB_max / (2 * kTileRows));
-        nsplit = min(nsplit, max_split);
+    // pick the slice count so that the grid covers the machine about twice
+    int S = 1;
+    while (S < 8 && ceil_div(nA_max, kKnnThreads / S) * pairs < 2 * kNumSMs) S *= 2;
+    const dim3 grid(ceil_div(nA_max, kKnnThreads / S), 1, pairs);
+#define ORB_KNN2_LAUNCH(SS)                                                                                         \
+    knn2_kernel<SS><<<grid, kKnnThreads, 0, st>>>((const uint4*)dA, d_nA, nA_max, strideA_rows, (const uint4*)dB, d_nB, \
+                                                   nB_max, strideB_rows, d_pairs, strideA_rows, d_idx, d_b1, d_b2)
+    switch (S) {
+        case 1: ORB_KNN2_LAUNCH(1); break;
+        case 2: ORB_KNN2_LAUNCH(2); break;
+        case 4: ORB_KNN2_LAUNCH(4); break;
+        default: ORB_KNN2_LAUNCH(8); break;
     }
-    int rows_per_split = ceil_div(ceil_div(max(nB_max, 1), nsplit), kTileRows) * kTileRows;
-    nsplit = max(1, ceil_div(max(nB_max, 1), rows_per_split));
-    dim3 grid(qblocks, nsplit, pairs);
-    if (nsplit == 1) {
-        knn2_kernel<<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)dA, d_nA, nA_max, strideA_rows, (const uint4*)dB,
-                                                       d_nB, nB_max, strideB_rows, rows_per_split, 1, strideA_rows,
-                                                       d_idx, d_b1, d_b2);
-        count_launch();
-        ORB_CUDA_TRY(cudaGetLastError());
-        return ORB_OK;
-    }
-    int* part = nullptr;
-    const size_t per = (size_t)pairs * nsplit * nA_max;
-    ORB_CUDA_TRY(cudaMallocAsync(&part, 3 * per * sizeof(int), st));
-    knn2_kernel<<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)dA, d_nA, nA_max, strideA_rows, (const uint4*)dB, d_nB,
-                                                   nB_max, strideB_rows, rows_per_split, nsplit, nA_max, part,
-                                                   part + per, part + 2 * per);
+#undef ORB_KNN2_LAUNCH
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
-    knn2_merge_kernel<<<dim3(ceil_div(nA_max, 256), pairs), 256, 0, st>>>(part, part + per, part + 2 * per, d_nA, nA_max,
-                                                                          nsplit, nA_max, strideA_rows, d_idx, d_b1, d_b2);
-    count_launch();
-    ORB_CUDA_TRY(cudaGetLastError());
-    ORB_CUDA_TRY(cudaFreeAsync(part, st));
     return ORB_OK;
 }
 
@@ -224,7 +240,7 @@ int orbm_knn2_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32
     ORB_REQUIRE(nA == 0 || (dA && d_idx && d_best && d_second), "null pointer");
     ORB_REQUIRE(nB == 0 || dB, "null database");
     ORB_REQUIRE(((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0, "descriptor arrays must be 16-byte aligned");
-    return launch_knn2(dA, nullptr, nA, nA, dB, nullptr, nB, nB, 1, d_idx, d_best, d_second, (cudaStream_t)stream);
+    return launch_knn2(dA, nullptr, nA, nA, dB, nullptr, nB, nB, nullptr, 1, d_idx, d_best, d_second, (cudaStream_t)stream);
 }
 
 int orbm_knn2_batched_device(const uint8_t* dA, const int32_t* d_nA, int strideA_rows, const uint8_t* dB,
@@ -233,8 +249,17 @@ int orbm_knn2_batched_device(const uint8_t* dA, const int32_t* d_nA, int strideA
     ORB_REQUIRE(pairs >= 0 && strideA_rows >= 0 && strideB_rows >= 0, "negative size");
     ORB_REQUIRE(dA && dB && d_idx && d_best && d_second, "null pointer");
     ORB_REQUIRE(((uintptr_t)dA & 15) == 0 && ((uintptr_t)dB & 15) == 0, "descriptor arrays must be 16-byte aligned");
-    return launch_knn2(dA, d_nA, strideA_rows, strideA_rows, dB, d_nB, strideB_rows, strideB_rows, pairs, d_idx, d_best,
+    return launch_knn2(dA, d_nA, strideA_rows, strideA_rows, dB, d_nB, strideB_rows, strideB_rows, nullptr, pairs, d_idx, d_best,
                        d_second, (cudaStream_t)stream);
+}
+
+int orbm_knn2_pairs_device(const uint8_t* d_sets, const int32_t* d_counts, int stride_rows, const int32_t* d_pairs, int pairs,
+                           int32_t* d_idx, int32_t* d_best, int32_t* d_second, void* stream) {
+    ORB_REQUIRE(pairs >= 0 && stride_rows >= 0, "negative size");
+    ORB_REQUIRE(d_sets && d_counts && d_pairs && d_idx && d_best && d_second, "null pointer");
+    ORB_REQUIRE(((uintptr_t)d_sets & 15) == 0, "descriptor arrays must be 16-byte aligned");
+    return launch_knn2(d_sets, d_counts, stride_rows, stride_rows, d_sets, d_counts, stride_rows, stride_rows, d_pairs, pairs, d_idx,
+                       d_best, d_second, (cudaStream_t)stream);
 }
 
 int orbm_knn2_lists_device(const uint8_t* dA, int nA, const uint8_t* dB, const int32_t* d_offsets,

@@ -31,6 +31,7 @@ class AgentFrontend:
             z = lambda: torch.empty((max_batch, self.cap), dtype=torch.int32, device=self.dev)
             self.idx, self.d1, self.d2, self.match = z(), z(), z(), z()
         self._pinned = None
+        self._pairs = {}
 
     # ---- device-resident path ---------------------------------------------------------------------
     def _stream(self):
@@ -40,16 +41,13 @@ class AgentFrontend:
         """frame i (queries) against frame (i+1) % n (database), i = 0..n-1, on the current stream."""
         st = C.c_void_p(self._stream())
         cap, L = self.cap, self.L
-        if n > 1:
-            _lib.check(L.orbm_knn2_batched_device(C.c_void_p(self.d_desc), C.c_void_p(self.d_counts), cap,
-                                                  C.c_void_p(self.d_desc + cap * 32), C.c_void_p(self.d_counts + 4), cap, n - 1,
-                                                  C.c_void_p(self.idx.data_ptr()), C.c_void_p(self.d1.data_ptr()),
-                                                  C.c_void_p(self.d2.data_ptr()), st))
-        last = n - 1
-        _lib.check(L.orbm_knn2_batched_device(C.c_void_p(self.d_desc + last * cap * 32), C.c_void_p(self.d_counts + 4 * last), cap,
-                                              C.c_void_p(self.d_desc), C.c_void_p(self.d_counts), cap, 1,
-                                              C.c_void_p(self.idx.data_ptr() + 4 * last * cap), C.c_void_p(self.d1.data_ptr() + 4 * last * cap),
-                                              C.c_void_p(self.d2.data_ptr() + 4 * last * cap), st))
+        pairs = self._pairs.get(n)
+        if pairs is None:
+            i = torch.arange(n, dtype=torch.int32)
+            pairs = self._pairs[n] = torch.stack([i, (i + 1) % n], 1).contiguous().to(self.dev)
+        _lib.check(L.orbm_knn2_pairs_device(C.c_void_p(self.d_desc), C.c_void_p(self.d_counts), cap, C.c_void_p(pairs.data_ptr()), n,
+                                            C.c_void_p(self.idx.data_ptr()), C.c_void_p(self.d1.data_ptr()),
+                                            C.c_void_p(self.d2.data_ptr()), st))
         _lib.check(L.orbm_ratio_filter_device(C.c_void_p(self.idx.data_ptr()), C.c_void_p(self.d1.data_ptr()), C.c_void_p(self.d2.data_ptr()),
                                               n * cap, self.th, 1, self.nnratio, C.c_void_p(self.match.data_ptr()), st))
 

@@ -173,3 +173,56 @@ def test_agent_frontend_extract_and_match_consecutive():
     fe.process_device(d_imgs)
     torch.cuda.synchronize()
     assert np.array_equal(fe.match[:n].cpu().numpy()[0, :counts[0]], match[0, :counts[0]])
+
+
+def test_device_frames_with_unaligned_pitch():
+    """Caller-owned device frames whose row pitch is not a multiple of 4 (1241 px wide, tightly packed)
+    take the byte-wise tile loads of FAST / blur; results must not change."""
+    import torch
+    img = synth.image("blocks", 1241, 376, 5)
+    ok, od = O.OracleExtractor(2000, 1.2, 8, 20, 7)(img)
+    g = ORBextractor(2000, 1.2, 8, 20, 7, width=1241, height=376, max_batch=2)
+    d = torch.from_numpy(np.stack([img, img])).cuda()
+    assert d.stride(1) == 1241
+    g.extract_device(d.data_ptr(), d.stride(1), d.stride(0), 2, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    from multiagent_orb_slam2_b200 import _lib
+    import ctypes as C
+    kps = np.empty((2, g.cap), dtype=[("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
+    desc = np.empty((2, g.cap, 32), np.uint8)
+    counts = np.empty(2, np.int32)
+    _lib.check(_lib.lib().orbx_download_results(g._h, 2, kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), g.cap,
+                                                counts.ctypes.data_as(C.c_void_p), None))
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert counts[i] == len(ok)
+        assert np.array_equal(kp_matrix(kps[i, :counts[i]]).view(np.uint32), ok.view(np.uint32))
+        assert np.array_equal(desc[i, :counts[i]], od)
+
+
+def test_knn2_pairs_all_slice_counts():
+    """orbm_knn2_pairs_device picks 1..8 slices per query depending on the grid size: cover them all."""
+    import torch
+    import ctypes as C
+    from multiagent_orb_slam2_b200 import _lib
+    L = _lib.lib()
+    for nsets, rows in [(2, 300), (6, 700), (40, 1100), (150, 500), (700, 300)]:
+        rng = np.random.default_rng(nsets)
+        counts = rng.integers(max(1, rows - 200), rows + 1, nsets).astype(np.int32)
+        counts[0] = rows
+        base = synth.descriptors(rows, 11)
+        sets = np.zeros((nsets, rows, 32), np.uint8)
+        for k in range(nsets):
+            sets[k, :counts[k]] = synth.descriptors_fast(int(counts[k]), 100 + k, base, 40)
+        pairs = np.stack([np.arange(nsets), (np.arange(nsets) + 1) % nsets], 1).astype(np.int32)
+        d_sets, d_counts, d_pairs = torch.from_numpy(sets).cuda(), torch.from_numpy(counts).cuda(), torch.from_numpy(pairs).cuda()
+        out = [torch.empty((nsets, rows), dtype=torch.int32, device="cuda") for _ in range(3)]
+        _lib.check(L.orbm_knn2_pairs_device(C.c_void_p(d_sets.data_ptr()), C.c_void_p(d_counts.data_ptr()), rows, C.c_void_p(d_pairs.data_ptr()),
+                                            nsets, *[C.c_void_p(o.data_ptr()) for o in out], None))
+        torch.cuda.synchronize()
+        gi, g1, g2 = [o.cpu().numpy() for o in out]
+        for p in rng.choice(nsets, min(nsets, 6), replace=False):
+            a, b = pairs[p]
+            oi, o1, o2 = O.knn2(sets[a, :counts[a]], sets[b, :counts[b]])
+            n = counts[a]
+            assert np.array_equal(gi[p, :n], oi) and np.array_equal(g1[p, :n], o1) and np.array_equal(g2[p, :n], o2), (nsets, p)
