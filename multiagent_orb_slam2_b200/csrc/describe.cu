@@ -38,100 +38,132 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 constexpr int kDescWarps = 8;
+constexpr int kDescSlots = 32;  // keypoint slots per block
 
-// grid (ceil(sel_words / 8), frames), block 256 = 8 keypoint slots
+struct SlotInfo { int valid, level, x, y, response, dst; };
+
+// grid (ceil(sel_words / 32), frames), block 256. Phases:
+//   0. thread i < 32 resolves slot i (level, position in the frame's output, packed candidate)
+//   A. every warp: intensity-centroid angle of 4 slots (lane = patch column, loop over rows)
+//   B. warp 0: lane i evaluates sin/cos (double, rounded once) for slot i - 32 keypoints per
+//      instruction stream instead of one
+//   C. every warp: rotated BRIEF of 4 slots (lane = output byte), keypoint record
 __global__ void __launch_bounds__(kDescWarps * 32)
 orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_t* __restrict__ pyr,
                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ selected,
                        const int* __restrict__ sel_counts, const int8_t* __restrict__ pattern,
                        orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int* __restrict__ counts) {
-    __shared__ int8_t pat[1024];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<int*>(pat)[i] = reinterpret_cast<const int*>(pattern)[i];
-    __syncthreads();
+    __shared__ float patf[1024];  // transposed: value (test t, component c) of byte `lane` at [(4t+c)*32 + lane]
+    __shared__ SlotInfo info[kDescSlots];
+    __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) patf[(i & 31) * 32 + (i >> 5)] = (float)pattern[i];
 
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kDescWarps + warp;
     const int nlevels = g->nlevels;
     const int* cnt = sel_counts + (size_t)frame * nlevels;
-    if (slot == 0 && lane == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 32) {
         int total = 0;
         for (int l = 0; l < nlevels; ++l) total += cnt[l];
-        counts[frame] = total;
+        counts[frame] = min(total, g->out_cap);
     }
-    if (slot >= g->sel_words) return;
-    // which level does this slot belong to, and where does the level start in the output?
-    int level = 0, dst0 = 0;
-    for (int l = 0; l < nlevels; ++l) {
-        if (slot >= g->lv[l].sel_off) level = l;
-    }
-    for (int l = 0; l < level; ++l) dst0 += cnt[l];
-    const LevelGeom& L = g->lv[level];
-    const int i = slot - L.sel_off;
-    if (i >= cnt[level]) return;
-    const int dst = dst0 + i;
-    if (dst >= g->out_cap) return;
-
-    const uint32_t p = selected[(size_t)frame * g->sel_words + slot];
-    const int x = (int)(p & 0xfff) + kMinBorder, y = (int)((p >> 12) & 0xfff) + kMinBorder;
-    const int response = (int)(p >> 24);
-
-    // ---- IC_Angle: lane = column u in [-15, 15], loop over rows ---------------------------------
-    int spitch;
-    const uint8_t* img = level_ptr(*g, fs, pyr, frame, level, &spitch);
-    const uint8_t* center = img + (size_t)y * spitch + x;
-    int m10 = 0, m01 = 0;
-    const int u = lane - kHalfPatch;
-    if (lane < 2 * kHalfPatch + 1) {
-        const int au = u < 0 ? -u : u;
-#pragma unroll 4
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            const int av = v < 0 ? -v : v;
-            if (au <= g->umax[av]) {
-                const int val = center[v * spitch + u];
-                m10 += u * val;
-                m01 += v * val;
+    if (threadIdx.x < kDescSlots) {
+        const int slot = blockIdx.x * kDescSlots + threadIdx.x;
+        SlotInfo si{0, 0, 0, 0, 0, 0};
+        if (slot < g->sel_words) {
+            int level = 0, dst0 = 0;
+            for (int l = 0; l < nlevels; ++l) if (slot >= g->lv[l].sel_off) level = l;
+            for (int l = 0; l < level; ++l) dst0 += cnt[l];
+            const int i = slot - g->lv[level].sel_off;
+            const int dst = dst0 + i;
+            if (i < cnt[level] && dst < g->out_cap) {
+                const uint32_t p = selected[(size_t)frame * g->sel_words + slot];
+                si.valid = 1; si.level = level; si.dst = dst;
+                si.x = (int)(p & 0xfff) + kMinBorder; si.y = (int)((p >> 12) & 0xfff) + kMinBorder; si.response = (int)(p >> 24);
             }
         }
+        info[threadIdx.x] = si;
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    __syncthreads();
 
-    // ---- rotated BRIEF: lane = output byte, 8 tests x 2 samples ---------------------------------
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    const float rad = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)rad), b = (float)sin((double)rad);
-    const uint8_t* bc = blur + (size_t)frame * g->blur_bytes + L.blur_off + (size_t)y * L.pitch + x;
-    const int bp = L.pitch;
-    const int8_t* pp = pat + lane * 32;
-    int val = 0;
+    // ---- A: IC_Angle -----------------------------------------------------------------------------
+    for (int k = 0; k < kDescSlots / kDescWarps; ++k) {
+        const int sidx = warp * (kDescSlots / kDescWarps) + k;
+        const SlotInfo si = info[sidx];
+        if (!si.valid) continue;
+        int spitch;
+        const uint8_t* img = level_ptr(*g, fs, pyr, frame, si.level, &spitch);
+        const uint8_t* center = img + (size_t)si.y * spitch + si.x;
+        int m10 = 0, m01 = 0;
+        const int u = lane - kHalfPatch;
+        if (lane < 2 * kHalfPatch + 1) {
+            // the circular patch is symmetric under transposition: column u spans rows |v| <= umax[|u|]
+            const int vext = g->umax[u < 0 ? -u : u];
+            const uint8_t* col = center + u;
+            int vals[2 * kHalfPatch + 1];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float x0 = (float)pp[4 * t], y0 = (float)pp[4 * t + 1], x1 = (float)pp[4 * t + 2], y1 = (float)pp[4 * t + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        val |= (int)(bc[r0 * bp + c0] < bc[r1 * bp + c1]) << t;
+            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+                const int av = v < 0 ? -v : v;
+                vals[v + kHalfPatch] = av <= vext ? (int)col[v * spitch] : 0;  // all loads in flight together
+            }
+            int colsum = 0;
+#pragma unroll
+            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) { colsum += vals[v + kHalfPatch]; m01 += v * vals[v + kHalfPatch]; }
+            m10 = u * colsum;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+        if (lane == 0) s_angle[sidx] = fast_atan2_deg((float)m01, (float)m10);
     }
-    desc[((size_t)frame * g->out_cap + dst) * 32 + lane] = (uint8_t)val;
+    __syncthreads();
 
-    if (lane == 0) {
-        orbx_keypoint k;
-        // `pt *= scale` (1095-1101) is applied for level != 0 only; scale[0] == 1 makes it uniform
-        k.x = __fmul_rn((float)x, L.scale);
-        k.y = __fmul_rn((float)y, L.scale);
-        k.size = (float)L.patch_size;
-        k.angle = angle;
-        k.response = (float)response;
-        k.octave = level;
-        kps[(size_t)frame * g->out_cap + dst] = k;
+    // ---- B: sin / cos, one keypoint per lane -------------------------------------------------------
+    if (warp == 0 && info[lane].valid) {
+        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+        const float rad = __fmul_rn(s_angle[lane], factorPI);
+        double sn, cs;
+        sincos((double)rad, &sn, &cs);
+        s_cos[lane] = (float)cs; s_sin[lane] = (float)sn;
+    }
+    __syncthreads();
+
+    // ---- C: rotated BRIEF + keypoint record ----------------------------------------------------------
+    for (int k = 0; k < kDescSlots / kDescWarps; ++k) {
+        const int sidx = warp * (kDescSlots / kDescWarps) + k;
+        const SlotInfo si = info[sidx];
+        if (!si.valid) continue;
+        const LevelGeom& L = g->lv[si.level];
+        const float a = s_cos[sidx], b = s_sin[sidx];
+        const uint8_t* bc = blur + (size_t)frame * g->blur_bytes + L.blur_off + (size_t)si.y * L.pitch + si.x;
+        const int bp = L.pitch;
+        const float* pp = patf + lane;
+        int val = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const float x0 = pp[(4 * t) * 32], y0 = pp[(4 * t + 1) * 32], x1 = pp[(4 * t + 2) * 32], y1 = pp[(4 * t + 3) * 32];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            val |= (int)(bc[r0 * bp + c0] < bc[r1 * bp + c1]) << t;
+        }
+        desc[((size_t)frame * g->out_cap + si.dst) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            orbx_keypoint kp;
+            // `pt *= scale` (1095-1101) is applied for level != 0 only; scale[0] == 1 makes it uniform
+            kp.x = __fmul_rn((float)si.x, L.scale);
+            kp.y = __fmul_rn((float)si.y, L.scale);
+            kp.size = (float)L.patch_size;
+            kp.angle = s_angle[sidx];
+            kp.response = (float)si.response;
+            kp.octave = si.level;
+            kps[(size_t)frame * g->out_cap + si.dst] = kp;
+        }
     }
 }
 
 int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
-    orient_describe_kernel<<<dim3(ceil_div(hg.sel_words, kDescWarps), n), kDescWarps * 32, 0, st>>>(
+    orient_describe_kernel<<<dim3(ceil_div(hg.sel_words, kDescSlots), n), kDescWarps * 32, 0, st>>>(
         db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.kps, db.desc, db.counts);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());

@@ -236,7 +236,7 @@ extern "C" {
 int orbx_create(const orbx_config* cfg, int device, int width, int height, int max_batch, orbx_handle* out) {
     ORB_REQUIRE(cfg && out, "null pointer");
     ORB_REQUIRE(cfg->nlevels >= 1 && cfg->nlevels <= kMaxLevels, "nlevels out of range (1..16)");
-    ORB_REQUIRE(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f, "nfeatures >= 1 and scale_factor > 1 required");
+    ORB_REQUIRE(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && cfg->scale_factor <= 2.0f, "nfeatures >= 1 and 1 < scale_factor <= 2 required");
     ORB_REQUIRE(cfg->min_th_fast >= 1 && cfg->ini_th_fast >= cfg->min_th_fast && cfg->ini_th_fast < 255, "FAST thresholds: 1 <= min <= ini < 255");
     ORB_REQUIRE(width > 0 && height > 0 && max_batch >= 1, "image size / batch must be positive");
     *out = nullptr;

@@ -33,16 +33,18 @@ __device__ __forceinline__ int ring_offset(int k, int tp) {
     return dy[k] * tp + dx[k];
 }
 
-// exact FAST score if the pixel is a corner at threshold th (th >= 1), else 0
-__device__ __forceinline__ int fast_score_full(const uint8_t* __restrict__ p, int tp, int th) {
+// full arc test at threshold th: 0 = no corner, 1 = bright arc (centre brighter than 9 contiguous ring
+// pixels by more than th), 2 = dark arc
+__device__ __forceinline__ int fast_arc_test(const uint8_t* __restrict__ p, int tp, int th) {
     const int v = p[0];
     const int lo = v - th, hi = v + th;
-    int r[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) r[k] = p[ring_offset(k, tp)];
     uint32_t mb = 0, md = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(r[k] < lo) << k; md |= (uint32_t)(r[k] > hi) << k; }
+    for (int k = 0; k < 16; ++k) {
+        const int r = p[ring_offset(k, tp)];
+        mb |= (uint32_t)(r < lo) << k;
+        md |= (uint32_t)(r > hi) << k;
+    }
     auto has_arc9 = [](uint32_t m) {
         m |= m << 16;
         uint32_t a = m & (m >> 1);
@@ -51,12 +53,16 @@ __device__ __forceinline__ int fast_score_full(const uint8_t* __restrict__ p, in
         a &= m >> 8;
         return a != 0;
     };
-    const bool cb = has_arc9(mb), cd = has_arc9(md);
-    if (!cb && !cd) return 0;
-    // signed margins on the winning side (both sides cannot hold a 9-arc at once)
+    return has_arc9(mb) ? 1 : (has_arc9(md) ? 2 : 0);
+}
+
+// exact score of a known corner: max over the 16 arcs of the minimum margin on the corner's side, - 1
+// (the other side cannot hold a 9-arc at the same time, so it cannot win the maximum)
+__device__ __forceinline__ int fast_score_side(const uint8_t* __restrict__ p, int tp, bool dark) {
+    const int v = p[0];
     int d[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = cb ? v - r[k] : r[k] - v;
+    for (int k = 0; k < 16; ++k) { const int r = p[ring_offset(k, tp)]; d[k] = dark ? r - v : v - r; }
     int m2[16], m4[16], best = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) m2[k] = min(d[k], d[(k + 1) & 15]);
@@ -67,7 +73,7 @@ __device__ __forceinline__ int fast_score_full(const uint8_t* __restrict__ p, in
         const int m8 = min(m4[k], m4[(k + 4) & 15]);
         best = max(best, min(m8, d[(k + 8) & 15]));
     }
-    return best - 1;  // >= th by construction
+    return best - 1;
 }
 
 // Shared memory (dynamic): tile | score | masks | offsets | two index lists.
@@ -115,10 +121,13 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         if (word_rows) {  // the row's own tail (x < level width) keeps the last word inside the row
             const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src - phase);
             const int spw = spitch >> 2;
+            int y = threadIdx.x / tpw, xw = threadIdx.x - y * tpw;
+            const int dy = kFastThreads / tpw, dxw = kFastThreads - dy * tpw;
             for (int i = threadIdx.x; i < th * tpw; i += kFastThreads) {
-                const int y = i / tpw, xw = i - y * tpw;
                 tilew[i] = xw < nwords ? __ldg(srcw + (size_t)y * spw + xw) : 0u;
                 scorew[i] = 0u;
+                xw += dxw; y += dy;
+                if (xw >= tpw) { xw -= tpw; ++y; }
             }
         } else {
             for (int i = threadIdx.x; i < th * tpw; i += kFastThreads) scorew[i] = 0u;
@@ -144,35 +153,28 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
                 const int r0 = p[3 * tp], r8 = p[-3 * tp], r4 = p[3], r12 = p[-3];
                 keep = ((r0 < lo || r8 < lo) && (r4 < lo || r12 < lo)) || ((r0 > hi || r8 > hi) && (r4 > hi || r12 > hi));
             }
-            const uint32_t ball = __ballot_sync(0xffffffffu, keep);
-            if (ball) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_n1, __popc(ball));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (keep) list1[base + __popc(ball & ((1u << lane) - 1))] = (uint16_t)(y * tp + x);
-            }
+            if (keep) list1[atomicAdd(&s_n1, 1)] = (uint16_t)(y * tp + x);  // ptxas aggregates per warp
         }
     __syncthreads();
 
-    // ---- phase 2: full arc test + exact score on the survivors -------------------------------------
+    // ---- phase 2a: full 16-pixel arc test on the survivors -> corner list (bit 15 = dark side) -------
     const int n1 = s_n1;
-    for (int i0 = 0; i0 < n1; i0 += kFastThreads) {
-        const int i = i0 + threadIdx.x;
-        int s = 0, at = 0;
-        if (i < n1) { at = list1[i]; s = fast_score_full(t0 + at, tp, minTh); }
-        if (s > 0) sc0[at] = (uint8_t)s;
-        const uint32_t ball = __ballot_sync(0xffffffffu, s > 0);
-        if (ball) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_n2, __popc(ball));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (s > 0) list2[base + __popc(ball & ((1u << lane) - 1))] = (uint16_t)at;
-        }
+    for (int i = threadIdx.x; i < n1; i += kFastThreads) {
+        const int at = list1[i];
+        const int side = fast_arc_test(t0 + at, tp, minTh);
+        if (side) list2[atomicAdd(&s_n2, 1)] = (uint16_t)(at | (side == 2 ? 0x8000 : 0));
+    }
+    __syncthreads();
+    // ---- phase 2b: exact score of the corners, dense -----------------------------------------------
+    const int n2 = s_n2;
+    for (int i = threadIdx.x; i < n2; i += kFastThreads) {
+        const int e = list2[i], at = e & 0x7fff;
+        sc0[at] = (uint8_t)fast_score_side(t0 + at, tp, (e & 0x8000) != 0);
+        list2[i] = (uint16_t)at;
     }
     __syncthreads();
 
     // ---- phase 3: 3x3 strict maximum on the corners -> bit masks per (row, 32-column chunk) --------
-    const int n2 = s_n2;
     int my_ini = 0;
     for (int i = threadIdx.x; i < n2; i += kFastThreads) {
         const int at = list2[i];

@@ -11,45 +11,90 @@
 namespace orb {
 
 // ------------------------------------------------------------------------------------------------
-// resize: each thread produces 4 horizontally adjacent pixels of one output row.
-// grid (ceil(w/128), ceil(h/8), frames), block (32, 8)
+// resize: one block = one 128 x 32 output tile. The source window of the tile is staged in shared
+// memory with aligned 32-bit loads; each thread keeps the column taps of its 4 output columns and
+// the row taps of its 4 output rows in registers (fetched up front, so the kernel pays two global
+// latencies - taps, then window - instead of three).
+constexpr int kRsTW = 128, kRsTH = 32;
+constexpr int kRsMaxWords = 72, kRsMaxRows = 68;  // source window budget: scale factors up to 2.0
+
 __global__ void __launch_bounds__(256)
 resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, FrameSet fs, uint8_t* __restrict__ pyr, int level) {
+    __shared__ __align__(16) uint32_t win[kRsMaxRows][kRsMaxWords];
     const LevelGeom& L = g->lv[level];
     const LevelGeom& S = g->lv[level - 1];
     const int frame = blockIdx.z;
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x0 >= L.w || y >= L.h) return;
+    const int X0 = blockIdx.x * kRsTW, Y0 = blockIdx.y * kRsTH;
+    const int X1 = min(X0 + kRsTW, L.w) - 1, Y1 = min(Y0 + kRsTH, L.h) - 1;  // last output column / row of the tile
     int spitch;
     const uint8_t* src = level_ptr(*g, fs, pyr, frame, level - 1, &spitch);
     uint8_t* dst = pyr + (size_t)frame * g->pyr_bytes + L.img_off;
+    const LinTap* tx = taps + L.tab_x_off;
+    const LinTap* ty = taps + L.tab_y_off;
 
-    const LinTap ty = taps[L.tab_y_off + y];
-    const uint8_t* r0 = src + (size_t)ty.ofs * spitch;
-    const uint8_t* r1 = src + (size_t)min(ty.ofs + 1, S.h - 1) * spitch;
-    const int b0 = ty.c0, b1 = ty.c1;
-    uint32_t packed = 0;
+    // all table reads of this thread, issued together
+    const int q = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int x0 = X0 + 4 * q;
+    LinTap tcol[4], trow[kRsTH / 8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int x = x0 + k;
-        if (x < L.w) {
-            const LinTap tx = taps[L.tab_x_off + x];
-            const int sx0 = tx.ofs, sx1 = min(tx.ofs + 1, S.w - 1);
-            const int h0 = r0[sx0] * tx.c0 + r0[sx1] * tx.c1;
-            const int h1 = r1[sx0] * tx.c0 + r1[sx1] * tx.c1;
+    for (int k = 0; k < 4; ++k) tcol[k] = tx[min(x0 + k, L.w - 1)];
+#pragma unroll
+    for (int rr = 0; rr < kRsTH / 8; ++rr) trow[rr] = ty[min(Y0 + rg + 8 * rr, L.h - 1)];
+    // source window [sx_lo, sx_hi] x [sy_lo, sy_hi] (taps are monotone)
+    const int sx_lo = tx[X0].ofs & ~3, sx_hi = min(tx[X1].ofs + 1, S.w - 1);
+    const int sy_lo = ty[Y0].ofs, sy_hi = min(ty[Y1].ofs + 1, S.h - 1);
+    const int nwords = (sx_hi - sx_lo) / 4 + 1, nrows = sy_hi - sy_lo + 1;
+    const bool word_rows = ((spitch & 3) == 0) && (((uintptr_t)src & 3) == 0);
+    {
+        int r = threadIdx.x / nwords, cw = threadIdx.x - r * nwords;
+        const int dr = 256 / nwords, dcw = 256 - dr * nwords;
+        for (int i = threadIdx.x; i < nrows * nwords; i += 256) {
+            const uint8_t* row = src + (size_t)(sy_lo + r) * spitch;
+            const int x = sx_lo + 4 * cw;
+            uint32_t v;
+            if (word_rows && x + 3 < S.w) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+            } else {
+                v = 0;
+                for (int b = 0; b < 4; ++b) v |= (uint32_t)row[min(x + b, S.w - 1)] << (8 * b);
+            }
+            win[r][cw] = v;
+            cw += dcw; r += dr;
+            if (cw >= nwords) { cw -= nwords; ++r; }
+        }
+    }
+    __syncthreads();
+
+    if (x0 >= L.w) return;
+    int ofs0[4], ofs1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ofs0[k] = tcol[k].ofs - sx_lo; ofs1[k] = min(tcol[k].ofs + 1, S.w - 1) - sx_lo; }
+    const uint8_t* wb = reinterpret_cast<const uint8_t*>(&win[0][0]);
+#pragma unroll
+    for (int rr = 0; rr < kRsTH / 8; ++rr) {
+        const int y = Y0 + rg + 8 * rr;
+        if (y >= L.h) break;
+        const LinTap t = trow[rr];
+        const uint8_t* r0 = wb + (size_t)(t.ofs - sy_lo) * (kRsMaxWords * 4);
+        const uint8_t* r1 = wb + (size_t)(min(t.ofs + 1, S.h - 1) - sy_lo) * (kRsMaxWords * 4);
+        const int b0 = t.c0, b1 = t.c1;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h0 = r0[ofs0[k]] * tcol[k].c0 + r0[ofs1[k]] * tcol[k].c1;
+            const int h1 = r1[ofs0[k]] * tcol[k].c0 + r1[ofs1[k]] * tcol[k].c1;
             const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
             packed |= (uint32_t)(v & 0xff) << (8 * k);
         }
+        // rows are 128-byte pitched and x0 is a multiple of 4: aligned 32-bit store (pitch slack absorbs the tail)
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x0) = packed;
     }
-    // rows are 128-byte pitched and x0 is a multiple of 4: aligned 32-bit store (pitch slack absorbs the tail)
-    *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x0) = packed;
 }
 
 int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int level, int n, cudaStream_t st) {
     const LevelGeom& L = hg.lv[level];
-    dim3 grid(ceil_div(L.w, 128), ceil_div(L.h, 8), n);
-    resize_kernel<<<grid, dim3(32, 8), 0, st>>>(db.geom, db.taps, fs, db.pyr, level);
+    dim3 grid(ceil_div(L.w, kRsTW), ceil_div(L.h, kRsTH), n);
+    resize_kernel<<<grid, 256, 0, st>>>(db.geom, db.taps, fs, db.pyr, level);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

@@ -18,11 +18,11 @@
 
 namespace orb {
 
-constexpr int kQtThreads = 1024;
+constexpr int kQtThreads = 256;  // several blocks per SM hide each other's barrier stalls
 constexpr int kQtWarps = kQtThreads / 32;
 
 struct QtShared {
-    int warp_tmp[kQtWarps];
+    int warp_tmp[32];
     int carry;
     int bcast[4];
     int hist[256];
@@ -43,7 +43,7 @@ __device__ int block_exclusive_scan(const int* in, int* out, int len, QtShared& 
         if (lane == 31) sh.warp_tmp[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            const int w = sh.warp_tmp[lane];
+            const int w = lane < kQtWarps ? sh.warp_tmp[lane] : 0;
             int winc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }

@@ -1,0 +1,42 @@
+"""Summarise an .ncu-rep (raw page) into a per-kernel table. Usage: python tools/ncu_summary.py rep [out.md]"""
+import csv, subprocess, sys
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+cols = [("gpu__time_duration.sum", "time"), ("smsp__inst_executed.sum", "warp_inst"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("launch__registers_per_thread", "regs"),
+        ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"), ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem%"),
+        ("smsp__average_warp_latency_issue_stalled_barrier_per_warp_active.pct", "st_barrier"),
+        ("smsp__average_warp_latency_issue_stalled_long_scoreboard_per_warp_active.pct", "st_long_sb"),
+        ("smsp__average_warp_latency_issue_stalled_short_scoreboard_per_warp_active.pct", "st_short_sb"),
+        ("smsp__average_warp_latency_issue_stalled_wait_per_warp_active.pct", "st_wait"),
+        ("smsp__average_warp_latency_issue_stalled_math_pipe_throttle_per_warp_active.pct", "st_math"),
+        ("smsp__average_warp_latency_issue_stalled_mio_throttle_per_warp_active.pct", "st_mio"),
+        ("smsp__average_warp_latency_issue_stalled_lg_throttle_per_warp_active.pct", "st_lg"),
+        ("smsp__average_warp_latency_issue_stalled_not_selected_per_warp_active.pct", "st_notsel"),
+        ("smsp__average_warp_latency_issue_stalled_branch_resolving_per_warp_active.pct", "st_branch")]
+out = ["| kernel | grid | " + " | ".join(c[1] for c in cols) + " |", "|---|---|" + "---|" * len(cols)]
+for r in rows[2:]:
+    name = r[idx["Kernel Name"]].split("(")[0]
+    cells = []
+    for k, _ in cols:
+        if k in idx:
+            v = r[idx[k]]
+            try:
+                f = float(v.replace(",", ""))
+                v = ("%.3g" % f) + (" " + units[idx[k]] if units[idx[k]] not in ("%", "", "inst", "register/thread") else "")
+            except ValueError:
+                pass
+            cells.append(v)
+        else:
+            cells.append("-")
+    out.append("| %s | %s | " % (name, r[idx["Grid Size"]]) + " | ".join(cells) + " |")
+txt = "\n".join(out)
+print(txt)
+if len(sys.argv) > 2:
+    open(sys.argv[2], "w").write("# ncu --set full summary of %s\n\n%s\n" % (rep, txt))
