@@ -160,6 +160,15 @@ int orbm_knn2_lists_device(const uint8_t* dA, int nA, const uint8_t* dB, const i
 int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* offsets,
                     const int32_t* cands, int32_t* idx, int32_t* best, int32_t* second);
 
+/* Raw distances of the same CSR lists, out[k] = distance(A[q], B[cands[k]]) for k in [offsets[q], offsets[q+1]).
+ * For the STATEFUL searches (SearchForInitialization's vMatchedDistance gate src/ORBmatcher.cc:446, the
+ * "already matched" flags at 211 / 578): the device does the popcounts, the caller replays the reference's
+ * loop over the precomputed distances in the reference's order, which keeps match sets bit-exact. */
+int orbm_list_distances_device(const uint8_t* dA, int nA, const uint8_t* dB, const int32_t* d_offsets,
+                               const int32_t* d_cands, int16_t* d_out, void* stream);
+int orbm_list_distances(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* offsets,
+                        const int32_t* cands, int16_t* out);
+
 /* Acceptance test of SearchByBoW(KF,KF) (src/ORBmatcher.cc:600-603): match[i] = idx[i] if
  * best < th_strict_upper && (float)best < ratio*(float)second, else -1. With inclusive != 0 the
  * threshold test is best <= th (SearchForInitialization / SearchByBoW(KF,F), 229-232, 461-463). */

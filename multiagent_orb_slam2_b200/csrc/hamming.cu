@@ -181,6 +181,18 @@ __global__ void knn2_lists_kernel(const uint4* __restrict__ A, int nA, const uin
     if (lane == 0) { o_idx[q] = t.pos >= 0 ? cands[t.pos] : -1; o_b1[q] = t.b1; o_b2[q] = t.b2; }
 }
 
+// distance of every (query, candidate) pair of a CSR candidate list: out[k] for k in [offsets[q], offsets[q+1])
+__global__ void list_distances_kernel(const uint4* __restrict__ A, int nA, const uint4* __restrict__ B,
+                                      const int* __restrict__ offsets, const int* __restrict__ cands, int16_t* __restrict__ out) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nA) return;
+    const uint4 a0 = __ldg(A + (size_t)q * 2), a1 = __ldg(A + (size_t)q * 2 + 1);
+    for (int k = offsets[q] + lane; k < offsets[q + 1]; k += 32) {
+        const int j = cands[k];
+        out[k] = (int16_t)hamming256(a0, a1, __ldg(B + (size_t)j * 2), __ldg(B + (size_t)j * 2 + 1));
+    }
+}
+
 __global__ void ratio_filter_kernel(const int* __restrict__ idx, const int* __restrict__ b1, const int* __restrict__ b2,
                                     int n, int th, int inclusive, float ratio, int* __restrict__ match) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +286,17 @@ int orbm_knn2_lists_device(const uint8_t* dA, int nA, const uint8_t* dB, const i
     return ORB_OK;
 }
 
+int orbm_list_distances_device(const uint8_t* dA, int nA, const uint8_t* dB, const int32_t* d_offsets, const int32_t* d_cands,
+                               int16_t* d_out, void* stream) {
+    ORB_REQUIRE(nA >= 0, "negative row count");
+    if (nA == 0) return ORB_OK;
+    ORB_REQUIRE(dA && dB && d_offsets && d_cands && d_out, "null pointer");
+    list_distances_kernel<<<ceil_div(nA * 32, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dA, nA, (const uint4*)dB, d_offsets, d_cands, d_out);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
 int orbm_ratio_filter_device(const int32_t* d_idx, const int32_t* d_best, const int32_t* d_second, int n, int th,
                              int inclusive, float ratio, int32_t* d_match, void* stream) {
     ORB_REQUIRE(n >= 0, "negative count");
@@ -351,6 +374,30 @@ int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int 
     ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
     ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
     ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
+    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    return ORB_OK;
+}
+
+int orbm_list_distances(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* offsets, const int32_t* cands,
+                        int16_t* out) {
+    ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
+    if (nA == 0) return ORB_OK;
+    ORB_REQUIRE(A && B && offsets && cands && out, "null pointer");
+    const int total = offsets[nA];
+    ORB_REQUIRE(total >= 0, "bad offsets");
+    if (total == 0) return ORB_OK;
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    DevBuf dA, dB, dOf, dC, dO;
+    int rc;
+    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dOf.alloc((size_t)(nA + 1) * 4)) ||
+        (rc = dC.alloc((size_t)total * 4)) || (rc = dO.alloc((size_t)total * 2)))
+        return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dOf.p, offsets, (size_t)(nA + 1) * 4, cudaMemcpyHostToDevice, 0));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dC.p, cands, (size_t)total * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = orbm_list_distances_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, (const int*)dOf.p, (const int*)dC.p, (int16_t*)dO.p, 0))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(out, dO.p, (size_t)total * 2, cudaMemcpyDeviceToHost, 0));
     ORB_CUDA_TRY(cudaStreamSynchronize(0));
     return ORB_OK;
 }

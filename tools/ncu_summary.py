@@ -11,15 +11,15 @@ cols = [("gpu__time_duration.sum", "time"), ("smsp__inst_executed.sum", "warp_in
         ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
         ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"), ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
         ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem%"),
-        ("smsp__average_warp_latency_issue_stalled_barrier_per_warp_active.pct", "st_barrier"),
-        ("smsp__average_warp_latency_issue_stalled_long_scoreboard_per_warp_active.pct", "st_long_sb"),
-        ("smsp__average_warp_latency_issue_stalled_short_scoreboard_per_warp_active.pct", "st_short_sb"),
-        ("smsp__average_warp_latency_issue_stalled_wait_per_warp_active.pct", "st_wait"),
-        ("smsp__average_warp_latency_issue_stalled_math_pipe_throttle_per_warp_active.pct", "st_math"),
-        ("smsp__average_warp_latency_issue_stalled_mio_throttle_per_warp_active.pct", "st_mio"),
-        ("smsp__average_warp_latency_issue_stalled_lg_throttle_per_warp_active.pct", "st_lg"),
-        ("smsp__average_warp_latency_issue_stalled_not_selected_per_warp_active.pct", "st_notsel"),
-        ("smsp__average_warp_latency_issue_stalled_branch_resolving_per_warp_active.pct", "st_branch")]
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_barrier"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long_sb"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st_short_sb"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"),
+        ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "st_mio"),
+        ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "st_lg"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "st_notsel"),
+        ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "st_branch")]
 out = ["| kernel | grid | " + " | ".join(c[1] for c in cols) + " |", "|---|---|" + "---|" * len(cols)]
 for r in rows[2:]:
     name = r[idx["Kernel Name"]].split("(")[0]
