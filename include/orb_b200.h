@@ -175,6 +175,19 @@ int orbm_list_distances(int device, const uint8_t* A, int nA, const uint8_t* B, 
 int orbm_ratio_filter_device(const int32_t* d_idx, const int32_t* d_best, const int32_t* d_second, int n,
                              int th, int inclusive, float ratio, int32_t* d_match, void* stream);
 
+/* Stereo matching of a rectified pair: replaces Frame::ComputeStereoMatches (src/Frame.cc:466-640) for
+ * frame `frame` of the last calls of two extractor handles (left, right; same device and geometry).
+ * Row-band candidate gate, best Hamming < TH_HIGH, 11x11 L1 patch refinement on the left keypoint's
+ * pyramid level (read in place from the handles' device pyramids), parabola sub-pixel fit, and the
+ * final 1.5*1.4*median rejection. mbf = baseline*fx, mb = baseline (mbf/mb = max disparity).
+ * Outputs for the left keypoints i < count: uRight[i], depth[i] (-1 = no match), the patch distance
+ * sad[i] (-1 = none) and *kept = number of surviving matches. The row index of mvuRight/mvDepth is the
+ * left keypoint index, as in the reference. */
+int orbm_stereo_match_device(orbx_handle left, orbx_handle right, int frame, float mbf, float mb, float* d_uRight,
+                             float* d_depth, int32_t* d_sad, int32_t* d_kept, void* stream);
+int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf, float mb, float* uRight,
+                      float* depth, int cap, int* kept);
+
 /* Full distance matrix (nA x nB, int16) for the ordered greedy resolve of the stateful searches and for
  * MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:246-311). */
 int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int16_t* d_out, void* stream);

@@ -64,6 +64,8 @@ def lib():
         "orbm_list_distances_device": [vp, i32, vp, vp, vp, vp, vp],
         "orbm_list_distances": [i32, vp, i32, vp, i32, vp, vp, vp],
         "orbm_ratio_filter_device": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
+        "orbm_stereo_match_device": [vp, vp, i32, f32, f32, vp, vp, vp, vp, vp],
+        "orbm_stereo_match": [vp, vp, i32, f32, f32, vp, vp, i32, C.POINTER(i32)],
         "orbm_distance_matrix_device": [vp, i32, vp, i32, vp, vp],
         "orbm_distance_matrix": [i32, vp, i32, vp, i32, vp],
     }

@@ -88,6 +88,18 @@ struct DeviceBuffers {
     int* counts;
 };
 
+struct StereoSide {  // one image of a stereo pair: geometry, pyramid and extraction results of a frame
+    const Geometry* g;
+    FrameSet fs;
+    const uint8_t* pyr;
+    const orbx_keypoint* kps;
+    const uint8_t* desc;
+    const int* count;
+    int frame;
+};
+int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, float mbf, float mb, float* d_uRight, float* d_depth, int* d_sad,
+                  int* d_kept, cudaStream_t st);
+
 // launchers (each enqueues on `st`; n = frames in this call)
 int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int level, int n, cudaStream_t st);
 int launch_blur(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st);

@@ -432,6 +432,50 @@ int orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t
     return ORB_OK;
 }
 
+// ---- stereo (Frame::ComputeStereoMatches, src/Frame.cc:466-640) on the results of two handles ----------
+static StereoSide stereo_side(orbx_extractor* h, int frame) {
+    StereoSide s;
+    s.g = h->db.geom; s.fs = h->last; s.pyr = h->db.pyr; s.frame = frame;
+    s.kps = h->db.kps + (size_t)frame * h->hg.out_cap;
+    s.desc = h->db.desc + (size_t)frame * h->hg.out_cap * 32;
+    s.count = h->db.counts + frame;
+    return s;
+}
+
+int orbm_stereo_match_device(orbx_handle left, orbx_handle right, int frame, float mbf, float mb, float* d_uRight, float* d_depth,
+                             int32_t* d_sad, int32_t* d_kept, void* stream) {
+    ORB_REQUIRE(left && right && d_uRight && d_depth && d_sad && d_kept, "null pointer");
+    ORB_REQUIRE(left->device == right->device && left->width == right->width && left->height == right->height &&
+                    left->cfg.nlevels == right->cfg.nlevels && left->cfg.scale_factor == right->cfg.scale_factor,
+                "left / right extractors must share device, image size and pyramid settings");
+    ORB_REQUIRE(frame >= 0 && frame < left->last_n && frame < right->last_n, "frame was not extracted by both handles");
+    ORB_REQUIRE(mb > 0 && mbf > 0, "baseline must be positive");
+    ORB_CUDA_TRY(cudaSetDevice(left->device));
+    return launch_stereo(stereo_side(left, frame), stereo_side(right, frame), left->hg.out_cap, mbf, mb, d_uRight, d_depth, d_sad, d_kept,
+                         (cudaStream_t)stream);
+}
+
+int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf, float mb, float* uRight, float* depth, int cap, int* kept) {
+    ORB_REQUIRE(left && uRight && depth && kept, "null pointer");
+    const int oc = left->hg.out_cap;
+    ORB_CUDA_TRY(cudaSetDevice(left->device));
+    float* d = nullptr;
+    ORB_CUDA_TRY(cudaMalloc(&d, (size_t)oc * 12 + 16));
+    float* d_u = d; float* d_d = d + oc; int* d_s = (int*)(d + 2 * (size_t)oc); int* d_k = d_s + oc;
+    cudaStream_t st = left->stream;
+    int rc = orbm_stereo_match_device(left, right, frame, mbf, mb, d_u, d_d, d_s, d_k, st);
+    if (rc == ORB_OK) {
+        const int take = std::min(cap, oc);
+        cudaError_t e = cudaMemcpyAsync(uRight, d_u, (size_t)take * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(depth, d_d, (size_t)take * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(kept, d_k, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("stereo copy failed: %s", cudaGetErrorString(e)); rc = ORB_ECUDA; }
+    }
+    cudaFree(d);
+    return rc;
+}
+
 int orbx_debug_blurred_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride) {
     ORB_REQUIRE(h && level >= 0 && level < h->cfg.nlevels && frame >= 0 && frame < h->last_n, "bad handle / level / frame");
     const LevelGeom& L = h->hg.lv[level];

@@ -150,3 +150,16 @@ def quadtree(xs, ys, scores, minX, maxX, minY, maxY, N, device=0):
     _lib.check(L.orbx_debug_quadtree(device, xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
                                      len(xs), minX, maxX, minY, maxY, N, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
     return out[:n.value].copy()
+
+
+def compute_stereo_matches(left, right, mbf, mb, frame=0):
+    """Frame::ComputeStereoMatches (/root/reference/src/Frame.cc:466-640) on the last results of two
+    ORBextractor objects (left, right image of a rectified pair). Returns (mvuRight, mvDepth, kept):
+    float32 arrays over the left keypoints (-1 = no match)."""
+    L = _lib.lib()
+    cap = left.cap
+    u = np.empty(cap, np.float32); d = np.empty(cap, np.float32)
+    kept = C.c_int()
+    _lib.check(L.orbm_stereo_match(left._h, right._h, frame, float(mbf), float(mb), u.ctypes.data_as(C.c_void_p),
+                                   d.ctypes.data_as(C.c_void_p), cap, C.byref(kept)))
+    return u, d, kept.value

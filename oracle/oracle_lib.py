@@ -42,6 +42,7 @@ def lib():
     L.orc_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.orc_level_selected.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_extract_mt.restype = C.c_long
+    L.orc_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -342,3 +343,16 @@ def search_for_initialization(F1, F2, prev_matched, window, nnratio=0.9, check_o
         if m12[i1] >= 0:
             prev_matched[i1] = F2.kps[m12[i1], :2]
     return nm, m12
+
+
+def stereo_match(oL, oR, mbf, mb):
+    """Frame::ComputeStereoMatches on the last results of two OracleExtractor objects (left, right)."""
+    n = lib().orc_extract  # noqa: F841 (bindings loaded)
+    w, h, nc, ns = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    nL = 0
+    for l in range(oL.nlevels):
+        lib().orc_level_dims(oL.h, l, C.byref(w), C.byref(h), C.byref(nc), C.byref(ns))
+        nL += ns.value
+    u = np.empty(max(nL, 1), np.float32); d = np.empty(max(nL, 1), np.float32)
+    kept = lib().orc_stereo_match(oL.h, oR.h, mbf, mb, u.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p))
+    return u[:nL], d[:nL], kept

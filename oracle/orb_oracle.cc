@@ -473,5 +473,95 @@ void orc_knn2_lists(const uint8_t* A, int nA, const uint8_t* B, const int* offse
     }
 }
 
-// throughput helper for the CPU baseline: nthreads-way split of the query rows
+// ---- stereo ---------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches, /root/reference/src/Frame.cc:466-640, on the results + pyramids that the
+// two extractor handles hold from their last orc_extract (left, right). uRight / depth: nL floats
+// (-1 = no match). Returns the number of matches kept.
+int orc_stereo_match(void* hL, void* hR, float mbf, float mb, float* uRight, float* depth) {
+    Extractor& EL = *(Extractor*)hL; Extractor& ER = *(Extractor*)hR;
+    const int N = (int)(EL.kps.size() / 6), Nr = (int)(ER.kps.size() / 6);
+    for (int i = 0; i < N; ++i) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+    if (N == 0) return 0;
+    const int thOrbDist = (100 + 50) / 2;
+    const int nRows = EL.lv[0].h;
+    std::vector<std::vector<size_t> > rows(nRows);
+    auto KP = [](Extractor& E, int i, int f) { return E.kps[(size_t)i * 6 + f]; };
+    for (int iR = 0; iR < Nr; ++iR) {
+        const float kpY = KP(ER, iR, 1);
+        const float r = 2.0f * ER.scale[(int)KP(ER, iR, 5)];
+        const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+        for (int yi = minr; yi <= maxr; ++yi) if (yi >= 0 && yi < nRows) rows[yi].push_back(iR);
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    std::vector<std::pair<int, int> > distIdx;
+    for (int iL = 0; iL < N; ++iL) {
+        const int levelL = (int)KP(EL, iL, 5);
+        const float vL = KP(EL, iL, 1), uL = KP(EL, iL, 0);
+        const std::vector<size_t>& cand = rows[(size_t)vL];
+        if (cand.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = 100;
+        size_t bestIdxR = 0;
+        for (size_t c = 0; c < cand.size(); ++c) {
+            const size_t iR = cand[c];
+            const int oR = (int)KP(ER, (int)iR, 5);
+            if (oR < levelL - 1 || oR > levelL + 1) continue;
+            const float uR = KP(ER, (int)iR, 0);
+            if (uR >= minU && uR <= maxU) {
+                const int d = hamming256(&EL.desc[(size_t)iL * 32], &ER.desc[iR * 32]);
+                if (d < bestDist) { bestDist = d; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = KP(ER, (int)bestIdxR, 0);
+            const float sf = EL.invScale[levelL];
+            const float scaleduL = std::round(uL * sf), scaledvL = std::round(vL * sf), scaleduR0 = std::round(uR0 * sf);
+            const int w = 5, L = 5;
+            const Level& PL = EL.lv[levelL]; const Level& PR = ER.lv[levelL];
+            const int cuL = (int)scaleduL, cvL = (int)scaledvL, cuR = (int)scaleduR0;
+            const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= PR.w) continue;
+            int best = 2147483647, bestinc = 0;
+            float vD[2 * 5 + 1];
+            // pixels outside the level come from the reference's 19 px BORDER_REFLECT_101 frame (1122-1128)
+            auto px = [](const Level& P, int x, int y) { return (int)P.img[(size_t)cvprim::reflect101(y, P.h) * P.w + cvprim::reflect101(x, P.w)]; };
+            const int cL = px(PL, cuL, cvL);
+            for (int inc = -L; inc <= L; ++inc) {
+                const int cR = px(PR, cuR + inc, cvL);
+                float dist = 0;
+                for (int dy = -w; dy <= w; ++dy)
+                    for (int dx = -w; dx <= w; ++dx) {
+                        const float a = (float)px(PL, cuL + dx, cvL + dy) - (float)cL;
+                        const float b = (float)px(PR, cuR + inc + dx, cvL + dy) - (float)cR;
+                        dist += std::fabs(a - b);
+                    }
+                if (dist < best) { best = (int)dist; bestinc = inc; }
+                vD[L + inc] = dist;
+            }
+            if (bestinc == -L || bestinc == L) continue;
+            const float d1 = vD[L + bestinc - 1], d2 = vD[L + bestinc], d3 = vD[L + bestinc + 1];
+            const float deltaR = (d1 - d3) / (2.0f * (d1 + d3 - 2.0f * d2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = EL.scale[levelL] * ((float)scaleduR0 + (float)bestinc + deltaR);
+            float disparity = uL - bestuR;
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                depth[iL] = mbf / disparity;
+                uRight[iL] = bestuR;
+                distIdx.push_back(std::pair<int, int>(best, iL));
+            }
+        }
+    }
+    if (distIdx.empty()) return 0;  // (the reference indexes an empty vector here)
+    std::sort(distIdx.begin(), distIdx.end());
+    const float median = (float)distIdx[distIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)distIdx.size();
+    for (int i = (int)distIdx.size() - 1; i >= 0; --i) {
+        if ((float)distIdx[i].first < thDist) break;
+        uRight[distIdx[i].second] = -1; depth[distIdx[i].second] = -1; --kept;
+    }
+    return kept;
+}
 }  // extern "C"

@@ -226,3 +226,23 @@ def test_knn2_pairs_all_slice_counts():
             oi, o1, o2 = O.knn2(sets[a, :counts[a]], sets[b, :counts[b]])
             n = counts[a]
             assert np.array_equal(gi[p, :n], oi) and np.array_equal(g1[p, :n], o1) and np.array_equal(g2[p, :n], o2), (nsets, p)
+
+
+@pytest.mark.parametrize("w,h,nf,kind,seed", [(1241, 376, 2000, "blocks", 0), (752, 480, 1200, "blocks", 1), (640, 480, 1000, "blurnoise", 2)])
+def test_stereo_matches_bit_exact(w, h, nf, kind, seed):
+    """Frame::ComputeStereoMatches: KITTI (fx 718.856, baseline*fx 386.1448) / EuRoC-like settings."""
+    from multiagent_orb_slam2_b200.extractor import compute_stereo_matches
+    left, right = synth.stereo_pair(kind, w, h, seed)
+    mbf, fx = np.float32(386.1448), np.float32(718.856)
+    mb = np.float32(mbf / fx)
+    oL, oR = O.OracleExtractor(nf, 1.2, 8, 20, 7), O.OracleExtractor(nf, 1.2, 8, 20, 7)
+    kL, _ = oL(left)
+    oR(right)
+    ou, od, okept = O.stereo_match(oL, oR, mbf, mb)
+    gL, gR = ORBextractor(nf, 1.2, 8, 20, 7), ORBextractor(nf, 1.2, 8, 20, 7)
+    gL(left); gR(right)
+    gu, gd, gkept = compute_stereo_matches(gL, gR, mbf, mb)
+    n = len(kL)
+    assert gkept == okept and okept > 100
+    assert np.array_equal(gu[:n].view(np.uint32), ou.view(np.uint32))
+    assert np.array_equal(gd[:n].view(np.uint32), od.view(np.uint32))
