@@ -170,6 +170,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     L = _lib.lib()
@@ -280,6 +281,41 @@ def run_b200(args):
                 "frac": a["frac_hbm"], "traffic": None, "peak_source": pk_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "stages": per_stage}
 
+    # ---- MapFusion cross-map matching (BASELINE config 5): G Hamming cmp/s over all ranks ------------------
+    mapf = None
+    if not args.no_mapfusion:
+        from multiagent_orb_slam2_b200 import mapfusion, synth
+        rows = args.map_rows
+        n_maps = max(2, world)
+        mine = [m for m in range(n_maps) if mapfusion.owner_of_map(m, world) == rank]
+        base = synth.descriptors(rows, 4242)
+        local = [torch.from_numpy(synth.descriptors_fast(rows, 5000 + m, base, 60)).to(dev) for m in mine]
+        cm = mapfusion.CrossMapMatcher(rows, 0.75)
+        cm.match(local)  # warm-up (NCCL channels, kernel load)
+        barrier()
+        reps = 2
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(reps):
+            res, _cnt = cm.match(local)
+        g1.record()
+        barrier()
+        mf_ms = max_over_ranks(g0.elapsed_time(g1)) / reps
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        mapfusion.exchange(local, rows)
+        a1.record()
+        torch.cuda.synchronize(dev)
+        cmps = float(n_maps * (n_maps - 1)) * rows * rows
+        accepted = int(sum(int((v[3][:rows] >= 0).sum()) for v in res.values()))
+        popc_roof = 148 * 16 * 1.965e9 / 8 * world
+        mapf = {"metric": "G Hamming cmp/s, cross-map brute force + ratio test", "value": cmps / (mf_ms * 1e-3) / 1e9, "unit": "Gcmp/s",
+                "maps": n_maps, "rows_per_map": rows, "directed_pairs": n_maps * (n_maps - 1), "ms_per_step": mf_ms,
+                "exchange_ms": a0.elapsed_time(a1), "accepted_matches_rank0": accepted,
+                "frac_of_plain_popc_roofline": cmps / (mf_ms * 1e-3) / popc_roof,
+                "popc_roofline": "148 SM x 16 POPC/clk x 1.965 GHz / 8 POPC per cmp per GPU (measured 15.3/clk/SM)"}
+        del local, res, cm
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------
@@ -305,7 +341,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * fe.h2d_bytes_per_frame(),
                     "d2h_bytes_per_step": B * fe.d2h_bytes_per_frame(), "ms_per_step": e2e_ms / args.steps,
                     "how": "pinned host frames -> orbx_upload_frames/extract_staged/orbm_knn2_batched/download, 2 buffers in flight"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mapfusion": mapf,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -319,6 +355,8 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-mapfusion", action="store_true", help="skip the cross-map Hamming leg")
+    ap.add_argument("--map-rows", type=int, default=200000, help="descriptors per map in the cross-map leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
