@@ -14,6 +14,7 @@
 // reference's vToDistributeKeys (src/ORBextractor.cc:820-825).
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace orb {
 
@@ -58,6 +59,8 @@ struct Geometry {  // device copy, read by every kernel
     int nlevels, ncells, ntiles;
     int iniTh, minTh;
     int max_tw, max_th;  // largest FAST tile
+    int fast_bw;         // TMA box of the FAST tiles: fast_bw x max_th bytes (fast_bw = row pitch in smem)
+    int rs_bw, rs_bh;    // TMA box of the resize source window
     int sel_words;       // per-frame selected capacity (sum of sel_cap)
     int out_cap;         // per-frame result capacity
     size_t pyr_bytes, blur_bytes, slot_words, cand_words;
@@ -101,9 +104,9 @@ int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, float mbf,
                   int* d_kept, cudaStream_t st);
 
 // launchers (each enqueues on `st`; n = frames in this call)
-int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int level, int n, cudaStream_t st);
-int launch_blur(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st);
-int launch_fast(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st);
+int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int level, int n, cudaStream_t st);
+int launch_blur(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st);
+int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st);
 int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStream_t st);
 int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st);
 int launch_quadtree_standalone(const uint32_t* d_cand, int n, int N, int nRoots, float rootW, int H, int key_depth,

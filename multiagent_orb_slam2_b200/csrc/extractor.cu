@@ -10,6 +10,32 @@
 
 namespace orb {
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+int tma_encode_u8_3d(CUtensorMap* out, const void* base, int w, int h, int frames, size_t pitch, size_t frame_stride, int bw, int bh) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ORB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return ORB_ECUDA; }
+        fn = (EncodeFn)p;
+    }
+    if (((uintptr_t)base & 15) || (pitch & 15) || (frame_stride & 15) || bw > 256 || bh > 256 || (bw & 15)) {
+        set_error("tensor map: base/strides must be 16-byte aligned, box <= 256 (pitch %zu, stride %zu, box %dx%d)", pitch, frame_stride, bw, bh);
+        return ORB_EINVAL;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ORB_ECUDA; }
+    return ORB_OK;
+}
+
 static const int kPatternInts[1024] = {
 #include "orb_pattern_31.inc"
 };
@@ -54,6 +80,10 @@ struct orbx_extractor {
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
     FrameSet last{};  // frames of the last call (for mvImagePyramid level 0)
     int last_n = 0;
+    // TMA tensor maps per level: source windows of the resize, blur tiles, FAST cell tiles.
+    // Levels >= 1 are encoded once; level 0 follows the frames of the call (cached on the FrameSet).
+    TmaMaps maps_resize, maps_blur, maps_fast;
+    FrameSet maps_l0{};
     // optional per-stage device timing (bench roofline): events around each stage of the pipeline
     bool stage_timing = false;
     cudaEvent_t ev_stage[ORBX_NUM_STAGES + 1] = {};
@@ -157,6 +187,11 @@ int build_geometry(orbx_extractor* h) {
             for (int tx = 0; tx < ceil_div(L.w, 128); ++tx) tiles.push_back(BlurTile{(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
     }
     g.ncells = (int)cells.size(); g.ntiles = (int)tiles.size();
+    // the innermost TMA coordinate is 16-byte granular: boxes carry up to 15 lead-in bytes
+    g.fast_bw = (int)align_up((size_t)g.max_tw + 15, 16);
+    g.rs_bw = (int)align_up((size_t)ceil(128.0 * sf) + 2 + 15, 16);
+    g.rs_bh = (int)ceil(32.0 * sf) + 3;
+    if (g.fast_bw > 256 || g.max_th > 256 || g.rs_bw > 256) { set_error("scale factor / cell size too large for the TMA tile boxes"); return ORB_EINVAL; }
     g.pyr_bytes = std::max<size_t>(pyr, 256); g.blur_bytes = blur; g.slot_words = slot; g.cand_words = slot;
     g.sel_words = sel; g.out_cap = sel;
     if (taps.empty()) taps.push_back(LinTap{0, 0, 0});
@@ -187,6 +222,14 @@ int build_geometry(orbx_extractor* h) {
         (rc = dalloc((void**)&h->d_input, (size_t)B * h->in_pitch * h->height)))
         return rc;
     ORB_CUDA_TRY(cudaMemset(db.counts, 0, (size_t)B * 4));
+    for (int l = 1; l < nl; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const uint8_t* base = db.pyr + L.img_off;
+        if ((rc = tma_encode_u8_3d(&h->maps_resize.m[l], base, L.w, L.h, B, L.pitch, g.pyr_bytes, g.rs_bw, g.rs_bh)) ||
+            (rc = tma_encode_u8_3d(&h->maps_blur.m[l], base, L.w, L.h, B, L.pitch, g.pyr_bytes, 160, 64)) ||
+            (rc = tma_encode_u8_3d(&h->maps_fast.m[l], base, L.w, L.h, B, L.pitch, g.pyr_bytes, g.fast_bw, g.max_th)))
+            return rc;
+    }
     ORB_CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     ORB_CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     ORB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming));
@@ -198,14 +241,23 @@ int build_geometry(orbx_extractor* h) {
 int enqueue_pipeline(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t st) {
     const Geometry& g = h->hg;
     int rc;
+    if (fs.base != h->maps_l0.base || fs.pitch != h->maps_l0.pitch || fs.frame_stride != h->maps_l0.frame_stride) {
+        const LevelGeom& L = g.lv[0];
+        // dims.z = max_batch: the frames of one call are always within the first n <= max_batch slices
+        if ((rc = tma_encode_u8_3d(&h->maps_resize.m[0], fs.base, L.w, L.h, h->max_batch, fs.pitch, fs.frame_stride, g.rs_bw, g.rs_bh)) ||
+            (rc = tma_encode_u8_3d(&h->maps_blur.m[0], fs.base, L.w, L.h, h->max_batch, fs.pitch, fs.frame_stride, 160, 64)) ||
+            (rc = tma_encode_u8_3d(&h->maps_fast.m[0], fs.base, L.w, L.h, h->max_batch, fs.pitch, fs.frame_stride, g.fast_bw, g.max_th)))
+            return rc;
+        h->maps_l0 = fs;
+    }
     if (h->stage_timing) {  // serialised on one stream so that every stage is timed alone
         ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[0], st));
         for (int l = 1; l < g.nlevels; ++l)
-            if ((rc = launch_resize_level(g, h->db, fs, l, n, st))) return rc;
+            if ((rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
         ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[1], st));
-        if ((rc = launch_blur(g, h->db, fs, n, st))) return rc;
+        if ((rc = launch_blur(g, h->db, h->maps_blur, n, st))) return rc;
         ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[2], st));
-        if ((rc = launch_fast(g, h->db, fs, n, st))) return rc;
+        if ((rc = launch_fast(g, h->db, h->maps_fast, n, st))) return rc;
         ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[3], st));
         if ((rc = launch_quadtree(g, h->db, n, st))) return rc;
         ORB_CUDA_TRY(cudaEventRecord(h->ev_stage[4], st));
@@ -215,13 +267,13 @@ int enqueue_pipeline(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t 
         return ORB_OK;
     }
     for (int l = 1; l < g.nlevels; ++l)
-        if ((rc = launch_resize_level(g, h->db, fs, l, n, st))) return rc;
+        if ((rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
     // fork: the Gaussian blur (1085-1086) only depends on the pyramid
     ORB_CUDA_TRY(cudaEventRecord(h->ev_pyr, st));
     ORB_CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_pyr, 0));
-    if ((rc = launch_blur(g, h->db, fs, n, h->stream2))) return rc;
+    if ((rc = launch_blur(g, h->db, h->maps_blur, n, h->stream2))) return rc;
     ORB_CUDA_TRY(cudaEventRecord(h->ev_blur, h->stream2));
-    if ((rc = launch_fast(g, h->db, fs, n, st))) return rc;
+    if ((rc = launch_fast(g, h->db, h->maps_fast, n, st))) return rc;
     if ((rc = launch_quadtree(g, h->db, n, st))) return rc;
     ORB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_blur, 0));
     if ((rc = launch_describe(g, h->db, fs, n, st))) return rc;
@@ -236,7 +288,7 @@ extern "C" {
 int orbx_create(const orbx_config* cfg, int device, int width, int height, int max_batch, orbx_handle* out) {
     ORB_REQUIRE(cfg && out, "null pointer");
     ORB_REQUIRE(cfg->nlevels >= 1 && cfg->nlevels <= kMaxLevels, "nlevels out of range (1..16)");
-    ORB_REQUIRE(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && cfg->scale_factor <= 2.0f, "nfeatures >= 1 and 1 < scale_factor <= 2 required");
+    ORB_REQUIRE(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && cfg->scale_factor <= 1.8f, "nfeatures >= 1 and 1 < scale_factor <= 1.8 required");
     ORB_REQUIRE(cfg->min_th_fast >= 1 && cfg->ini_th_fast >= cfg->min_th_fast && cfg->ini_th_fast < 255, "FAST thresholds: 1 <= min <= ini < 255");
     ORB_REQUIRE(width > 0 && height > 0 && max_batch >= 1, "image size / batch must be positive");
     *out = nullptr;
@@ -326,6 +378,15 @@ int orbx_extract_device(orbx_handle h, const uint8_t* d_images, size_t stride, s
     if (n == 0) return ORB_OK;
     ORB_REQUIRE(d_images && stride >= (size_t)h->width && frame_stride >= stride * (size_t)(h->height - 1) + h->width, "bad frame layout");
     ORB_CUDA_TRY(cudaSetDevice(h->device));
+    if (((uintptr_t)d_images & 15) || (stride & 15) || (frame_stride & 15)) {
+        // the TMA tile loads need 16-byte aligned rows: copy such frames into the handle's staging area first
+        const size_t dev_frame = h->in_pitch * h->height;
+        for (int i = 0; i < n; ++i)
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input + i * dev_frame, h->in_pitch, d_images + i * frame_stride, stride, h->width, h->height,
+                                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        FrameSet staged{h->d_input, h->in_pitch, dev_frame};
+        return enqueue_pipeline(h, staged, n, (cudaStream_t)stream);
+    }
     FrameSet fs{d_images, stride, frame_stride};
     return enqueue_pipeline(h, fs, n, (cudaStream_t)stream);
 }

@@ -76,14 +76,15 @@ __device__ __forceinline__ int fast_score_side(const uint8_t* __restrict__ p, in
     return best - 1;
 }
 
-// Shared memory (dynamic): tile | score | masks | offsets | two index lists.
-// The tile keeps the 4-byte phase of global memory (column c of the tile sits at byte c + phase)
-// so that rows can be fetched with aligned 32-bit loads.
+// Shared memory (dynamic): tile | score | masks | offsets | corner lists. The tile (fast_bw x max_th
+// bytes: the largest cell of the handle + 15 bytes, because the innermost TMA coordinate must be a
+// multiple of 16 bytes) arrives by one TMA box load per block; whatever lies beyond this cell's own
+// tw x th window is simply not looked at.
 __global__ void __launch_bounds__(kFastThreads)
-fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, FrameSet fs,
-                  const uint8_t* __restrict__ pyr, uint32_t* __restrict__ slots, int* __restrict__ cell_counts, int tp) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int max_th = g->max_th;
+fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, const __grid_constant__ TmaMaps maps,
+                  uint32_t* __restrict__ slots, int* __restrict__ cell_counts) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int max_th = g->max_th, tp = g->fast_bw;
     uint8_t* tile = smem;
     uint8_t* score = smem + (size_t)max_th * tp;
     uint32_t* mask_ini = reinterpret_cast<uint32_t*>(score + (size_t)max_th * tp);  // [max_th][2]
@@ -91,6 +92,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     int* offs = reinterpret_cast<int*>(mask_all + 2 * max_th);                      // [2*max_th + 1]
     uint16_t* list1 = reinterpret_cast<uint16_t*>(offs + 2 * max_th + 2);           // survivors of the 4-point test
     uint16_t* list2 = list1 + (size_t)max_th * tp;                                  // corners
+    __shared__ __align__(8) uint64_t bar;
     __shared__ int s_n1, s_n2, s_total_ini;
 
     const CellDesc c = cells[blockIdx.x];
@@ -104,41 +106,23 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         if (threadIdx.x == 0) *count_out = 0;
         return;
     }
-    int spitch;
-    const uint8_t* img = level_ptr(*g, fs, pyr, frame, c.level, &spitch);
-    const uint8_t* src = img + (size_t)c.y0 * spitch + c.x0;
-    // rows can be fetched as aligned words when every row of the level starts 4-byte aligned (always
-    // true for pyramid levels >= 1; for level 0 it depends on the caller's frame pitch)
-    const bool word_rows = ((spitch & 3) == 0) && (((uintptr_t)img & 3) == 0);
-    const int phase = word_rows ? (int)((uintptr_t)src & 3) : 0;
-    const int nwords = (phase + tw + 3) >> 2;  // aligned words per tile row
-
-    if (threadIdx.x == 0) { s_n1 = 0; s_n2 = 0; s_total_ini = 0; }
-    {
-        uint32_t* tilew = reinterpret_cast<uint32_t*>(tile);
+    if (threadIdx.x == 0) {
+        s_n1 = 0; s_n2 = 0; s_total_ini = 0;
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, (uint32_t)(max_th * tp));
+        tma_load_3d(tile, &maps.m[c.level], c.x0 & ~15, c.y0, frame, &bar);  // innermost TMA coordinate: 16-byte granular
+    }
+    {   // meanwhile: clear the score map and the masks
         uint32_t* scorew = reinterpret_cast<uint32_t*>(score);
-        const int tpw = tp >> 2;
-        if (word_rows) {  // the row's own tail (x < level width) keeps the last word inside the row
-            const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src - phase);
-            const int spw = spitch >> 2;
-            int y = threadIdx.x / tpw, xw = threadIdx.x - y * tpw;
-            const int dy = kFastThreads / tpw, dxw = kFastThreads - dy * tpw;
-            for (int i = threadIdx.x; i < th * tpw; i += kFastThreads) {
-                tilew[i] = xw < nwords ? __ldg(srcw + (size_t)y * spw + xw) : 0u;
-                scorew[i] = 0u;
-                xw += dxw; y += dy;
-                if (xw >= tpw) { xw -= tpw; ++y; }
-            }
-        } else {
-            for (int i = threadIdx.x; i < th * tpw; i += kFastThreads) scorew[i] = 0u;
-            for (int y = warp; y < th; y += kFastWarps)
-                for (int x = lane; x < tp; x += 32) tile[y * tp + x] = x < tw ? src[(size_t)y * spitch + x] : 0;
-        }
+        for (int i = threadIdx.x; i < (max_th * tp) >> 2; i += kFastThreads) scorew[i] = 0u;
         for (int i = threadIdx.x; i < 4 * max_th; i += kFastThreads) mask_ini[i] = 0u;  // mask_ini + mask_all
     }
-    __syncthreads();
+    __syncthreads();       // barrier init + cleared maps visible
+    mbar_wait(&bar, 0);    // tile landed
 
     const int minTh = g->minTh, iniTh = g->iniTh;
+    const int phase = c.x0 & 15;
     const uint8_t* t0 = tile + phase;  // pixel (x, y) of the cell tile at t0[y * tp + x]
     uint8_t* sc0 = score + phase;
 
@@ -231,10 +215,9 @@ static size_t fast_smem_bytes(const Geometry& hg, int tp) {
     return 2 * px + (size_t)hg.max_th * 4 * sizeof(uint32_t) + (2 * (size_t)hg.max_th + 2) * sizeof(int) + 2 * px * sizeof(uint16_t);
 }
 
-int launch_fast(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
-    const int tp = (hg.max_tw + 3 + 3) & ~3;  // + up to 3 bytes of alignment phase
-    fast_cells_kernel<<<dim3(hg.ncells, n), kFastThreads, fast_smem_bytes(hg, tp), st>>>(db.geom, db.cells, fs, db.pyr, db.slots,
-                                                                                       db.cell_counts, tp);
+int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st) {
+    fast_cells_kernel<<<dim3(hg.ncells, n), kFastThreads, fast_smem_bytes(hg, hg.fast_bw), st>>>(db.geom, db.cells, maps, db.slots,
+                                                                                               db.cell_counts);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

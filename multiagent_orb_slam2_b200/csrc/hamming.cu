@@ -26,6 +26,9 @@ __device__ __forceinline__ void top2_update(Top2& t, int d, int pos) {
     t.pos = d < t.b1 ? pos : t.pos;
     t.b1 = min(t.b1, d);
 }
+__device__ __noinline__ void top2_update4(Top2& t, int d0, int d1, int d2, int d3, int pos) {
+    top2_update(t, d0, pos); top2_update(t, d1, pos + 1); top2_update(t, d2, pos + 2); top2_update(t, d3, pos + 3);
+}
 // a precedes b in iteration order
 __device__ __forceinline__ Top2 top2_merge(const Top2& a, const Top2& b) {
     Top2 r;
@@ -132,10 +135,19 @@ knn2_kernel(const uint4* __restrict__ A, const int* __restrict__ nA_dev, int nA_
         const int rows = min(kTileRows, nB - r0);
         const int jlo = slice * R, jhi = min(jlo + R, rows);
         const uint4* tp = tile[s];
-#pragma unroll 4
-        for (int j = jlo; j < jhi; ++j) {
+        // four rows per trip; the (best, second) update runs only when one of the four can change it,
+        // which is rare once the running second-best is small - a real branch, not predication
+        int j = jlo;
+        for (; j + 4 <= jhi; j += 4) {
+            const int d0 = hamming256_csa(a0, a1, tp[2 * j], tp[2 * j + 1]);
+            const int d1 = hamming256_csa(a0, a1, tp[2 * j + 2], tp[2 * j + 3]);
+            const int d2 = hamming256_csa(a0, a1, tp[2 * j + 4], tp[2 * j + 5]);
+            const int d3 = hamming256_csa(a0, a1, tp[2 * j + 6], tp[2 * j + 7]);
+            if (min(min(d0, d1), min(d2, d3)) < best.b2) top2_update4(best, d0, d1, d2, d3, r0 + j);
+        }
+        for (; j < jhi; ++j) {
             const int d = hamming256_csa(a0, a1, tp[2 * j], tp[2 * j + 1]);
-            if (d < best.b2) top2_update(best, d, r0 + j);  // rare once the running second-best is small
+            if (d < best.b2) top2_update(best, d, r0 + j);
         }
         __syncthreads();  // every thread is done with stage s
         if (threadIdx.x == 0 && t + kStages < ntiles) issue(t + kStages);

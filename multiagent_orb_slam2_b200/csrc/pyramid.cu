@@ -11,28 +11,35 @@
 namespace orb {
 
 // ------------------------------------------------------------------------------------------------
-// resize: one block = one 128 x 32 output tile. The source window of the tile is staged in shared
-// memory with aligned 32-bit loads; each thread keeps the column taps of its 4 output columns and
-// the row taps of its 4 output rows in registers (fetched up front, so the kernel pays two global
-// latencies - taps, then window - instead of three).
+// resize: one block = one 128 x 32 output tile. The source window of the tile arrives in shared
+// memory by one TMA box load (rs_bw x rs_bh bytes, zero fill beyond the level - never read); while
+// it is in flight each thread fetches the column taps of its 4 output columns and the row taps of
+// its 4 output rows into registers.
 constexpr int kRsTW = 128, kRsTH = 32;
-constexpr int kRsMaxWords = 72, kRsMaxRows = 68;  // source window budget: scale factors up to 2.0
 
 __global__ void __launch_bounds__(256)
-resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, FrameSet fs, uint8_t* __restrict__ pyr, int level) {
-    __shared__ __align__(16) uint32_t win[kRsMaxRows][kRsMaxWords];
+resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, const __grid_constant__ TmaMaps maps,
+              uint8_t* __restrict__ pyr, int level) {
+    extern __shared__ __align__(128) uint8_t win[];  // rs_bh rows of rs_bw bytes: the TMA box
+    __shared__ __align__(8) uint64_t bar;
     const LevelGeom& L = g->lv[level];
     const LevelGeom& S = g->lv[level - 1];
     const int frame = blockIdx.z;
     const int X0 = blockIdx.x * kRsTW, Y0 = blockIdx.y * kRsTH;
-    const int X1 = min(X0 + kRsTW, L.w) - 1, Y1 = min(Y0 + kRsTH, L.h) - 1;  // last output column / row of the tile
-    int spitch;
-    const uint8_t* src = level_ptr(*g, fs, pyr, frame, level - 1, &spitch);
     uint8_t* dst = pyr + (size_t)frame * g->pyr_bytes + L.img_off;
     const LinTap* tx = taps + L.tab_x_off;
     const LinTap* ty = taps + L.tab_y_off;
+    const int bw = g->rs_bw;
 
-    // all table reads of this thread, issued together
+    // source window origin (taps are monotone); the box covers the whole tile at any supported scale
+    const int sx_lo = tx[X0].ofs & ~15, sy_lo = ty[Y0].ofs;  // innermost TMA coordinate: 16-byte granular
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, (uint32_t)(bw * g->rs_bh));
+        tma_load_3d(win, &maps.m[level - 1], sx_lo, sy_lo, frame, &bar);
+    }
+    // all table reads of this thread, issued while the window is in flight
     const int q = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int x0 = X0 + 4 * q;
     LinTap tcol[4], trow[kRsTH / 8];
@@ -40,43 +47,21 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, F
     for (int k = 0; k < 4; ++k) tcol[k] = tx[min(x0 + k, L.w - 1)];
 #pragma unroll
     for (int rr = 0; rr < kRsTH / 8; ++rr) trow[rr] = ty[min(Y0 + rg + 8 * rr, L.h - 1)];
-    // source window [sx_lo, sx_hi] x [sy_lo, sy_hi] (taps are monotone)
-    const int sx_lo = tx[X0].ofs & ~3, sx_hi = min(tx[X1].ofs + 1, S.w - 1);
-    const int sy_lo = ty[Y0].ofs, sy_hi = min(ty[Y1].ofs + 1, S.h - 1);
-    const int nwords = (sx_hi - sx_lo) / 4 + 1, nrows = sy_hi - sy_lo + 1;
-    const bool word_rows = ((spitch & 3) == 0) && (((uintptr_t)src & 3) == 0);
-    {
-        int r = threadIdx.x / nwords, cw = threadIdx.x - r * nwords;
-        const int dr = 256 / nwords, dcw = 256 - dr * nwords;
-        for (int i = threadIdx.x; i < nrows * nwords; i += 256) {
-            const uint8_t* row = src + (size_t)(sy_lo + r) * spitch;
-            const int x = sx_lo + 4 * cw;
-            uint32_t v;
-            if (word_rows && x + 3 < S.w) {
-                v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
-            } else {
-                v = 0;
-                for (int b = 0; b < 4; ++b) v |= (uint32_t)row[min(x + b, S.w - 1)] << (8 * b);
-            }
-            win[r][cw] = v;
-            cw += dcw; r += dr;
-            if (cw >= nwords) { cw -= nwords; ++r; }
-        }
-    }
     __syncthreads();
+    mbar_wait(&bar, 0);
 
     if (x0 >= L.w) return;
     int ofs0[4], ofs1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { ofs0[k] = tcol[k].ofs - sx_lo; ofs1[k] = min(tcol[k].ofs + 1, S.w - 1) - sx_lo; }
-    const uint8_t* wb = reinterpret_cast<const uint8_t*>(&win[0][0]);
+    const uint8_t* wb = win;
 #pragma unroll
     for (int rr = 0; rr < kRsTH / 8; ++rr) {
         const int y = Y0 + rg + 8 * rr;
         if (y >= L.h) break;
         const LinTap t = trow[rr];
-        const uint8_t* r0 = wb + (size_t)(t.ofs - sy_lo) * (kRsMaxWords * 4);
-        const uint8_t* r1 = wb + (size_t)(min(t.ofs + 1, S.h - 1) - sy_lo) * (kRsMaxWords * 4);
+        const uint8_t* r0 = wb + (size_t)(t.ofs - sy_lo) * bw;
+        const uint8_t* r1 = wb + (size_t)(min(t.ofs + 1, S.h - 1) - sy_lo) * bw;
         const int b0 = t.c0, b1 = t.c1;
         uint32_t packed = 0;
 #pragma unroll
@@ -91,10 +76,10 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, F
     }
 }
 
-int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int level, int n, cudaStream_t st) {
+int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int level, int n, cudaStream_t st) {
     const LevelGeom& L = hg.lv[level];
     dim3 grid(ceil_div(L.w, kRsTW), ceil_div(L.h, kRsTH), n);
-    resize_kernel<<<grid, 256, 0, st>>>(db.geom, db.taps, fs, db.pyr, level);
+    resize_kernel<<<grid, 256, (size_t)hg.rs_bw * hg.rs_bh, st>>>(db.geom, db.taps, maps, db.pyr, level);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
@@ -103,14 +88,15 @@ int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const Frame
 // ------------------------------------------------------------------------------------------------
 // blur: separable {18,34,48,56,48,34,18}, single rounding (sum + 2^15) >> 16, BORDER_REFLECT_101.
 // One block = one 128 x 58 output tile of one level of one frame (input 136 x 64 incl. halo).
-//   load : aligned 32-bit words of the input rows into shared memory (reflected bytes at the borders)
+//   load : one TMA box (144 x 64 bytes) into shared memory; border tiles patch the reflected bytes
 //   h    : 4 outputs per thread from 3 words: byte windows by funnel shift, 2 x IDP.4A per output
 //          (4+3 taps, u8 x u8 -> u32, exact); rows are processed in vertical pairs and stored as
 //          (row 2m | row 2m+1 << 16) so that
 //   v    : one IDP.2A covers two vertical taps: 4 x IDP.2A per output, accumulator preloaded with
 //          the rounding constant; 4 columns per thread, sliding window down the tile.
 // ~14 instructions per pixel instead of ~120 for the straightforward byte-wise version.
-constexpr int kBlurTW = 128, kBlurTH = 58, kBlurInRows = 64, kBlurInWords = 34;
+constexpr int kBlurTW = 128, kBlurTH = 58, kBlurInRows = 64, kBlurInWords = 40;  // 160-byte TMA box rows
+constexpr int kBlurLead = 16;  // bytes left of the tile in the box: innermost TMA coordinate is 16-byte granular (3 needed)
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     p = p < 0 ? -p : p;
@@ -119,34 +105,48 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 __global__ void __launch_bounds__(256)
-blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, FrameSet fs, const uint8_t* __restrict__ pyr,
+blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, const __grid_constant__ TmaMaps maps,
             uint8_t* __restrict__ blur) {
-    __shared__ __align__(16) uint32_t in_w[kBlurInRows][kBlurInWords];
+    __shared__ __align__(128) uint32_t in_w[kBlurInRows][kBlurInWords];
     __shared__ __align__(16) uint32_t hsv[kBlurInRows / 2][kBlurTW];
+    __shared__ __align__(8) uint64_t bar;
     const BlurTile t = tiles[blockIdx.x];
     const int frame = blockIdx.y;
     const LevelGeom& L = g->lv[t.level];
-    int spitch;
-    const uint8_t* src = level_ptr(*g, fs, pyr, frame, t.level, &spitch);
     uint8_t* dst = blur + (size_t)frame * g->blur_bytes + L.blur_off;
     const int X0 = t.tx * kBlurTW, Y0 = t.ty * kBlurTH;
     const int tid = threadIdx.x;
-    const bool word_rows = ((spitch & 3) == 0) && (((uintptr_t)src & 3) == 0);
 
-    for (int i = tid; i < kBlurInRows * kBlurInWords; i += 256) {
-        const int r = i / kBlurInWords, cw = i - r * kBlurInWords;
-        const uint8_t* row = src + (size_t)reflect101(Y0 + r - 3, L.h) * spitch;
-        const int x = X0 - 4 + 4 * cw;
-        uint32_t v;
-        if (word_rows && x >= 0 && x + 3 < L.w) {
-            v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
-        } else {
-            v = (uint32_t)row[reflect101(x, L.w)] | (uint32_t)row[reflect101(x + 1, L.w)] << 8 |
-                (uint32_t)row[reflect101(x + 2, L.w)] << 16 | (uint32_t)row[reflect101(x + 3, L.w)] << 24;
-        }
-        in_w[r][cw] = v;
+    // input tile: columns X0-16 .. X0+143, rows Y0-3 .. Y0+60, zero filled outside the level by the TMA unit
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, (uint32_t)(kBlurInRows * kBlurInWords * 4));
+        tma_load_3d(in_w, &maps.m[t.level], X0 - kBlurLead, Y0 - 3, frame, &bar);
     }
     __syncthreads();
+    mbar_wait(&bar, 0);
+    // BORDER_REFLECT_101: tiles that touch the level's frame rebuild their out-of-level bytes from the
+    // in-level ones (which are inside the same tile: the reflection reaches at most 4 px / 3 rows in)
+    {
+        constexpr int BW = kBlurInWords * 4;
+        uint8_t* inb = reinterpret_cast<uint8_t*>(&in_w[0][0]);
+        const int x_lo = X0 - kBlurLead, y_lo = Y0 - 3;
+        const bool top = Y0 == 0, left = X0 == 0, bottom = y_lo + kBlurInRows > L.h, right = x_lo + BW > L.w;
+        if (top || left || bottom || right) {
+            // only the 3 rows / 3-4 columns next to the frame can reach an output of this tile
+            auto fix = [&](int r, int c) {
+                const int y = y_lo + r, x = x_lo + c;
+                const int sr = reflect101(y, L.h) - y_lo, sc = reflect101(x, L.w) - x_lo;
+                if (r < kBlurInRows && c < BW && sr >= 0 && sr < kBlurInRows && sc >= 0 && sc < BW) inb[r * BW + c] = inb[sr * BW + sc];
+            };
+            if (top) for (int i = tid; i < 3 * BW; i += 256) fix(i / BW, i % BW);
+            if (bottom) for (int i = tid; i < 3 * BW; i += 256) fix(L.h - y_lo + i / BW, i % BW);
+            if (left) for (int i = tid; i < 4 * kBlurInRows; i += 256) fix(i >> 2, kBlurLead - 4 + (i & 3));
+            if (right) for (int i = tid; i < 4 * kBlurInRows; i += 256) fix(i >> 2, L.w - x_lo + (i & 3));
+            __syncthreads();
+        }
+    }
 
     // horizontal pass: item = (row pair, column quad)
     constexpr uint32_t kLo = 18u | 34u << 8 | 48u << 16 | 56u << 24, kHi = 48u | 34u << 8 | 18u << 16;
@@ -155,7 +155,8 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
         uint32_t h[2][4];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const uint32_t w0 = in_w[2 * pr + rr][k], w1 = in_w[2 * pr + rr][k + 1], w2 = in_w[2 * pr + rr][k + 2];
+            const uint32_t* wr = &in_w[2 * pr + rr][kBlurLead / 4 - 1 + k];  // word of bytes X0+4k-4 .. X0+4k-1
+            const uint32_t w0 = wr[0], w1 = wr[1], w2 = wr[2];
             // output j (column 4k+j) uses bytes j+1..j+4 and j+5..j+8 of the 12-byte string w0 w1 w2
             const uint32_t a1 = __funnelshift_r(w0, w1, 8), a2 = __funnelshift_r(w0, w1, 16), a3 = __funnelshift_r(w0, w1, 24);
             const uint32_t b1 = __funnelshift_r(w1, w2, 8), b2 = __funnelshift_r(w1, w2, 16), b3 = __funnelshift_r(w1, w2, 24);
@@ -204,8 +205,8 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
     }
 }
 
-int launch_blur(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
-    blur_kernel<<<dim3(hg.ntiles, n), 256, 0, st>>>(db.geom, db.tiles, fs, db.pyr, db.blur);
+int launch_blur(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st) {
+    blur_kernel<<<dim3(hg.ntiles, n), 256, 0, st>>>(db.geom, db.tiles, maps, db.blur);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
