@@ -38,12 +38,14 @@ __device__ __forceinline__ int ring_offset(int k, int tp) {
 __device__ __forceinline__ int fast_arc_test(const uint8_t* __restrict__ p, int tp, int th) {
     const int v = p[0];
     const int lo = v - th, hi = v + th;
+    // sign bits shifted into the masks: one IADD + one funnel shift per comparison. The ring ends up
+    // in reverse bit order, which does not matter for circular contiguity.
     uint32_t mb = 0, md = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int r = p[ring_offset(k, tp)];
-        mb |= (uint32_t)(r < lo) << k;
-        md |= (uint32_t)(r > hi) << k;
+        mb = __funnelshift_l((uint32_t)(r - lo), mb, 1);  // r < lo
+        md = __funnelshift_l((uint32_t)(hi - r), md, 1);  // r > hi
     }
     auto has_arc9 = [](uint32_t m) {
         m |= m << 16;
@@ -93,7 +95,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     uint16_t* list1 = reinterpret_cast<uint16_t*>(offs + 2 * max_th + 2);           // survivors of the 4-point test
     uint16_t* list2 = list1 + (size_t)max_th * tp;                                  // corners
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_n1, s_n2, s_total_ini;
+    __shared__ int s_cnt[kFastWarps], s_n2, s_total_ini;
 
     const CellDesc c = cells[blockIdx.x];
     const int frame = blockIdx.y;
@@ -107,7 +109,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         return;
     }
     if (threadIdx.x == 0) {
-        s_n1 = 0; s_n2 = 0; s_total_ini = 0;
+        s_n2 = 0; s_total_ini = 0;
         mbar_init(&bar, 1);
         mbar_fence_init();
         mbar_expect_tx(&bar, (uint32_t)(max_th * tp));
@@ -127,24 +129,39 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     uint8_t* sc0 = score + phase;
 
     // ---- phase 1: 4-point rejection on every interior pixel ----------------------------------------
-    for (int y = 3 + warp; y < th - 3; y += kFastWarps)
-        for (int x0 = 3; x0 < tw - 3; x0 += 32) {
-            const int x = x0 + lane;
+    // branch-free test, incremental addressing, survivors appended to a list private to the warp
+    // (no atomics): warp w owns list1[w * seg .. (w+1) * seg)
+    const int seg = (max_th * tp) / kFastWarps;
+    uint16_t* mylist = list1 + warp * seg;
+    int cnt = 0;
+    for (int x0 = 3; x0 < tw - 3; x0 += 32) {  // one trip unless the cell is wider than 38 px
+        const int x = x0 + lane;
+        const bool xin = x < tw - 3;
+        const uint8_t* p = t0 + (3 + warp) * tp + x;
+        const int up = -3 * tp, dn = 3 * tp;
+        int at = (3 + warp) * tp + x;
+        for (int y = 3 + warp; y < th - 3; y += kFastWarps, p += kFastWarps * tp, at += kFastWarps * tp) {
             bool keep = false;
-            if (x < tw - 3) {
-                const uint8_t* p = t0 + y * tp + x;
+            if (xin) {
                 const int v = p[0], lo = v - minTh, hi = v + minTh;
-                const int r0 = p[3 * tp], r8 = p[-3 * tp], r4 = p[3], r12 = p[-3];
-                keep = ((r0 < lo || r8 < lo) && (r4 < lo || r12 < lo)) || ((r0 > hi || r8 > hi) && (r4 > hi || r12 > hi));
+                const int r0 = p[dn], r8 = p[up], r4 = p[3], r12 = p[-3];
+                keep = max(min(r0, r8), min(r4, r12)) < lo || min(max(r0, r8), max(r4, r12)) > hi;
             }
-            if (keep) list1[atomicAdd(&s_n1, 1)] = (uint16_t)(y * tp + x);  // ptxas aggregates per warp
+            const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+            if (keep) mylist[cnt + __popc(ball & ((1u << lane) - 1))] = (uint16_t)at;
+            cnt += __popc(ball);
         }
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
     __syncthreads();
 
     // ---- phase 2a: full 16-pixel arc test on the survivors -> corner list (bit 15 = dark side) -------
-    const int n1 = s_n1;
+    int c0 = s_cnt[0], c1 = s_cnt[1], c2 = s_cnt[2], c3 = s_cnt[3];
+    const int n1 = c0 + c1 + c2 + c3;
     for (int i = threadIdx.x; i < n1; i += kFastThreads) {
-        const int at = list1[i];
+        int k = i, w = 0;
+        if (k >= c0) { k -= c0; w = 1; if (k >= c1) { k -= c1; w = 2; if (k >= c2) { k -= c2; w = 3; } } }
+        const int at = list1[w * seg + k];
         const int side = fast_arc_test(t0 + at, tp, minTh);
         if (side) list2[atomicAdd(&s_n2, 1)] = (uint16_t)(at | (side == 2 ? 0x8000 : 0));
     }
