@@ -207,3 +207,94 @@ def _search_for_initialization(self, F1, F2, vbPrevMatched, windowSize=10):
 
 
 ORBmatcher.SearchForInitialization = _search_for_initialization
+
+
+def _search_by_bow_kf_kf(self, desc1, featvec1, valid1, angle1, desc2, featvec2, valid2, angle2):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (/root/reference/src/ORBmatcher.cc:524-657),
+    the matcher MapFusion::ComputeSim3 and CovisibilityDiscovery call (src/MapFusion.cc:275, 849).
+    featvec*: DBoW2 FeatureVector as a list of (node_id, [feature indices]) sorted by node id;
+    valid*: per feature, "has a map point that is not bad" (the pMP / isBad() tests at 560-564, 576-582).
+    Device: all Hamming distances inside equal nodes in one launch; host: the reference's ordered,
+    stateful (vbMatched2) resolve. Returns (nmatches, match12) with match12[i1] = i2 or -1."""
+    desc1, desc2 = _desc(desc1), _desc(desc2)
+    n1, n2 = len(desc1), len(desc2)
+    # merge walk of the two feature vectors (552-634): pairs of index lists with equal node id
+    node_pairs = []
+    i = j = 0
+    while i < len(featvec1) and j < len(featvec2):
+        a, b = featvec1[i][0], featvec2[j][0]
+        if a == b:
+            node_pairs.append((featvec1[i][1], featvec2[j][1]))
+            i += 1; j += 1
+        elif a < b:
+            i += 1  # lower_bound(f2it->first): first element not less than b
+        else:
+            j += 1
+    # CSR over (idx1 occurrence) -> candidates idx2 of the same node, in the reference's loop order
+    q_rows, offsets, cands = [], [0], []
+    for l1, l2 in node_pairs:
+        for idx1 in l1:
+            q_rows.append(idx1)
+            cands.extend(l2)
+            offsets.append(len(cands))
+    q_rows = np.asarray(q_rows, np.int64)
+    offsets = np.asarray(offsets, np.int32); cands = np.asarray(cands, np.int32)
+    dist = np.empty(len(cands), np.int16)
+    if len(cands):
+        A = np.ascontiguousarray(desc1[q_rows])
+        _lib.check(self._L.orbm_list_distances(self.device, _p(A), len(A), _p(desc2), n2, _p(offsets), _p(cands), _p(dist)))
+    match12 = np.full(n1, -1, np.int32)
+    matched2 = np.zeros(n2, bool)
+    rot = [[] for _ in range(self.HISTO_LENGTH)]
+    factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+    ratio = np.float32(self.mfNNratio)
+    nm = 0
+    for q, idx1 in enumerate(q_rows):
+        if not valid1[idx1]:
+            continue
+        b1 = b2 = 256
+        bidx = -1
+        for k in range(offsets[q], offsets[q + 1]):
+            idx2 = int(cands[k])
+            if matched2[idx2] or not valid2[idx2]:
+                continue
+            d = int(dist[k])
+            if d < b1:
+                b2, b1, bidx = b1, d, idx2
+            elif d < b2:
+                b2 = d
+        if b1 < self.TH_LOW and np.float32(b1) < ratio * np.float32(b2):
+            match12[idx1] = bidx
+            matched2[bidx] = True
+            if self.mbCheckOrientation:
+                r = np.float32(np.float32(angle1[idx1]) - np.float32(angle2[bidx]))
+                if r < 0:
+                    r = np.float32(r + np.float32(360.0))
+                b = int(np.floor(float(np.float32(r * factor)) + 0.5))
+                rot[0 if b == self.HISTO_LENGTH else b].append(int(idx1))
+            nm += 1
+    if self.mbCheckOrientation:
+        keep = self.ComputeThreeMaxima([len(x) for x in rot])
+        for i in range(self.HISTO_LENGTH):
+            if i not in keep:
+                for idx1 in rot[i]:
+                    match12[idx1] = -1
+                    nm -= 1
+    return nm, match12
+
+
+def _distinctive_descriptor(self, descs):
+    """MapPoint::ComputeDistinctiveDescriptors (/root/reference/src/MapPoint.cc:246-311): index of the
+    observation with the least median Hamming distance to the others (first one wins ties). The N x N
+    distances come from the device (orbm_distance_matrix)."""
+    descs = _desc(descs)
+    n = len(descs)
+    if n == 0:
+        return -1
+    D = self.distance_matrix(descs, descs).astype(np.int32)
+    med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+    return int(np.argmin(med))  # argmin returns the first minimum, like the strict '<' loop
+
+
+ORBmatcher.SearchByBoW_KF_KF = _search_by_bow_kf_kf
+ORBmatcher.ComputeDistinctiveDescriptor = _distinctive_descriptor

@@ -356,3 +356,68 @@ def stereo_match(oL, oR, mbf, mb):
     u = np.empty(max(nL, 1), np.float32); d = np.empty(max(nL, 1), np.float32)
     kept = lib().orc_stereo_match(oL.h, oR.h, mbf, mb, u.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p))
     return u[:nL], d[:nL], kept
+
+
+def search_by_bow_kf_kf(desc1, fv1, valid1, ang1, desc2, fv2, valid2, ang2, nnratio=0.75, check_ori=True, th_low=50, histo=30):
+    """ORBmatcher::SearchByBoW(KF1, KF2), src/ORBmatcher.cc:524-657; feature vectors as sorted
+    (node, [indices]) lists, valid* = map point present and not bad."""
+    n1, n2 = len(desc1), len(desc2)
+    m12 = np.full(n1, -1, np.int32)
+    matched2 = np.zeros(n2, bool)
+    rot = [[] for _ in range(histo)]
+    factor = np.float32(1.0) / np.float32(histo)
+    ratio = np.float32(nnratio)
+    nm = 0
+    i = j = 0
+    while i < len(fv1) and j < len(fv2):
+        if fv1[i][0] == fv2[j][0]:
+            for idx1 in fv1[i][1]:
+                if not valid1[idx1]:
+                    continue
+                b1 = b2 = 256
+                bidx = -1
+                for idx2 in fv2[j][1]:
+                    if matched2[idx2] or not valid2[idx2]:
+                        continue
+                    d = hamming(desc1[idx1], desc2[idx2])
+                    if d < b1:
+                        b2, b1, bidx = b1, d, idx2
+                    elif d < b2:
+                        b2 = d
+                if b1 < th_low and np.float32(b1) < ratio * np.float32(b2):
+                    m12[idx1] = bidx
+                    matched2[bidx] = True
+                    if check_ori:
+                        r = np.float32(np.float32(ang1[idx1]) - np.float32(ang2[bidx]))
+                        if r < 0:
+                            r = np.float32(r + np.float32(360.0))
+                        b = int(np.floor(float(np.float32(r * factor)) + 0.5))
+                        rot[0 if b == histo else b].append(idx1)
+                    nm += 1
+            i += 1; j += 1
+        elif fv1[i][0] < fv2[j][0]:
+            while i < len(fv1) and fv1[i][0] < fv2[j][0]:  # lower_bound
+                i += 1
+        else:
+            while j < len(fv2) and fv2[j][0] < fv1[i][0]:
+                j += 1
+    if check_ori:
+        keep = three_maxima([len(x) for x in rot])
+        for b in range(histo):
+            if b not in keep:
+                for idx1 in rot[b]:
+                    m12[idx1] = -1
+                    nm -= 1
+    return nm, m12
+
+
+def distinctive_descriptor(descs):
+    """MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:246-311."""
+    n = len(descs)
+    best, best_i = 2**31 - 1, 0
+    for i in range(n):
+        v = sorted(0 if i == j else hamming(descs[i], descs[j]) for j in range(n))
+        med = v[int(0.5 * (n - 1))]
+        if med < best:
+            best, best_i = med, i
+    return best_i

@@ -1,0 +1,84 @@
+"""Edge cases of the boundary on a GPU: batch limits, capacity errors, unsupported geometry, handle reuse,
+concurrent handles (the reference runs a left and a right extractor in two threads, src/Frame.cc:78-81)."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from multiagent_orb_slam2_b200 import ORBextractor, ORBmatcher, OrbError, _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batch_larger_than_max_batch_is_rejected():
+    g = ORBextractor(500, 1.2, 8, 20, 7, max_batch=2)
+    with pytest.raises(OrbError):
+        g.extract_batch(np.zeros((3, 240, 320), np.uint8))
+
+
+def test_too_small_image_is_rejected_like_the_reference_would_crash():
+    with pytest.raises(OrbError) as e:
+        ORBextractor(500, 1.2, 8, 20, 7, width=120, height=100)  # level 7 is 33 px: nCols = 0 in the reference
+    assert "smaller than one 30 px cell" in str(e.value)
+
+
+def test_capacity_error_still_fills_the_buffer():
+    img = synth.image("blocks", 640, 480, 0)
+    g = ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480)
+    L = _lib.lib()
+    cap = 100
+    kps = np.empty(cap, dtype=[("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
+    desc = np.empty((cap, 32), np.uint8)
+    n = C.c_int()
+    rc = L.orbx_extract(g._h, C.c_void_p(img.ctypes.data), img.strides[0], kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+    assert rc == _lib.ORB_ECAPACITY and n.value > cap
+    ok, od = O.OracleExtractor()(img)
+    assert np.array_equal(desc, od[:cap])
+
+
+def test_handle_reuse_and_image_size_change():
+    g = ORBextractor(800, 1.2, 8, 20, 7)
+    for (w, h, seed) in [(640, 480, 0), (752, 480, 1), (640, 480, 2)]:
+        img = synth.image("blocks", w, h, seed)
+        gk, gd = g(img)
+        ok, od = O.OracleExtractor(800)(img)
+        assert len(gk) == len(ok) and np.array_equal(gd, od)
+
+
+def test_two_extractors_in_two_threads():
+    left, right = synth.stereo_pair("blocks", 752, 480, 4)
+    ex = [ORBextractor(1200, 1.2, 8, 20, 7, width=752, height=480) for _ in range(2)]
+    out = [None, None]
+
+    def run(i, img):
+        for _ in range(5):
+            out[i] = ex[i](img)
+
+    th = [threading.Thread(target=run, args=(i, im)) for i, im in enumerate((left, right))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i, im in enumerate((left, right)):
+        ok, od = O.OracleExtractor(1200)(im)
+        assert np.array_equal(out[i][1], od)
+
+
+def test_many_features_and_many_levels():
+    img = synth.image("noise", 1241, 376, 9)
+    for nf, s, nl in [(5000, 1.2, 8), (2000, 1.1, 12)]:
+        gk, gd = ORBextractor(nf, s, nl, 20, 7)(img)
+        ok, od = O.OracleExtractor(nf, s, nl, 20, 7)(img)
+        assert len(gk) == len(ok) and np.array_equal(gd, od)
+
+
+def test_matcher_empty_and_degenerate_sets():
+    m = ORBmatcher(0.8)
+    A = synth.descriptors(10, 1)
+    idx, d1, d2 = m.knn2(A, np.empty((0, 32), np.uint8))
+    assert (idx == -1).all() and (d1 == 256).all() and (d2 == 256).all()
+    idx, d1, d2 = m.knn2(A, A[:1])
+    assert (idx == 0).all() and (d2 == 256).all() and d1[0] == 0
+    comp = (~A[:1]).copy()  # complement: distance 256 is not < 256 => no candidate, as in the reference
+    idx, d1, d2 = m.knn2(A[:1], comp)
+    assert idx[0] == -1 and d1[0] == 256

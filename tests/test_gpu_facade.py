@@ -89,3 +89,50 @@ def test_python_search_for_initialization_matches_oracle(seed, window):
     assert gnm == nm and np.array_equal(gm12, m12)
     assert np.array_equal(prev.view(np.uint32), prev_ref.view(np.uint32))
     assert nm > 30
+
+
+def _feature_vectors(rng, n1, n2, twin_of_2, nodes=60):
+    """Synthetic DBoW2 FeatureVectors: every feature gets a vocabulary node; a feature of frame 2 that is a
+    noisy copy of feature t of frame 1 lands in t's node 90 % of the time."""
+    node1 = rng.integers(0, nodes, n1)
+    node2 = np.where(rng.random(n2) < 0.9, node1[twin_of_2], rng.integers(0, nodes, n2))
+    fv = []
+    for node in (node1, node2):
+        d = {}
+        for i, k in enumerate(node):
+            d.setdefault(int(k), []).append(i)
+        fv.append(sorted(d.items()))
+    return fv
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,ratio", [(0, 0.75), (1, 0.9)])
+def test_search_by_bow_kf_kf_matches_oracle(seed, ratio):
+    """The matcher MapFusion calls (src/MapFusion.cc:275): SearchByBoW(KF,KF) with its vbMatched2 state."""
+    rng = np.random.default_rng(seed)
+    n1, n2 = 900, 850
+    d1 = synth.descriptors(n1, 10 + seed)
+    twin = rng.integers(0, n1, n2)
+    d2 = d1[twin].copy()
+    bits = np.unpackbits(d2, axis=1)
+    for i in range(n2):
+        bits[i, rng.choice(256, rng.integers(0, 70), replace=False)] ^= 1
+    d2 = np.packbits(bits, axis=1)
+    fv1, fv2 = _feature_vectors(rng, n1, n2, twin)
+    v1, v2 = rng.random(n1) < 0.85, rng.random(n2) < 0.85
+    a1 = rng.uniform(0, 360, n1).astype(np.float32)
+    a2 = (a1[twin] + rng.normal(0, 8, n2)).astype(np.float32) % np.float32(360)
+    onm, om = O.search_by_bow_kf_kf(d1, fv1, v1, a1, d2, fv2, v2, a2, ratio)
+    gnm, gm = ORBmatcher(ratio, True).SearchByBoW_KF_KF(d1, fv1, v1, a1, d2, fv2, v2, a2)
+    assert gnm == onm and np.array_equal(gm, om)
+    assert (om >= 0).sum() > 100
+
+
+@pytest.mark.gpu
+def test_distinctive_descriptor_matches_oracle():
+    rng = np.random.default_rng(3)
+    m = ORBmatcher()
+    for n in (1, 2, 3, 8, 30):
+        base = synth.descriptors(1, 50 + n)
+        obs = synth.descriptors(n, 60 + n, dup_from=base, max_flips=40)
+        assert m.ComputeDistinctiveDescriptor(obs) == O.distinctive_descriptor(obs)
