@@ -133,7 +133,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(cores * 4, 32)
+    sample = max(cores * 8, 64)
     frames = make_frames(sample, 0)
     for _ in range(args.warmup):
         cpu_reference_run(frames[:cores], cores)
@@ -322,7 +322,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        sample = max(cores * 8, 64)
+        sample = max(cores * 24, 192)  # ~15-20 CPU-seconds of reference work
         cf = make_frames(sample, 0)
         cpu_reference_run(cf[:cores], cores)
         dt, kind = cpu_reference_run(cf, cores)

@@ -1,6 +1,7 @@
 // Extractor handle: geometry tables (the reference ctor, /root/reference/src/ORBextractor.cc:410-470,
 // plus the per-level cell grid of ComputeKeyPointsOctTree 771-787), HBM buffers, kernel
 // orchestration (operator(), 1043-1105) and the orbx_* C ABI.
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -14,13 +15,15 @@ namespace orb {
 int tma_encode_u8_3d(CUtensorMap* out, const void* base, int w, int h, int frames, size_t pitch, size_t frame_stride, int bw, int bh) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn fn = nullptr;
+    static std::atomic<EncodeFn> cached{nullptr};  // resolved once; racing threads resolve the same pointer
+    EncodeFn fn = cached.load();
     if (!fn) {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         ORB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
         if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return ORB_ECUDA; }
         fn = (EncodeFn)p;
+        cached.store(fn);
     }
     if (((uintptr_t)base & 15) || (pitch & 15) || (frame_stride & 15) || bw > 256 || bh > 256 || (bw & 15)) {
         set_error("tensor map: base/strides must be 16-byte aligned, box <= 256 (pitch %zu, stride %zu, box %dx%d)", pitch, frame_stride, bw, bh);

@@ -14,6 +14,8 @@
 //      (744-760).
 // The CPU statement of exactly this formulation is oracle/quadtree_arrayform.cc (checked against the
 // direct std::list restatement); integer only, so results are bit-exact.
+#include <atomic>
+
 #include "extract_kernels.cuh"
 
 namespace orb {
@@ -356,7 +358,7 @@ quadtree_standalone_kernel(const uint32_t* cand, int n, int N, int nRoots, float
 // opt in once per device to the large dynamic shared memory carve-out
 constexpr size_t kQtMaxDynSmem = 160 * 1024;
 static int qt_configure(size_t need) {
-    static bool done[64] = {};
+    static std::atomic<bool> done[64];  // idempotent per device; a racing second call only repeats the attribute set
     if (need > kQtMaxDynSmem) { set_error("nfeatures too large for the quadtree kernel's shared memory"); return ORB_EINVAL; }
     int dev = 0;
     ORB_CUDA_TRY(cudaGetDevice(&dev));
