@@ -192,7 +192,7 @@ int build_geometry(orbx_extractor* h) {
     g.ncells = (int)cells.size(); g.ntiles = (int)tiles.size();
     // the innermost TMA coordinate is 16-byte granular: boxes carry up to 15 lead-in bytes
     g.fast_bw = (int)align_up((size_t)g.max_tw + 15, 16);
-    g.rs_bw = (int)align_up((size_t)ceil(128.0 * sf) + 2 + 15, 16);
+    g.rs_bw = (int)align_up((size_t)ceil(128.0 * sf) + 2 + 15 + 12, 16);  // + 3-word read window of the last column quad
     g.rs_bh = (int)ceil(32.0 * sf) + 3;
     if (g.fast_bw > 256 || g.max_th > 256 || g.rs_bw > 256) { set_error("scale factor / cell size too large for the TMA tile boxes"); return ORB_EINVAL; }
     g.pyr_bytes = std::max<size_t>(pyr, 256); g.blur_bytes = blur; g.slot_words = slot; g.cand_words = slot;
@@ -291,7 +291,7 @@ extern "C" {
 int orbx_create(const orbx_config* cfg, int device, int width, int height, int max_batch, orbx_handle* out) {
     ORB_REQUIRE(cfg && out, "null pointer");
     ORB_REQUIRE(cfg->nlevels >= 1 && cfg->nlevels <= kMaxLevels, "nlevels out of range (1..16)");
-    ORB_REQUIRE(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && cfg->scale_factor <= 1.8f, "nfeatures >= 1 and 1 < scale_factor <= 1.8 required");
+    ORB_REQUIRE(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && cfg->scale_factor <= 1.75f, "nfeatures >= 1 and 1 < scale_factor <= 1.75 required");
     ORB_REQUIRE(cfg->min_th_fast >= 1 && cfg->ini_th_fast >= cfg->min_th_fast && cfg->ini_th_fast < 255, "FAST thresholds: 1 <= min <= ini < 255");
     ORB_REQUIRE(width > 0 && height > 0 && max_batch >= 1, "image size / batch must be positive");
     *out = nullptr;

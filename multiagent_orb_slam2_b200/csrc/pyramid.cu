@@ -51,23 +51,38 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
     mbar_wait(&bar, 0);
 
     if (x0 >= L.w) return;
-    int ofs0[4], ofs1[4];
+    // Per thread constants of its 4 columns: the source bytes (sx, sx+1) of all four lie within 12
+    // bytes of the word-aligned base (scale <= 1.8), i.e. in 3 words w0 w1 w2 of a window row. For
+    // column k a byte permute picks its two taps out of (w0,w1) or (w1,w2); one IDP.2A applies the two
+    // 11-bit weights (u16 pair) to the two pixels (u8 pair).
+    const int wbase = (tcol[0].ofs - sx_lo) & ~3;
+    uint32_t sel[4], coef[4];
+    bool hi[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { ofs0[k] = tcol[k].ofs - sx_lo; ofs1[k] = min(tcol[k].ofs + 1, S.w - 1) - sx_lo; }
-    const uint8_t* wb = win;
+    for (int k = 0; k < 4; ++k) {
+        int o = tcol[k].ofs - sx_lo - wbase;  // 0..10
+        hi[k] = o >= 7;                        // second tap beyond byte 7: use the (w1,w2) pair
+        o -= hi[k] ? 4 : 0;
+        sel[k] = (uint32_t)o | (uint32_t)(o + 1) << 4 | 0x4400u;  // bytes: tap0, tap1, 0, 0  (4 = a zero byte... see below)
+        coef[k] = (uint32_t)(uint16_t)tcol[k].c0 | (uint32_t)(uint16_t)tcol[k].c1 << 16;
+    }
 #pragma unroll
     for (int rr = 0; rr < kRsTH / 8; ++rr) {
         const int y = Y0 + rg + 8 * rr;
         if (y >= L.h) break;
         const LinTap t = trow[rr];
-        const uint8_t* r0 = wb + (size_t)(t.ofs - sy_lo) * bw;
-        const uint8_t* r1 = wb + (size_t)(min(t.ofs + 1, S.h - 1) - sy_lo) * bw;
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(win + (size_t)(t.ofs - sy_lo) * bw + wbase);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(win + (size_t)(min(t.ofs + 1, S.h - 1) - sy_lo) * bw + wbase);
+        const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2], c0 = r1[0], c1 = r1[1], c2 = r1[2];
         const int b0 = t.c0, b1 = t.c1;
         uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int h0 = r0[ofs0[k]] * tcol[k].c0 + r0[ofs1[k]] * tcol[k].c1;
-            const int h1 = r1[ofs0[k]] * tcol[k].c0 + r1[ofs1[k]] * tcol[k].c1;
+            // only the two low bytes of the permute result are used by IDP.2A (lo variant)
+            const uint32_t p0 = hi[k] ? __byte_perm(a1, a2, sel[k]) : __byte_perm(a0, a1, sel[k]);
+            const uint32_t p1 = hi[k] ? __byte_perm(c1, c2, sel[k]) : __byte_perm(c0, c1, sel[k]);
+            const int h0 = (int)__dp2a_lo(coef[k], p0, 0u);
+            const int h1 = (int)__dp2a_lo(coef[k], p1, 0u);
             const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
             packed |= (uint32_t)(v & 0xff) << (8 * k);
         }
