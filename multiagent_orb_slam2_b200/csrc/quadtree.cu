@@ -22,6 +22,7 @@ namespace orb {
 
 constexpr int kQtThreads = 256;  // several blocks per SM hide each other's barrier stalls
 constexpr int kQtWarps = kQtThreads / 32;
+constexpr int kQtSmemKeys = 4096;  // candidates per (level, frame) served from shared memory; more fall back to global
 
 struct QtShared {
     int warp_tmp[32];
@@ -31,9 +32,29 @@ struct QtShared {
     int wcount[kQtWarps][256];
 };
 
-// exclusive scan of in[0..len) into out[0..len) (may alias); returns the total to every thread
+// exclusive scan of in[0..len) into out[0..len) (may alias); returns the total to every thread.
+// Short arrays (the node lists: a few hundred entries) are scanned by warp 0 alone - each lane owns a
+// contiguous chunk - so that the whole scan costs two block barriers instead of six.
 __device__ int block_exclusive_scan(const int* in, int* out, int len, QtShared& sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();  // inputs written by other warps are visible
+    if (len <= 32 * 32) {
+        if (warp == 0) {
+            const int per = (len + 31) >> 5, lo = lane * per, hi = min(lo + per, len);
+            int sum = 0;
+            for (int i = lo; i < hi; ++i) sum += in[i];
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            int run = inc - sum;
+            for (int i = lo; i < hi; ++i) { const int v = in[i]; out[i] = run; run += v; }
+            if (lane == 31) sh.carry = inc;
+        }
+        __syncthreads();
+        const int total = len > 0 ? sh.carry : 0;
+        __syncthreads();  // nobody may still be reading carry when the next scan overwrites it
+        return total;
+    }
     if (threadIdx.x == 0) sh.carry = 0;
     __syncthreads();
     for (int base = 0; base < len; base += kQtThreads) {
@@ -172,8 +193,22 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
     int root_bits = 0;
     while ((1 << root_bits) < nRoots) ++root_bits;
     const int flip = block_radix_sort(kA, vA, kB, vB, n, 2 * depth + root_bits, sh);
-    const uint32_t* sk = flip ? kB : kA;
+    const uint32_t* sk = flip ? kB : kA;  // re-pointed to shared memory on the fast path
     const uint32_t* sv = flip ? vB : vA;
+    // Fast path (the usual case): sorted keys and a per-element selection word live in shared memory, so
+    // the binary searches of the list simulation and the per-node maximum never leave the SM.
+    const bool fast = n <= kQtSmemKeys;
+    uint32_t* skey = reinterpret_cast<uint32_t*>(nodemem + 14 * sel_cap);
+    uint32_t* comb = skey + kQtSmemKeys;  // response << 24 | (0xffffff - candidate index): max = best, earliest on ties
+    if (fast) {
+        for (int i = threadIdx.x; i < n; i += kQtThreads) {
+            const uint32_t c = sv[i];
+            skey[i] = sk[i];
+            comb[i] = (cand[c] >> 24) << 24 | (0xffffffu - c);
+        }
+        __syncthreads();
+        sk = skey;
+    }
 
     const int cap = sel_cap;
     QtNodes q;
@@ -207,22 +242,22 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
         const int before = count;
         int *lo = q.lo[cur], *hi = q.hi[cur], *dep = q.dep[cur];
         int *nlo = q.lo[cur ^ 1], *nhi = q.hi[cur ^ 1], *ndep = q.dep[cur ^ 1];
-        // children of every expandable node
-        for (int i = threadIdx.x; i < before; i += kQtThreads) {
+        // children of every expandable node: one thread per (node, inner boundary)
+        for (int it = threadIdx.x; it < 3 * before; it += kQtThreads) {
+            const int i = it / 3, t = it - 3 * i + 1;
             const int l = lo[i], h = hi[i], d = dep[i];
-            int c = 0;
             if (h - l >= 2 && d < depth) {
                 const int sft = 2 * (depth - d - 1);
-                int bnd[3];
-#pragma unroll
-                for (int t = 1; t < 4; ++t) {
-                    int a = l, b = h;
-                    while (a < b) { const int mid = (a + b) >> 1; if (((sk[mid] >> sft) & 3u) >= (uint32_t)t) b = mid; else a = mid + 1; }
-                    bnd[t - 1] = a;
-                }
-                q.b1[i] = bnd[0]; q.b2[i] = bnd[1]; q.b3[i] = bnd[2];
-                c = (bnd[0] > l) + (bnd[1] > bnd[0]) + (bnd[2] > bnd[1]) + (h > bnd[2]);
+                int a = l, b = h;
+                while (a < b) { const int mid = (a + b) >> 1; if (((sk[mid] >> sft) & 3u) >= (uint32_t)t) b = mid; else a = mid + 1; }
+                (t == 1 ? q.b1 : t == 2 ? q.b2 : q.b3)[i] = a;
             }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < before; i += kQtThreads) {
+            const int l = lo[i], h = hi[i];
+            int c = 0;
+            if (h - l >= 2 && dep[i] < depth) c = (q.b1[i] > l) + (q.b2[i] > q.b1[i]) + (q.b3[i] > q.b2[i]) + (h > q.b3[i]);
             q.cc[i] = c;
             q.flag[i] = c > 0;
         }
@@ -297,23 +332,31 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
         __syncthreads();
     }
 
-    // best candidate per node: max response, earliest candidate on ties; one warp per node
+    // best candidate per node: max response, earliest candidate on ties
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int* lo = q.lo[cur]; const int* hi = q.hi[cur];
-    for (int p = warp; p < count; p += kQtWarps) {
-        uint32_t best = 0;
-        for (int i = lo[p] + lane; i < hi[p]; i += 32) {
-            const uint32_t c = sv[i];
-            best = max(best, (cand[c] >> 24) << 24 | (0xffffffu - c));
+    if (fast) {  // one thread per node over the shared-memory selection words
+        for (int p = threadIdx.x; p < count; p += kQtThreads) {
+            uint32_t best = 0;
+            for (int i = lo[p]; i < hi[p]; ++i) best = max(best, comb[i]);
+            if (p < sel_cap) sel[p] = cand[0xffffffu - (best & 0xffffffu)];
         }
+    } else {     // one warp per node over the global arrays
+        for (int p = warp; p < count; p += kQtWarps) {
+            uint32_t best = 0;
+            for (int i = lo[p] + lane; i < hi[p]; i += 32) {
+                const uint32_t c = sv[i];
+                best = max(best, (cand[c] >> 24) << 24 | (0xffffffu - c));
+            }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-        if (lane == 0 && p < sel_cap) sel[p] = cand[0xffffffu - (best & 0xffffffu)];
+            for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0 && p < sel_cap) sel[p] = cand[0xffffffu - (best & 0xffffffu)];
+        }
     }
     if (threadIdx.x == 0) *count_out = min(count, sel_cap);
 }
 
-static size_t qt_smem_bytes(int sel_cap) { return (size_t)sel_cap * 14 * sizeof(int); }
+static size_t qt_smem_bytes(int sel_cap) { return (size_t)sel_cap * 14 * sizeof(int) + 2 * (size_t)kQtSmemKeys * sizeof(uint32_t); }
 
 // grid (levels, frames)
 __global__ void __launch_bounds__(kQtThreads)
