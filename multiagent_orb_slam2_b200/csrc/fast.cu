@@ -135,18 +135,15 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     uint16_t* mylist = list1 + warp * seg;
     int cnt = 0;
     for (int x0 = 3; x0 < tw - 3; x0 += 32) {  // one trip unless the cell is wider than 38 px
-        const int x = x0 + lane;
-        const bool xin = x < tw - 3;
+        const bool xin = x0 + lane < tw - 3;
+        const int x = xin ? x0 + lane : tw - 4;  // idle lanes re-test the last column (no branch), masked below
         const uint8_t* p = t0 + (3 + warp) * tp + x;
         const int up = -3 * tp, dn = 3 * tp;
         int at = (3 + warp) * tp + x;
         for (int y = 3 + warp; y < th - 3; y += kFastWarps, p += kFastWarps * tp, at += kFastWarps * tp) {
-            bool keep = false;
-            if (xin) {
-                const int v = p[0], lo = v - minTh, hi = v + minTh;
-                const int r0 = p[dn], r8 = p[up], r4 = p[3], r12 = p[-3];
-                keep = max(min(r0, r8), min(r4, r12)) < lo || min(max(r0, r8), max(r4, r12)) > hi;
-            }
+            const int v = p[0], lo = v - minTh, hi = v + minTh;
+            const int r0 = p[dn], r8 = p[up], r4 = p[3], r12 = p[-3];
+            const bool keep = xin & ((max(min(r0, r8), min(r4, r12)) < lo) | (min(max(r0, r8), max(r4, r12)) > hi));
             const uint32_t ball = __ballot_sync(0xffffffffu, keep);
             if (keep) mylist[cnt + __popc(ball & ((1u << lane) - 1))] = (uint16_t)at;
             cnt += __popc(ball);
