@@ -100,8 +100,8 @@ knn2_kernel(const uint4* __restrict__ A, const int* __restrict__ nA_dev, int nA_
 
     const int pair = blockIdx.z;
     const int ia = pairs ? pairs[2 * pair] : pair, ib = pairs ? pairs[2 * pair + 1] : pair;
-    const int nA = nA_dev ? nA_dev[ia] : nA_const;
-    const int nB = nB_dev ? nB_dev[ib] : nB_const;
+    const int nA = nA_dev ? min(nA_dev[ia], strideA_rows) : nA_const;  // device counts never exceed the set capacity
+    const int nB = nB_dev ? min(nB_dev[ib], strideB_rows) : nB_const;
     const int q0 = blockIdx.x * QB;
     if (q0 >= nA) return;  // whole block exits together
     const int slice = threadIdx.x / QB, qi = threadIdx.x % QB;
