@@ -193,6 +193,23 @@ int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf,
 int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int16_t* d_out, void* stream);
 int orbm_distance_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int16_t* out);
 
+/* ------------------------------------------------------------------------------------------
+ * Vocabulary tree descent (the step right after extraction): replaces the per-feature
+ * TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) with FORB::distance
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259, FORB.cpp:81-101) for all features of a frame,
+ * as called from Frame::ComputeBoW (src/Frame.cc:395-402). The vocabulary is given as the node table of the
+ * ORBvoc text format (TemplatedVocabulary.h:1338-1424): nodes in id order, node 0 = root, parent[i] < i.
+ * Outputs per feature: word id, node id at level L - levelsup, word weight. The caller folds them into its
+ * DBoW2::BowVector / FeatureVector exactly like TemplatedVocabulary.h:1150-1163 does
+ * (if (w > 0) { v.addWeight(id, w); fv.addFeature(nid, i); } ... v.normalize(norm)). */
+typedef struct orbv_vocabulary* orbv_handle;
+int orbv_create(int device, const int32_t* parent, const uint8_t* desc, const double* weight, int n_nodes, int k, int L,
+                orbv_handle* out);
+void orbv_destroy(orbv_handle v);
+int orbv_descend_device(orbv_handle v, const uint8_t* d_desc, int n, int levelsup, int32_t* d_word, int32_t* d_node,
+                        double* d_weight, void* stream);
+int orbv_descend(orbv_handle v, const uint8_t* desc, int n, int levelsup, int32_t* word, int32_t* node, double* weight);
+
 #ifdef __cplusplus
 }
 #endif

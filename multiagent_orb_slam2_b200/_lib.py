@@ -66,6 +66,9 @@ def lib():
         "orbm_ratio_filter_device": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
         "orbm_stereo_match_device": [vp, vp, i32, f32, f32, vp, vp, vp, vp, vp],
         "orbm_stereo_match": [vp, vp, i32, f32, f32, vp, vp, i32, C.POINTER(i32)],
+        "orbv_create": [i32, vp, vp, vp, i32, i32, i32, C.POINTER(vp)],
+        "orbv_descend_device": [vp, vp, i32, i32, vp, vp, vp, vp],
+        "orbv_descend": [vp, vp, i32, i32, vp, vp, vp],
         "orbm_distance_matrix_device": [vp, i32, vp, i32, vp, vp],
         "orbm_distance_matrix": [i32, vp, i32, vp, i32, vp],
     }
@@ -75,6 +78,8 @@ def lib():
         fn.restype = C.c_int
     L.orb_launch_count.argtypes = []
     L.orb_launch_count.restype = C.c_longlong
+    L.orbv_destroy.argtypes = [vp]
+    L.orbv_destroy.restype = None
     L.orbx_destroy.argtypes = [vp]
     L.orbx_destroy.restype = None
     _lib = L

@@ -88,3 +88,78 @@ def descriptors_fast(n, seed, dup_from, max_flips=60):
     p = pos.ravel()[mask.ravel()]
     np.bitwise_xor.at(src, (rows, p >> 3), (1 << (7 - (p & 7))).astype(np.uint8))
     return src
+
+
+def vocabulary(k=10, L=3, seed=0, stop_fraction=0.02):
+    """Synthetic DBoW2 vocabulary tree (the real ORBvoc.txt, k=10 L=6, is not shipped with the reference):
+    nodes in breadth-first id order (root 0, children of a node contiguous), every child a noisy copy of
+    its parent so that descents are meaningful. Returns dict(parent, desc, weight, k, L); leaves carry a
+    positive idf-like weight, a few are 'stopped' (weight 0)."""
+    rng = np.random.default_rng(seed)
+    parent, desc, level = [-1], [np.zeros(32, np.uint8)], [0]
+    frontier = [0]
+    for lvl in range(1, L + 1):
+        nxt = []
+        flips = max(4, 96 >> (lvl - 1))
+        for p in frontier:
+            for _ in range(k):
+                if lvl == 1:
+                    d = rng.integers(0, 256, 32, dtype=np.uint8)
+                else:
+                    bits = np.unpackbits(desc[p])
+                    bits[rng.choice(256, flips, replace=False)] ^= 1
+                    d = np.packbits(bits)
+                parent.append(p); desc.append(d); level.append(lvl)
+                nxt.append(len(parent) - 1)
+        frontier = nxt
+    n = len(parent)
+    level = np.asarray(level)
+    weight = np.zeros(n, np.float64)
+    leaves = level == L
+    weight[leaves] = rng.uniform(0.5, 12.0, leaves.sum())
+    weight[leaves & (rng.random(n) < stop_fraction)] = 0.0
+    return dict(parent=np.asarray(parent, np.int32), desc=np.stack(desc).astype(np.uint8), weight=weight, k=k, L=L)
+
+
+def vocabulary_fast(k=10, L=6, seed=0):
+    """Vectorised variant for the full-size tree (k=10, L=6: 1 111 111 nodes) used by the benchmark."""
+    rng = np.random.default_rng(seed)
+    descs = [np.zeros((1, 32), np.uint8)]
+    parents = [np.full(1, -1, np.int32)]
+    first = 0
+    for lvl in range(1, L + 1):
+        prev = descs[-1]
+        npar = len(prev)
+        if lvl == 1:
+            d = rng.integers(0, 256, (npar * k, 32), dtype=np.uint8)
+        else:
+            d = np.repeat(prev, k, axis=0)
+            flips = max(4, 96 >> (lvl - 1))
+            pos = rng.integers(0, 256, (len(d), flips))
+            rows = np.repeat(np.arange(len(d)), flips)
+            np.bitwise_xor.at(d, (rows, pos.ravel() >> 3), (1 << (7 - (pos.ravel() & 7))).astype(np.uint8))
+        parents.append(np.repeat(np.arange(first, first + npar, dtype=np.int32), k))
+        descs.append(d)
+        first += npar
+    desc = np.concatenate(descs)
+    parent = np.concatenate(parents)
+    weight = np.zeros(len(desc), np.float64)
+    weight[first:] = rng.uniform(0.5, 12.0, len(desc) - first)
+    return dict(parent=parent, desc=desc, weight=weight, k=k, L=L)
+
+
+def write_vocabulary_text(path, voc):
+    """ORBvoc text format of TemplatedVocabulary::saveToTextFile / loadFromTextFile
+    (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1450): 'k L scoring weighting' then one line per node
+    'parent isLeaf d0..d31 weight' in node id order."""
+    parent, desc, weight = voc["parent"], voc["desc"], voc["weight"]
+    n = len(parent)
+    has_child = np.zeros(n, bool)
+    has_child[parent[1:]] = True
+    with open(path, "w") as f:
+        f.write("%d %d 0 0\n" % (voc["k"], voc["L"]))  # L1_NORM, TF_IDF
+        lines = ["%d %d %s %s" % (parent[i], 0 if has_child[i] else 1, " ".join(str(int(b)) for b in desc[i]), repr(float(weight[i])))
+                 for i in range(1, n)]
+        # no trailing newline: loadFromTextFile's `while(!f.eof())` loop would otherwise parse one empty line into a
+        # bogus extra child of the root (its failed `>> pid` yields 0)
+        f.write("\n".join(lines))

@@ -18,4 +18,10 @@ common=(-std=c++14 -O3 -march=x86-64-v3 -ffp-contract=off -fPIC -shared -w
         -I"$here/shim" -I"$ref/include" "$ref/src/ORBextractor.cc" "$here/ref_wrap.cc")
 g++ "${common[@]}" -o "$here/_ref/libref_orb_verbatim.so"
 g++ -include "$here/shim/canonical_sort.h" "${common[@]}" -o "$here/_ref/libref_orb_canonical.so"
+#   libref_dbow.so           the vendored DBoW2 (FORB, BowVector, FeatureVector, ScoringObject,
+#                            TemplatedVocabulary.h) unmodified + ref_dbow_wrap.cc: ORBVocabulary::transform
+dbow="$ref/Thirdparty/DBoW2"
+g++ -std=c++14 -O3 -march=x86-64-v3 -ffp-contract=off -fPIC -shared -w -I"$here/shim" -I"$dbow" \
+    "$dbow/DBoW2/FORB.cpp" "$dbow/DBoW2/BowVector.cpp" "$dbow/DBoW2/FeatureVector.cpp" "$dbow/DBoW2/ScoringObject.cpp" \
+    "$dbow/DUtils/Random.cpp" "$dbow/DUtils/Timestamp.cpp" "$here/ref_dbow_wrap.cc" -o "$here/_ref/libref_dbow.so"
 echo "build_ref: built $(ls "$here/_ref")"

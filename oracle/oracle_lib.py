@@ -421,3 +421,76 @@ def distinctive_descriptor(descs):
         if med < best:
             best, best_i = med, i
     return best_i
+
+
+# ---- DBoW2 vocabulary transform (oracle restatement + the vendored DBoW2 itself) -----------------
+class OracleVocabulary:
+    def __init__(self, voc):
+        L = lib()
+        L.orc_voc_create.restype = C.c_void_p
+        L.orc_voc_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_voc_destroy.argtypes = [C.c_void_p]
+        L.orc_voc_descend.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        self.L = L
+        parent = np.ascontiguousarray(voc["parent"], np.int32)
+        desc = np.ascontiguousarray(voc["desc"], np.uint8)
+        weight = np.ascontiguousarray(voc["weight"], np.float64)
+        self.h = L.orc_voc_create(parent.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), weight.ctypes.data_as(C.c_void_p),
+                                  len(parent), voc["k"], voc["L"])
+        self.fn_descend, self.fn_transform = L.orc_voc_descend, L.orc_voc_transform
+
+    def __del__(self):
+        if getattr(self, "h", None) and hasattr(self.L, "orc_voc_destroy"):
+            self.L.orc_voc_destroy(self.h)
+            self.h = None
+
+    def descend(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8)
+        n = len(d)
+        word = np.empty(n, np.int32); node = np.empty(n, np.int32); weight = np.empty(n, np.float64)
+        self.fn_descend(self.h, d.ctypes.data_as(C.c_void_p), n, levelsup, word.ctypes.data_as(C.c_void_p),
+                        node.ctypes.data_as(C.c_void_p), weight.ctypes.data_as(C.c_void_p))
+        return word, node, weight
+
+    def transform(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8)
+        n = len(d)
+        bid = np.empty(n + 1, np.int32); bval = np.empty(n + 1, np.float64)
+        fnode = np.empty(n + 1, np.int32); foff = np.empty(n + 2, np.int32); ffeat = np.empty(n + 1, np.int32)
+        nb, nf = C.c_int(), C.c_int()
+        self.fn_transform(self.h, d.ctypes.data_as(C.c_void_p), n, levelsup, bid.ctypes.data_as(C.c_void_p), bval.ctypes.data_as(C.c_void_p),
+                          n + 1, C.byref(nb), fnode.ctypes.data_as(C.c_void_p), foff.ctypes.data_as(C.c_void_p),
+                          ffeat.ctypes.data_as(C.c_void_p), n + 1, C.byref(nf))
+        fv = [(int(fnode[i]), ffeat[foff[i]:foff[i + 1]].tolist()) for i in range(nf.value)]
+        return bid[:nb.value].copy(), bval[:nb.value].copy(), fv
+
+
+class RefVocabulary(OracleVocabulary):
+    """The reference's vendored DBoW2 (oracle/_ref/libref_dbow.so), loaded from an ORBvoc-format text file."""
+
+    def __init__(self, text_file):
+        L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_dbow.so"))
+        L.refv_load.restype = C.c_void_p
+        L.refv_load.argtypes = [C.c_char_p]
+        L.refv_destroy.argtypes = [C.c_void_p]
+        L.refv_descend.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refv_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        self.L = L
+        self.h = L.refv_load(text_file.encode())
+        assert self.h, "vocabulary text file rejected by DBoW2"
+        self.fn_descend, self.fn_transform = L.refv_descend, L.refv_transform
+
+    def size(self):
+        return self.L.refv_size(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refv_destroy(self.h)
+            self.h = None
+
+
+def dbow_ref_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_dbow.so"))

@@ -9,8 +9,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <iterator>
+#include <sstream>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "../cvprim.h"
@@ -20,6 +23,7 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 
 static inline int cvRound(double v) { return cvprim::round_half_even(v); }
 static inline int cvRound(float v) { return cvprim::round_half_even(v); }
@@ -64,18 +68,20 @@ public:
     int rows = 0, cols = 0;
     size_t step = 0;
     uchar* data = nullptr;
+    int mtype = CV_8U;  // CV_8U or CV_32F (the latter only so that DBoW2's FORB::toMat32F compiles)
     std::shared_ptr<std::vector<uchar>> buf;
 
     Mat() {}
-    Mat(Size s, int /*type*/) { create(s.height, s.width, 0); }
-    Mat(int r, int c, int /*type*/) { create(r, c, 0); }
+    Mat(Size s, int type) { create(s.height, s.width, type); }
+    Mat(int r, int c, int type) { create(r, c, type); }
     // external data, not owned
     Mat(int r, int c, int /*type*/, void* ext, size_t stp) : rows(r), cols(c), step(stp), data((uchar*)ext) {}
 
-    void create(int r, int c, int /*type*/) {
-        if (data && r == rows && c == cols) return;
-        buf = std::make_shared<std::vector<uchar>>((size_t)r * c);
-        rows = r; cols = c; step = (size_t)c; data = buf->data();
+    void create(int r, int c, int type) {
+        if (data && r == rows && c == cols && type == mtype) return;
+        const size_t es = type == CV_32F ? 4 : 1;
+        buf = std::make_shared<std::vector<uchar>>((size_t)r * c * es);
+        rows = r; cols = c; step = (size_t)c * es; data = buf->data(); mtype = type;
     }
     void release() { buf.reset(); data = nullptr; rows = cols = 0; step = 0; }
     static MatExpr zeros(int r, int c, int /*type*/) { return MatExpr{r, c}; }
@@ -86,7 +92,7 @@ public:
         return *this;
     }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    int type() const { return CV_8UC1; }
+    int type() const { return mtype; }
     size_t step1() const { return step; }
     Mat clone() const {
         Mat m(rows, cols, 0);
@@ -103,6 +109,32 @@ public:
     template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step + c * sizeof(T)); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
+    template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
+    Mat row(int r) const { return view(0, r, cols, 1); }
+};
+
+// cv::FileStorage / cv::FileNode: only so that the (virtual, hence always instantiated) YAML save/load
+// members of DBoW2::TemplatedVocabulary compile; the oracle loads vocabularies from text files only.
+class FileNode {
+public:
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0; }
+    operator float() const { return 0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const char*) const { return FileNode(); }
+    template <typename T> FileStorage& operator<<(const T&) { return *this; }
 };
 
 class _InputArray {
