@@ -343,6 +343,31 @@ def run_b200(args):
                 "popc_roofline": "148 SM x 16 POPC/clk x 1.965 GHz / 8 POPC per cmp per GPU (measured 15.3/clk/SM)"}
         del local, res, cm
 
+    # ---- DBoW2 vocabulary transform of the batch's descriptors (Frame::ComputeBoW), rank 0 -----
+    bow = None
+    if rank == 0 and not args.no_bow:
+        from multiagent_orb_slam2_b200 import synth
+        from multiagent_orb_slam2_b200.vocabulary import ORBVocabulary
+        voc = ORBVocabulary(synth.vocabulary_fast(10, 6, 7), device=local_rank)  # ORBvoc shape: k=10, L=6, 1.1 M nodes
+        nfeat = B * fe.cap
+        ow = torch.empty(nfeat, dtype=torch.int32, device=dev); on = torch.empty_like(ow)
+        owt = torch.empty(nfeat, dtype=torch.float64, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        call = lambda: _lib.check(L.orbv_descend_device(voc._h, C.c_void_p(fe.d_desc), nfeat, 4, C.c_void_p(ow.data_ptr()),
+                                                        C.c_void_p(on.data_ptr()), C.c_void_p(owt.data_ptr()), st))
+        for _ in range(3):
+            call()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(10):
+            call()
+        b1.record()
+        torch.cuda.synchronize(dev)
+        bms = b0.elapsed_time(b1) / 10
+        bow = {"metric": "vocabulary descents/s (k=10, L=6 synthetic tree, levelsup 4)", "value": nfeat / (bms * 1e-3), "unit": "features/s",
+               "features_per_launch": nfeat, "ms_per_launch": bms, "hamming_per_feature": 60}
+        del voc
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------
@@ -369,7 +394,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * fe.h2d_bytes_per_frame(),
                     "d2h_bytes_per_step": B * fe.d2h_bytes_per_frame(), "ms_per_step": e2e_ms / args.steps,
                     "how": "pinned host frames -> orbx_upload_frames/extract_staged/orbm_knn2_batched/download, 2 buffers in flight"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mapfusion": mapf,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mapfusion": mapf, "bow_transform": bow,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -384,6 +409,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mapfusion", action="store_true", help="skip the cross-map Hamming leg")
+    ap.add_argument("--no-bow", action="store_true", help="skip the vocabulary transform leg")
     ap.add_argument("--map-rows", type=int, default=200000, help="descriptors per map in the cross-map leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
