@@ -10,6 +10,7 @@ namespace orb {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);  // kernels launched by this library (bench.py's gpu_launches)
+extern "C" long long orb_launch_count(void);
 
 #define ORB_CUDA_TRY(expr)                                                                  \
     do {                                                                                    \

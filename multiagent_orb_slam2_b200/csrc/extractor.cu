@@ -87,6 +87,12 @@ struct orbx_extractor {
     // Levels >= 1 are encoded once; level 0 follows the frames of the call (cached on the FrameSet).
     TmaMaps maps_resize, maps_blur, maps_fast;
     FrameSet maps_l0{};
+    // CUDA graph of the kernel sequence for small batches (the per-frame operator() path is launch bound:
+    // 11 launches + fork/join). Keyed on (frames, n): state 0 = nothing, 1 = ran eagerly once, 2 = captured.
+    cudaGraphExec_t graph_exec = nullptr;
+    FrameSet graph_fs{};
+    int graph_n = 0, graph_state = 0, graph_kernels = 0;
+    bool use_graphs = true;
     // optional per-stage device timing (bench roofline): events around each stage of the pipeline
     bool stage_timing = false;
     cudaEvent_t ev_stage[ORBX_NUM_STAGES + 1] = {};
@@ -240,7 +246,25 @@ int build_geometry(orbx_extractor* h) {
     return ORB_OK;
 }
 
-// the whole of operator() for n frames, enqueued on st (blur runs on the side stream)
+// the kernel sequence of operator(): resize chain, then blur on the side stream next to FAST + quadtree, joined
+// before orientation + description
+int launch_sequence(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t st) {
+    const Geometry& g = h->hg;
+    int rc;
+    for (int l = 1; l < g.nlevels; ++l)
+        if ((rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
+    // fork: the Gaussian blur (1085-1086) only depends on the pyramid
+    ORB_CUDA_TRY(cudaEventRecord(h->ev_pyr, st));
+    ORB_CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_pyr, 0));
+    if ((rc = launch_blur(g, h->db, h->maps_blur, n, h->stream2))) return rc;
+    ORB_CUDA_TRY(cudaEventRecord(h->ev_blur, h->stream2));
+    if ((rc = launch_fast(g, h->db, h->maps_fast, n, st))) return rc;
+    if ((rc = launch_quadtree(g, h->db, n, st))) return rc;
+    ORB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_blur, 0));
+    return launch_describe(g, h->db, fs, n, st);
+}
+
+// the whole of operator() for n frames, enqueued on st
 int enqueue_pipeline(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t st) {
     const Geometry& g = h->hg;
     int rc;
@@ -269,17 +293,48 @@ int enqueue_pipeline(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t 
         h->last = fs; h->last_n = n;
         return ORB_OK;
     }
-    for (int l = 1; l < g.nlevels; ++l)
-        if ((rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
-    // fork: the Gaussian blur (1085-1086) only depends on the pyramid
-    ORB_CUDA_TRY(cudaEventRecord(h->ev_pyr, st));
-    ORB_CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_pyr, 0));
-    if ((rc = launch_blur(g, h->db, h->maps_blur, n, h->stream2))) return rc;
-    ORB_CUDA_TRY(cudaEventRecord(h->ev_blur, h->stream2));
-    if ((rc = launch_fast(g, h->db, h->maps_fast, n, st))) return rc;
-    if ((rc = launch_quadtree(g, h->db, n, st))) return rc;
-    ORB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_blur, 0));
-    if ((rc = launch_describe(g, h->db, fs, n, st))) return rc;
+    // small batches: replay the captured graph of the kernel sequence
+    constexpr int kGraphMaxBatch = 16;
+    const bool capturable = h->use_graphs && n <= kGraphMaxBatch && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    if (capturable) {
+        const bool same = h->graph_n == n && h->graph_fs.base == fs.base && h->graph_fs.pitch == fs.pitch && h->graph_fs.frame_stride == fs.frame_stride;
+        if (same && h->graph_state == 2) {
+            ORB_CUDA_TRY(cudaGraphLaunch(h->graph_exec, st));
+            count_launch(h->graph_kernels);
+            h->last = fs; h->last_n = n;
+            return ORB_OK;
+        }
+        if (same && h->graph_state == 1) {  // second identical call: capture
+            const long long before = orb_launch_count();
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                rc = launch_sequence(h, fs, n, st);
+                e = cudaStreamEndCapture(st, &graph);
+                const int captured = (int)(orb_launch_count() - before);
+                count_launch(-captured);  // nothing ran during capture
+                if (rc == ORB_OK && e == cudaSuccess && graph) {
+                    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+                    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (e == cudaSuccess) {
+                        h->graph_state = 2; h->graph_kernels = captured;
+                        ORB_CUDA_TRY(cudaGraphLaunch(h->graph_exec, st));
+                        count_launch(captured);
+                        h->last = fs; h->last_n = n;
+                        return ORB_OK;
+                    }
+                } else if (graph) {
+                    cudaGraphDestroy(graph);
+                }
+            }
+            cudaGetLastError();      // capture not possible here (e.g. the caller's stream is already capturing):
+            h->use_graphs = false;   // stay on plain launches
+        } else {
+            h->graph_fs = fs; h->graph_n = n; h->graph_state = 1;
+        }
+    }
+    if ((rc = launch_sequence(h, fs, n, st))) return rc;
     h->last = fs; h->last_n = n;
     return ORB_OK;
 }
@@ -313,6 +368,7 @@ void orbx_destroy(orbx_handle h) {
     void* ptrs[] = {h->d_geom, h->d_cells, h->d_taps, h->d_tiles, h->d_pattern, h->db.pyr, h->db.blur, h->db.slots, h->db.cell_counts,
                     h->db.sortbuf, h->db.selected, h->db.sel_counts, h->db.kps, h->db.desc, h->db.counts, h->d_input};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     for (cudaEvent_t e : h->ev_stage) if (e) cudaEventDestroy(e);
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
