@@ -194,6 +194,24 @@ int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, in
 int orbm_distance_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int16_t* out);
 
 /* ------------------------------------------------------------------------------------------
+ * Device-resident Frame grid + windowed search. orbm_grid_build_device replaces
+ * Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:230-245, 382-392) on the keypoints an extractor left on the
+ * device (bounds = mnMinX, mnMinY, mnMaxX, mnMaxY); orbm_window_knn2_device replaces Frame::GetFeaturesInArea
+ * (src/Frame.cc:327-380) fused with the best / second loop that consumes it (e.g. src/ORBmatcher.cc:84-116): query q
+ * = (x, y, r, minLevel, maxLevel, descriptor row q of d_queries); candidates are visited in the reference's order
+ * (cell column, cell row, insertion), so ties resolve identically. Outputs also carry the octaves of best and second
+ * (src/ORBmatcher.cc:119-122). Stateless form; capacity < 2^20 keypoints per frame. */
+typedef struct orbm_grid* orbm_grid_handle;
+int orbm_grid_create(int device, int capacity, orbm_grid_handle* out);
+void orbm_grid_destroy(orbm_grid_handle g);
+int orbm_grid_build_device(orbm_grid_handle g, const orbx_keypoint* d_kps, const int32_t* d_count, float min_x, float min_y,
+                           float max_x, float max_y, void* stream);
+int orbm_window_knn2_device(orbm_grid_handle g, const uint8_t* d_desc_frame, const uint8_t* d_queries, int nq, const float* d_x,
+                            const float* d_y, const float* d_r, const int32_t* d_min_level, const int32_t* d_max_level,
+                            int32_t* d_idx, int32_t* d_best, int32_t* d_second, int32_t* d_best_level, int32_t* d_second_level,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Vocabulary tree descent (the step right after extraction): replaces the per-feature
  * TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) with FORB::distance
  * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259, FORB.cpp:81-101) for all features of a frame,

@@ -66,6 +66,9 @@ def lib():
         "orbm_ratio_filter_device": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
         "orbm_stereo_match_device": [vp, vp, i32, f32, f32, vp, vp, vp, vp, vp],
         "orbm_stereo_match": [vp, vp, i32, f32, f32, vp, vp, i32, C.POINTER(i32)],
+        "orbm_grid_create": [i32, i32, C.POINTER(vp)],
+        "orbm_grid_build_device": [vp, vp, vp, f32, f32, f32, f32, vp],
+        "orbm_window_knn2_device": [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "orbv_create": [i32, vp, vp, vp, i32, i32, i32, C.POINTER(vp)],
         "orbv_descend_device": [vp, vp, i32, i32, vp, vp, vp, vp],
         "orbv_descend": [vp, vp, i32, i32, vp, vp, vp],
@@ -78,6 +81,8 @@ def lib():
         fn.restype = C.c_int
     L.orb_launch_count.argtypes = []
     L.orb_launch_count.restype = C.c_longlong
+    L.orbm_grid_destroy.argtypes = [vp]
+    L.orbm_grid_destroy.restype = None
     L.orbv_destroy.argtypes = [vp]
     L.orbv_destroy.restype = None
     L.orbx_destroy.argtypes = [vp]

@@ -1,0 +1,206 @@
+// K11 + K12: the reference Frame's 64 x 48 keypoint lookup grid on the device, and the windowed
+// nearest-neighbour search that walks it (no host round trip for the candidate gate).
+//
+//   K11 frame_grid_build   Frame::AssignFeaturesToGrid + PosInGrid     /root/reference/src/Frame.cc:230-245, 382-392
+//   K12 window_knn2        Frame::GetFeaturesInArea                    src/Frame.cc:327-380
+//                          + the best/second loop that consumes it     e.g. src/ORBmatcher.cc:84-116, 1385-1426
+// The candidate ORDER of GetFeaturesInArea (cell column ix, then cell row iy, then insertion order inside the
+// cell) decides which of two equally distant candidates wins; K12 reproduces it by giving every candidate its
+// position in that order and reducing (distance, position) lexicographically. Stateless form only: searches whose
+// gate depends on earlier matches take the distances (orbm_list_distances) and replay the loop on the host.
+#include <new>
+
+#include "common.cuh"
+
+struct orbm_grid {
+    int device = 0, cap = 0;
+    float min_x = 0, min_y = 0, w_inv = 0, h_inv = 0;
+    int* d_cell_start = nullptr;  // [64*48 + 1]
+    int* d_items = nullptr;       // [cap] keypoint indices, cell-major (ix-major, iy), insertion order inside a cell
+    int n = 0;                    // keypoints of the last build (host copy not needed by the kernels)
+    const orbx_keypoint* d_kps = nullptr;
+    const int* d_count = nullptr;
+};
+
+namespace orb {
+
+constexpr int kGridCols = 64, kGridRows = 48, kGridCells = kGridCols * kGridRows;
+
+__device__ __forceinline__ int c_round(float v) { return (int)roundf(v); }  // C round(): half away from zero
+
+// single block: counting sort of the keypoints by cell (cell id = ix * 48 + iy, the reference's iteration order)
+__global__ void __launch_bounds__(1024)
+frame_grid_build_kernel(const orbx_keypoint* __restrict__ kps, const int* __restrict__ count, int cap, float min_x, float min_y,
+                        float w_inv, float h_inv, int* __restrict__ cell_start, int* __restrict__ items) {
+    __shared__ int s_cnt[kGridCells];
+    __shared__ int s_warp[32];
+    const int n = min(*count, cap);
+    for (int i = threadIdx.x; i < kGridCells; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    auto cell_of = [&](int i) {
+        const int px = c_round(__fmul_rn(__fsub_rn(kps[i].x, min_x), w_inv));
+        const int py = c_round(__fmul_rn(__fsub_rn(kps[i].y, min_y), h_inv));
+        return (px < 0 || px >= kGridCols || py < 0 || py >= kGridRows) ? -1 : px * kGridRows + py;
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const int c = cell_of(i); if (c >= 0) atomicAdd(&s_cnt[c], 1); }
+    __syncthreads();
+    // exclusive scan of the 3072 counters: 3 per thread
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int v[3], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[k] = s_cnt[threadIdx.x * 3 + k]; sum += v[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        s_warp[lane] = winc - w;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + inc - sum;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { cell_start[threadIdx.x * 3 + k] = run; s_cnt[threadIdx.x * 3 + k] = run; run += v[k]; }
+    if (threadIdx.x == blockDim.x - 1) cell_start[kGridCells] = run;
+    __syncthreads();
+    // stable fill: one thread per cell walks the keypoints in index order would be O(n) per cell; instead every
+    // keypoint finds its rank among EARLIER keypoints of the same cell (n is ~1-2 k, cells hold a handful)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = cell_of(i);
+        if (c < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < i; ++j) rank += cell_of(j) == c;
+        items[s_cnt[c] + rank] = i;
+    }
+}
+
+// one warp per query. Query q: centre (x, y), radius r, level window [minLevel, maxLevel] (GetFeaturesInArea's
+// arguments), descriptor row q of A. Output: best / second distance, index of the first minimum, and the
+// octaves of best and second (SearchByProjection(F, MPs) compares them, src/ORBmatcher.cc:119-122).
+__global__ void __launch_bounds__(256)
+window_knn2_kernel(const uint4* __restrict__ A, int nq, const float* __restrict__ qx, const float* __restrict__ qy,
+                   const float* __restrict__ qr, const int* __restrict__ qmin, const int* __restrict__ qmax,
+                   const orbx_keypoint* __restrict__ kps, const uint4* __restrict__ B, const int* __restrict__ cell_start,
+                   const int* __restrict__ items, float min_x, float min_y, float w_inv, float h_inv,
+                   int* __restrict__ o_idx, int* __restrict__ o_b1, int* __restrict__ o_b2, int* __restrict__ o_l1, int* __restrict__ o_l2) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float x = qx[q], y = qy[q], r = qr[q];
+    const int minLevel = qmin[q], maxLevel = qmax[q];
+    const bool check = minLevel > 0 || maxLevel >= 0;
+    // cell window, exactly as src/Frame.cc:332-346
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, min_x), r), w_inv)));
+    const int cx1 = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, min_x), r), w_inv)));
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, min_y), r), h_inv)));
+    const int cy1 = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, min_y), r), h_inv)));
+    const uint4 a0 = __ldg(A + (size_t)q * 2), a1 = __ldg(A + (size_t)q * 2 + 1);
+    // per lane: best (dist, pos) and second dist with the octave that came with them
+    uint32_t best = 0xffffffffu, second = 0xffffffffu;  // dist << 20 | pos  (pos < 2^20), octave kept aside
+    int best_i = -1, best_l = -1, second_l = -1;
+    int pos_base = 0;
+    if (cx0 < kGridCols && cx1 >= 0 && cy0 < kGridRows && cy1 >= 0)
+        for (int ix = cx0; ix <= cx1; ++ix) {
+            // cells (ix, cy0..cy1) are contiguous in the cell-major item array
+            const int lo = cell_start[ix * kGridRows + cy0], hi = cell_start[ix * kGridRows + cy1 + 1];
+            for (int k = lo + lane; k < hi; k += 32) {
+                const int j = items[k];
+                const orbx_keypoint kp = kps[j];
+                if (check && (kp.octave < minLevel || (maxLevel >= 0 && kp.octave > maxLevel))) continue;
+                if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+                const uint4 b0 = __ldg(B + (size_t)j * 2), b1 = __ldg(B + (size_t)j * 2 + 1);
+                const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                   __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                const uint32_t key = d << 20 | (uint32_t)(pos_base + k - lo);
+                if (key < best) { second = best; second_l = best_l; best = key; best_i = j; best_l = kp.octave; }
+                else if (key < second) { second = key; second_l = kp.octave; }
+            }
+            pos_base += hi - lo;
+        }
+    // merge lanes: the two smallest keys overall (keys are unique: positions differ)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+        const int obi = __shfl_xor_sync(0xffffffffu, best_i, o), obl = __shfl_xor_sync(0xffffffffu, best_l, o);
+        const int osl = __shfl_xor_sync(0xffffffffu, second_l, o);
+        if (ob < best) {
+            // other's best wins; second = min(my best, other's second)
+            if (best < os) { second = best; second_l = best_l; } else { second = os; second_l = osl; }
+            best = ob; best_i = obi; best_l = obl;
+        } else {
+            if (ob < second) { second = ob; second_l = obl; }
+        }
+    }
+    if (lane == 0) {
+        // the reference starts both distances at 256 and only accepts d < best (strict): a candidate at distance
+        // 256 never enters, and ties go to the earlier position - both are what the (dist, pos) minimum yields
+        const int d1 = best == 0xffffffffu ? 256 : (int)(best >> 20), d2 = second == 0xffffffffu ? 256 : (int)(second >> 20);
+        const bool has1 = d1 < 256, has2 = d2 < 256;
+        o_idx[q] = has1 ? best_i : -1; o_b1[q] = has1 ? d1 : 256; o_b2[q] = has2 ? d2 : 256;
+        o_l1[q] = has1 ? best_l : -1; o_l2[q] = has2 ? second_l : -1;
+    }
+}
+
+}  // namespace orb
+
+using namespace orb;
+
+extern "C" {
+
+int orbm_grid_create(int device, int capacity, orbm_grid_handle* out) {
+    ORB_REQUIRE(out && capacity > 0 && capacity < (1 << 20), "bad grid capacity");
+    *out = nullptr;
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    orbm_grid* g = new (std::nothrow) orbm_grid();
+    ORB_REQUIRE(g, "out of host memory");
+    g->device = device; g->cap = capacity;
+    cudaError_t e = cudaMalloc(&g->d_cell_start, (kGridCells + 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_items, (size_t)capacity * sizeof(int));
+    if (e != cudaSuccess) { set_error("grid allocation failed: %s", cudaGetErrorString(e)); orbm_grid_destroy(g); return ORB_ECUDA; }
+    *out = g;
+    return ORB_OK;
+}
+
+void orbm_grid_destroy(orbm_grid_handle g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->d_cell_start) cudaFree(g->d_cell_start);
+    if (g->d_items) cudaFree(g->d_items);
+    delete g;
+}
+
+int orbm_grid_build_device(orbm_grid_handle g, const orbx_keypoint* d_kps, const int32_t* d_count, float min_x, float min_y, float max_x,
+                           float max_y, void* stream) {
+    ORB_REQUIRE(g && d_kps && d_count && max_x > min_x && max_y > min_y, "bad grid arguments");
+    ORB_CUDA_TRY(cudaSetDevice(g->device));
+    g->min_x = min_x; g->min_y = min_y;
+    g->w_inv = (float)kGridCols / (max_x - min_x);  // mfGridElementWidthInv (src/Frame.cc:101-102)
+    g->h_inv = (float)kGridRows / (max_y - min_y);
+    g->d_kps = d_kps; g->d_count = d_count;
+    frame_grid_build_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_kps, d_count, g->cap, g->min_x, g->min_y, g->w_inv, g->h_inv, g->d_cell_start,
+                                                                 g->d_items);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbm_window_knn2_device(orbm_grid_handle g, const uint8_t* d_desc_frame, const uint8_t* d_queries, int nq, const float* d_x,
+                            const float* d_y, const float* d_r, const int32_t* d_min_level, const int32_t* d_max_level, int32_t* d_idx,
+                            int32_t* d_best, int32_t* d_second, int32_t* d_best_level, int32_t* d_second_level, void* stream) {
+    ORB_REQUIRE(g && nq >= 0, "bad arguments");
+    if (nq == 0) return ORB_OK;
+    ORB_REQUIRE(g->d_kps && d_desc_frame && d_queries && d_x && d_y && d_r && d_min_level && d_max_level && d_idx && d_best && d_second &&
+                    d_best_level && d_second_level,
+                "null pointer / grid not built");
+    ORB_CUDA_TRY(cudaSetDevice(g->device));
+    window_knn2_kernel<<<ceil_div(nq * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)d_queries, nq, d_x, d_y, d_r, d_min_level, d_max_level, g->d_kps, (const uint4*)d_desc_frame, g->d_cell_start, g->d_items,
+        g->min_x, g->min_y, g->w_inv, g->h_inv, d_idx, d_best, d_second, d_best_level, d_second_level);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+}  // extern "C"

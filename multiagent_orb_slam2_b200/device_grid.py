@@ -1,0 +1,58 @@
+"""Device-resident Frame grid + windowed search: the keypoints and descriptors an extractor
+left in HBM are bucketed into the reference Frame's 64 x 48 grid on the device (Frame::AssignFeaturesToGrid,
+/root/reference/src/Frame.cc:230-245) and queried without a host round trip (Frame::GetFeaturesInArea 327-380 fused with
+the best / second Hamming loop). torch is plumbing (device arrays for the queries and results)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class DeviceFrameGrid:
+    def __init__(self, extractor, frame=0, min_x=0.0, min_y=0.0, max_x=None, max_y=None):
+        """extractor: an ORBextractor whose last call produced `frame`; bounds default to the image
+        (mnMinX.. of an undistorted / rectified camera, src/Frame.cc:457-462)."""
+        self.L = _lib.lib()
+        self.ex = extractor
+        h, w = extractor._shape
+        kp, de, cn, cap = extractor.device_results()
+        self.cap = cap
+        self.d_kps = kp + frame * cap * 24
+        self.d_desc = de + frame * cap * 32
+        self.d_count = cn + frame * 4
+        self.dev = torch.device("cuda", extractor.device)
+        g = C.c_void_p()
+        _lib.check(self.L.orbm_grid_create(extractor.device, cap, C.byref(g)))
+        self._g = g
+        _lib.check(self.L.orbm_grid_build_device(g, C.c_void_p(self.d_kps), C.c_void_p(self.d_count), float(min_x), float(min_y),
+                                                 float(w if max_x is None else max_x), float(h if max_y is None else max_y), None))
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self.L.orbm_grid_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def window_knn2(self, query_desc, x, y, r, min_level=-1, max_level=-1):
+        """For every query (descriptor, window centre x/y, radius r, level window): best / second Hamming distance
+        among the frame's keypoints inside the window, index of the first minimum in GetFeaturesInArea order, and
+        the octaves of best / second. Arrays in, numpy arrays out."""
+        n = len(query_desc)
+        t = lambda a, dt: torch.as_tensor(np.broadcast_to(np.asarray(a, dt), (n,)).copy()).to(self.dev)
+        q = torch.as_tensor(np.ascontiguousarray(query_desc, np.uint8)).to(self.dev)
+        tx, ty, tr = t(x, np.float32), t(y, np.float32), t(r, np.float32)
+        tmin, tmax = t(min_level, np.int32), t(max_level, np.int32)
+        out = [torch.empty(n, dtype=torch.int32, device=self.dev) for _ in range(5)]
+        p = lambda z: C.c_void_p(z.data_ptr())
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(self.L.orbm_window_knn2_device(self._g, C.c_void_p(self.d_desc), p(q), n, p(tx), p(ty), p(tr), p(tmin), p(tmax),
+                                                  p(out[0]), p(out[1]), p(out[2]), p(out[3]), p(out[4]), st))
+        torch.cuda.synchronize(self.dev)
+        return [o.cpu().numpy() for o in out]

@@ -136,3 +136,39 @@ def test_distinctive_descriptor_matches_oracle():
         base = synth.descriptors(1, 50 + n)
         obs = synth.descriptors(n, 60 + n, dup_from=base, max_flips=40)
         assert m.ComputeDistinctiveDescriptor(obs) == O.distinctive_descriptor(obs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,radius", [(0, 15.0), (1, 40.0), (2, 3.0)])
+def test_device_grid_window_search_matches_oracle(seed, radius):
+    """GetFeaturesInArea + best/second loop entirely on the device vs the oracle grid walk (same candidate order,
+    so the first-minimum index and the octaves of best / second agree even with distance ties)."""
+    from multiagent_orb_slam2_b200.device_grid import DeviceFrameGrid
+    w, h = 640, 480
+    a, b, (dx, dy) = synth.shifted_pair("blocks", w, h, seed)
+    ex_a, ex_b = ORBextractor(1000, 1.2, 8, 20, 7), ORBextractor(1000, 1.2, 8, 20, 7)
+    ka, da = ex_a(a)
+    kb, db = ex_b(b)
+    grid = DeviceFrameGrid(ex_b)
+    # queries: keypoints of frame a projected by the known shift; level window like SearchByProjection (pred-1 .. pred)
+    qx, qy = ka["x"] - np.float32(dx), ka["y"] - np.float32(dy)
+    lo = np.maximum(ka["octave"] - 1, 0).astype(np.int32) * (seed != 2) + (-1) * (seed == 2)
+    hi = ka["octave"].astype(np.int32) * (seed != 2) + (-1) * (seed == 2)
+    r = (np.float32(radius) * ex_a.GetScaleFactors()[ka["octave"]]).astype(np.float32)
+    gi, g1, g2, gl1, gl2 = grid.window_knn2(da, qx, qy, r, lo, hi)
+    okb = np.stack([kb["x"], kb["y"], kb["size"], kb["angle"], kb["response"], kb["octave"].astype(np.float32)], 1)
+    F = O.OracleFrame(okb, db, w, h)
+    hits = 0
+    for i in range(len(ka)):
+        cand = F.features_in_area(qx[i], qy[i], r[i], int(lo[i]), int(hi[i]))
+        b1 = b2 = 256
+        bi = l1 = l2 = -1
+        for j in cand:
+            d = O.hamming(da[i], db[j])
+            if d < b1:
+                b2, l2, b1, l1, bi = b1, l1, d, int(kb["octave"][j]), j
+            elif d < b2:
+                b2, l2 = d, int(kb["octave"][j])
+        assert (gi[i], g1[i], g2[i], gl1[i], gl2[i]) == (bi, b1, b2, l1, l2), i
+        hits += bi >= 0
+    assert hits > len(ka) // 3
