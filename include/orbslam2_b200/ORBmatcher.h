@@ -119,6 +119,96 @@ public:
         return nmatches;
     }
 
+    // Search matches between MapPoints in two keyframes, constrained to features of the same vocabulary node
+    // (src/ORBmatcher.cc:524-657) - the matcher of MapFusion::ComputeSim3 / CovisibilityDiscovery
+    // (src/MapFusion.cc:275, 849) and of LoopClosing (src/LoopClosing.cc:288). KeyFrameT needs mvKeysUn, mFeatVec
+    // (DBoW2::FeatureVector or any ordered map node -> vector<unsigned>), GetMapPointMatches() and mDescriptors;
+    // MapPointT needs isBad(). Same split: host merge-walk of the two feature vectors, one device launch for all
+    // distances inside equal nodes, the reference's ordered resolve with its vbMatched2 state on the host.
+    template <class KeyFrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12) {
+        const auto& vKeysUn1 = pKF1->mvKeysUn;
+        const auto& vFeatVec1 = pKF1->mFeatVec;
+        const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches();
+        const cv::Mat& Descriptors1 = pKF1->mDescriptors;
+        const auto& vKeysUn2 = pKF2->mvKeysUn;
+        const auto& vFeatVec2 = pKF2->mFeatVec;
+        const std::vector<MapPointT*> vpMapPoints2 = pKF2->GetMapPointMatches();
+        const cv::Mat& Descriptors2 = pKF2->mDescriptors;
+
+        vpMatches12 = std::vector<MapPointT*>(vpMapPoints1.size(), static_cast<MapPointT*>(NULL));
+        std::vector<bool> vbMatched2(vpMapPoints2.size(), false);
+        std::vector<int> rotHist[HISTO_LENGTH];
+        for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+        const float factor = 1.0f / HISTO_LENGTH;
+        int nmatches = 0;
+
+        // 1. host: merge walk (552-634) -> CSR of (idx1 occurrence) x (features of the same node in KF2)
+        std::vector<int32_t> qrow, offsets(1, 0), cands;
+        auto f1it = vFeatVec1.begin(), f1end = vFeatVec1.end();
+        auto f2it = vFeatVec2.begin(), f2end = vFeatVec2.end();
+        while (f1it != f1end && f2it != f2end) {
+            if (f1it->first == f2it->first) {
+                for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+                    qrow.push_back((int32_t)f1it->second[i1]);
+                    for (size_t i2 = 0; i2 < f2it->second.size(); i2++) cands.push_back((int32_t)f2it->second[i2]);
+                    offsets.push_back((int32_t)cands.size());
+                }
+                f1it++; f2it++;
+            } else if (f1it->first < f2it->first) f1it = vFeatVec1.lower_bound(f2it->first);
+            else f2it = vFeatVec2.lower_bound(f1it->first);
+        }
+        // 2. device: all distances
+        std::vector<int16_t> dist(cands.size());
+        if (!cands.empty()) {
+            std::vector<uint8_t> A(qrow.size() * 32);
+            for (size_t q = 0; q < qrow.size(); ++q) std::memcpy(&A[q * 32], Descriptors1.ptr(qrow[q]), 32);
+            const std::vector<uint8_t> B = pack(Descriptors2);
+            const int rc = orbm_list_distances(device_, A.data(), (int)qrow.size(), B.data(), Descriptors2.rows, offsets.data(), cands.data(), dist.data());
+            if (rc != ORB_OK) throw std::runtime_error(std::string("orb_b200: ") + orb_last_error());
+        }
+        // 3. host: ordered resolve (556-620)
+        for (size_t q = 0; q < qrow.size(); ++q) {
+            const size_t idx1 = (size_t)qrow[q];
+            MapPointT* pMP1 = vpMapPoints1[idx1];
+            if (!pMP1) continue;
+            if (pMP1->isBad()) continue;
+            int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+            for (int k = offsets[q]; k < offsets[q + 1]; ++k) {
+                const size_t idx2 = (size_t)cands[k];
+                MapPointT* pMP2 = vpMapPoints2[idx2];
+                if (vbMatched2[idx2] || !pMP2) continue;
+                if (pMP2->isBad()) continue;
+                const int d = dist[k];
+                if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdx2 = (int)idx2; }
+                else if (d < bestDist2) bestDist2 = d;
+            }
+            if (bestDist1 < TH_LOW) {
+                if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+                    vpMatches12[idx1] = vpMapPoints2[bestIdx2];
+                    vbMatched2[bestIdx2] = true;
+                    if (mbCheckOrientation) {
+                        float rot = vKeysUn1[idx1].angle - vKeysUn2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back((int)idx1);
+                    }
+                    nmatches++;
+                }
+            }
+        }
+        if (mbCheckOrientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) { vpMatches12[rotHist[i][j]] = static_cast<MapPointT*>(NULL); nmatches--; }
+            }
+        }
+        return nmatches;
+    }
+
     // Brute-force ratio-test matching of two descriptor matrices (the SearchByBoW(KF,KF) inner loop,
     // src/ORBmatcher.cc:566-603, with the vocabulary gate removed): vnMatches12[i] = row of D2 or -1.
     int SearchBruteForce(const cv::Mat& D1, const cv::Mat& D2, std::vector<int>& vnMatches12, int th = TH_LOW) {

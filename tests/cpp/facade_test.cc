@@ -4,6 +4,7 @@
 //   facade_test <w> <h> <imgA.raw> <imgB.raw> <out.bin> [nfeatures]
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <vector>
 
 #include "orbslam2_b200/FrameGrid.h"
@@ -17,6 +18,15 @@ struct FrameLite {  // the members ORBmatcher::SearchForInitialization touches o
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, int minLevel, int maxLevel) const {
         return grid.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
     }
+};
+
+struct MapPointLite { bool bad; bool isBad() const { return bad; } };
+struct KeyFrameLite {  // the members ORBmatcher::SearchByBoW(KF,KF) touches on the reference's KeyFrame
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::map<unsigned, std::vector<unsigned> > mFeatVec;  // DBoW2::FeatureVector is such a map
+    std::vector<MapPointLite*> mps;
+    cv::Mat mDescriptors;
+    std::vector<MapPointLite*> GetMapPointMatches() { return mps; }
 };
 
 static std::vector<unsigned char> read_all(const char* path, size_t n) {
@@ -69,7 +79,29 @@ int main(int argc, char** argv) {
     const int nb = matcher.SearchBruteForce(F[0].mDescriptors, F[1].mDescriptors, bf);
     fwrite(&nb, 4, 1, out);
     fwrite(bf.data(), 4, bf.size(), out);
+    // SearchByBoW(KF,KF): feature vectors = a fixed hash of the keypoint position (nodes 0..39); map points on
+    // 7 of 8 keypoints, every 13th one bad
+    KeyFrameLite K[2];
+    std::vector<MapPointLite> pool[2];
+    for (int k = 0; k < 2; ++k) {
+        K[k].mvKeysUn = F[k].mvKeysUn; K[k].mDescriptors = F[k].mDescriptors;
+        const int n = (int)K[k].mvKeysUn.size();
+        pool[k].resize(n);
+        K[k].mps.assign(n, (MapPointLite*)NULL);
+        for (int i = 0; i < n; ++i) {
+            const cv::KeyPoint& kp = K[k].mvKeysUn[i];
+            K[k].mFeatVec[(unsigned)(((int)(kp.pt.x / 80) + 8 * (int)(kp.pt.y / 96)) % 40)].push_back((unsigned)i);
+            pool[k][i].bad = i % 13 == 5;
+            if (i % 8 != 3) K[k].mps[i] = &pool[k][i];
+        }
+    }
+    std::vector<MapPointLite*> m12bow;
+    ORB_SLAM2::ORBmatcher bowMatcher(0.75f, true);
+    const int nbow = bowMatcher.SearchByBoW<KeyFrameLite, MapPointLite>(&K[0], &K[1], m12bow);
+    fwrite(&nbow, 4, 1, out);
+    for (size_t i = 0; i < m12bow.size(); ++i) { const int v = m12bow[i] ? (int)(m12bow[i] - &pool[1][0]) : -1; fwrite(&v, 4, 1, out); }
     fclose(out);
+    printf("bow matches %d; ", nbow);
     printf("facade ok: %d + %d keypoints, %d init matches, %d brute-force matches\n", (int)F[0].mvKeysUn.size(), (int)F[1].mvKeysUn.size(), nm, nb);
     return 0;
 }

@@ -72,6 +72,21 @@ def test_cpp_facade_matches_oracle(tmp_path):
     oi, o1, o2 = O.knn2(da, db)
     ref = np.where((o1 < 50) & (o1.astype(np.float32) < np.float32(0.9) * o2.astype(np.float32)), oi, -1)
     assert np.array_equal(bf, ref) and nb == int((ref >= 0).sum())
+    # SearchByBoW(KF,KF) of the C++ facade vs the oracle, with the driver's synthetic feature vectors / map points
+    nbow = int(take(np.int32, 1)[0])
+    m12bow = take(np.int32, n1)
+
+    def kf(kps):
+        fv = {}
+        for i in range(len(kps)):
+            fv.setdefault((int(kps[i, 0] / np.float32(80)) + 8 * int(kps[i, 1] / np.float32(96))) % 40, []).append(i)
+        idx = np.arange(len(kps))
+        return sorted(fv.items()), (idx % 8 != 3) & ~(idx % 13 == 5)
+
+    fv1, v1 = kf(ka)
+    fv2, v2 = kf(kb)
+    onm, om = O.search_by_bow_kf_kf(da, fv1, v1, ka[:, 3], db, fv2, v2, kb[:, 3], 0.75)
+    assert nbow == onm and np.array_equal(m12bow, om) and onm > 20
 
 
 @pytest.mark.gpu
