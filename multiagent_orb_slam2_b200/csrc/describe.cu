@@ -48,7 +48,7 @@ struct SlotInfo { int valid, level, x, y, response, dst; };
 //   B. warp 0: lane i evaluates sin/cos (double, rounded once) for slot i - 32 keypoints per
 //      instruction stream instead of one
 //   C. every warp: rotated BRIEF of 4 slots (lane = output byte), keypoint record
-__global__ void __launch_bounds__(kDescWarps * 32)
+__global__ void __launch_bounds__(kDescWarps * 32, 5)
 orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_t* __restrict__ pyr,
                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ selected,
                        const int* __restrict__ sel_counts, const int8_t* __restrict__ pattern,
