@@ -189,7 +189,9 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the contract is ONE JSON line
+        # keep NCCL's version banner / logging off stdout: the contract is ONE JSON line
+        os.environ.pop("NCCL_DEBUG", None)
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     L = _lib.lib()

@@ -17,7 +17,7 @@ from multiagent_orb_slam2_b200 import mapfusion, synth  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.pop("NCCL_DEBUG", None)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rows = 20000
 base = synth.descriptors(rows, 99)
