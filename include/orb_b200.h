@@ -211,6 +211,14 @@ int orbm_window_knn2_device(orbm_grid_handle g, const uint8_t* d_desc_frame, con
                             int32_t* d_idx, int32_t* d_best, int32_t* d_second, int32_t* d_best_level, int32_t* d_second_level,
                             void* stream);
 
+/* The same windows as candidate lists for the stateful searches: d_offsets[nq+1], and for query q the candidates
+ * d_cands[d_offsets[q] .. d_offsets[q+1]) in GetFeaturesInArea order with their Hamming distances d_dist[]. Two passes
+ * (count, scan, fill); synchronises the stream once to return the total (*total_out); ORB_ECAPACITY if total > cap
+ * (call again with larger buffers). The caller then replays the reference's loop (e.g. src/ORBmatcher.cc:434-488). */
+int orbm_window_lists_device(orbm_grid_handle g, const uint8_t* d_desc_frame, const uint8_t* d_queries, int nq, const float* d_x,
+                             const float* d_y, const float* d_r, const int32_t* d_min_level, const int32_t* d_max_level,
+                             int32_t* d_offsets, int32_t* d_cands, int16_t* d_dist, int cap, int32_t* total_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Vocabulary tree descent (the step right after extraction): replaces the per-feature
  * TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) with FORB::distance

@@ -143,6 +143,86 @@ window_knn2_kernel(const uint4* __restrict__ A, int nq, const float* __restrict_
     }
 }
 
+// Candidate lists of the same windows for the STATEFUL searches: pass 1 counts the in-window candidates of every
+// query, pass 2 (after an exclusive scan of the counts) writes their indices in GetFeaturesInArea order together
+// with the Hamming distances. The caller replays the reference's loop over (offsets, cands, dist).
+template <bool kFill>
+__global__ void __launch_bounds__(256)
+window_lists_kernel(const uint4* __restrict__ A, int nq, const float* __restrict__ qx, const float* __restrict__ qy,
+                    const float* __restrict__ qr, const int* __restrict__ qmin, const int* __restrict__ qmax,
+                    const orbx_keypoint* __restrict__ kps, const uint4* __restrict__ B, const int* __restrict__ cell_start,
+                    const int* __restrict__ items, float min_x, float min_y, float w_inv, float h_inv, int* __restrict__ counts,
+                    const int* __restrict__ offsets, int* __restrict__ cands, int16_t* __restrict__ dist) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float x = qx[q], y = qy[q], r = qr[q];
+    const int minLevel = qmin[q], maxLevel = qmax[q];
+    const bool check = minLevel > 0 || maxLevel >= 0;
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, min_x), r), w_inv)));
+    const int cx1 = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, min_x), r), w_inv)));
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, min_y), r), h_inv)));
+    const int cy1 = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, min_y), r), h_inv)));
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (kFill) { a0 = __ldg(A + (size_t)q * 2); a1 = __ldg(A + (size_t)q * 2 + 1); }
+    int written = kFill ? offsets[q] : 0;
+    if (cx0 < kGridCols && cx1 >= 0 && cy0 < kGridRows && cy1 >= 0)
+        for (int ix = cx0; ix <= cx1; ++ix) {
+            const int lo = cell_start[ix * kGridRows + cy0], hi = cell_start[ix * kGridRows + cy1 + 1];
+            for (int k0 = lo; k0 < hi; k0 += 32) {  // warp-uniform trip count: ballots keep the order
+                const int k = k0 + lane;
+                bool in = false;
+                int j = 0;
+                if (k < hi) {
+                    j = items[k];
+                    const orbx_keypoint kp = kps[j];
+                    in = !(check && (kp.octave < minLevel || (maxLevel >= 0 && kp.octave > maxLevel))) &&
+                         fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+                }
+                const uint32_t ball = __ballot_sync(0xffffffffu, in);
+                if (kFill && in) {
+                    const int at = written + __popc(ball & ((1u << lane) - 1));
+                    const uint4 b0 = __ldg(B + (size_t)j * 2), b1 = __ldg(B + (size_t)j * 2 + 1);
+                    cands[at] = j;
+                    dist[at] = (int16_t)(__popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w));
+                }
+                written += __popc(ball);
+            }
+        }
+    if (!kFill && lane == 0) counts[q] = written;
+}
+
+// single block exclusive scan of counts[0..n) -> offsets[0..n]
+__global__ void __launch_bounds__(1024) window_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? counts[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < n) offsets[i] = carry + s_warp[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = s_carry;
+}
+
 }  // namespace orb
 
 using namespace orb;
@@ -198,6 +278,40 @@ int orbm_window_knn2_device(orbm_grid_handle g, const uint8_t* d_desc_frame, con
     window_knn2_kernel<<<ceil_div(nq * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)d_queries, nq, d_x, d_y, d_r, d_min_level, d_max_level, g->d_kps, (const uint4*)d_desc_frame, g->d_cell_start, g->d_items,
         g->min_x, g->min_y, g->w_inv, g->h_inv, d_idx, d_best, d_second, d_best_level, d_second_level);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbm_window_lists_device(orbm_grid_handle g, const uint8_t* d_desc_frame, const uint8_t* d_queries, int nq, const float* d_x,
+                             const float* d_y, const float* d_r, const int32_t* d_min_level, const int32_t* d_max_level,
+                             int32_t* d_offsets, int32_t* d_cands, int16_t* d_dist, int cap, int32_t* total_out, void* stream) {
+    ORB_REQUIRE(g && nq >= 0 && total_out, "bad arguments");
+    *total_out = 0;
+    if (nq == 0) return ORB_OK;
+    ORB_REQUIRE(g->d_kps && d_desc_frame && d_queries && d_x && d_y && d_r && d_min_level && d_max_level && d_offsets, "null pointer / grid not built");
+    ORB_CUDA_TRY(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_counts = nullptr;
+    ORB_CUDA_TRY(cudaMallocAsync(&d_counts, (size_t)nq * sizeof(int), st));
+    const int blocks = ceil_div(nq * 32, 256);
+    window_lists_kernel<false><<<blocks, 256, 0, st>>>((const uint4*)d_queries, nq, d_x, d_y, d_r, d_min_level, d_max_level, g->d_kps,
+                                                       (const uint4*)d_desc_frame, g->d_cell_start, g->d_items, g->min_x, g->min_y, g->w_inv,
+                                                       g->h_inv, d_counts, nullptr, nullptr, nullptr);
+    window_scan_kernel<<<1, 1024, 0, st>>>(d_counts, nq, d_offsets);
+    count_launch(2);
+    ORB_CUDA_TRY(cudaGetLastError());
+    int total = 0;
+    ORB_CUDA_TRY(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(st));  // the caller needs the total to size / check its buffers
+    ORB_CUDA_TRY(cudaFreeAsync(d_counts, st));
+    *total_out = total;
+    if (total > cap) { set_error("window lists hold %d candidates, buffer has room for %d", total, cap); return ORB_ECAPACITY; }
+    if (total == 0) return ORB_OK;
+    ORB_REQUIRE(d_cands && d_dist, "null output");
+    window_lists_kernel<true><<<blocks, 256, 0, st>>>((const uint4*)d_queries, nq, d_x, d_y, d_r, d_min_level, d_max_level, g->d_kps,
+                                                      (const uint4*)d_desc_frame, g->d_cell_start, g->d_items, g->min_x, g->min_y, g->w_inv,
+                                                      g->h_inv, nullptr, d_offsets, d_cands, d_dist);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

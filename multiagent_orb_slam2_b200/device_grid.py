@@ -56,3 +56,29 @@ class DeviceFrameGrid:
                                                   p(out[0]), p(out[1]), p(out[2]), p(out[3]), p(out[4]), st))
         torch.cuda.synchronize(self.dev)
         return [o.cpu().numpy() for o in out]
+
+    def window_lists(self, query_desc, x, y, r, min_level=-1, max_level=-1, cap=None):
+        """CSR candidate lists (offsets, cands, dist) of the windows, candidates in GetFeaturesInArea order with
+        their Hamming distances - input of the host-side replay of the stateful searches."""
+        n = len(query_desc)
+        t = lambda a, dt: torch.as_tensor(np.broadcast_to(np.asarray(a, dt), (n,)).copy()).to(self.dev)
+        q = torch.as_tensor(np.ascontiguousarray(query_desc, np.uint8)).to(self.dev)
+        tx, ty, tr = t(x, np.float32), t(y, np.float32), t(r, np.float32)
+        tmin, tmax = t(min_level, np.int32), t(max_level, np.int32)
+        cap = cap or 64 * n
+        p = lambda z: C.c_void_p(z.data_ptr())
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        while True:
+            offs = torch.empty(n + 1, dtype=torch.int32, device=self.dev)
+            cands = torch.empty(cap, dtype=torch.int32, device=self.dev)
+            dist = torch.empty(cap, dtype=torch.int16, device=self.dev)
+            total = C.c_int()
+            rc = self.L.orbm_window_lists_device(self._g, C.c_void_p(self.d_desc), p(q), n, p(tx), p(ty), p(tr), p(tmin), p(tmax),
+                                                 p(offs), p(cands), p(dist), cap, C.byref(total), st)
+            if rc == _lib.ORB_ECAPACITY:
+                cap = total.value
+                continue
+            _lib.check(rc)
+            break
+        torch.cuda.synchronize(self.dev)
+        return offs.cpu().numpy(), cands[:total.value].cpu().numpy(), dist[:total.value].cpu().numpy()

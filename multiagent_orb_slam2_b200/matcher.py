@@ -141,24 +141,28 @@ class FrameGrid:
         return out
 
 
-def _search_for_initialization(self, F1, F2, vbPrevMatched, windowSize=10):
+def _search_for_initialization(self, F1, F2, vbPrevMatched, windowSize=10, device_grid=None):
     """ORBmatcher::SearchForInitialization (/root/reference/src/ORBmatcher.cc:407-522) on two FrameGrid
-    objects. Host: candidate gating in the reference's order; device: all Hamming distances of the
-    gated pairs (orbm_list_distances); host: the reference's ordered, stateful resolve replayed over
-    the precomputed distances. vbPrevMatched: (n1, 2) float32, updated in place.
-    Returns (nmatches, vnMatches12)."""
+    objects. Candidate gating in the reference's order - on the host (F2.GetFeaturesInArea) or, with
+    device_grid (a DeviceFrameGrid of frame 2), on the device (orbm_window_lists_device); device: all Hamming
+    distances of the gated pairs; host: the reference's ordered, stateful resolve replayed over the precomputed
+    distances. vbPrevMatched: (n1, 2) float32, updated in place. Returns (nmatches, vnMatches12)."""
     INT_MAX = 2**31 - 1
     n1, n2 = len(F1.kps), len(F2.kps)
-    offsets = np.zeros(n1 + 1, np.int32)
-    cands = []
-    for i1 in range(n1):
-        if F1.octave[i1] <= 0:
-            cands += F2.GetFeaturesInArea(vbPrevMatched[i1, 0], vbPrevMatched[i1, 1], windowSize, 0, 0)
-        offsets[i1 + 1] = len(cands)
-    cands = np.asarray(cands, np.int32)
-    dist = np.empty(len(cands), np.int16)
-    if len(cands):
-        _lib.check(self._L.orbm_list_distances(self.device, _p(F1.desc), n1, _p(F2.desc), n2, _p(offsets), _p(cands), _p(dist)))
+    if device_grid is not None:
+        r = np.where(F1.octave <= 0, np.float32(windowSize), np.float32(0)).astype(np.float32)  # level1 > 0: no window
+        offsets, cands, dist = device_grid.window_lists(F1.desc, vbPrevMatched[:, 0], vbPrevMatched[:, 1], r, 0, 0)
+    else:
+        offsets = np.zeros(n1 + 1, np.int32)
+        cands = []
+        for i1 in range(n1):
+            if F1.octave[i1] <= 0:
+                cands += F2.GetFeaturesInArea(vbPrevMatched[i1, 0], vbPrevMatched[i1, 1], windowSize, 0, 0)
+            offsets[i1 + 1] = len(cands)
+        cands = np.asarray(cands, np.int32)
+        dist = np.empty(len(cands), np.int16)
+        if len(cands):
+            _lib.check(self._L.orbm_list_distances(self.device, _p(F1.desc), n1, _p(F2.desc), n2, _p(offsets), _p(cands), _p(dist)))
     m12 = np.full(n1, -1, np.int32)
     m21 = np.full(n2, -1, np.int32)
     mdist = np.full(n2, INT_MAX, np.int64)

@@ -95,15 +95,20 @@ def test_python_search_for_initialization_matches_oracle(seed, window):
     w, h, nf = 640, 480, 500
     a, b, _ = synth.shifted_pair("blocks", w, h, seed)
     _, ka, da, kb, db, nm, m12, prev_ref = oracle_init_search(a, b, nf, window)
-    ex = ORBextractor(2 * nf, 1.2, 8, 20, 7)
+    ex, ex_b = ORBextractor(2 * nf, 1.2, 8, 20, 7), ORBextractor(2 * nf, 1.2, 8, 20, 7)
     ga, gda = ex(a)
-    gb, gdb = ex(b)
+    gb, gdb = ex_b(b)
     F1, F2 = FrameGrid(ga, gda, w, h), FrameGrid(gb, gdb, w, h)
     prev = np.stack([ga["x"], ga["y"]], 1).astype(np.float32)
     gnm, gm12 = ORBmatcher(0.9, True).SearchForInitialization(F1, F2, prev, window)
     assert gnm == nm and np.array_equal(gm12, m12)
     assert np.array_equal(prev.view(np.uint32), prev_ref.view(np.uint32))
     assert nm > 30
+    # same search with the candidate gate on the device (Frame grid + window lists in HBM)
+    from multiagent_orb_slam2_b200.device_grid import DeviceFrameGrid
+    prev2 = np.stack([ga["x"], ga["y"]], 1).astype(np.float32)
+    dnm, dm12 = ORBmatcher(0.9, True).SearchForInitialization(F1, F2, prev2, window, device_grid=DeviceFrameGrid(ex_b))
+    assert dnm == nm and np.array_equal(dm12, m12) and np.array_equal(prev2.view(np.uint32), prev_ref.view(np.uint32))
 
 
 def _feature_vectors(rng, n1, n2, twin_of_2, nodes=60):
