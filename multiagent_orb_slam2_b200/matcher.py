@@ -302,3 +302,51 @@ def _distinctive_descriptor(self, descs):
 
 ORBmatcher.SearchByBoW_KF_KF = _search_by_bow_kf_kf
 ORBmatcher.ComputeDistinctiveDescriptor = _distinctive_descriptor
+
+
+def _search_by_projection_frame_mappoints(self, grid, kp_octave, uright, occupied, scale_factors, mp, th):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (/root/reference/src/ORBmatcher.cc:45-131)
+    on arrays, with the candidate gate and all Hamming distances on the device (DeviceFrameGrid.window_lists) and the
+    reference's ordered, stateful loop replayed on the host. mp: per-map-point arrays in_view (mbTrackInView), bad,
+    level (mnTrackScaleLevel), view_cos, proj_x, proj_y, proj_xr, desc. occupied[kp]: the keypoint already holds a map
+    point with observations (90-92). Returns (nmatches, assigned[kp] = map point index or -1)."""
+    f32 = np.float32
+    n_mp = len(mp["level"])
+    live = np.asarray(mp["in_view"], bool) & ~np.asarray(mp["bad"], bool)
+    lvl = np.asarray(mp["level"], np.int32)
+    r = np.where(np.asarray(mp["view_cos"], f32) > f32(0.998), f32(2.5), f32(4.0)).astype(f32)  # RadiusByViewingCos (133-139)
+    if th != 1.0:
+        r = (r * f32(th)).astype(f32)
+    rad = (r * np.asarray(scale_factors, f32)[lvl]).astype(f32)
+    rad_q = np.where(live, rad, f32(0)).astype(f32)  # dead map points: empty window
+    offsets, cands, dist = grid.window_lists(mp["desc"], mp["proj_x"], mp["proj_y"], rad_q, lvl - 1, lvl)
+    occupied = np.asarray(occupied, bool).copy()
+    assigned = np.full(len(kp_octave), -1, np.int32)
+    ratio = f32(self.mfNNratio)
+    nm = 0
+    for i in range(n_mp):
+        if not live[i] or offsets[i] == offsets[i + 1]:
+            continue
+        b1 = b2 = 256
+        l1 = l2 = bi = -1
+        for k in range(offsets[i], offsets[i + 1]):
+            idx = int(cands[k])
+            if occupied[idx]:
+                continue
+            if uright[idx] > 0 and abs(f32(mp["proj_xr"][i]) - f32(uright[idx])) > rad[i]:
+                continue
+            d = int(dist[k])
+            if d < b1:
+                b2, b1, l2, l1, bi = b1, d, l1, int(kp_octave[idx]), idx
+            elif d < b2:
+                l2, b2 = int(kp_octave[idx]), d
+        if b1 <= self.TH_HIGH:
+            if l1 == l2 and f32(b1) > ratio * f32(b2):
+                continue
+            assigned[bi] = i
+            occupied[bi] = True
+            nm += 1
+    return nm, assigned
+
+
+ORBmatcher.SearchByProjection_Frame_MapPoints = _search_by_projection_frame_mappoints

@@ -494,3 +494,49 @@ class RefVocabulary(OracleVocabulary):
 
 def dbow_ref_available():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_dbow.so"))
+
+
+def search_by_projection_frame_mappoints(F, mp, th, nnratio=0.8, th_high=100):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45-131, on arrays.
+    F: OracleFrame plus F.scale (mvScaleFactors), F.uright (mvuRight), F.occupied (bool per keypoint: holds a map point
+    with observations > 0). mp: dict of per-map-point arrays: in_view, bad, level (mnTrackScaleLevel), view_cos,
+    proj_x, proj_y, proj_xr, desc. Returns (nmatches, assigned) with assigned[kp] = map point index or -1; keypoints
+    assigned here count as occupied for the following map points (they get a map point with observations)."""
+    n_kp = len(F.kps)
+    assigned = np.full(n_kp, -1, np.int32)
+    occupied = F.occupied.copy()
+    nm = 0
+    bfactor = th != 1.0
+    ratio = np.float32(nnratio)
+    for i in range(len(mp["level"])):
+        if not mp["in_view"][i] or mp["bad"][i]:
+            continue
+        lvl = int(mp["level"][i])
+        r = np.float32(2.5) if mp["view_cos"][i] > 0.998 else np.float32(4.0)
+        if bfactor:
+            r = np.float32(r * np.float32(th))
+        rad = np.float32(r * F.scale[lvl])
+        cand = F.features_in_area(mp["proj_x"][i], mp["proj_y"][i], rad, lvl - 1, lvl)
+        if not cand:
+            continue
+        b1 = b2 = 256
+        l1 = l2 = bi = -1
+        for idx in cand:
+            if occupied[idx]:
+                continue
+            if F.uright[idx] > 0:
+                er = abs(np.float32(mp["proj_xr"][i]) - np.float32(F.uright[idx]))
+                if er > rad:
+                    continue
+            d = hamming(mp["desc"][i], F.desc[idx])
+            if d < b1:
+                b2, b1, l2, l1, bi = b1, d, l1, int(F.kps[idx, 5]), idx
+            elif d < b2:
+                l2, b2 = int(F.kps[idx, 5]), d
+        if b1 <= th_high:
+            if l1 == l2 and np.float32(b1) > ratio * np.float32(b2):
+                continue
+            assigned[bi] = i
+            occupied[bi] = True
+            nm += 1
+    return nm, assigned

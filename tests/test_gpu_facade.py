@@ -192,3 +192,33 @@ def test_device_grid_window_search_matches_oracle(seed, radius):
         assert (gi[i], g1[i], g2[i], gl1[i], gl2[i]) == (bi, b1, b2, l1, l2), i
         hits += bi >= 0
     assert hits > len(ka) // 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,th", [(0, 1.0), (1, 3.0), (2, 5.0)])
+def test_search_by_projection_frame_mappoints_matches_oracle(seed, th):
+    """SearchByProjection(Frame, MapPoints, th) (src/ORBmatcher.cc:45-131): local map points = the keypoints of a shifted
+    view, projected into the frame by the known shift with a little noise; device window lists + host replay vs oracle."""
+    from multiagent_orb_slam2_b200.device_grid import DeviceFrameGrid
+    w, h = 640, 480
+    a, b, (dx, dy) = synth.shifted_pair("blocks", w, h, seed + 20)
+    ex_a, ex_b = ORBextractor(1000, 1.2, 8, 20, 7), ORBextractor(1000, 1.2, 8, 20, 7)
+    ka, da = ex_a(a)
+    kb, db = ex_b(b)
+    rng = np.random.default_rng(seed)
+    n = len(ka)
+    mp = dict(in_view=rng.random(n) < 0.9, bad=rng.random(n) < 0.05, level=ka["octave"].astype(np.int32),
+              view_cos=rng.uniform(0.99, 1.0, n).astype(np.float32),
+              proj_x=(ka["x"] - np.float32(dx) + rng.normal(0, 1.0, n)).astype(np.float32),
+              proj_y=(ka["y"] - np.float32(dy) + rng.normal(0, 1.0, n)).astype(np.float32), desc=da)
+    mp["proj_xr"] = (mp["proj_x"] - rng.uniform(2, 40, n)).astype(np.float32)
+    uright = np.where(rng.random(len(kb)) < 0.5, kb["x"] - rng.uniform(2, 40, len(kb)), -1).astype(np.float32)
+    occupied = rng.random(len(kb)) < 0.1
+    scale = ex_b.GetScaleFactors()
+    okb = np.stack([kb["x"], kb["y"], kb["size"], kb["angle"], kb["response"], kb["octave"].astype(np.float32)], 1)
+    F = O.OracleFrame(okb, db, w, h)
+    F.scale, F.uright, F.occupied = scale, uright, occupied
+    onm, oas = O.search_by_projection_frame_mappoints(F, mp, th, 0.8)
+    gnm, gas = ORBmatcher(0.8).SearchByProjection_Frame_MapPoints(DeviceFrameGrid(ex_b), kb["octave"], uright, occupied, scale, mp, th)
+    assert gnm == onm and np.array_equal(gas, oas)
+    assert onm > 100
