@@ -82,3 +82,13 @@ def test_matcher_empty_and_degenerate_sets():
     comp = (~A[:1]).copy()  # complement: distance 256 is not < 256 => no candidate, as in the reference
     idx, d1, d2 = m.knn2(A[:1], comp)
     assert idx[0] == -1 and d1[0] == 256
+
+
+@pytest.mark.parametrize("w,h,nf", [(1920, 1080, 3000), (480, 640, 800), (3000, 700, 2500)])
+def test_other_image_geometries(w, h, nf):
+    """Full HD, portrait (aspect < 1: a single quadtree root) and a wide panorama (4 roots)."""
+    img = synth.image("blocks", w, h, 77)
+    gk, gd = ORBextractor(nf, 1.2, 8, 20, 7)(img)
+    ok, od = O.OracleExtractor(nf, 1.2, 8, 20, 7)(img)
+    got = np.stack([gk["x"], gk["y"], gk["size"], gk["angle"], gk["response"], gk["octave"].astype(np.float32)], 1)
+    assert len(gk) == len(ok) and np.array_equal(got.view(np.uint32), ok.view(np.uint32)) and np.array_equal(gd, od)
