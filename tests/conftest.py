@@ -20,4 +20,8 @@ def _built_oracle():
     so = os.path.join(ROOT, "oracle", "liborb_oracle.so")
     if not os.path.exists(so):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liborb_oracle.so"])
+    # the product library (nvcc cross-compiles without a GPU); normally built by __graft_entry__.build()
+    from multiagent_orb_slam2_b200 import build as b
+    if not os.path.exists(b.LIB):
+        b.build()
     return so
