@@ -24,4 +24,38 @@ dbow="$ref/Thirdparty/DBoW2"
 g++ -std=c++14 -O3 -march=x86-64-v3 -ffp-contract=off -fPIC -shared -w -I"$here/shim" -I"$dbow" \
     "$dbow/DBoW2/FORB.cpp" "$dbow/DBoW2/BowVector.cpp" "$dbow/DBoW2/FeatureVector.cpp" "$dbow/DBoW2/ScoringObject.cpp" \
     "$dbow/DUtils/Random.cpp" "$dbow/DUtils/Timestamp.cpp" "$here/ref_dbow_wrap.cc" -o "$here/_ref/libref_dbow.so"
-echo "build_ref: built $(ls "$here/_ref")"
+#   libref_matcher_bits.so   the two self-contained members of src/ORBmatcher.cc - ComputeThreeMaxima (1603-1644) and
+#                            DescriptorDistance (1647-1665) - piped straight from the reference file into the compiler
+#                            between a stub class declaration and C wrappers (the rest of ORBmatcher.cc needs the SLAM graph
+#                            types and cannot be built here). Nothing of the reference is written to disk.
+{
+  cat <<'PRE'
+#include <cstdint>
+#include <vector>
+#include "cvshim.h"
+using namespace std;
+namespace ORB_SLAM2 {
+class ORBmatcher {
+public:
+    static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3);
+};
+PRE
+  sed -n '1603,1665p' "$ref/src/ORBmatcher.cc"
+  cat <<'POST'
+}  // namespace ORB_SLAM2
+extern "C" int refm_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    cv::Mat ma(1, 32, CV_8U, (void*)a, 32), mb(1, 32, CV_8U, (void*)b, 32);
+    return ORB_SLAM2::ORBmatcher::DescriptorDistance(ma, mb);
+}
+extern "C" void refm_three_maxima(const int* sizes, int L, int* out3) {
+    std::vector<std::vector<int> > h(L);
+    for (int i = 0; i < L; ++i) h[i].resize(sizes[i]);
+    int a = -1, b = -1, c = -1;
+    ORB_SLAM2::ORBmatcher m;
+    m.ComputeThreeMaxima(h.data(), L, a, b, c);
+    out3[0] = a; out3[1] = b; out3[2] = c;
+}
+POST
+} | g++ -std=c++14 -O3 -march=x86-64-v3 -fPIC -shared -w -I"$here/shim" -x c++ - -o "$here/_ref/libref_matcher_bits.so"
+echo "build_ref: built $(ls "$here/_ref" | tr '\n' ' ')"

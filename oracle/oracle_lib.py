@@ -540,3 +540,25 @@ def search_by_projection_frame_mappoints(F, mp, th, nnratio=0.8, th_high=100):
             occupied[bi] = True
             nm += 1
     return nm, assigned
+
+
+# ---- the reference's own DescriptorDistance / ComputeThreeMaxima (oracle/_ref/libref_matcher_bits.so) ----
+def matcher_bits_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_matcher_bits.so"))
+
+
+class RefMatcherBits:
+    """src/ORBmatcher.cc:1603-1665 compiled from the reference file itself (see build_ref.sh)."""
+
+    def __init__(self):
+        self.L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_matcher_bits.so"))
+        self.L.refm_descriptor_distance.restype = C.c_int
+
+    def descriptor_distance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(32); b = np.ascontiguousarray(b, np.uint8).reshape(32)
+        return int(self.L.refm_descriptor_distance(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+    def three_maxima(self, sizes):
+        s = np.ascontiguousarray(sizes, np.int32); out = np.zeros(3, np.int32)
+        self.L.refm_three_maxima(s.ctypes.data_as(C.c_void_p), len(s), out.ctypes.data_as(C.c_void_p))
+        return tuple(int(x) for x in out)

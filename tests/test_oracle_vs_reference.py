@@ -74,3 +74,26 @@ def test_verbatim_tiebreak_differs_only_slightly():
         diff += len(a - b)
     print("canonical-vs-verbatim differing keypoints: %d / %d = %.2f%%" % (diff, tot, 100.0 * diff / tot))
     assert diff / tot < 0.05
+
+
+@pytest.mark.skipif(not O.matcher_bits_available(), reason="libref_matcher_bits.so absent")
+def test_descriptor_distance_and_three_maxima_equal_reference():
+    """src/ORBmatcher.cc:1603-1665 compiled from the reference file, against the oracle restatement and the
+    product's host mirrors (ORBmatcher.DescriptorDistance / ComputeThreeMaxima)."""
+    from multiagent_orb_slam2_b200.matcher import ORBmatcher
+    ref = O.RefMatcherBits()
+    rng = np.random.default_rng(5)
+    D = rng.integers(0, 256, (400, 32), dtype=np.uint8)
+    D[0] = 0; D[1] = 255; D[2] = D[3]
+    for i in range(0, 400, 2):
+        want = ref.descriptor_distance(D[i], D[i + 1])
+        assert O.hamming(D[i], D[i + 1]) == want
+        assert ORBmatcher.DescriptorDistance(D[i], D[i + 1]) == want
+    assert ref.descriptor_distance(D[0], D[1]) == 256
+    cases = [rng.integers(0, hi, 30) for hi in (1, 2, 5, 50, 1000) for _ in range(40)]
+    cases += [np.zeros(30, int), np.full(30, 7), np.arange(30), np.arange(30)[::-1], [100, 10, 9] + [0] * 27,
+              [100, 9, 9] + [0] * 27, [100, 10, 10] + [0] * 27, [10, 1, 0] + [0] * 27, [11, 1, 1] + [0] * 27]
+    for s in cases:
+        want = ref.three_maxima(s)
+        assert O.three_maxima([int(x) for x in s]) == want, list(s)
+        assert ORBmatcher.ComputeThreeMaxima(s) == want, list(s)
