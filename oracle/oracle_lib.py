@@ -562,3 +562,311 @@ class RefMatcherBits:
         s = np.ascontiguousarray(sizes, np.int32); out = np.zeros(3, np.int32)
         self.L.refm_three_maxima(s.ctypes.data_as(C.c_void_p), len(s), out.ctypes.data_as(C.c_void_p))
         return tuple(int(x) for x in out)
+
+
+# ---- the remaining guided searches (rows a-11 ... a-15), scalar restatements on arrays ------------------
+def _c_round(x):
+    x = float(x)
+    return int(np.floor(x + 0.5)) if x >= 0 else -int(np.floor(-x + 0.5))
+
+
+def _rot_bin(a1, a2, L=30):
+    rot = np.float32(np.float32(a1) - np.float32(a2))
+    if rot < 0.0:
+        rot = np.float32(rot + np.float32(360.0))
+    b = _c_round(np.float32(rot * (np.float32(1.0) / np.float32(L))))
+    return 0 if b == L else b
+
+
+def _rot_cleanup(rot, clear, L=30):
+    keep = three_maxima([len(x) for x in rot])
+    removed = 0
+    for i in range(L):
+        if i not in keep:
+            for j in rot[i]:
+                clear(j)
+                removed += 1
+    return removed
+
+
+def search_by_projection_cur_last(F, last, th, forward, backward, check_ori=True, th_high=100):
+    """src/ORBmatcher.cc:1330-1472. F: OracleFrame (current) with F.scale, F.uright, F.occupied; last: dict of arrays
+    valid, u, v, ur, octave, angle, desc, has_obs."""
+    assigned = np.full(len(F.kps), -1, np.int32)
+    occupied = F.occupied.copy()
+    rot = [[] for _ in range(30)]
+    nm = 0
+    for i in range(len(last["octave"])):
+        if not last["valid"][i]:
+            continue
+        o = int(last["octave"][i])
+        radius = np.float32(np.float32(th) * F.scale[o])
+        if forward:
+            cand = F.features_in_area(last["u"][i], last["v"][i], radius, o)
+        elif backward:
+            cand = F.features_in_area(last["u"][i], last["v"][i], radius, 0, o)
+        else:
+            cand = F.features_in_area(last["u"][i], last["v"][i], radius, o - 1, o + 1)
+        if not cand:
+            continue
+        best, bi = 256, -1
+        for i2 in cand:
+            if occupied[i2]:
+                continue
+            if F.uright[i2] > 0:
+                er = abs(np.float32(last["ur"][i]) - np.float32(F.uright[i2]))
+                if er > radius:
+                    continue
+            d = hamming(last["desc"][i], F.desc[i2])
+            if d < best:
+                best, bi = d, i2
+        if best <= th_high:
+            assigned[bi] = i
+            occupied[bi] = bool(last["has_obs"][i])
+            nm += 1
+            if check_ori:
+                rot[_rot_bin(last["angle"][i], F.kps[bi, 3])].append(bi)
+    if check_ori:
+        def clear(j):
+            assigned[j] = -1
+        nm -= _rot_cleanup(rot, clear)
+    return nm, assigned
+
+
+def search_by_projection_cur_kf(F, q, th, orb_dist, check_ori=True):
+    """src/ORBmatcher.cc:1474-1601. F.occupied[kp]: mvpMapPoints[kp] set. q: valid, u, v, level, angle, desc."""
+    assigned = np.full(len(F.kps), -1, np.int32)
+    occupied = F.occupied.copy()
+    rot = [[] for _ in range(30)]
+    nm = 0
+    for i in range(len(q["level"])):
+        if not q["valid"][i]:
+            continue
+        lvl = int(q["level"][i])
+        radius = np.float32(np.float32(th) * F.scale[lvl])
+        cand = F.features_in_area(q["u"][i], q["v"][i], radius, lvl - 1, lvl + 1)
+        if not cand:
+            continue
+        best, bi = 256, -1
+        for i2 in cand:
+            if occupied[i2]:
+                continue
+            d = hamming(q["desc"][i], F.desc[i2])
+            if d < best:
+                best, bi = d, i2
+        if best <= orb_dist:
+            assigned[bi] = i
+            occupied[bi] = True
+            nm += 1
+            if check_ori:
+                rot[_rot_bin(q["angle"][i], F.kps[bi, 3])].append(bi)
+    if check_ori:
+        def clear(j):
+            assigned[j] = -1
+        nm -= _rot_cleanup(rot, clear)
+    return nm, assigned
+
+
+def search_by_projection_kf_sim3(F, matched, q, th, th_low=50):
+    """src/ORBmatcher.cc:292-405."""
+    matched = np.asarray(matched, bool).copy()
+    assigned = np.full(len(F.kps), -1, np.int32)
+    nm = 0
+    for i in range(len(q["level"])):
+        if not q["valid"][i]:
+            continue
+        lvl = int(q["level"][i])
+        radius = np.float32(np.float32(int(th)) * F.scale[lvl])
+        cand = F.features_in_area(q["u"][i], q["v"][i], radius)
+        if not cand:
+            continue
+        best, bi = 256, -1
+        for idx in cand:
+            if matched[idx]:
+                continue
+            kl = int(F.kps[idx, 5])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            d = hamming(q["desc"][i], F.desc[idx])
+            if d < best:
+                best, bi = d, idx
+        if best <= th_low:
+            matched[bi] = True
+            assigned[bi] = i
+            nm += 1
+    return nm, assigned
+
+
+def _walk(fv1, fv2):
+    i = j = 0
+    while i < len(fv1) and j < len(fv2):
+        if fv1[i][0] == fv2[j][0]:
+            yield fv1[i][1], fv2[j][1]
+            i += 1; j += 1
+        elif fv1[i][0] < fv2[j][0]:
+            while i < len(fv1) and fv1[i][0] < fv2[j][0]:
+                i += 1
+        else:
+            while j < len(fv2) and fv2[j][0] < fv1[i][0]:
+                j += 1
+
+
+def search_by_bow_kf_f(desc_kf, fv_kf, valid_kf, angle_kf, desc_f, fv_f, angle_f, nnratio=0.7, check_ori=True, th_low=50):
+    """src/ORBmatcher.cc:161-290."""
+    assigned = np.full(len(desc_f), -1, np.int32)
+    rot = [[] for _ in range(30)]
+    ratio = np.float32(nnratio)
+    nm = 0
+    for lkf, lf in _walk(fv_kf, fv_f):
+        for ikf in lkf:
+            if not valid_kf[ikf]:
+                continue
+            b1 = b2 = 256
+            bi = -1
+            for jf in lf:
+                if assigned[jf] >= 0:
+                    continue
+                d = hamming(desc_kf[ikf], desc_f[jf])
+                if d < b1:
+                    b2, b1, bi = b1, d, jf
+                elif d < b2:
+                    b2 = d
+            if b1 <= th_low:
+                if np.float32(b1) < ratio * np.float32(b2):
+                    assigned[bi] = ikf
+                    if check_ori:
+                        rot[_rot_bin(angle_kf[ikf], angle_f[bi])].append(bi)
+                    nm += 1
+    if check_ori:
+        def clear(j):
+            assigned[j] = -1
+        nm -= _rot_cleanup(rot, clear)
+    return nm, assigned
+
+
+def check_dist_epipolar_line(x1, y1, x2, y2, o2, F12, level_sigma2):
+    """src/ORBmatcher.cc:142-159."""
+    f = np.float32
+    a = f(f(f(x1) * F12[0, 0] + f(y1) * F12[1, 0]) + F12[2, 0])
+    b = f(f(f(x1) * F12[0, 1] + f(y1) * F12[1, 1]) + F12[2, 1])
+    c = f(f(f(x1) * F12[0, 2] + f(y1) * F12[1, 2]) + F12[2, 2])
+    num = f(f(a * f(x2) + b * f(y2)) + c)
+    den = f(a * a + b * b)
+    if den == 0:
+        return False
+    dsqr = f(f(num * num) / den)
+    return float(dsqr) < 3.84 * float(level_sigma2[o2])
+
+
+def search_for_triangulation(kf1, kf2, F12, epipole, scale2, sigma2_2, only_stereo=False, check_ori=True, th_low=50):
+    """src/ORBmatcher.cc:659-825."""
+    f = np.float32
+    F12 = np.asarray(F12, f)
+    ex, ey = f(epipole[0]), f(epipole[1])
+    n1 = len(kf1["desc"])
+    m12 = np.full(n1, -1, np.int32)
+    matched2 = np.zeros(len(kf2["desc"]), bool)  # never set by the reference either
+    rot = [[] for _ in range(30)]
+    nm = 0
+    for l1, l2 in _walk(kf1["featvec"], kf2["featvec"]):
+        for idx1 in l1:
+            if kf1["has_mp"][idx1]:
+                continue
+            st1 = kf1["uright"][idx1] >= 0
+            if only_stereo and not st1:
+                continue
+            best, bi = th_low, -1
+            for idx2 in l2:
+                if matched2[idx2] or kf2["has_mp"][idx2]:
+                    continue
+                st2 = kf2["uright"][idx2] >= 0
+                if only_stereo and not st2:
+                    continue
+                d = hamming(kf1["desc"][idx1], kf2["desc"][idx2])
+                if d > th_low or d > best:
+                    continue
+                if not st1 and not st2:
+                    dx = f(ex - f(kf2["x"][idx2])); dy = f(ey - f(kf2["y"][idx2]))
+                    if f(f(dx * dx) + f(dy * dy)) < f(f(100) * f(scale2[int(kf2["octave"][idx2])])):
+                        continue
+                if check_dist_epipolar_line(kf1["x"][idx1], kf1["y"][idx1], kf2["x"][idx2], kf2["y"][idx2],
+                                            int(kf2["octave"][idx2]), F12, sigma2_2):
+                    bi, best = idx2, d
+            if bi >= 0:
+                m12[idx1] = bi
+                nm += 1
+                if check_ori:
+                    rot[_rot_bin(kf1["angle"][idx1], kf2["angle"][bi])].append(idx1)
+    if check_ori:
+        def clear(j):
+            m12[j] = -1
+        nm -= _rot_cleanup(rot, clear)
+    return [(i, int(m12[i])) for i in range(n1) if m12[i] >= 0]
+
+
+def fuse_kf_mappoints(F, inv_sigma2, q, th, th_low=50):
+    """The search of src/ORBmatcher.cc:827-977 (bookkeeping 953-972 left to the caller)."""
+    f = np.float32
+    n = len(q["level"])
+    best_idx = np.full(n, -1, np.int32); best_dist = np.full(n, 256, np.int32)
+    for i in range(n):
+        if not q["valid"][i]:
+            continue
+        lvl = int(q["level"][i])
+        radius = f(f(th) * F.scale[lvl])
+        u, v, ur = f(q["u"][i]), f(q["v"][i]), f(q["ur"][i])
+        best, bi = 256, -1
+        for idx in F.features_in_area(u, v, radius):
+            kl = int(F.kps[idx, 5])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            exx = f(u - F.kps[idx, 0]); eyy = f(v - F.kps[idx, 1])
+            if F.uright[idx] >= 0:
+                er = f(ur - f(F.uright[idx]))
+                e2 = f(f(f(exx * exx) + f(eyy * eyy)) + f(er * er))
+                if float(f(e2 * f(inv_sigma2[kl]))) > 7.8:
+                    continue
+            else:
+                e2 = f(f(exx * exx) + f(eyy * eyy))
+                if float(f(e2 * f(inv_sigma2[kl]))) > 5.99:
+                    continue
+            d = hamming(q["desc"][i], F.desc[idx])
+            if d < best:
+                best, bi = d, idx
+        best_dist[i] = best
+        if best <= th_low:
+            best_idx[i] = bi
+    return int((best_idx >= 0).sum()), best_idx, best_dist
+
+
+def best_in_window(F, q, th, limit):
+    """The inner search shared by Fuse(KF,Scw,...) (src/ORBmatcher.cc:1050-1082) and SearchBySim3 (1189-1221, 1269-1301)."""
+    n = len(q["level"])
+    out = np.full(n, -1, np.int32)
+    for i in range(n):
+        if not q["valid"][i]:
+            continue
+        lvl = int(q["level"][i])
+        radius = np.float32(np.float32(th) * F.scale[lvl])
+        best, bi = 2**31 - 1, -1
+        for idx in F.features_in_area(q["u"][i], q["v"][i], radius):
+            kl = int(F.kps[idx, 5])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            d = hamming(q["desc"][i], F.desc[idx])
+            if d < best:
+                best, bi = d, idx
+        if best <= limit:
+            out[i] = bi
+    return out
+
+
+def search_by_sim3(F1, F2, q1, q2, th, th_high=100):
+    """src/ORBmatcher.cc:1104-1328."""
+    m1 = best_in_window(F2, q1, th, th_high)
+    m2 = best_in_window(F1, q2, th, th_high)
+    m12 = np.full(len(m1), -1, np.int32)
+    for i1 in range(len(m1)):
+        if m1[i1] >= 0 and m2[m1[i1]] == i1:
+            m12[i1] = m1[i1]
+    return int((m12 >= 0).sum()), m12
