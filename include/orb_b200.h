@@ -220,6 +220,32 @@ int orbm_window_lists_device(orbm_grid_handle g, const uint8_t* d_desc_frame, co
                              int32_t* d_offsets, int32_t* d_cands, int16_t* d_dist, int cap, int32_t* total_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Map-point projection: Frame::isInFrustum (src/Frame.cc:269-325; mode 0) and the projection
+ * prologue of ORBmatcher::Fuse / SearchByProjection(KF, Scw, ...) / SearchBySim3 (src/ORBmatcher.cc:849-889, 323-363,
+ * 1169-1186; mode 1) for n map points kept as arrays on the device: world position and normal (n x 3 float),
+ * mfMaxDistance / mfMinDistance (the raw members; the 1.2 / 0.8 factors of Get*DistanceInvariance are applied inside).
+ * Outputs per point: alive (every gate the reference evaluates before GetFeaturesInArea passed), u, v, ur (= u - bf/z),
+ * predicted level, viewing cosine; optionally the search window for orbm_window_*_device: radius (mode 0:
+ * RadiusByViewingCos * th (th applied when != 1) * scale[level], src/ORBmatcher.cc:60-67,133-139; mode 1: th * scale[level]),
+ * 0 when not alive, and the level window [level-1, level]. d_radius / d_min_level / d_max_level may be NULL. */
+#define ORBM_MAX_LEVELS 32
+typedef struct orbm_camera {
+    float Rcw[9];   /* row-major rotation, world -> camera (Frame::mRcw / KeyFrame::GetRotation()) */
+    float tcw[3];   /* translation (mtcw) */
+    float Ow[3];    /* camera centre (mOw), as the caller's pose update computed it */
+    float fx, fy, cx, cy, bf;
+    float min_x, max_x, min_y, max_y; /* mnMinX ... mnMaxY */
+    float log_scale_factor;            /* mfLogScaleFactor */
+    int32_t n_levels;                  /* mnScaleLevels */
+    float scale_factors[ORBM_MAX_LEVELS]; /* mvScaleFactors */
+} orbm_camera;
+int orbm_project_points_device(int device, const orbm_camera* cam, int mode, float viewing_cos_limit, float th,
+                               const float* d_world_pos, const float* d_normal, const float* d_max_distance,
+                               const float* d_min_distance, int n, uint8_t* d_alive, float* d_u, float* d_v, float* d_ur,
+                               int32_t* d_level, float* d_view_cos, float* d_radius, int32_t* d_min_level,
+                               int32_t* d_max_level, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Vocabulary tree descent (the step right after extraction): replaces the per-feature
  * TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) with FORB::distance
  * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259, FORB.cpp:81-101) for all features of a frame,

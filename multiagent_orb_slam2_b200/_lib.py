@@ -75,6 +75,7 @@ def lib():
         "orbv_descend": [vp, vp, i32, i32, vp, vp, vp],
         "orbm_distance_matrix_device": [vp, i32, vp, i32, vp, vp],
         "orbm_distance_matrix": [i32, vp, i32, vp, i32, vp],
+        "orbm_project_points_device": [i32, vp, i32, f32, f32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)

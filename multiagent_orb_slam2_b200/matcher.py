@@ -320,11 +320,17 @@ def _search_by_projection_frame_mappoints(self, grid, kp_octave, uright, occupie
     rad = (r * np.asarray(scale_factors, f32)[lvl]).astype(f32)
     rad_q = np.where(live, rad, f32(0)).astype(f32)  # dead map points: empty window
     offsets, cands, dist = grid.window_lists(mp["desc"], mp["proj_x"], mp["proj_y"], rad_q, lvl - 1, lvl)
+    return _replay_frame_mappoints(self, offsets, cands, dist, live, rad, mp["proj_xr"], kp_octave, uright, occupied)
+
+
+def _replay_frame_mappoints(self, offsets, cands, dist, live, rad, proj_xr, kp_octave, uright, occupied):
+    """The ordered loop of src/ORBmatcher.cc:52-128 over the device's candidate lists."""
+    f32 = np.float32
     occupied = np.asarray(occupied, bool).copy()
     assigned = np.full(len(kp_octave), -1, np.int32)
     ratio = f32(self.mfNNratio)
     nm = 0
-    for i in range(n_mp):
+    for i in range(len(live)):
         if not live[i] or offsets[i] == offsets[i + 1]:
             continue
         b1 = b2 = 256
@@ -333,7 +339,7 @@ def _search_by_projection_frame_mappoints(self, grid, kp_octave, uright, occupie
             idx = int(cands[k])
             if occupied[idx]:
                 continue
-            if uright[idx] > 0 and abs(f32(mp["proj_xr"][i]) - f32(uright[idx])) > rad[i]:
+            if uright[idx] > 0 and abs(f32(proj_xr[i]) - f32(uright[idx])) > rad[i]:
                 continue
             d = int(dist[k])
             if d < b1:
@@ -349,4 +355,18 @@ def _search_by_projection_frame_mappoints(self, grid, kp_octave, uright, occupie
     return nm, assigned
 
 
+def _search_local_points_device(self, grid, cam, mp_arrays, bad, kp_octave, uright, occupied, th, viewing_cos_limit=0.5):
+    """Tracking::SearchLocalPoints (/root/reference/src/Tracking.cc:1156-1206) as one device chain: Frame::isInFrustum for every
+    local map point (projection.project, mode 0), the window lookup and all Hamming distances (orbm_window_lists_device) with
+    nothing brought to the host in between, then the ordered replay of SearchByProjection(F, vpMapPoints, th)
+    (src/ORBmatcher.cc:45-131). mp_arrays: projection.MapPointArrays; bad[i]: pMP->isBad().
+    Returns (nmatches, assigned[kp], projection outputs on the host)."""
+    from . import projection
+    pr, offsets, cands, dist = projection.project_and_window_lists(grid, cam, mp_arrays, 0, viewing_cos_limit, th)
+    live = pr["alive"].astype(bool) & ~np.asarray(bad, bool)
+    nm, assigned = _replay_frame_mappoints(self, offsets, cands, dist, live, pr["radius"], pr["ur"], kp_octave, uright, occupied)
+    return nm, assigned, pr
+
+
+ORBmatcher.SearchLocalPoints_device = _search_local_points_device
 ORBmatcher.SearchByProjection_Frame_MapPoints = _search_by_projection_frame_mappoints

@@ -870,3 +870,79 @@ def search_by_sim3(F1, F2, q1, q2, th, th_high=100):
         if m1[i1] >= 0 and m2[m1[i1]] == i1:
             m12[i1] = m1[i1]
     return int((m12 >= 0).sum()), m12
+
+
+# ---- map point projection (Frame::isInFrustum and the Fuse / Sim3 prologue), scalar restatement -----------
+def _mat3_vec(R, x, t):
+    """cv::Mat Rcw*P+tcw for 3x3 * 3x1 floats: OpenCV's small-matrix gemm accumulates left to right in float
+    (pinned against cv2.gemm in tests/test_projection_oracle.py), then the float matrix add."""
+    f = np.float32
+    return [f(f(f(f(R[i][0] * x[0]) + f(R[i][1] * x[1])) + f(R[i][2] * x[2])) + t[i]) for i in range(3)]
+
+
+def _norm3(v):
+    """cv::norm of a 3x1 float Mat: squares accumulated in double in order, double sqrt; the caller assigns to float."""
+    d = [float(x) for x in v]
+    return np.float32(np.sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]))
+
+
+def _dot3(a, b):
+    """cv::Mat::dot of 3x1 float Mats: products and sum in double, in order."""
+    return (float(a[0]) * float(b[0]) + float(a[1]) * float(b[1])) + float(a[2]) * float(b[2])
+
+
+def predict_scale(max_distance, dist, log_scale_factor, n_levels):
+    """MapPoint::PredictScale, src/MapPoint.cc:389-421: ceil(log(ratio)/mfLogScaleFactor), all float (std::log(float))."""
+    f = np.float32
+    ratio = f(f(max_distance) / f(dist))
+    n = int(np.ceil(f(np.log(ratio, dtype=np.float32) / f(log_scale_factor))))
+    return 0 if n < 0 else (n_levels - 1 if n >= n_levels else n)
+
+
+def project_points(cam, pos, normal, max_d, min_d, mode, cos_limit=0.5, th=1.0):
+    """mode 0: Frame::isInFrustum, src/Frame.cc:269-325 (+ the radius of src/ORBmatcher.cc:60-67, 133-139);
+    mode 1: the prologue of ORBmatcher::Fuse, src/ORBmatcher.cc:849-889 (+ radius th*scale, 892).
+    cam: dict Rcw (3x3), tcw, Ow, fx, fy, cx, cy, bf, min_x, max_x, min_y, max_y, log_scale_factor, scale (array)."""
+    f = np.float32
+    n = len(pos)
+    out = dict(alive=np.zeros(n, np.uint8), u=np.zeros(n, f), v=np.zeros(n, f), ur=np.zeros(n, f), level=np.zeros(n, np.int32),
+               view_cos=np.zeros(n, f), radius=np.zeros(n, f))
+    R = np.asarray(cam["Rcw"], f).reshape(3, 3); t = np.asarray(cam["tcw"], f); Ow = np.asarray(cam["Ow"], f)
+    fx, fy, cx, cy, bf = (f(cam[k]) for k in ("fx", "fy", "cx", "cy", "bf"))
+    scale = np.asarray(cam["scale"], f)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for i in range(n):
+            P = np.asarray(pos[i], f)
+            x, y, z = _mat3_vec(R, P, t)
+            ok = not (z < f(0))
+            invz = f(f(1.0) / z)
+            if mode == 0:
+                u = f(f(f(fx * x) * invz) + cx); v = f(f(f(fy * y) * invz) + cy)
+                ok = ok and not (u < cam["min_x"] or u > cam["max_x"]) and not (v < cam["min_y"] or v > cam["max_y"])
+            else:
+                u = f(f(fx * f(x * invz)) + cx); v = f(f(fy * f(y * invz)) + cy)
+                ok = ok and bool(u >= cam["min_x"] and u < cam["max_x"] and v >= cam["min_y"] and v < cam["max_y"])
+            ur = f(u - f(bf * invz))
+            maxd, mind = f(f(1.2) * f(max_d[i])), f(f(0.8) * f(min_d[i]))
+            PO = [f(P[k] - Ow[k]) for k in range(3)]
+            dist = _norm3(PO)
+            ok = ok and not (dist < mind or dist > maxd)
+            dot = _dot3(PO, np.asarray(normal[i], f))
+            view_cos = f(dot / float(dist))
+            if mode == 0:
+                ok = ok and not (view_cos < f(cos_limit))
+            else:
+                ok = ok and not (dot < 0.5 * float(dist))
+            level, radius = 0, f(0)
+            if ok:
+                level = predict_scale(max_d[i], dist, cam["log_scale_factor"], len(scale))
+                if mode == 0:
+                    r = f(2.5) if view_cos > 0.998 else f(4.0)
+                    if th != 1.0:
+                        r = f(r * f(th))
+                    radius = f(r * scale[level])
+                else:
+                    radius = f(f(th) * scale[level])
+            out["alive"][i] = ok; out["u"][i] = u; out["v"][i] = v; out["ur"][i] = ur
+            out["level"][i] = level; out["view_cos"][i] = view_cos; out["radius"][i] = radius
+    return out
