@@ -16,8 +16,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <set>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #if defined(__has_include)
@@ -33,6 +36,85 @@
 #include "../orb_b200.h"
 
 namespace ORB_SLAM2 {
+
+namespace b200_detail {
+
+// Float arithmetic with every intermediate rounded to float (no fused multiply-add whatever -ffp-contract / -march the
+// including translation unit uses): the canonical evaluation of the reference's float expressions.
+inline float mulf(float a, float b) { volatile float r = a * b; return r; }
+inline float addf(float a, float b) { volatile float r = a + b; return r; }
+inline float subf(float a, float b) { volatile float r = a - b; return r; }
+inline float divf(float a, float b) { volatile float r = a / b; return r; }
+
+struct Vec3 { float v[3]; float operator[](int i) const { return v[i]; } };
+struct Rot3 { float m[9]; };
+
+template <class M> inline Vec3 column3(const M& m, int c = 0) { Vec3 r = {{m.template at<float>(0, c), m.template at<float>(1, c), m.template at<float>(2, c)}}; return r; }
+template <class M> inline Rot3 rotation3(const M& m) {
+    Rot3 r;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[3 * i + j] = m.template at<float>(i, j);
+    return r;
+}
+// cv::Mat R*p + t for 3x3 * 3x1 CV_32F: OpenCV's small-matrix product sums left to right in float, then the matrix add
+inline Vec3 transform(const Rot3& R, const Vec3& p, const Vec3& t) {
+    Vec3 r;
+    for (int i = 0; i < 3; ++i)
+        r.v[i] = addf(addf(addf(mulf(R.m[3 * i], p[0]), mulf(R.m[3 * i + 1], p[1])), mulf(R.m[3 * i + 2], p[2])), t[i]);
+    return r;
+}
+// cv::Mat -R.t()*t: a product with a transposed operand goes through the general gemm, which accumulates floats in double
+inline Vec3 minusRtT(const Rot3& R, const Vec3& t) {
+    Vec3 r;
+    for (int i = 0; i < 3; ++i) {
+        volatile double s = (double)R.m[i] * (double)t[0];
+        s = s + (double)R.m[3 + i] * (double)t[1];
+        s = s + (double)R.m[6 + i] * (double)t[2];
+        r.v[i] = (float)(-1.0 * s);
+    }
+    return r;
+}
+inline Vec3 minus3(const Vec3& a, const Vec3& b) { Vec3 r = {{subf(a[0], b[0]), subf(a[1], b[1]), subf(a[2], b[2])}}; return r; }
+// cv::Mat::dot / cv::norm of 3x1 CV_32F: products and sums in double, in order
+inline double dot3(const Vec3& a, const Vec3& b) {
+    volatile double s = (double)a[0] * (double)b[0];
+    s = s + (double)a[1] * (double)b[1];
+    s = s + (double)a[2] * (double)b[2];
+    return s;
+}
+inline double norm3(const Vec3& a) { return std::sqrt(dot3(a, a)); }
+
+// The (query, candidate) pairs a search gathers on the host; one orbm_list_distances launch computes every distance.
+class GatedPairs {
+public:
+    explicit GatedPairs(int device) : device_(device), offsets_(1, 0) {}
+    int open(const cv::Mat& desc) {  // a new query row (32 bytes)
+        const unsigned char* p = desc.ptr();
+        queries_.insert(queries_.end(), p, p + 32);
+        return (int)offsets_.size() - 1;
+    }
+    template <class Indices> void add(const Indices& v) { for (size_t k = 0; k < v.size(); ++k) cands_.push_back((int32_t)v[k]); }
+    void close() { offsets_.push_back((int32_t)cands_.size()); }
+    void run(const cv::Mat& target) {
+        dist_.resize(cands_.size());
+        if (cands_.empty()) return;
+        std::vector<uint8_t> B((size_t)target.rows * 32);
+        for (int i = 0; i < target.rows; ++i) std::memcpy(&B[(size_t)i * 32], target.ptr(i), 32);
+        const int rc = orbm_list_distances(device_, queries_.data(), (int)offsets_.size() - 1, B.data(), target.rows, offsets_.data(),
+                                           cands_.data(), dist_.data());
+        if (rc != ORB_OK) throw std::runtime_error(std::string("orb_b200: ") + orb_last_error());
+    }
+    int begin(int q) const { return offsets_[q]; }
+    int end(int q) const { return offsets_[q + 1]; }
+    size_t cand(int k) const { return (size_t)cands_[k]; }
+    int dist(int k) const { return dist_[k]; }
+private:
+    int device_;
+    std::vector<uint8_t> queries_;
+    std::vector<int32_t> offsets_, cands_;
+    std::vector<int16_t> dist_;
+};
+
+}  // namespace b200_detail
 
 class ORBmatcher {
 public:
@@ -209,6 +291,556 @@ public:
         return nmatches;
     }
 
+    // ---- the projection / BoW guided searches (SURVEY.md section 8 rows a-10 ... a-15) --------------------------------
+    // All of them: (1) host: the reference's outer loop with every gate that does not depend on matches made earlier in the
+    // same call, collecting the GetFeaturesInArea / BoW-node candidates in the reference's order; (2) device: one
+    // orbm_list_distances launch; (3) host: the reference's ordered selection replayed over the precomputed distances on
+    // the caller's live objects (so mvpMapPoints / vpMatched state behaves exactly as in the reference).
+
+    // Search matches between Frame keypoints and projected MapPoints (src/ORBmatcher.cc:45-131); used to track the local
+    // map (Tracking::SearchLocalPoints). FrameT: mpSystem, mvScaleFactors, GetFeaturesInArea, mvpMapPoints, mvuRight,
+    // mDescriptors, mvKeysUn. MapPointT: mbTrackInView / mnTrackScaleLevel / mTrackViewCos / mTrackProjX / mTrackProjY /
+    // mTrackProjXR (per System*), isBad(), GetDescriptor(), Observations().
+    template <class FrameT, class MapPointT>
+    int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float th = 3) {
+        struct Query { MapPointT* mp; int level; float radius; int q; };
+        std::vector<Query> queries;
+        b200_detail::GatedPairs pairs(device_);
+        const bool bFactor = th != 1.0;
+        auto pSystem = F.mpSystem;
+        for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {
+            MapPointT* pMP = vpMapPoints[iMP];
+            if (!pMP->mbTrackInView[pSystem] || pMP->isBad()) continue;
+            const int nPredictedLevel = pMP->mnTrackScaleLevel[pSystem];
+            float r = RadiusByViewingCos(pMP->mTrackViewCos[pSystem]);  // window size depends on the viewing direction
+            if (bFactor) r *= th;
+            const float radius = r * F.mvScaleFactors[nPredictedLevel];
+            const std::vector<size_t> vIndices =
+                F.GetFeaturesInArea(pMP->mTrackProjX[pSystem], pMP->mTrackProjY[pSystem], radius, nPredictedLevel - 1, nPredictedLevel);
+            if (vIndices.empty()) continue;
+            const Query q = {pMP, nPredictedLevel, radius, pairs.open(pMP->GetDescriptor())};
+            pairs.add(vIndices);
+            pairs.close();
+            queries.push_back(q);
+        }
+        pairs.run(F.mDescriptors);
+        int nmatches = 0;
+        for (size_t n = 0; n < queries.size(); ++n) {
+            const Query& q = queries[n];
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
+                const size_t idx = pairs.cand(k);
+                if (F.mvpMapPoints[idx] && F.mvpMapPoints[idx]->Observations() > 0) continue;
+                if (F.mvuRight[idx] > 0) {
+                    const float er = fabs(q.mp->mTrackProjXR[pSystem] - F.mvuRight[idx]);
+                    if (er > q.radius) continue;
+                }
+                const int dist = pairs.dist(k);
+                if (dist < bestDist) {
+                    bestDist2 = bestDist; bestDist = dist;
+                    bestLevel2 = bestLevel; bestLevel = F.mvKeysUn[idx].octave;
+                    bestIdx = (int)idx;
+                } else if (dist < bestDist2) {
+                    bestLevel2 = F.mvKeysUn[idx].octave;
+                    bestDist2 = dist;
+                }
+            }
+            if (bestDist <= TH_HIGH) {  // ratio to the second match only when both are at the same scale level
+                if (bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2) continue;
+                F.mvpMapPoints[bestIdx] = q.mp;
+                nmatches++;
+            }
+        }
+        return nmatches;
+    }
+
+    // Project MapPoints tracked in the last frame into the current frame and search matches (src/ORBmatcher.cc:1330-1472);
+    // used to track from the previous frame (Tracking::TrackWithMotionModel).
+    template <class FrameT>
+    int SearchByProjection(FrameT& CurrentFrame, const FrameT& LastFrame, const float th, const bool bMono) {
+        using namespace b200_detail;
+        typedef typename std::remove_cv<typename std::remove_reference<decltype(CurrentFrame.mvpMapPoints[0])>::type>::type MapPointPtr;
+        const Rot3 Rcw = rotation3(CurrentFrame.mTcw);
+        const Vec3 tcw = column3(CurrentFrame.mTcw, 3);
+        const Vec3 twc = minusRtT(Rcw, tcw);
+        const Vec3 tlc = transform(rotation3(LastFrame.mTcw), twc, column3(LastFrame.mTcw, 3));
+        const bool bForward = tlc[2] > CurrentFrame.mb && !bMono;
+        const bool bBackward = -tlc[2] > CurrentFrame.mb && !bMono;
+
+        struct Query { int i; MapPointPtr mp; float ur, radius; int q; };
+        std::vector<Query> queries;
+        GatedPairs pairs(device_);
+        for (int i = 0; i < LastFrame.N; i++) {
+            MapPointPtr pMP = LastFrame.mvpMapPoints[i];
+            if (!pMP || LastFrame.mvbOutlier[i]) continue;
+            const Vec3 x3Dc = transform(Rcw, column3(pMP->GetWorldPos()), tcw);
+            const float invzc = 1.0 / x3Dc[2];
+            if (invzc < 0) continue;
+            const float u = addf(mulf(mulf(CurrentFrame.fx, x3Dc[0]), invzc), CurrentFrame.cx);
+            const float v = addf(mulf(mulf(CurrentFrame.fy, x3Dc[1]), invzc), CurrentFrame.cy);
+            if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+            if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+            const int nLastOctave = LastFrame.mvKeys[i].octave;
+            const float radius = th * CurrentFrame.mvScaleFactors[nLastOctave];  // window size depends on the scale
+            std::vector<size_t> vIndices2;
+            if (bForward) vIndices2 = CurrentFrame.GetFeaturesInArea(u, v, radius, nLastOctave);
+            else if (bBackward) vIndices2 = CurrentFrame.GetFeaturesInArea(u, v, radius, 0, nLastOctave);
+            else vIndices2 = CurrentFrame.GetFeaturesInArea(u, v, radius, nLastOctave - 1, nLastOctave + 1);
+            if (vIndices2.empty()) continue;
+            const Query q = {i, pMP, subf(u, mulf(CurrentFrame.mbf, invzc)), radius, pairs.open(pMP->GetDescriptor())};
+            pairs.add(vIndices2);
+            pairs.close();
+            queries.push_back(q);
+        }
+        pairs.run(CurrentFrame.mDescriptors);
+
+        int nmatches = 0;
+        std::vector<int> rotHist[HISTO_LENGTH];
+        for (size_t n = 0; n < queries.size(); ++n) {
+            const Query& q = queries[n];
+            int bestDist = 256, bestIdx2 = -1;
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
+                const size_t i2 = pairs.cand(k);
+                if (CurrentFrame.mvpMapPoints[i2] && CurrentFrame.mvpMapPoints[i2]->Observations() > 0) continue;
+                if (CurrentFrame.mvuRight[i2] > 0) {
+                    const float er = fabs(q.ur - CurrentFrame.mvuRight[i2]);
+                    if (er > q.radius) continue;
+                }
+                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx2 = (int)i2; }
+            }
+            if (bestDist <= TH_HIGH) {
+                CurrentFrame.mvpMapPoints[bestIdx2] = q.mp;
+                nmatches++;
+                if (mbCheckOrientation) rotHist[RotationBin(LastFrame.mvKeysUn[q.i].angle, CurrentFrame.mvKeysUn[bestIdx2].angle)].push_back(bestIdx2);
+            }
+        }
+        if (mbCheckOrientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) { CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPointPtr>(NULL); nmatches--; }
+            }
+        }
+        return nmatches;
+    }
+
+    // Project MapPoints seen in a KeyFrame into the Frame and search matches (src/ORBmatcher.cc:1474-1601); relocalisation.
+    template <class FrameT, class KeyFrameT, class MapPointT>
+    int SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th, const int ORBdist) {
+        using namespace b200_detail;
+        const Rot3 Rcw = rotation3(CurrentFrame.mTcw);
+        const Vec3 tcw = column3(CurrentFrame.mTcw, 3);
+        const Vec3 Ow = minusRtT(Rcw, tcw);
+        const std::vector<MapPointT*> vpMPs = pKF->GetMapPointMatches();
+
+        struct Query { size_t i; MapPointT* mp; int q; };
+        std::vector<Query> queries;
+        GatedPairs pairs(device_);
+        for (size_t i = 0, iend = vpMPs.size(); i < iend; i++) {
+            MapPointT* pMP = vpMPs[i];
+            if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+            const Vec3 x3Dw = column3(pMP->GetWorldPos());
+            const Vec3 x3Dc = transform(Rcw, x3Dw, tcw);
+            const float invzc = 1.0 / x3Dc[2];
+            const float u = addf(mulf(mulf(CurrentFrame.fx, x3Dc[0]), invzc), CurrentFrame.cx);
+            const float v = addf(mulf(mulf(CurrentFrame.fy, x3Dc[1]), invzc), CurrentFrame.cy);
+            if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+            if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+            float dist3D = norm3(minus3(x3Dw, Ow));  // depth must be inside the scale pyramid of the image
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            const int nPredictedLevel = pMP->PredictScale(dist3D, &CurrentFrame);
+            const float radius = th * CurrentFrame.mvScaleFactors[nPredictedLevel];
+            const std::vector<size_t> vIndices2 = CurrentFrame.GetFeaturesInArea(u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1);
+            if (vIndices2.empty()) continue;
+            const Query q = {i, pMP, pairs.open(pMP->GetDescriptor())};
+            pairs.add(vIndices2);
+            pairs.close();
+            queries.push_back(q);
+        }
+        pairs.run(CurrentFrame.mDescriptors);
+
+        int nmatches = 0;
+        std::vector<int> rotHist[HISTO_LENGTH];
+        for (size_t n = 0; n < queries.size(); ++n) {
+            const Query& q = queries[n];
+            int bestDist = 256, bestIdx2 = -1;
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
+                const size_t i2 = pairs.cand(k);
+                if (CurrentFrame.mvpMapPoints[i2]) continue;
+                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx2 = (int)i2; }
+            }
+            if (bestDist <= ORBdist) {
+                CurrentFrame.mvpMapPoints[bestIdx2] = q.mp;
+                nmatches++;
+                if (mbCheckOrientation) rotHist[RotationBin(pKF->mvKeysUn[q.i].angle, CurrentFrame.mvKeysUn[bestIdx2].angle)].push_back(bestIdx2);
+            }
+        }
+        if (mbCheckOrientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) { CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPointT*>(NULL); nmatches--; }
+            }
+        }
+        return nmatches;
+    }
+
+    // Project MapPoints using a Similarity Transformation and search matches (src/ORBmatcher.cc:292-405); loop detection.
+    template <class KeyFrameT, class MapPointT>
+    int SearchByProjection(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th) {
+        using namespace b200_detail;
+        const Sim3Camera cam = DecomposeSim3(Scw);
+        std::set<MapPointT*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+        spAlreadyFound.erase(static_cast<MapPointT*>(NULL));
+
+        struct Query { MapPointT* mp; int q; };
+        std::vector<Query> queries;
+        GatedPairs pairs(device_);
+        for (int iMP = 0, iendMP = (int)vpPoints.size(); iMP < iendMP; iMP++) {
+            MapPointT* pMP = vpPoints[iMP];
+            if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+            const Vec3 p3Dw = column3(pMP->GetWorldPos());
+            const Vec3 p3Dc = transform(cam.R, p3Dw, cam.t);
+            if (p3Dc[2] < 0.0) continue;
+            const float invz = divf(1.0f, p3Dc[2]);
+            const float u = addf(mulf(pKF->fx, mulf(p3Dc[0], invz)), pKF->cx);
+            const float v = addf(mulf(pKF->fy, mulf(p3Dc[1], invz)), pKF->cy);
+            if (!pKF->IsInImage(u, v)) continue;
+            const Vec3 PO = minus3(p3Dw, cam.Ow);
+            const float dist = norm3(PO);
+            if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+            if (dot3(PO, column3(pMP->GetNormal())) < 0.5 * dist) continue;  // viewing angle must be less than 60 deg
+            const int nPredictedLevel = pMP->PredictScale(dist, pKF);
+            const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+            const std::vector<size_t> vIndices = pKF->GetFeaturesInArea(u, v, radius);
+            if (vIndices.empty()) continue;
+            const Query q = {pMP, pairs.open(pMP->GetDescriptor())};
+            pairs.add(LevelWindow(vIndices, pKF->mvKeysUn, nPredictedLevel));
+            pairs.close();
+            queries.push_back(q);
+        }
+        pairs.run(pKF->mDescriptors);
+
+        int nmatches = 0;
+        for (size_t n = 0; n < queries.size(); ++n) {
+            const Query& q = queries[n];
+            int bestDist = 256, bestIdx = -1;
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
+                const size_t idx = pairs.cand(k);
+                if (vpMatched[idx]) continue;
+                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx = (int)idx; }
+            }
+            if (bestDist <= TH_LOW) { vpMatched[bestIdx] = q.mp; nmatches++; }
+        }
+        return nmatches;
+    }
+
+    // Search matches between MapPoints in a KeyFrame and ORB in a Frame, constrained to features of the same vocabulary
+    // node (src/ORBmatcher.cc:161-290); relocalisation and TrackReferenceKeyFrame.
+    template <class KeyFrameT, class FrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {
+        const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+        vpMapPointMatches = std::vector<MapPointT*>(F.N, static_cast<MapPointT*>(NULL));
+        struct Query { unsigned idxKF; MapPointT* mp; int q; };
+        std::vector<Query> queries;
+        b200_detail::GatedPairs pairs(device_);
+        auto KFit = pKF->mFeatVec.begin(), KFend = pKF->mFeatVec.end();
+        auto Fit = F.mFeatVec.begin(), Fend = F.mFeatVec.end();
+        while (KFit != KFend && Fit != Fend) {
+            if (KFit->first == Fit->first) {
+                for (size_t iKF = 0; iKF < KFit->second.size(); iKF++) {
+                    const unsigned realIdxKF = KFit->second[iKF];
+                    MapPointT* pMP = vpMapPointsKF[realIdxKF];
+                    if (!pMP || pMP->isBad()) continue;
+                    const Query q = {realIdxKF, pMP, pairs.open(pKF->mDescriptors.row((int)realIdxKF))};
+                    pairs.add(Fit->second);
+                    pairs.close();
+                    queries.push_back(q);
+                }
+                KFit++; Fit++;
+            } else if (KFit->first < Fit->first) KFit = pKF->mFeatVec.lower_bound(Fit->first);
+            else Fit = F.mFeatVec.lower_bound(KFit->first);
+        }
+        pairs.run(F.mDescriptors);
+
+        int nmatches = 0;
+        std::vector<int> rotHist[HISTO_LENGTH];
+        for (size_t n = 0; n < queries.size(); ++n) {
+            const Query& q = queries[n];
+            int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
+                const size_t realIdxF = pairs.cand(k);
+                if (vpMapPointMatches[realIdxF]) continue;
+                const int dist = pairs.dist(k);
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = (int)realIdxF; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            if (bestDist1 <= TH_LOW && static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+                vpMapPointMatches[bestIdxF] = q.mp;
+                if (mbCheckOrientation) rotHist[RotationBin(pKF->mvKeysUn[q.idxKF].angle, F.mvKeys[bestIdxF].angle)].push_back(bestIdxF);
+                nmatches++;
+            }
+        }
+        if (mbCheckOrientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) { vpMapPointMatches[rotHist[i][j]] = static_cast<MapPointT*>(NULL); nmatches--; }
+            }
+        }
+        return nmatches;
+    }
+
+    // Matching to triangulate new MapPoints, with the epipolar constraint (src/ORBmatcher.cc:659-825); LocalMapping.
+    template <class KeyFrameT>
+    int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                               const bool bOnlyStereo) {
+        using namespace b200_detail;
+        // epipole in the second image
+        const Vec3 C2 = transform(rotation3(pKF2->GetRotation()), column3(pKF1->GetCameraCenter()), column3(pKF2->GetTranslation()));
+        const float invz = divf(1.0f, C2[2]);
+        const float ex = addf(mulf(mulf(pKF2->fx, C2[0]), invz), pKF2->cx);
+        const float ey = addf(mulf(mulf(pKF2->fy, C2[1]), invz), pKF2->cy);
+
+        struct Query { size_t idx1; bool stereo1; int q; };
+        std::vector<Query> queries;
+        GatedPairs pairs(device_);
+        auto f1it = pKF1->mFeatVec.begin(), f1end = pKF1->mFeatVec.end();
+        auto f2it = pKF2->mFeatVec.begin(), f2end = pKF2->mFeatVec.end();
+        std::vector<size_t> open2;
+        while (f1it != f1end && f2it != f2end) {
+            if (f1it->first == f2it->first) {
+                open2.clear();  // features of this node in KF2 that have no MapPoint yet (and are stereo if required)
+                for (size_t i2 = 0; i2 < f2it->second.size(); i2++) {
+                    const size_t idx2 = f2it->second[i2];
+                    if (pKF2->GetMapPoint(idx2)) continue;
+                    if (bOnlyStereo && !(pKF2->mvuRight[idx2] >= 0)) continue;
+                    open2.push_back(idx2);
+                }
+                for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+                    const size_t idx1 = f1it->second[i1];
+                    if (pKF1->GetMapPoint(idx1)) continue;
+                    const bool bStereo1 = pKF1->mvuRight[idx1] >= 0;
+                    if (bOnlyStereo && !bStereo1) continue;
+                    const Query q = {idx1, bStereo1, pairs.open(pKF1->mDescriptors.row((int)idx1))};
+                    pairs.add(open2);
+                    pairs.close();
+                    queries.push_back(q);
+                }
+                f1it++; f2it++;
+            } else if (f1it->first < f2it->first) f1it = pKF1->mFeatVec.lower_bound(f2it->first);
+            else f2it = pKF2->mFeatVec.lower_bound(f1it->first);
+        }
+        pairs.run(pKF2->mDescriptors);
+
+        int nmatches = 0;
+        std::vector<int> vMatches12(pKF1->N, -1);
+        std::vector<int> rotHist[HISTO_LENGTH];
+        for (size_t n = 0; n < queries.size(); ++n) {
+            const Query& q = queries[n];
+            const cv::KeyPoint& kp1 = pKF1->mvKeysUn[q.idx1];
+            int bestDist = TH_LOW, bestIdx2 = -1;
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
+                const size_t idx2 = pairs.cand(k);
+                const int dist = pairs.dist(k);
+                if (dist > TH_LOW || dist > bestDist) continue;
+                const cv::KeyPoint& kp2 = pKF2->mvKeysUn[idx2];
+                if (!q.stereo1 && !(pKF2->mvuRight[idx2] >= 0)) {  // too close to the epipole: skip
+                    const float distex = subf(ex, kp2.pt.x), distey = subf(ey, kp2.pt.y);
+                    if (addf(mulf(distex, distex), mulf(distey, distey)) < 100 * pKF2->mvScaleFactors[kp2.octave]) continue;
+                }
+                if (CheckDistEpipolarLine(kp1, kp2, F12, pKF2)) { bestIdx2 = (int)idx2; bestDist = dist; }
+            }
+            if (bestIdx2 >= 0) {
+                vMatches12[q.idx1] = bestIdx2;
+                nmatches++;
+                if (mbCheckOrientation) rotHist[RotationBin(kp1.angle, pKF2->mvKeysUn[bestIdx2].angle)].push_back((int)q.idx1);
+            }
+        }
+        if (mbCheckOrientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) { vMatches12[rotHist[i][j]] = -1; nmatches--; }
+            }
+        }
+        vMatchedPairs.clear();
+        vMatchedPairs.reserve(nmatches);
+        for (size_t i = 0; i < vMatches12.size(); i++)
+            if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
+        return nmatches;
+    }
+
+    // Project MapPoints into a KeyFrame and search for duplicated MapPoints (src/ORBmatcher.cc:827-977); LocalMapping.
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th = 3.0) {
+        using namespace b200_detail;
+        const Rot3 Rcw = rotation3(pKF->GetRotation());
+        const Vec3 tcw = column3(pKF->GetTranslation());
+        const Vec3 Ow = column3(pKF->GetCameraCenter());
+        struct Query { MapPointT* mp; int q; };
+        std::vector<Query> queries;
+        GatedPairs pairs(device_);
+        std::vector<size_t> kept;
+        for (int i = 0, nMPs = (int)vpMapPoints.size(); i < nMPs; i++) {
+            MapPointT* pMP = vpMapPoints[i];
+            if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+            const Vec3 p3Dw = column3(pMP->GetWorldPos());
+            const Vec3 p3Dc = transform(Rcw, p3Dw, tcw);
+            if (p3Dc[2] < 0.0f) continue;
+            const float invz = divf(1.0f, p3Dc[2]);
+            const float u = addf(mulf(pKF->fx, mulf(p3Dc[0], invz)), pKF->cx);
+            const float v = addf(mulf(pKF->fy, mulf(p3Dc[1], invz)), pKF->cy);
+            if (!pKF->IsInImage(u, v)) continue;
+            const float ur = subf(u, mulf(pKF->mbf, invz));
+            const Vec3 PO = minus3(p3Dw, Ow);
+            const float dist3D = norm3(PO);
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            if (dot3(PO, column3(pMP->GetNormal())) < 0.5 * dist3D) continue;
+            const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+            const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+            const std::vector<size_t> vIndices = pKF->GetFeaturesInArea(u, v, radius);
+            if (vIndices.empty()) continue;
+            kept.clear();  // level window and reprojection-error gate (stateless): 902-936
+            for (size_t n = 0; n < vIndices.size(); ++n) {
+                const size_t idx = vIndices[n];
+                const cv::KeyPoint& kp = pKF->mvKeysUn[idx];
+                const int kpLevel = kp.octave;
+                if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+                const float ex = subf(u, kp.pt.x), ey = subf(v, kp.pt.y);
+                float e2 = addf(mulf(ex, ex), mulf(ey, ey));
+                if (pKF->mvuRight[idx] >= 0) {
+                    const float er = subf(ur, pKF->mvuRight[idx]);
+                    e2 = addf(e2, mulf(er, er));
+                    if (mulf(e2, pKF->mvInvLevelSigma2[kpLevel]) > 7.8) continue;
+                } else if (mulf(e2, pKF->mvInvLevelSigma2[kpLevel]) > 5.99) continue;
+                kept.push_back(idx);
+            }
+            const Query q = {pMP, pairs.open(pMP->GetDescriptor())};
+            pairs.add(kept);
+            pairs.close();
+            queries.push_back(q);
+        }
+        pairs.run(pKF->mDescriptors);
+
+        int nFused = 0;
+        for (size_t n = 0; n < queries.size(); ++n) {
+            MapPointT* pMP = queries[n].mp;
+            if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;  // earlier replacements of this call may have changed it
+            int bestDist = 256, bestIdx = -1;
+            for (int k = pairs.begin(queries[n].q); k < pairs.end(queries[n].q); ++k)
+                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx = (int)pairs.cand(k); }
+            if (bestDist <= TH_LOW) {  // replace if the keypoint already has a MapPoint, otherwise add the measurement
+                MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx);
+                if (pMPinKF) {
+                    if (!pMPinKF->isBad()) {
+                        if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                        else pMPinKF->Replace(pMP);
+                    }
+                } else {
+                    pMP->AddObservation(pKF, bestIdx);
+                    pKF->AddMapPoint(pMP, bestIdx);
+                }
+                nFused++;
+            }
+        }
+        return nFused;
+    }
+
+    // Project MapPoints into a KeyFrame using a given Sim3 and search for duplicated MapPoints (src/ORBmatcher.cc:979-1102).
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint) {
+        using namespace b200_detail;
+        const Sim3Camera cam = DecomposeSim3(Scw);
+        const std::set<MapPointT*> spAlreadyFound = pKF->GetMapPoints();
+        struct Query { int iMP; MapPointT* mp; int q; };
+        std::vector<Query> queries;
+        GatedPairs pairs(device_);
+        for (int iMP = 0, nPoints = (int)vpPoints.size(); iMP < nPoints; iMP++) {
+            MapPointT* pMP = vpPoints[iMP];
+            if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+            const Vec3 p3Dw = column3(pMP->GetWorldPos());
+            const Vec3 p3Dc = transform(cam.R, p3Dw, cam.t);
+            if (p3Dc[2] < 0.0f) continue;
+            const float invz = 1.0 / p3Dc[2];
+            const float u = addf(mulf(pKF->fx, mulf(p3Dc[0], invz)), pKF->cx);
+            const float v = addf(mulf(pKF->fy, mulf(p3Dc[1], invz)), pKF->cy);
+            if (!pKF->IsInImage(u, v)) continue;
+            const Vec3 PO = minus3(p3Dw, cam.Ow);
+            const float dist3D = norm3(PO);
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            if (dot3(PO, column3(pMP->GetNormal())) < 0.5 * dist3D) continue;
+            const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+            const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+            const std::vector<size_t> vIndices = pKF->GetFeaturesInArea(u, v, radius);
+            if (vIndices.empty()) continue;
+            const Query q = {iMP, pMP, pairs.open(pMP->GetDescriptor())};
+            pairs.add(LevelWindow(vIndices, pKF->mvKeysUn, nPredictedLevel));
+            pairs.close();
+            queries.push_back(q);
+        }
+        pairs.run(pKF->mDescriptors);
+
+        int nFused = 0;
+        for (size_t n = 0; n < queries.size(); ++n) {
+            const Query& q = queries[n];
+            int bestDist = INT_MAX, bestIdx = -1;
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k)
+                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx = (int)pairs.cand(k); }
+            if (bestDist <= TH_LOW) {
+                MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx);
+                if (pMPinKF) {
+                    if (!pMPinKF->isBad()) vpReplacePoint[q.iMP] = pMPinKF;
+                } else {
+                    q.mp->AddObservation(pKF, bestIdx);
+                    pKF->AddMapPoint(q.mp, bestIdx);
+                }
+                nFused++;
+            }
+        }
+        return nFused;
+    }
+
+    // Search matches between MapPoints seen in KF1 and KF2, transforming by a Sim3 [s12*R12|t12]
+    // (src/ORBmatcher.cc:1104-1328); loop closing and MapFusion::ComputeSim3.
+    template <class KeyFrameT, class MapPointT>
+    int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                     const cv::Mat& t12, const float th) {
+        using namespace b200_detail;
+        // transformation between the cameras: sR12 = s12*R12, sR21 = (1.0/s12)*R12.t(), t21 = -sR21*t12 (cv::Mat scaling
+        // multiplies every element by the float of the double factor)
+        Rot3 sR12 = rotation3(R12), sR21;
+        const float inv_s = (float)(1.0 / s12);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sR21.m[3 * i + j] = mulf(sR12.m[3 * j + i], inv_s);
+        for (int i = 0; i < 9; ++i) sR12.m[i] = mulf(sR12.m[i], s12);
+        const Vec3 t12v = column3(t12), zero = {{0.f, 0.f, 0.f}};
+        Vec3 t21 = transform(sR21, t12v, zero);
+        for (int i = 0; i < 3; ++i) t21.v[i] = -t21.v[i];
+
+        const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+        std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+        for (int i = 0; i < N1; i++) {
+            MapPointT* pMP = vpMatches12[i];
+            if (!pMP) continue;
+            vbAlreadyMatched1[i] = true;
+            const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+        const std::vector<int> vnMatch1 = Sim3Direction(pKF1, pKF2, pKF1, vpMapPoints1, vbAlreadyMatched1, sR21, t21, th);  // KF1 -> KF2
+        const std::vector<int> vnMatch2 = Sim3Direction(pKF2, pKF1, pKF1, vpMapPoints2, vbAlreadyMatched2, sR12, t12v, th);  // KF2 -> KF1
+        int nFound = 0;  // check agreement
+        for (int i1 = 0; i1 < N1; i1++) {
+            const int idx2 = vnMatch1[i1];
+            if (idx2 >= 0 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
+        }
+        return nFound;
+    }
+
     // Brute-force ratio-test matching of two descriptor matrices (the SearchByBoW(KF,KF) inner loop,
     // src/ORBmatcher.cc:566-603, with the vocabulary gate removed): vnMatches12[i] = row of D2 or -1.
     int SearchBruteForce(const cv::Mat& D1, const cv::Mat& D2, std::vector<int>& vnMatches12, int th = TH_LOW) {
@@ -230,6 +862,103 @@ public:
     static const int HISTO_LENGTH = 30;
 
 protected:
+    static float RadiusByViewingCos(const float& viewCos) { return viewCos > 0.998 ? 2.5f : 4.0f; }  // src/ORBmatcher.cc:133-139
+
+    // the rotation-histogram slot of a match (e.g. src/ORBmatcher.cc:1434-1441): bin = round(rot * 1/HISTO_LENGTH)
+    static int RotationBin(float angle1, float angle2) {
+        float rot = angle1 - angle2;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * (1.0f / HISTO_LENGTH));
+        if (bin == HISTO_LENGTH) bin = 0;
+        return bin;
+    }
+
+    // candidates at the levels [nPredictedLevel-1, nPredictedLevel], order kept (e.g. src/ORBmatcher.cc:375-378)
+    template <class KeyPoints>
+    static std::vector<size_t> LevelWindow(const std::vector<size_t>& vIndices, const KeyPoints& vKeysUn, int nPredictedLevel) {
+        std::vector<size_t> kept;
+        for (size_t n = 0; n < vIndices.size(); ++n) {
+            const int kpLevel = vKeysUn[vIndices[n]].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            kept.push_back(vIndices[n]);
+        }
+        return kept;
+    }
+
+    // "Decompose Scw" (src/ORBmatcher.cc:300-305, 987-992): scw = |first row of sR|, Rcw = sRcw/scw, tcw = t/scw, Ow = -Rcw.t()*tcw.
+    // cv::Mat / scalar multiplies every element by the float of the double reciprocal.
+    struct Sim3Camera { b200_detail::Rot3 R; b200_detail::Vec3 t, Ow; };
+    static Sim3Camera DecomposeSim3(const cv::Mat& Scw) {
+        using namespace b200_detail;
+        Sim3Camera c;
+        const Rot3 sR = rotation3(Scw);
+        const Vec3 row0 = {{sR.m[0], sR.m[1], sR.m[2]}};
+        const float scw = std::sqrt(dot3(row0, row0));
+        const float inv = (float)(1.0 / scw);
+        for (int i = 0; i < 9; ++i) c.R.m[i] = mulf(sR.m[i], inv);
+        const Vec3 t = column3(Scw, 3);
+        for (int i = 0; i < 3; ++i) c.t.v[i] = mulf(t[i], inv);
+        c.Ow = minusRtT(c.R, c.t);
+        return c;
+    }
+
+    // Epipolar line in the second image l = x1'F12 = [a b c]; distance test (src/ORBmatcher.cc:142-159)
+    template <class KeyFrameT>
+    static bool CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat& F12, const KeyFrameT* pKF2) {
+        using namespace b200_detail;
+        const float a = addf(addf(mulf(kp1.pt.x, F12.at<float>(0, 0)), mulf(kp1.pt.y, F12.at<float>(1, 0))), F12.at<float>(2, 0));
+        const float b = addf(addf(mulf(kp1.pt.x, F12.at<float>(0, 1)), mulf(kp1.pt.y, F12.at<float>(1, 1))), F12.at<float>(2, 1));
+        const float c = addf(addf(mulf(kp1.pt.x, F12.at<float>(0, 2)), mulf(kp1.pt.y, F12.at<float>(1, 2))), F12.at<float>(2, 2));
+        const float num = addf(addf(mulf(a, kp2.pt.x), mulf(b, kp2.pt.y)), c);
+        const float den = addf(mulf(a, a), mulf(b, b));
+        if (den == 0) return false;
+        const float dsqr = divf(mulf(num, num), den);
+        return dsqr < 3.84 * pKF2->mvLevelSigma2[kp2.octave];
+    }
+
+    // One direction of SearchBySim3 (src/ORBmatcher.cc:1152-1229 / 1232-1309): the MapPoints of pKFa transformed into pKFb
+    // by [sRba|tba] after their own camera transform, projected with pKFcal's intrinsics; no state between queries, so the device result is used as is.
+    template <class KeyFrameT, class MapPointT>
+    std::vector<int> Sim3Direction(KeyFrameT* pKFa, KeyFrameT* pKFb, KeyFrameT* pKFcal, const std::vector<MapPointT*>& vpMapPointsA,
+                                   const std::vector<bool>& vbAlreadyMatchedA, const b200_detail::Rot3& sRba, const b200_detail::Vec3& tba,
+                                   const float th) {
+        using namespace b200_detail;
+        const Rot3 Raw = rotation3(pKFa->GetRotation());
+        const Vec3 taw = column3(pKFa->GetTranslation());
+        const int NA = (int)vpMapPointsA.size();
+        std::vector<int> vnMatch(NA, -1), owner;
+        GatedPairs pairs(device_);
+        for (int i = 0; i < NA; i++) {
+            MapPointT* pMP = vpMapPointsA[i];
+            if (!pMP || vbAlreadyMatchedA[i] || pMP->isBad()) continue;
+            const Vec3 p3Dca = transform(Raw, column3(pMP->GetWorldPos()), taw);
+            const Vec3 p3Dcb = transform(sRba, p3Dca, tba);
+            if (p3Dcb[2] < 0.0) continue;
+            const float invz = 1.0 / p3Dcb[2];
+            const float u = addf(mulf(pKFcal->fx, mulf(p3Dcb[0], invz)), pKFcal->cx);  // pKF1's intrinsics in both directions (1107-1110)
+            const float v = addf(mulf(pKFcal->fy, mulf(p3Dcb[1], invz)), pKFcal->cy);
+            if (!pKFb->IsInImage(u, v)) continue;
+            const float dist3D = norm3(p3Dcb);
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            const int nPredictedLevel = pMP->PredictScale(dist3D, pKFb);
+            const float radius = th * pKFb->mvScaleFactors[nPredictedLevel];
+            const std::vector<size_t> vIndices = pKFb->GetFeaturesInArea(u, v, radius);
+            if (vIndices.empty()) continue;
+            pairs.open(pMP->GetDescriptor());
+            pairs.add(LevelWindow(vIndices, pKFb->mvKeysUn, nPredictedLevel));
+            pairs.close();
+            owner.push_back(i);
+        }
+        pairs.run(pKFb->mDescriptors);
+        for (size_t q = 0; q < owner.size(); ++q) {
+            int bestDist = INT_MAX, bestIdx = -1;
+            for (int k = pairs.begin((int)q); k < pairs.end((int)q); ++k)
+                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx = (int)pairs.cand(k); }
+            if (bestDist <= TH_HIGH) vnMatch[owner[q]] = bestIdx;
+        }
+        return vnMatch;
+    }
+
     static std::vector<uint8_t> pack(const cv::Mat& D) {  // rows contiguous, 32 bytes each
         std::vector<uint8_t> v((size_t)D.rows * 32);
         for (int i = 0; i < D.rows; ++i) std::memcpy(&v[(size_t)i * 32], D.ptr(i), 32);

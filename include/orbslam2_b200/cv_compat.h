@@ -10,6 +10,8 @@
 #ifndef CV_8U
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
 #endif
 
 namespace cv {
@@ -38,16 +40,17 @@ public:
     uchar* data = nullptr;
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
-    Mat(int r, int c, int /*type*/, void* ext, size_t stp) : rows(r), cols(c), step(stp), data((uchar*)ext) {}
-    void create(int r, int c, int /*type*/) {
-        if (data && r == rows && c == cols) return;
-        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * c);
-        rows = r; cols = c; step = (size_t)c; data = buf_->data();
+    Mat(int r, int c, int type, void* ext, size_t stp) : rows(r), cols(c), step(stp), data((uchar*)ext), type_(type) {}
+    void create(int r, int c, int type) {  // CV_8U or CV_32F, one channel
+        if (data && r == rows && c == cols && type == type_) return;
+        const size_t esz = type == CV_32F ? 4 : 1;
+        buf_ = std::make_shared<std::vector<uchar>>((size_t)r * c * esz);
+        rows = r; cols = c; step = (size_t)c * esz; data = buf_->data(); type_ = type;
     }
     void release() { buf_.reset(); data = nullptr; rows = cols = 0; step = 0; }
     bool empty() const { return !data || rows == 0 || cols == 0; }
-    int type() const { return CV_8UC1; }
-    Mat row(int r) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.data = data + (size_t)r * step; m.buf_ = buf_; return m; }
+    int type() const { return type_; }
+    Mat row(int r) const { Mat m; m.rows = 1; m.cols = cols; m.step = step; m.data = data + (size_t)r * step; m.buf_ = buf_; m.type_ = type_; return m; }
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }
@@ -56,6 +59,7 @@ public:
     template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step + c * sizeof(T)); }
 private:
     std::shared_ptr<std::vector<uchar>> buf_;
+    int type_ = CV_8UC1;
 };
 
 class _InputArray {

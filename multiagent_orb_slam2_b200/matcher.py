@@ -320,10 +320,10 @@ def _search_by_projection_frame_mappoints(self, grid, kp_octave, uright, occupie
     rad = (r * np.asarray(scale_factors, f32)[lvl]).astype(f32)
     rad_q = np.where(live, rad, f32(0)).astype(f32)  # dead map points: empty window
     offsets, cands, dist = grid.window_lists(mp["desc"], mp["proj_x"], mp["proj_y"], rad_q, lvl - 1, lvl)
-    return _replay_frame_mappoints(self, offsets, cands, dist, live, rad, mp["proj_xr"], kp_octave, uright, occupied)
+    return _replay_frame_mappoints(self, offsets, cands, dist, live, rad, mp["proj_xr"], kp_octave, uright, occupied, mp.get("has_obs"))
 
 
-def _replay_frame_mappoints(self, offsets, cands, dist, live, rad, proj_xr, kp_octave, uright, occupied):
+def _replay_frame_mappoints(self, offsets, cands, dist, live, rad, proj_xr, kp_octave, uright, occupied, has_obs=None):
     """The ordered loop of src/ORBmatcher.cc:52-128 over the device's candidate lists."""
     f32 = np.float32
     occupied = np.asarray(occupied, bool).copy()
@@ -350,7 +350,7 @@ def _replay_frame_mappoints(self, offsets, cands, dist, live, rad, proj_xr, kp_o
             if l1 == l2 and f32(b1) > ratio * f32(b2):
                 continue
             assigned[bi] = i
-            occupied[bi] = True
+            occupied[bi] = True if has_obs is None else bool(has_obs[i])  # Observations() > 0 of the assigned point (90-92)
             nm += 1
     return nm, assigned
 

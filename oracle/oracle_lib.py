@@ -537,7 +537,7 @@ def search_by_projection_frame_mappoints(F, mp, th, nnratio=0.8, th_high=100):
             if l1 == l2 and np.float32(b1) > ratio * np.float32(b2):
                 continue
             assigned[bi] = i
-            occupied[bi] = True
+            occupied[bi] = bool(mp["has_obs"][i]) if "has_obs" in mp else True
             nm += 1
     return nm, assigned
 
@@ -589,7 +589,7 @@ def _rot_cleanup(rot, clear, L=30):
     return removed
 
 
-def search_by_projection_cur_last(F, last, th, forward, backward, check_ori=True, th_high=100):
+def search_by_projection_cur_last(F, last, th, forward, backward, check_ori=True, th_high=100, cleared=None):
     """src/ORBmatcher.cc:1330-1472. F: OracleFrame (current) with F.scale, F.uright, F.occupied; last: dict of arrays
     valid, u, v, ur, octave, angle, desc, has_obs."""
     assigned = np.full(len(F.kps), -1, np.int32)
@@ -629,11 +629,13 @@ def search_by_projection_cur_last(F, last, th, forward, backward, check_ori=True
     if check_ori:
         def clear(j):
             assigned[j] = -1
+            if cleared is not None:
+                cleared.add(j)
         nm -= _rot_cleanup(rot, clear)
     return nm, assigned
 
 
-def search_by_projection_cur_kf(F, q, th, orb_dist, check_ori=True):
+def search_by_projection_cur_kf(F, q, th, orb_dist, check_ori=True, cleared=None):
     """src/ORBmatcher.cc:1474-1601. F.occupied[kp]: mvpMapPoints[kp] set. q: valid, u, v, level, angle, desc."""
     assigned = np.full(len(F.kps), -1, np.int32)
     occupied = F.occupied.copy()
@@ -663,6 +665,8 @@ def search_by_projection_cur_kf(F, q, th, orb_dist, check_ori=True):
     if check_ori:
         def clear(j):
             assigned[j] = -1
+            if cleared is not None:
+                cleared.add(j)
         nm -= _rot_cleanup(rot, clear)
     return nm, assigned
 
@@ -945,4 +949,103 @@ def project_points(cam, pos, normal, max_d, min_d, mode, cos_limit=0.5, th=1.0):
                     radius = f(f(th) * scale[level])
             out["alive"][i] = ok; out["u"][i] = u; out["v"][i] = v; out["ur"][i] = ur
             out["level"][i] = level; out["view_cos"][i] = view_cos; out["radius"][i] = radius
+    return out
+
+
+# ---- the projection prologues of the guided searches with their individual quirks (C++ facade parity) ----------
+def _project_one(R, P, t, fx, fy, cx, cy, invz_double, uform):
+    """Pc = R*P+t; invz as `1.0/z` (double division rounded to float) or `1/z`, `1.0f/z` (float division);
+    uform 0: fx*x*invz+cx (src/ORBmatcher.cc:1371-1372), 1: fx*(x*invz)+cx (e.g. 337-341)."""
+    f = np.float32
+    pc = _mat3_vec(R, P, t)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        invz = f(1.0 / float(pc[2])) if invz_double else f(f(1.0) / pc[2])
+        if uform == 0:
+            u = f(f(f(fx * pc[0]) * invz) + cx); v = f(f(f(fy * pc[1]) * invz) + cy)
+        else:
+            u = f(f(fx * f(pc[0] * invz)) + cx); v = f(f(fy * f(pc[1] * invz)) + cy)
+    return pc, invz, u, v
+
+
+def minus_Rt_t(R, t):
+    """cv::Mat -R.t()*t (general gemm: double accumulation), e.g. mOw, src/ORBmatcher.cc:1343, 1480."""
+    R = np.asarray(R, np.float32).reshape(3, 3).astype(np.float64); t = np.asarray(t, np.float32).astype(np.float64)
+    return np.array([-1.0 * ((R[0, i] * t[0] + R[1, i] * t[1]) + R[2, i] * t[2]) for i in range(3)]).astype(np.float32)
+
+
+def decompose_sim3(Scw):
+    """src/ORBmatcher.cc:300-305: scw = sqrt(row0.row0), Rcw = sRcw/scw, tcw = t/scw (cv::Mat / scalar = times the float of the
+    double reciprocal), Ow = -Rcw.t()*tcw."""
+    f = np.float32
+    S = np.asarray(Scw, f).reshape(4, 4)
+    scw = f(np.sqrt(_dot3(S[0, :3], S[0, :3])))
+    inv = f(1.0 / float(scw))
+    R = (S[:3, :3] * inv).astype(f); t = (S[:3, 3] * inv).astype(f)
+    return R, t, minus_Rt_t(R, t)
+
+
+def _in_frame(u, v, b):   # Frame bounds test: u<mnMinX || u>mnMaxX -> out
+    return not (u < b[0] or u > b[1]) and not (v < b[2] or v > b[3])
+
+
+def _in_image(u, v, b):   # KeyFrame::IsInImage, src/KeyFrame.cc:630-633
+    return bool(u >= b[0] and u < b[1] and v >= b[2] and v < b[3])
+
+
+def prologue_cur_last(cam, Tcw_cur, pos, alive):
+    """src/ORBmatcher.cc:1361-1380. Returns valid, u, v, ur per point."""
+    f = np.float32
+    T = np.asarray(Tcw_cur, f).reshape(4, 4)
+    n = len(pos)
+    out = dict(valid=np.zeros(n, bool), u=np.zeros(n, f), v=np.zeros(n, f), ur=np.zeros(n, f))
+    b = (cam["min_x"], cam["max_x"], cam["min_y"], cam["max_y"])
+    for i in range(n):
+        if not alive[i]:
+            continue
+        pc, invz, u, v = _project_one(T[:3, :3], np.asarray(pos[i], f), T[:3, 3], cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, 0)
+        if invz < 0 or not _in_frame(u, v, b):
+            continue
+        out["valid"][i] = True; out["u"][i] = u; out["v"][i] = v; out["ur"][i] = f(u - f(f(cam["bf"]) * invz))
+    return out
+
+
+def motion_direction(Tcw_cur, Tcw_last, mb, mono):
+    """bForward / bBackward, src/ORBmatcher.cc:1340-1351."""
+    f = np.float32
+    Tc = np.asarray(Tcw_cur, f).reshape(4, 4); Tl = np.asarray(Tcw_last, f).reshape(4, 4)
+    twc = minus_Rt_t(Tc[:3, :3], Tc[:3, 3])
+    tlc = _mat3_vec(Tl[:3, :3], twc, Tl[:3, 3])
+    return bool(tlc[2] > f(mb) and not mono), bool(-tlc[2] > f(mb) and not mono)
+
+
+def prologue_scaled(cam, R, t, Ow, pos, normal, max_d, min_d, alive, invz_double, zcheck, uform, bounds, normal_gate, pre=None,
+                    dist_from_cam=False):
+    """The common shape of src/ORBmatcher.cc:1497-1527 (Cur,KF), 323-363 (KF,Scw), 1007-1047 (Fuse Scw), 1169-1186 (Sim3):
+    project, bounds, distance-invariance range, optional viewing-angle gate, PredictScale. pre=(R0,t0): a first camera
+    transform (SearchBySim3). Returns valid, u, v, level."""
+    f = np.float32
+    n = len(pos)
+    out = dict(valid=np.zeros(n, bool), u=np.zeros(n, f), v=np.zeros(n, f), level=np.zeros(n, np.int32))
+    b = (cam["min_x"], cam["max_x"], cam["min_y"], cam["max_y"])
+    for i in range(n):
+        if not alive[i]:
+            continue
+        P = np.asarray(pos[i], f)
+        Pin = np.array(_mat3_vec(pre[0], P, pre[1]), f) if pre is not None else P
+        pc, invz, u, v = _project_one(R, Pin, t, cam["fx"], cam["fy"], cam["cx"], cam["cy"], invz_double, uform)
+        if zcheck and pc[2] < 0:
+            continue
+        if not (_in_frame(u, v, b) if bounds == "frame" else _in_image(u, v, b)):
+            continue
+        if dist_from_cam:
+            PO = pc
+        else:
+            PO = [f(P[k] - Ow[k]) for k in range(3)]
+        dist = _norm3(PO)
+        if dist < f(f(0.8) * f(min_d[i])) or dist > f(f(1.2) * f(max_d[i])):
+            continue
+        if normal_gate and _dot3(PO, np.asarray(normal[i], f)) < 0.5 * float(dist):
+            continue
+        out["valid"][i] = True; out["u"][i] = u; out["v"][i] = v
+        out["level"][i] = predict_scale(max_d[i], dist, cam["log_scale_factor"], len(cam["scale"]))
     return out
