@@ -245,6 +245,12 @@ int orbm_project_points_device(int device, const orbm_camera* cam, int mode, flo
                                int32_t* d_level, float* d_view_cos, float* d_radius, int32_t* d_min_level,
                                int32_t* d_max_level, void* stream);
 
+/* Frame::ComputeStereoFromRGBD (src/Frame.cc:643-664) for the keypoints an extractor left on the device
+ * (orbx_device_results: d_kps, d_count, cap): depth image (float, device, stride in bytes) sampled at the truncated
+ * keypoint position; d_depth[i] = d and d_uRight[i] = x - mbf/d when d > 0, else -1 (also for i >= count). */
+int orbm_stereo_from_rgbd_device(int device, const orbx_keypoint* d_kps, const int32_t* d_count, int cap, const float* d_depth_image,
+                                 int width, int height, size_t stride_bytes, float mbf, float* d_uRight, float* d_depth, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Vocabulary tree descent (the step right after extraction): replaces the per-feature
  * TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) with FORB::distance
@@ -261,6 +267,26 @@ void orbv_destroy(orbv_handle v);
 int orbv_descend_device(orbv_handle v, const uint8_t* d_desc, int n, int levelsup, int32_t* d_word, int32_t* d_node,
                         double* d_weight, void* stream);
 int orbv_descend(orbv_handle v, const uint8_t* desc, int n, int levelsup, int32_t* word, int32_t* node, double* weight);
+
+/* ------------------------------------------------------------------------------------------
+ * Keyframe database scoring: for a query BowVector, the number of words shared with every
+ * keyframe of the database (the inverted-file walk of KeyFrameDatabase::DetectLoopCandidates, src/KeyFrameDatabase.cc:85-105),
+ * the first shared word (which fixes the order in which the reference meets the keyframes) and the similarity
+ * mpVoc->score(query, keyframe) (131) = L1Scoring::score (Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-66), bit-identical
+ * doubles. BowVectors are given as (ascending word id, weight) arrays - the iteration order of DBoW2::BowVector.
+ * orbdb_add replaces KeyFrameDatabase::add (40-46) and returns the keyframe's slot; orbdb_erase replaces erase (48-66).
+ * The candidate bookkeeping that follows (minCommonWords, covisibility accumulation, 0.75*best filter) walks the
+ * keyframe graph and stays with the caller. */
+typedef struct orbdb_database* orbdb_handle;
+int orbdb_create(int device, int n_words, orbdb_handle* out);
+void orbdb_destroy(orbdb_handle db);
+int orbdb_size(orbdb_handle db);
+int orbdb_add(orbdb_handle db, const int32_t* word_ids, const double* weights, int n, int* slot_out);
+int orbdb_erase(orbdb_handle db, int slot);
+int orbdb_query_device(orbdb_handle db, const int32_t* q_word_ids, const double* q_weights, int nq, int32_t* d_common,
+                       int32_t* d_first_word, double* d_score, void* stream);
+int orbdb_query(orbdb_handle db, const int32_t* q_word_ids, const double* q_weights, int nq, int32_t* common, int32_t* first_word,
+                double* score, int cap);
 
 #ifdef __cplusplus
 }

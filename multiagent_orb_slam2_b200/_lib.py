@@ -75,6 +75,13 @@ def lib():
         "orbv_descend": [vp, vp, i32, i32, vp, vp, vp],
         "orbm_distance_matrix_device": [vp, i32, vp, i32, vp, vp],
         "orbm_distance_matrix": [i32, vp, i32, vp, i32, vp],
+        "orbdb_create": [i32, i32, C.POINTER(vp)],
+        "orbdb_add": [vp, vp, vp, i32, C.POINTER(i32)],
+        "orbdb_erase": [vp, i32],
+        "orbdb_size": [vp],
+        "orbdb_query": [vp, vp, vp, i32, vp, vp, vp, i32],
+        "orbdb_query_device": [vp, vp, vp, i32, vp, vp, vp, vp],
+        "orbm_stereo_from_rgbd_device": [i32, vp, vp, i32, vp, i32, i32, C.c_size_t, f32, vp, vp, vp],
         "orbm_project_points_device": [i32, vp, i32, f32, f32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sigs.items():
@@ -85,6 +92,8 @@ def lib():
     L.orb_launch_count.restype = C.c_longlong
     L.orbm_grid_destroy.argtypes = [vp]
     L.orbm_grid_destroy.restype = None
+    L.orbdb_destroy.argtypes = [vp]
+    L.orbdb_destroy.restype = None
     L.orbv_destroy.argtypes = [vp]
     L.orbv_destroy.restype = None
     L.orbx_destroy.argtypes = [vp]
@@ -104,4 +113,4 @@ def exported_symbols():
     import re
     hdr = open(os.path.join(HERE, "..", "include", "orb_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(orb[xm]?_[a-z0-9_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(orb[a-z]*_[a-z0-9_]+)\s*\(", hdr)))

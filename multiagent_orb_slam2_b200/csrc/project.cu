@@ -87,6 +87,29 @@ __global__ void __launch_bounds__(256) project_points_kernel(const ProjectParams
     if (out_max_level) out_max_level[i] = level;
 }
 
+// Frame::ComputeStereoFromRGBD (/root/reference/src/Frame.cc:643-664): the depth image sampled at the (truncated) keypoint
+// position gives mvDepth, and mvuRight = x - mbf/depth, for the keypoints an extractor left on the device.
+__global__ void __launch_bounds__(256) stereo_from_rgbd_kernel(const orbx_keypoint* __restrict__ kps, const int32_t* __restrict__ count, int cap,
+                                                               const float* __restrict__ depth_img, int width, int height, size_t pitch_floats,
+                                                               float mbf, float* __restrict__ uright, float* __restrict__ depth) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    float ur = -1.0f, dz = -1.0f;
+    if (i < min(*count, cap)) {
+        const orbx_keypoint kp = kps[i];
+        const int u = (int)kp.x, v = (int)kp.y;  // imDepth.at<float>(v,u) with float arguments: truncation
+        if (u >= 0 && u < width && v >= 0 && v < height) {
+            const float d = depth_img[(size_t)v * pitch_floats + u];
+            if (d > 0) {
+                dz = d;
+                ur = __fsub_rn(kp.x, __fdiv_rn(mbf, d));
+            }
+        }
+    }
+    uright[i] = ur;
+    depth[i] = dz;
+}
+
 }  // namespace orb
 
 extern "C" int orbm_project_points_device(int device, const orbm_camera* cam, int mode, float viewing_cos_limit, float th,
@@ -110,6 +133,19 @@ extern "C" int orbm_project_points_device(int device, const orbm_camera* cam, in
     project_points_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p, d_world_pos, d_normal, d_max_distance, d_min_distance,
                                                                              d_alive, d_u, d_v, d_ur, d_level, d_view_cos, d_radius,
                                                                              d_min_level, d_max_level);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+extern "C" int orbm_stereo_from_rgbd_device(int device, const orbx_keypoint* d_kps, const int32_t* d_count, int cap, const float* d_depth_image,
+                                            int width, int height, size_t stride_bytes, float mbf, float* d_uRight, float* d_depth, void* stream) {
+    using namespace orb;
+    ORB_REQUIRE(d_kps && d_count && d_depth_image && d_uRight && d_depth, "null pointer");
+    ORB_REQUIRE(cap > 0 && width > 0 && height > 0 && stride_bytes >= (size_t)width * 4 && stride_bytes % 4 == 0, "bad geometry");
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    stereo_from_rgbd_kernel<<<ceil_div(cap, 256), 256, 0, (cudaStream_t)stream>>>(d_kps, d_count, cap, d_depth_image, width, height,
+                                                                                 stride_bytes / 4, mbf, d_uRight, d_depth);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

@@ -1049,3 +1049,80 @@ def prologue_scaled(cam, R, t, Ow, pos, normal, max_d, min_d, alive, invz_double
         out["valid"][i] = True; out["u"][i] = u; out["v"][i] = v
         out["level"][i] = predict_scale(max_d[i], dist, cam["log_scale_factor"], len(cam["scale"]))
     return out
+
+
+# ---- keyframe database scoring (src/KeyFrameDatabase.cc + DBoW2 L1Scoring), scalar restatement ------------------
+def l1_score(id1, w1, id2, w2):
+    """L1Scoring::score, Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-66: merge walk over ascending word ids."""
+    i = j = 0
+    s = 0.0
+    while i < len(id1) and j < len(id2):
+        if id1[i] == id2[j]:
+            vi, wi = float(w1[i]), float(w2[j])
+            s += abs(vi - wi) - abs(vi) - abs(wi)
+            i += 1; j += 1
+        elif id1[i] < id2[j]:
+            i += 1
+        else:
+            j += 1
+    return -s / 2.0
+
+
+def ref_l1_score(id1, w1, id2, w2):
+    """The vendored DBoW2 itself (oracle/_ref/libref_dbow.so)."""
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_dbow.so"))
+    L.refv_l1_score.restype = C.c_double
+    L.refv_l1_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    a, b = np.ascontiguousarray(id1, np.int32), np.ascontiguousarray(id2, np.int32)
+    x, y = np.ascontiguousarray(w1, np.float64), np.ascontiguousarray(w2, np.float64)
+    return L.refv_l1_score(a.ctypes.data, x.ctypes.data, len(a), b.ctypes.data, y.ctypes.data, len(b))
+
+
+def detect_loop_candidates(db, alive, q_ids, q_w, min_score, connected, neighbours):
+    """KeyFrameDatabase::DetectLoopCandidates, src/KeyFrameDatabase.cc:76-197, on a list of BowVectors db[slot] = (ids, weights)
+    added in slot order; connected: set of slots; neighbours(slot): GetBestCovisibilityKeyFrames(10) of that keyframe.
+    Returns the candidate slots in the reference's output order."""
+    inverted = {}
+    for slot, (ids, _) in enumerate(db):
+        if alive[slot]:
+            for w in ids:
+                inverted.setdefault(int(w), []).append(slot)
+    sharing, words, queried = [], {}, set()
+    for w in q_ids:
+        for slot in inverted.get(int(w), []):
+            if slot not in queried:
+                words[slot] = 0
+                if slot not in connected:
+                    queried.add(slot)
+                    sharing.append(slot)
+            words[slot] += 1
+    if not sharing:
+        return []
+    max_common = max(words[s] for s in sharing)
+    min_common = int(np.float32(max_common) * np.float32(0.8))
+    score, matches = {}, []
+    for slot in sharing:
+        if words[slot] > min_common:
+            si = np.float32(l1_score(q_ids, q_w, db[slot][0], db[slot][1]))
+            score[slot] = si
+            if si >= np.float32(min_score):
+                matches.append((si, slot))
+    if not matches:
+        return []
+    acc, best_acc = [], np.float32(min_score)
+    for si, slot in matches:
+        best_score, acc_score, best_kf = si, si, slot
+        for nb in neighbours(slot):
+            if nb in queried and words[nb] > min_common:
+                acc_score = np.float32(acc_score + score[nb])
+                if score[nb] > best_score:
+                    best_kf, best_score = nb, score[nb]
+        acc.append((acc_score, best_kf))
+        if acc_score > best_acc:
+            best_acc = acc_score
+    retain = np.float32(np.float32(0.75) * best_acc)
+    out, seen = [], set()
+    for a, kf in acc:
+        if a > retain and kf not in seen:
+            out.append(kf); seen.add(kf)
+    return out

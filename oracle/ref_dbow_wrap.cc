@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "DBoW2/FORB.h"
+#include "DBoW2/ScoringObject.h"
 #include "DBoW2/TemplatedVocabulary.h"
 
 typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> ORBVocabulary;  // include/ORBVocabulary.h
@@ -64,6 +65,14 @@ int refv_transform(void* v, const uint8_t* desc, int n, int levelsup, int32_t* b
     }
     *n_fv = m;
     return 0;
+}
+
+// mpVoc->score(v1, v2) for the L1_NORM scoring of the ORB vocabulary: the vendored L1Scoring::score on two BowVectors
+double refv_l1_score(const int32_t* id1, const double* w1, int n1, const int32_t* id2, const double* w2, int n2) {
+    DBoW2::BowVector a, b;
+    for (int i = 0; i < n1; ++i) a.addWeight((DBoW2::WordId)id1[i], w1[i]);
+    for (int i = 0; i < n2; ++i) b.addWeight((DBoW2::WordId)id2[i], w2[i]);
+    return DBoW2::L1Scoring().score(a, b);
 }
 
 }  // extern "C"

@@ -108,3 +108,25 @@ def test_search_local_points_device_chain_matches_oracle(seed, th):
                                                           bad, k["octave"], uright, occupied, th)
     assert gnm == onm and np.array_equal(gas, oas)
     assert onm > 100
+
+
+def test_stereo_from_rgbd_matches_restatement():
+    """Frame::ComputeStereoFromRGBD (src/Frame.cc:643-664): depth sampled at the truncated keypoint position."""
+    from multiagent_orb_slam2_b200.extractor import compute_stereo_from_rgbd
+    rng = np.random.default_rng(4)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    k, _ = ex(synth.image("blocks", W, H, 90))
+    depth = rng.uniform(0.3, 8.0, (H, W)).astype(f32)
+    depth[rng.random((H, W)) < 0.2] = 0.0     # holes of the sensor
+    depth[rng.random((H, W)) < 0.02] = -1.0
+    mbf = f32(40.0)
+    ur, dz = compute_stereo_from_rgbd(ex, depth, mbf)
+    n = len(k)
+    want_d = np.full(len(ur), -1, f32); want_u = np.full(len(ur), -1, f32)
+    for i in range(n):  # scalar restatement of the reference loop
+        d = depth[int(k["y"][i]), int(k["x"][i])]
+        if d > 0:
+            want_d[i] = d
+            want_u[i] = f32(k["x"][i] - f32(mbf / d))
+    assert np.array_equal(dz.view(np.uint32), want_d.view(np.uint32)) and np.array_equal(ur.view(np.uint32), want_u.view(np.uint32))
+    assert 0.6 < (want_d[:n] > 0).mean() < 0.9
