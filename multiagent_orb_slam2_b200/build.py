@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "liborb_b200.so")
-SOURCES = ["runtime.cu", "hamming.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "extractor.cu", "stereo.cu", "bow.cu", "grid.cu", "project.cu", "kfdb.cu"]
+SOURCES = ["runtime.cu", "hamming.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "extractor.cu", "stereo.cu", "bow.cu", "grid.cu", "project.cu", "kfdb.cu", "hamming_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--fmad=false", "-cudart", "static"]
 

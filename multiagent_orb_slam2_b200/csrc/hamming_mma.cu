@@ -1,0 +1,222 @@
+// K7t: Hamming kNN-2 on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+// The Hamming distance of two 256-bit descriptors is a dot product in disguise: with the bits mapped to +1 / -1,
+// dot(a, b) = 256 - 2 * hamming(a, b). The best / second-best loop of ORBmatcher (/root/reference/src/ORBmatcher.cc:566-603
+// and every other `DescriptorDistance` loop, 1649-1665) over a whole descriptor set is then an int8 GEMM
+// (M = queries, N = candidates, K = 256) followed by a row-wise top-2 - and sm_100a's int8 tensor throughput is an order of
+// magnitude above the POPC pipe (0.58 T comparisons/s/GPU) even at 8 bytes per bit-octet.
+//
+//   expand_pm1_kernel : 32-byte descriptors -> 256 int8 (+1 / -1), row-major, K contiguous (the K-major operand layout)
+//   knn2_mma_kernel   : one CTA = 128 query rows; TMA (SWIZZLE_128B) streams 256-candidate tiles through a shared-memory
+//                       ring, one elected thread issues 8 tcgen05.mma (K = 32 each) per tile into a double-buffered
+//                       128 x 256 int32 accumulator in TMEM, 8 epilogue warps read it back with tcgen05.ld and keep the
+//                       two largest dot products (= two smallest distances, first minimum by candidate order) per row.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace orb {
+
+// ---- bits -> +-1 bytes ---------------------------------------------------------------------------------------------
+// thread = one 32-bit word of a descriptor -> 32 output bytes. Bit b of the word lands in byte b; any fixed permutation
+// of K is fine as long as both operands use the same one.
+__global__ void __launch_bounds__(256) expand_pm1_kernel(const uint32_t* __restrict__ bits, long long n_words, uint4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint32_t w = bits[i];
+    uint32_t o[8];
+#pragma unroll
+    for (int nib = 0; nib < 8; ++nib) {
+        const uint32_t x = (w >> (4 * nib)) & 0xFu;
+        const uint32_t t = (x * 0x00204081u) & 0x01010101u;  // bit k of the nibble -> bit 0 of byte k
+        o[nib] = 0xFFFFFFFFu ^ (t * 0xFEu);                  // 1 -> 0x01 (+1), 0 -> 0xFF (-1)
+    }
+    out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---- tcgen05 / TMA plumbing ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+// mbarrier wait that traps instead of hanging the GPU when a producer never arrives (a descriptor mistake must not cost
+// a whole box): ~2^26 polls is seconds of wall clock, far beyond any legitimate wait here
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {  // one full warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {  // arrives on bar when all MMAs issued so far by this thread are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, one thread issues for the CTA
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);  // start address, 16-byte units
+    d |= (uint64_t)1u << 16;                      // leading byte offset (unused for swizzled K-major), 16-byte units
+    d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset between 8-row groups
+    d |= (uint64_t)1u << 46;                      // descriptor version of sm_100
+    d |= (uint64_t)2u << 61;                      // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, M x N
+__host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 32 lanes x 32 consecutive columns: thread t of the warp gets lane (base lane + t), registers = columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+constexpr int kMmaM = 128, kMmaN = 256, kMmaKBytes = 256;
+constexpr int kATileBytes = kMmaM * kMmaKBytes;      // 32 KB: two 128-byte K chunks of 128 rows
+constexpr int kBTileBytes = kMmaN * kMmaKBytes;      // 64 KB: two 128-byte K chunks of 256 rows
+
+// the 8 MMAs of one 128 x 256 x 256 tile: K chunk c (128 bytes, its own swizzled block), K step k (32 bytes inside it)
+__device__ __forceinline__ void issue_tile_mmas(uint32_t a_smem, uint32_t b_smem, uint32_t tmem_d) {
+    constexpr uint32_t idesc = idesc_i8(kMmaM, kMmaN);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t da = smem_desc_k_sw128(a_smem + c * (kMmaM * 128) + k * 32);
+            const uint64_t db = smem_desc_k_sw128(b_smem + c * (kMmaN * 128) + k * 32);
+            mma_i8(tmem_d, da, db, idesc, (c | k) ? 1u : 0u);
+        }
+    }
+}
+
+// ---- debug: one tile, the raw dot products ----------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mma_dot_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                           int32_t* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_load, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* sa = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);  // SWIZZLE_128B blocks must be 1024-byte aligned
+    uint8_t* sb = sa + kATileBytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_load, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar_load, kATileBytes + kBTileBytes);
+        tma_load_2d(sa, &map_a, 0, 0, &bar_load);
+        tma_load_2d(sa + kMmaM * 128, &map_a, 128, 0, &bar_load);
+        tma_load_2d(sb, &map_b, 0, 0, &bar_load);
+        tma_load_2d(sb + kMmaN * 128, &map_b, 128, 0, &bar_load);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) {
+        mbar_wait_or_trap(&bar_load, 0);
+        tc_fence_after();
+        issue_tile_mmas(smem_u32(sa), smem_u32(sb), tmem_base);
+        tc_commit(&bar_mma);
+    }
+    mbar_wait_or_trap(&bar_mma, 0);
+    tc_fence_after();
+    for (int chunk = 0; chunk < kMmaN / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + chunk * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) out[(size_t)(warp * 32 + lane) * kMmaN + chunk * 32 + i] = (int32_t)r[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// host: 2-D tensor map over an expanded descriptor array [rows][256 bytes], box = 128 bytes x box_rows, SWIZZLE_128B
+static int encode_expanded_map(CUtensorMap* out, const void* base, long long rows, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ORB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return ORB_ECUDA; }
+    const cuuint64_t dims[2] = {256u, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {256u};
+    const cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = ((EncodeFn)p)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (expanded descriptors) failed with CUresult %d", (int)r); return ORB_ECUDA; }
+    return ORB_OK;
+}
+
+}  // namespace orb
+
+// Debug tap: dot products (+-1 encoding) of 128 x 256 descriptors through expand + TMA + tcgen05.mma + tcgen05.ld.
+extern "C" int orbm_debug_mma_dot(int device, const uint8_t* A128, const uint8_t* B256, int32_t* out) {
+    using namespace orb;
+    ORB_REQUIRE(A128 && B256 && out, "null pointer");
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    uint8_t *d_bits = nullptr, *d_exp = nullptr;
+    int32_t* d_out = nullptr;
+    ORB_CUDA_TRY(cudaMalloc(&d_bits, (128 + 256) * 32));
+    ORB_CUDA_TRY(cudaMalloc(&d_exp, (128 + 256) * 256));
+    ORB_CUDA_TRY(cudaMalloc(&d_out, 128 * 256 * 4));
+    ORB_CUDA_TRY(cudaMemcpy(d_bits, A128, 128 * 32, cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(d_bits + 128 * 32, B256, 256 * 32, cudaMemcpyHostToDevice));
+    expand_pm1_kernel<<<ceil_div((128 + 256) * 8, 256), 256>>>((const uint32_t*)d_bits, (128 + 256) * 8, (uint4*)d_exp);
+    CUtensorMap ma, mb;
+    int rc = encode_expanded_map(&ma, d_exp, 128, 128);
+    if (rc == ORB_OK) rc = encode_expanded_map(&mb, d_exp + 128 * 256, 256, 256);
+    if (rc == ORB_OK) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(mma_dot_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kATileBytes + kBTileBytes + 1024));
+        mma_dot_tile_kernel<<<1, 128, kATileBytes + kBTileBytes + 1024>>>(ma, mb, d_out);
+        count_launch(2);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("mma_dot_tile_kernel failed: %s", cudaGetErrorString(e)); rc = ORB_ECUDA; }
+        else ORB_CUDA_TRY(cudaMemcpy(out, d_out, 128 * 256 * 4, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_bits); cudaFree(d_exp); cudaFree(d_out);
+    return rc;
+}
