@@ -128,6 +128,197 @@ __device__ __forceinline__ void issue_tile_mmas(uint32_t a_smem, uint32_t b_smem
     }
 }
 
+// ---- the pair-list expansion ---------------------------------------------------------------------------------------
+// side 0 = query sets (A), side 1 = database sets (B); pair p uses set d_pairs[2p + side] (or p when d_pairs is null);
+// output row p * stride_rows + r. Rows beyond the set's count are left as they are (never used as results).
+__global__ void __launch_bounds__(256) expand_pairs_kernel(const uint32_t* __restrict__ dA, const int* __restrict__ d_nA, int nA_max, int strideA,
+                                                           const uint32_t* __restrict__ dB, const int* __restrict__ d_nB, int nB_max, int strideB,
+                                                           const int* __restrict__ d_pairs, uint4* __restrict__ outA, uint4* __restrict__ outB) {
+    const int p = blockIdx.y, side = blockIdx.z;
+    const int set = d_pairs ? d_pairs[2 * p + side] : p;
+    const int n = side ? (d_nB ? min(d_nB[set], nB_max) : nB_max) : (d_nA ? min(d_nA[set], nA_max) : nA_max);
+    const int stride = side ? strideB : strideA;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // word index inside the set
+    if (i >= n * 8) return;
+    const uint32_t w = (side ? dB : dA)[(size_t)set * stride * 8 + i];
+    uint32_t o[8];
+#pragma unroll
+    for (int nib = 0; nib < 8; ++nib) {
+        const uint32_t x = (w >> (4 * nib)) & 0xFu;
+        const uint32_t t = (x * 0x00204081u) & 0x01010101u;
+        o[nib] = 0xFFFFFFFFu ^ (t * 0xFEu);
+    }
+    uint4* out = (side ? outB : outA) + ((size_t)p * stride * 8 + i) * 2;
+    out[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    out[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---- the matcher ---------------------------------------------------------------------------------------------------
+constexpr int kMmaStages = 2;                 // B tiles in flight in shared memory
+constexpr int kMmaThreads = 320;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int kMmaSmemBytes = kATileBytes + kMmaStages * kBTileBytes + 1024;
+
+// two largest keys of a stream, 4 interleaved accumulators for instruction-level parallelism
+struct Top2x4 {
+    int m1[4], m2[4];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m1[i] = m2[i] = 0;
+    }
+    __device__ __forceinline__ void push(int slot, int key) {
+        const int t = min(m1[slot], key);
+        m1[slot] = max(m1[slot], key);
+        m2[slot] = max(m2[slot], t);
+    }
+    __device__ __forceinline__ void reduce(int& k1, int& k2) const {
+        int a1 = max(m1[0], m1[1]), a2 = max(min(m1[0], m1[1]), max(m2[0], m2[1]));
+        int b1 = max(m1[2], m1[3]), b2 = max(min(m1[2], m1[3]), max(m2[2], m2[3]));
+        k1 = max(a1, b1);
+        k2 = max(min(a1, b1), max(a2, b2));
+    }
+};
+
+__global__ void __launch_bounds__(kMmaThreads, 1)
+knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const int* __restrict__ d_nA, int nA_max,
+                int strideA, const int* __restrict__ d_nB, int nB_max, int strideB, const int* __restrict__ d_pairs, int out_stride,
+                int* __restrict__ out_idx, int* __restrict__ out_b1, int* __restrict__ out_b2) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a, bar_full[kMmaStages], bar_empty[kMmaStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_r1[kMmaM], s_r2[kMmaM], s_ri[kMmaM];
+
+    const int p = blockIdx.y, mtile = blockIdx.x;
+    const int setA = d_pairs ? d_pairs[2 * p] : p, setB = d_pairs ? d_pairs[2 * p + 1] : p;
+    const int na = d_nA ? min(d_nA[setA], nA_max) : nA_max;
+    const int nb = d_nB ? min(d_nB[setB], nB_max) : nB_max;
+    const int row0 = mtile * kMmaM;
+    if (row0 >= na) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* o_idx = out_idx + (size_t)p * out_stride;
+    int* o_b1 = out_b1 + (size_t)p * out_stride;
+    int* o_b2 = out_b2 + (size_t)p * out_stride;
+    if (nb <= 0) {  // no candidates: the initial state of the reference loop
+        for (int r = threadIdx.x; r < kMmaM; r += kMmaThreads)
+            if (row0 + r < na) { o_idx[row0 + r] = -1; o_b1[row0 + r] = 256; o_b2[row0 + r] = 256; }
+        return;
+    }
+    const int ntiles = (nb + kMmaN - 1) / kMmaN;
+    uint8_t* sa = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sb = sa + kATileBytes;
+
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_a, 1);
+        for (int s = 0; s < kMmaStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 8); }
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int arow = p * strideA + row0, brow = p * strideB;
+            mbar_expect_tx(&bar_a, kATileBytes);
+            tma_load_2d(sa, &map_a, 0, arow, &bar_a);
+            tma_load_2d(sa + kMmaM * 128, &map_a, 128, arow, &bar_a);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kMmaStages;
+                if (t >= kMmaStages) mbar_wait_or_trap(&bar_empty[s], ((t / kMmaStages) & 1) ^ 1);
+                uint8_t* dst = sb + s * kBTileBytes;
+                mbar_expect_tx(&bar_full[s], kBTileBytes);
+                tma_load_2d(dst, &map_b, 0, brow + t * kMmaN, &bar_full[s]);
+                tma_load_2d(dst + kMmaN * 128, &map_b, 128, brow + t * kMmaN, &bar_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait_or_trap(&bar_a, 0);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kMmaStages, a = t & 1;
+                if (t >= 2) mbar_wait_or_trap(&bar_tempty[a], ((t >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+                mbar_wait_or_trap(&bar_full[s], (t / kMmaStages) & 1);
+                tc_fence_after();
+                issue_tile_mmas(smem_u32(sa), smem_u32(sb + s * kBTileBytes), tmem_base + a * kMmaN);
+                tc_commit(&bar_empty[s]);   // the shared-memory slot is free once these MMAs have read it
+                tc_commit(&bar_tfull[a]);   // and the accumulator is complete
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps = 4 lane quarters x 2 column halves =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int R1 = 0, R2 = 0, Ridx = -1;  // running (dot + 256) of best / second: 0 = distance 256 = "none yet"
+        for (int t = 0; t < ntiles; ++t) {
+            const int a = t & 1;
+            mbar_wait_or_trap(&bar_tfull[a], (t >> 1) & 1);
+            tc_fence_after();
+            const int col0 = t * kMmaN + h * 128;      // candidate index of this half's first column
+            const int valid = nb - col0;               // columns of this half that are real candidates
+            Top2x4 acc;
+            acc.reset();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kMmaN + h * 128;
+            if (valid >= 128) {
+#pragma unroll
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + chunk * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc.push(i & 3, (int)r[i] * 128 + (32768 + 127 - (chunk * 32 + i)));
+                }
+            } else {
+#pragma unroll
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + chunk * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = chunk * 32 + i;
+                        acc.push(i & 3, c < valid ? (int)r[i] * 128 + (32768 + 127 - c) : 0);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[a]);
+            int k1, k2;
+            acc.reduce(k1, k2);
+            const int d1 = k1 >> 7, d2 = k2 >> 7;
+            if (d1 > R1) {
+                R2 = max(R1, d2);
+                R1 = d1;
+                Ridx = col0 + 127 - (k1 & 127);
+            } else {
+                R2 = max(R2, d1);
+            }
+        }
+        if (h == 1) { s_r1[row] = R1; s_r2[row] = R2; s_ri[row] = Ridx; }
+        // the two column halves of a row meet here (epilogue warps only: named barrier 1, 256 threads)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (h == 0 && row0 + row < na) {
+            const int B1 = s_r1[row], B2 = s_r2[row], Bi = s_ri[row];
+            const int m1 = max(R1, B1);
+            const int m2 = max(min(R1, B1), max(R2, B2));
+            int idx;
+            if (B1 > R1) idx = Bi;
+            else if (B1 < R1) idx = Ridx;
+            else idx = (Ridx < 0 || Bi < 0) ? max(Ridx, Bi) : min(Ridx, Bi);
+            o_idx[row0 + row] = idx;
+            o_b1[row0 + row] = (512 - m1) >> 1;
+            o_b2[row0 + row] = (512 - m2) >> 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- debug: one tile, the raw dot products ----------------------------------------------------------------------
 __global__ void __launch_bounds__(128) mma_dot_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                            int32_t* __restrict__ out) {
@@ -192,6 +383,65 @@ static int encode_expanded_map(CUtensorMap* out, const void* base, long long row
 }
 
 }  // namespace orb
+
+namespace orb {
+
+// scratch for the expanded operands, one per device, grown on demand and kept
+struct MmaScratch { uint8_t* a = nullptr; uint8_t* b = nullptr; size_t cap_a = 0, cap_b = 0; };
+static MmaScratch g_mma_scratch[16];
+
+int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
+                    int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st) {
+    if (pairs <= 0 || nA_max <= 0) return ORB_OK;
+    int device = 0;
+    ORB_CUDA_TRY(cudaGetDevice(&device));
+    ORB_REQUIRE(device >= 0 && device < 16, "device index out of range");
+    MmaScratch& sc = g_mma_scratch[device];
+    const size_t rows_a = (size_t)pairs * strideA_rows, rows_b = (size_t)pairs * strideB_rows;
+    ORB_REQUIRE(rows_a < (1ull << 31) && rows_b < (1ull << 31), "too many descriptor rows for the tensor-core matcher");
+    if (rows_a * 256 > sc.cap_a) {
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(sc.a);
+        sc.cap_a = 0;
+        ORB_CUDA_TRY(cudaMalloc(&sc.a, rows_a * 256));
+        sc.cap_a = rows_a * 256;
+    }
+    if (rows_b * 256 > sc.cap_b) {
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(sc.b);
+        sc.cap_b = 0;
+        ORB_CUDA_TRY(cudaMalloc(&sc.b, rows_b * 256));
+        sc.cap_b = rows_b * 256;
+    }
+    CUtensorMap ma, mb;
+    int rc = encode_expanded_map(&ma, sc.a, (long long)rows_a, kMmaM);
+    if (rc == ORB_OK) rc = encode_expanded_map(&mb, sc.b, (long long)rows_b, kMmaN);
+    if (rc != ORB_OK) return rc;
+    const int words = 8 * (nA_max > nB_max ? nA_max : nB_max);
+    expand_pairs_kernel<<<dim3(ceil_div(words, 256), pairs, 2), 256, 0, st>>>((const uint32_t*)dA, d_nA, nA_max, strideA_rows, (const uint32_t*)dB,
+                                                                             d_nB, nB_max, strideB_rows, d_pairs, (uint4*)sc.a, (uint4*)sc.b);
+    static bool attr_set[16] = {};
+    if (!attr_set[device]) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
+        attr_set[device] = true;
+    }
+    knn2_mma_kernel<<<dim3(ceil_div(nA_max, kMmaM), pairs), kMmaThreads, kMmaSmemBytes, st>>>(ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max,
+                                                                                          strideB_rows, d_pairs, out_stride, d_idx, d_b1, d_b2);
+    count_launch(2);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+}  // namespace orb
+
+// Debug / experiment entry: the tensor-core matcher on one pair of device arrays.
+extern "C" int orbm_knn2_mma_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best, int32_t* d_second,
+                                    void* stream) {
+    using namespace orb;
+    ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
+    ORB_REQUIRE(nA == 0 || (dA && d_idx && d_best && d_second), "null pointer");
+    return launch_knn2_mma(dA, nullptr, nA, nA, dB, nullptr, nB, nB, nullptr, 1, nA, d_idx, d_best, d_second, (cudaStream_t)stream);
+}
 
 // Debug tap: dot products (+-1 encoding) of 128 x 256 descriptors through expand + TMA + tcgen05.mma + tcgen05.ld.
 extern "C" int orbm_debug_mma_dot(int device, const uint8_t* A128, const uint8_t* B256, int32_t* out) {
