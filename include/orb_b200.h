@@ -134,6 +134,11 @@ int orbx_debug_quadtree(int device, const int32_t* xs, const int32_t* ys, const 
  * updates in iteration order => (two smallest distances, index of the FIRST minimum); both
  * distances start at 256; idx = -1 when no candidate is closer than 256. */
 
+/* The brute-force searches below have two implementations with identical results: the POPC kernel (csrc/hamming.cu) and the
+ * tensor-core kernel (csrc/hamming_mma.cu: +-1 int8 expansion, tcgen05.mma kind::i8, top-2 epilogue out of TMEM), chosen by
+ * problem size. backend: 0 = automatic (default), 1 = POPC only, 2 = tensor cores only (tests and measurements). */
+int orbm_set_knn2_backend(int backend);
+
 /* Brute force: every row of A against every row of B (SearchByBoW inner loop with the gate removed,
  * src/ORBmatcher.cc:566-598; BASELINE configs 3 and 5). */
 int orbm_knn2_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best,

@@ -15,6 +15,8 @@
 // clk / SM => 0.58 T cmp/s per B200); the carry-save form used here needs 4 POPC + 16 LOP3 and is bound by the
 // 64-lane ALU pipe instead (0.71-0.87 T cmp/s measured). Memory traffic is (nA + nB) * 32 B per pass plus
 // L2-resident tile re-reads, i.e. irrelevant next to the bit counting.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace orb {
@@ -231,10 +233,20 @@ __global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, cons
 }
 
 // ---- host launcher ----------------------------------------------------------------------------
+int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
+                    int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st);
+static std::atomic<int> g_knn2_backend{0};        // 0 = by problem size, 1 = POPC kernel, 2 = tensor-core kernel
+constexpr long long kMmaMinWork = 1ll << 24;      // comparisons per call from which the tensor-core path is used
+
 static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB,
                        const int* d_nB, int nB_max, int strideB_rows, const int* d_pairs, int pairs, int* d_idx, int* d_b1,
                        int* d_b2, cudaStream_t st) {
     if (pairs <= 0 || nA_max <= 0) return ORB_OK;
+    // large problems go to the tensor cores (hamming_mma.cu): same results, several times the POPC pipe's throughput
+    const long long work = (long long)pairs * nA_max * nB_max;
+    const int backend = g_knn2_backend.load();
+    if (nB_max > 0 && (backend == 2 || (backend == 0 && work >= kMmaMinWork && nB_max >= 64)))
+        return launch_knn2_mma(dA, d_nA, nA_max, strideA_rows, dB, d_nB, nB_max, strideB_rows, d_pairs, pairs, strideA_rows, d_idx, d_b1, d_b2, st);
     // pick the slice count so that the grid covers the machine about twice
     int S = 1;
     while (S < 8 && ceil_div(nA_max, kKnnThreads / S) * pairs < 2 * kNumSMs) S *= 2;
@@ -259,6 +271,12 @@ static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strid
 using namespace orb;
 
 extern "C" {
+
+int orbm_set_knn2_backend(int backend) {
+    ORB_REQUIRE(backend >= 0 && backend <= 2, "backend must be 0 (auto), 1 (POPC) or 2 (tensor cores)");
+    g_knn2_backend.store(backend);
+    return ORB_OK;
+}
 
 int orbm_knn2_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best,
                      int32_t* d_second, void* stream) {

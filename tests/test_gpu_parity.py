@@ -105,8 +105,17 @@ def test_quadtree_kernel_on_random_candidate_sets(seed):
 
 
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("nA,nB", [(1000, 1000), (2013, 2013), (1, 1), (7, 5000), (3000, 33), (257, 513), (5, 0)])
-def test_knn2_bit_exact(nA, nB):
+@pytest.fixture(params=[1, 2], ids=["popc", "tensorcore"])
+def knn2_backend(request):
+    """Run a test once per brute-force implementation (csrc/hamming.cu POPC kernel, csrc/hamming_mma.cu tcgen05 kernel)."""
+    from multiagent_orb_slam2_b200 import _lib
+    _lib.check(_lib.lib().orbm_set_knn2_backend(request.param))
+    yield request.param
+    _lib.check(_lib.lib().orbm_set_knn2_backend(0))
+
+
+@pytest.mark.parametrize("nA,nB", [(1000, 1000), (2013, 2013), (1, 1), (7, 5000), (3000, 33), (257, 513), (5, 0), (128, 256), (129, 255), (640, 1)])
+def test_knn2_bit_exact(nA, nB, knn2_backend):
     B = synth.descriptors(nB, 1)
     A = synth.descriptors(nA, 2, dup_from=B) if nB else synth.descriptors(nA, 2)
     if nB > 10:  # exact duplicates: ties between best and second, first index must win
@@ -117,7 +126,7 @@ def test_knn2_bit_exact(nA, nB):
     assert np.array_equal(gi, oi) and np.array_equal(g1, o1) and np.array_equal(g2, o2)
 
 
-def test_knn2_large_split_database():
+def test_knn2_large_split_database(knn2_backend):
     B = synth.descriptors(60000, 3)
     A = synth.descriptors_fast(4000, 4, B)
     m = ORBmatcher(0.75)
@@ -200,7 +209,21 @@ def test_device_frames_with_unaligned_pitch():
         assert np.array_equal(desc[i, :counts[i]], od)
 
 
-def test_knn2_pairs_all_slice_counts():
+def test_knn2_extreme_distances(knn2_backend):
+    """Distance 0 and distance 256 (complement: never closer than the initial 256, idx stays -1), all-equal candidates."""
+    rng = np.random.default_rng(9)
+    A = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    m = ORBmatcher(0.75)
+    for B in (~A[:1], np.repeat(~A[:1], 700, 0), np.repeat(A[5:6], 513, 0), np.concatenate([~A[:1], A[:1], A[:1]])):
+        B = np.ascontiguousarray(B)
+        gi, g1, g2 = m.knn2(A, B)
+        oi, o1, o2 = O.knn2(A, B)
+        assert np.array_equal(gi, oi) and np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    gi, g1, g2 = m.knn2(A[:1], np.ascontiguousarray(~A[:1]))
+    assert gi[0] == -1 and g1[0] == 256 and g2[0] == 256
+
+
+def test_knn2_pairs_all_slice_counts(knn2_backend):
     """orbm_knn2_pairs_device picks 1..8 slices per query depending on the grid size: cover them all."""
     import torch
     import ctypes as C
