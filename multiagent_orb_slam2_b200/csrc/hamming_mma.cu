@@ -129,8 +129,10 @@ __device__ __forceinline__ void issue_tile_mmas(uint32_t a_smem, uint32_t b_smem
 }
 
 // ---- the pair-list expansion ---------------------------------------------------------------------------------------
-// side 0 = query sets (A), side 1 = database sets (B); pair p uses set d_pairs[2p + side] (or p when d_pairs is null);
-// output row p * stride_rows + r. Rows beyond the set's count are left as they are (never used as results).
+// side 0 = query sets (A, expanded to +-64), side 1 = database sets (B, +-1); pair p uses set d_pairs[2p + side] (or p when
+// d_pairs is null); output row p * stride_rows + r. Rows beyond the set's count are left as they are (never used as results).
+// The factor 64 on the query side makes the accumulator 64 * dot = 128 * (128 - distance): its low 16 bits are the selection
+// key's upper field already, so the epilogue needs one packed add per two candidates to form the keys.
 __global__ void __launch_bounds__(256) expand_pairs_kernel(const uint32_t* __restrict__ dA, const int* __restrict__ d_nA, int nA_max, int strideA,
                                                            const uint32_t* __restrict__ dB, const int* __restrict__ d_nB, int nB_max, int strideB,
                                                            const int* __restrict__ d_pairs, uint4* __restrict__ outA, uint4* __restrict__ outB) {
@@ -141,12 +143,13 @@ __global__ void __launch_bounds__(256) expand_pairs_kernel(const uint32_t* __res
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // word index inside the set
     if (i >= n * 8) return;
     const uint32_t w = (side ? dB : dA)[(size_t)set * stride * 8 + i];
+    const uint32_t neg = side ? 0xFFFFFFFFu : 0xC0C0C0C0u, flip = side ? 0xFEu : 0x80u;  // -1 / +1 or -64 / +64
     uint32_t o[8];
 #pragma unroll
     for (int nib = 0; nib < 8; ++nib) {
         const uint32_t x = (w >> (4 * nib)) & 0xFu;
         const uint32_t t = (x * 0x00204081u) & 0x01010101u;
-        o[nib] = 0xFFFFFFFFu ^ (t * 0xFEu);
+        o[nib] = neg ^ (t * flip);
     }
     uint4* out = (side ? outB : outA) + ((size_t)p * stride * 8 + i) * 2;
     out[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -154,31 +157,61 @@ __global__ void __launch_bounds__(256) expand_pairs_kernel(const uint32_t* __res
 }
 
 // ---- the matcher ---------------------------------------------------------------------------------------------------
+constexpr int kTileN = 128;                   // candidates per tile: 128 x 128 x 256 per 8 MMAs
+constexpr int kBStageBytes = kTileN * kMmaKBytes;  // 32 KB
 constexpr int kMmaStages = 2;                 // B tiles in flight in shared memory
 constexpr int kMmaThreads = 320;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
-constexpr int kMmaSmemBytes = kATileBytes + kMmaStages * kBTileBytes + 1024;
+constexpr int kMmaSmemBytes = kATileBytes + kMmaStages * kBStageBytes + 1024;  // 97 KB: two CTAs per SM
+constexpr int kTmemCols = 2 * kTileN;         // double-buffered accumulator; two CTAs per SM share the 512 columns
 
-// two largest keys of a stream, 4 interleaved accumulators for instruction-level parallelism
-struct Top2x4 {
-    int m1[4], m2[4];
-    __device__ __forceinline__ void reset() {
+__device__ __forceinline__ void issue_tile_mmas_n128(uint32_t a_smem, uint32_t b_smem, uint32_t tmem_d) {
+    constexpr uint32_t idesc = idesc_i8(kMmaM, kTileN);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m1[i] = m2[i] = 0;
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t da = smem_desc_k_sw128(a_smem + c * (kMmaM * 128) + k * 32);
+            const uint64_t db = smem_desc_k_sw128(b_smem + c * (kTileN * 128) + k * 32);
+            mma_i8(tmem_d, da, db, idesc, (c | k) ? 1u : 0u);
+        }
     }
-    __device__ __forceinline__ void push(int slot, int key) {
-        const int t = min(m1[slot], key);
-        m1[slot] = max(m1[slot], key);
-        m2[slot] = max(m2[slot], t);
+}
+
+// 32 lanes x 64 consecutive columns, the low 16 bits of two adjacent columns packed per register
+__device__ __forceinline__ void tmem_ld64_pack16(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// Selection keys, 16 bit: (256 - distance) << 7 | (127 - column). The accumulator's low half is 64 * dot = 128 * (128 - distance);
+// adding 16384 + 127 - column gives the key. Larger key = smaller distance, and among equal distances the smaller column.
+// Two candidates per register (VIADD.16x2 / VIMNMX.U16x2), two registers of running (best, second) for ILP.
+struct Top2Packed {
+    uint32_t m1[2], m2[2];
+    __device__ __forceinline__ void reset() { m1[0] = m1[1] = m2[0] = m2[1] = 0u; }
+    __device__ __forceinline__ void push(int slot, uint32_t keys) {
+        const uint32_t t = __vminu2(m1[slot], keys);
+        m1[slot] = __vmaxu2(m1[slot], keys);
+        m2[slot] = __vmaxu2(m2[slot], t);
     }
     __device__ __forceinline__ void reduce(int& k1, int& k2) const {
-        int a1 = max(m1[0], m1[1]), a2 = max(min(m1[0], m1[1]), max(m2[0], m2[1]));
-        int b1 = max(m1[2], m1[3]), b2 = max(min(m1[2], m1[3]), max(m2[2], m2[3]));
-        k1 = max(a1, b1);
-        k2 = max(min(a1, b1), max(a2, b2));
+        const int a1 = m1[0] & 0xFFFF, b1 = m1[0] >> 16, c1 = m1[1] & 0xFFFF, d1 = m1[1] >> 16;
+        const int a2 = m2[0] & 0xFFFF, b2 = m2[0] >> 16, c2 = m2[1] & 0xFFFF, d2 = m2[1] >> 16;
+        const int x1 = max(a1, b1), x2 = max(min(a1, b1), max(a2, b2));
+        const int y1 = max(c1, d1), y2 = max(min(c1, d1), max(c2, d2));
+        k1 = max(x1, y1);
+        k2 = max(min(x1, y1), max(x2, y2));
     }
 };
 
-__global__ void __launch_bounds__(kMmaThreads, 1)
+__global__ void __launch_bounds__(kMmaThreads, 2)
 knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const int* __restrict__ d_nA, int nA_max,
                 int strideA, const int* __restrict__ d_nB, int nB_max, int strideB, const int* __restrict__ d_pairs, int out_stride,
                 int* __restrict__ out_idx, int* __restrict__ out_b1, int* __restrict__ out_b2) {
@@ -202,11 +235,11 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (row0 + r < na) { o_idx[row0 + r] = -1; o_b1[row0 + r] = 256; o_b2[row0 + r] = 256; }
         return;
     }
-    const int ntiles = (nb + kMmaN - 1) / kMmaN;
-    uint8_t* sa = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int ntiles = (nb + kTileN - 1) / kTileN;
+    uint8_t* sa = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B blocks: 1024-byte aligned
     uint8_t* sb = sa + kATileBytes;
 
-    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    if (warp == 1) tmem_alloc(&tmem_base_s, kTmemCols);
     if (threadIdx.x == 0) {
         mbar_init(&bar_a, 1);
         for (int s = 0; s < kMmaStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
@@ -228,10 +261,10 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kMmaStages;
                 if (t >= kMmaStages) mbar_wait_or_trap(&bar_empty[s], ((t / kMmaStages) & 1) ^ 1);
-                uint8_t* dst = sb + s * kBTileBytes;
-                mbar_expect_tx(&bar_full[s], kBTileBytes);
-                tma_load_2d(dst, &map_b, 0, brow + t * kMmaN, &bar_full[s]);
-                tma_load_2d(dst + kMmaN * 128, &map_b, 128, brow + t * kMmaN, &bar_full[s]);
+                uint8_t* dst = sb + s * kBStageBytes;
+                mbar_expect_tx(&bar_full[s], kBStageBytes);
+                tma_load_2d(dst, &map_b, 0, brow + t * kTileN, &bar_full[s]);
+                tma_load_2d(dst + kTileN * 128, &map_b, 128, brow + t * kTileN, &bar_full[s]);
             }
         }
     } else if (warp == 1) {
@@ -240,53 +273,47 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait_or_trap(&bar_a, 0);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kMmaStages, a = t & 1;
-                if (t >= 2) mbar_wait_or_trap(&bar_tempty[a], ((t >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+                if (t >= 2) mbar_wait_or_trap(&bar_tempty[a], ((t >> 1) & 1) ^ 1);  // the epilogue drained this accumulator
                 mbar_wait_or_trap(&bar_full[s], (t / kMmaStages) & 1);
                 tc_fence_after();
-                issue_tile_mmas(smem_u32(sa), smem_u32(sb + s * kBTileBytes), tmem_base + a * kMmaN);
+                issue_tile_mmas_n128(smem_u32(sa), smem_u32(sb + s * kBStageBytes), tmem_base + a * kTileN);
                 tc_commit(&bar_empty[s]);   // the shared-memory slot is free once these MMAs have read it
                 tc_commit(&bar_tfull[a]);   // and the accumulator is complete
             }
         }
     } else {
-        // ===== epilogue: 8 warps = 4 lane quarters x 2 column halves =====
+        // ===== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves of 64 =====
         const int q = warp & 3, h = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        int R1 = 0, R2 = 0, Ridx = -1;  // running (dot + 256) of best / second: 0 = distance 256 = "none yet"
+        int R1 = 0, R2 = 0, Ridx = -1;  // running (256 - distance) of best / second: 0 = distance 256 = "none yet"
         for (int t = 0; t < ntiles; ++t) {
             const int a = t & 1;
             mbar_wait_or_trap(&bar_tfull[a], (t >> 1) & 1);
             tc_fence_after();
-            const int col0 = t * kMmaN + h * 128;      // candidate index of this half's first column
+            const int col0 = t * kTileN + h * 64;      // candidate index of this half's first column
             const int valid = nb - col0;               // columns of this half that are real candidates
-            Top2x4 acc;
+            uint32_t r[32];
+            tmem_ld64_pack16(tmem_base + ((uint32_t)(q * 32) << 16) + a * kTileN + h * 64, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[a]);  // values are in registers: the accumulator can be overwritten
+            Top2Packed acc;
             acc.reset();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kMmaN + h * 128;
-            if (valid >= 128) {
+            if (valid >= 64) {
 #pragma unroll
-                for (int chunk = 0; chunk < 4; ++chunk) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + chunk * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc.push(i & 3, (int)r[i] * 128 + (32768 + 127 - (chunk * 32 + i)));
+                for (int i = 0; i < 32; ++i) {
+                    const uint32_t bias = (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16;
+                    acc.push(i & 1, __vadd2(r[i], bias));
                 }
             } else {
 #pragma unroll
-                for (int chunk = 0; chunk < 4; ++chunk) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + chunk * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = chunk * 32 + i;
-                        acc.push(i & 3, c < valid ? (int)r[i] * 128 + (32768 + 127 - c) : 0);
-                    }
+                for (int i = 0; i < 32; ++i) {
+                    const uint32_t bias = (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16;
+                    const uint32_t mask = (2 * i < valid ? 0xFFFFu : 0u) | (2 * i + 1 < valid ? 0xFFFF0000u : 0u);
+                    acc.push(i & 1, __vadd2(r[i], bias) & mask);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[a]);
             int k1, k2;
             acc.reduce(k1, k2);
             const int d1 = k1 >> 7, d2 = k2 >> 7;
@@ -310,13 +337,13 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             else if (B1 < R1) idx = Ridx;
             else idx = (Ridx < 0 || Bi < 0) ? max(Ridx, Bi) : min(Ridx, Bi);
             o_idx[row0 + row] = idx;
-            o_b1[row0 + row] = (512 - m1) >> 1;
-            o_b2[row0 + row] = (512 - m2) >> 1;
+            o_b1[row0 + row] = 256 - m1;
+            o_b2[row0 + row] = 256 - m2;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- debug: one tile, the raw dot products ----------------------------------------------------------------------
@@ -415,7 +442,7 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
     }
     CUtensorMap ma, mb;
     int rc = encode_expanded_map(&ma, sc.a, (long long)rows_a, kMmaM);
-    if (rc == ORB_OK) rc = encode_expanded_map(&mb, sc.b, (long long)rows_b, kMmaN);
+    if (rc == ORB_OK) rc = encode_expanded_map(&mb, sc.b, (long long)rows_b, kTileN);
     if (rc != ORB_OK) return rc;
     const int words = 8 * (nA_max > nB_max ? nA_max : nB_max);
     expand_pairs_kernel<<<dim3(ceil_div(words, 256), pairs, 2), 256, 0, st>>>((const uint32_t*)dA, d_nA, nA_max, strideA_rows, (const uint32_t*)dB,

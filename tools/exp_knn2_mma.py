@@ -11,6 +11,7 @@ L = _lib.lib()
 vp = C.c_void_p
 L.orbm_knn2_mma_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
 dev = torch.device("cuda", 0)
+L.orbm_set_knn2_backend(1)  # orbm_knn2_device = the POPC kernel in this script
 
 
 def run(fn, A, B):
