@@ -342,7 +342,13 @@ def run_b200(args):
                 "maps": n_maps, "rows_per_map": rows, "directed_pairs": n_maps * (n_maps - 1), "ms_per_step": mf_ms,
                 "exchange_ms": a0.elapsed_time(a1), "accepted_matches_rank0": accepted,
                 "frac_of_plain_popc_roofline": cmps / (mf_ms * 1e-3) / popc_roof,
-                "popc_roofline": "148 SM x 16 POPC/clk x 1.965 GHz / 8 POPC per cmp per GPU (measured 15.3/clk/SM)"}
+                "popc_roofline": "148 SM x 16 POPC/clk x 1.965 GHz / 8 POPC per cmp per GPU (measured 15.3/clk/SM)",
+                # the kernel that runs at this size is the tcgen05 int8 one: 256 multiply-adds per comparison on +-1 bytes
+                "kernel": "knn2_mma_kernel (tcgen05.mma kind::i8, 128x128x256 tiles, top-2 out of TMEM)",
+                "tensor": {"achieved_int8_tops": cmps * 512 / (mf_ms * 1e-3) / 1e12 / world,
+                           "peak_int8_tops_per_gpu": 2 * peaks()[0].get("bf16_tflops", 2250.0),
+                           "frac": cmps * 512 / (mf_ms * 1e-3) / 1e12 / world / (2 * peaks()[0].get("bf16_tflops", 2250.0)),
+                           "peak_source": "2 x the measured dense bf16 cuBLAS figure of MEASURED_PEAKS.json (int8 = 2 x bf16 on sm_100a; 2 x 2250 nominal if absent)"}}
         del local, res, cm
 
     # ---- DBoW2 vocabulary transform of the batch's descriptors (Frame::ComputeBoW), rank 0 -----
