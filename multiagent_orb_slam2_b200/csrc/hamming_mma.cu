@@ -196,10 +196,12 @@ __device__ __forceinline__ void tmem_ld64_pack16(uint32_t taddr, uint32_t (&r)[3
 struct Top2Packed {
     uint32_t m1[2], m2[2];
     __device__ __forceinline__ void reset() { m1[0] = m1[1] = m2[0] = m2[1] = 0u; }
-    __device__ __forceinline__ void push(int slot, uint32_t keys) {
-        const uint32_t t = __vminu2(m1[slot], keys);
-        m1[slot] = __vmaxu2(m1[slot], keys);
-        m2[slot] = __vmaxu2(m2[slot], t);
+    // two registers (four candidates) at a time: 5 min/max instructions, the last one three-input (VIMNMX3.U16x2)
+    __device__ __forceinline__ void push2(int slot, uint32_t ka, uint32_t kb) {
+        const uint32_t hi = __vmaxu2(ka, kb), lo = __vminu2(ka, kb);
+        const uint32_t t = __vminu2(m1[slot], hi);
+        m1[slot] = __vmaxu2(m1[slot], hi);
+        m2[slot] = __vimax3_u16x2(m2[slot], t, lo);
     }
     __device__ __forceinline__ void reduce(int& k1, int& k2) const {
         const int a1 = m1[0] & 0xFFFF, b1 = m1[0] >> 16, c1 = m1[1] & 0xFFFF, d1 = m1[1] >> 16;
@@ -300,19 +302,15 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (lane == 0) mbar_arrive(&bar_tempty[a]);  // values are in registers: the accumulator can be overwritten
             Top2Packed acc;
             acc.reset();
+            auto bias = [](int i) { return (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16; };
             if (valid >= 64) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint32_t bias = (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16;
-                    acc.push(i & 1, __vadd2(r[i], bias));
-                }
+                for (int i = 0; i < 32; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
             } else {
+                auto mask = [valid](int i) { return (2 * i < valid ? 0xFFFFu : 0u) | (2 * i + 1 < valid ? 0xFFFF0000u : 0u); };
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint32_t bias = (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16;
-                    const uint32_t mask = (2 * i < valid ? 0xFFFFu : 0u) | (2 * i + 1 < valid ? 0xFFFF0000u : 0u);
-                    acc.push(i & 1, __vadd2(r[i], bias) & mask);
-                }
+                for (int i = 0; i < 32; i += 2)
+                    acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)) & mask(i), __vadd2(r[i + 1], bias(i + 1)) & mask(i + 1));
             }
             int k1, k2;
             acc.reduce(k1, k2);
