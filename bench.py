@@ -322,7 +322,7 @@ def run_b200(args):
         cm = mapfusion.CrossMapMatcher(rows, 0.75)
         cm.match(local)  # warm-up (NCCL channels, kernel load)
         barrier()
-        reps = 2
+        reps = 5
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(reps):

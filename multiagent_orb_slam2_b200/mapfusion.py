@@ -86,7 +86,11 @@ class CrossMapMatcher:
         dev = sets.device
         if dev.type != "cuda":
             raise _lib.OrbError(_lib.ORB_ECUDA, "cross-map matching needs CUDA tensors (no CPU fallback)")
-        p = torch.tensor(pairs, dtype=torch.int32, device=dev).reshape(-1, 2)
+        key = (tuple(pairs), str(dev))
+        if getattr(self, "_pairs_key", None) != key:  # the pair list of a rank is static: upload it once
+            self._pairs_dev = torch.tensor(pairs, dtype=torch.int32, device=dev).reshape(-1, 2)
+            self._pairs_key = key
+        p = self._pairs_dev
         n = len(pairs)
         out = [torch.empty((n, self.rows_cap), dtype=torch.int32, device=dev) for _ in range(4)]
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
