@@ -138,6 +138,12 @@ int orbx_debug_quadtree(int device, const int32_t* xs, const int32_t* ys, const 
  * tensor-core kernel (csrc/hamming_mma.cu: +-1 int8 expansion, tcgen05.mma kind::i8, top-2 epilogue out of TMEM), chosen by
  * problem size. backend: 0 = automatic (default), 1 = POPC only, 2 = tensor cores only (tests and measurements). */
 int orbm_set_knn2_backend(int backend);
+/* The tensor-core implementation called directly (one query set against one database set), whatever the size. */
+int orbm_knn2_mma_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best,
+                         int32_t* d_second, void* stream);
+/* Debug tap of its data path: the +-1 dot products (= 256 - 2 * distance) of 128 x 256 host descriptors through the bit
+ * expansion, the SWIZZLE_128B TMA loads, tcgen05.mma kind::i8 and tcgen05.ld; out = int32 [128][256]. */
+int orbm_debug_mma_dot(int device, const uint8_t* A128, const uint8_t* B256, int32_t* out);
 
 /* Brute force: every row of A against every row of B (SearchByBoW inner loop with the gate removed,
  * src/ORBmatcher.cc:566-598; BASELINE configs 3 and 5). */
