@@ -13,6 +13,11 @@
 //                       two largest dot products (= two smallest distances, first minimum by candidate order) per row.
 #include <cuda.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace orb {
@@ -392,10 +397,14 @@ __global__ void __launch_bounds__(128) mma_dot_tile_kernel(const __grid_constant
 static int encode_expanded_map(CUtensorMap* out, const void* base, long long rows, int box_rows) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    ORB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-    if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return ORB_ECUDA; }
+    static std::atomic<void*> cached{nullptr};  // resolved once; racing threads resolve the same pointer
+    void* p = cached.load();
+    if (!p) {
+        cudaDriverEntryPointQueryResult q;
+        ORB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return ORB_ECUDA; }
+        cached.store(p);
+    }
     const cuuint64_t dims[2] = {256u, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {256u};
     const cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
@@ -411,32 +420,39 @@ static int encode_expanded_map(CUtensorMap* out, const void* base, long long row
 
 namespace orb {
 
-// scratch for the expanded operands, one per device, grown on demand and kept
+// Scratch for the expanded operands: one pair of buffers per (device, stream), grown on demand and kept. Calls on the same
+// stream are ordered, so they can share buffers; calls on different streams (two agents' frontends on one GPU) must not.
 struct MmaScratch { uint8_t* a = nullptr; uint8_t* b = nullptr; size_t cap_a = 0, cap_b = 0; };
-static MmaScratch g_mma_scratch[16];
+static std::mutex g_mma_mutex;
+static std::map<std::pair<int, cudaStream_t>, MmaScratch> g_mma_scratch;
 
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
                     int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st) {
     if (pairs <= 0 || nA_max <= 0) return ORB_OK;
+    ORB_REQUIRE(pairs <= 65535, "more than 65535 set pairs in one call");
     int device = 0;
     ORB_CUDA_TRY(cudaGetDevice(&device));
-    ORB_REQUIRE(device >= 0 && device < 16, "device index out of range");
-    MmaScratch& sc = g_mma_scratch[device];
     const size_t rows_a = (size_t)pairs * strideA_rows, rows_b = (size_t)pairs * strideB_rows;
     ORB_REQUIRE(rows_a < (1ull << 31) && rows_b < (1ull << 31), "too many descriptor rows for the tensor-core matcher");
-    if (rows_a * 256 > sc.cap_a) {
-        ORB_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(sc.a);
-        sc.cap_a = 0;
-        ORB_CUDA_TRY(cudaMalloc(&sc.a, rows_a * 256));
-        sc.cap_a = rows_a * 256;
-    }
-    if (rows_b * 256 > sc.cap_b) {
-        ORB_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(sc.b);
-        sc.cap_b = 0;
-        ORB_CUDA_TRY(cudaMalloc(&sc.b, rows_b * 256));
-        sc.cap_b = rows_b * 256;
+    MmaScratch sc;
+    {
+        std::lock_guard<std::mutex> lock(g_mma_mutex);
+        MmaScratch& slot = g_mma_scratch[std::make_pair(device, st)];
+        if (rows_a * 256 > slot.cap_a) {
+            ORB_CUDA_TRY(cudaStreamSynchronize(st));  // earlier calls on this stream may still read the old buffer
+            cudaFree(slot.a);
+            slot.a = nullptr; slot.cap_a = 0;
+            ORB_CUDA_TRY(cudaMalloc(&slot.a, rows_a * 256));
+            slot.cap_a = rows_a * 256;
+        }
+        if (rows_b * 256 > slot.cap_b) {
+            ORB_CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(slot.b);
+            slot.b = nullptr; slot.cap_b = 0;
+            ORB_CUDA_TRY(cudaMalloc(&slot.b, rows_b * 256));
+            slot.cap_b = rows_b * 256;
+        }
+        sc = slot;
     }
     CUtensorMap ma, mb;
     int rc = encode_expanded_map(&ma, sc.a, (long long)rows_a, kMmaM);
@@ -445,10 +461,10 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
     const int words = 8 * (nA_max > nB_max ? nA_max : nB_max);
     expand_pairs_kernel<<<dim3(ceil_div(words, 256), pairs, 2), 256, 0, st>>>((const uint32_t*)dA, d_nA, nA_max, strideA_rows, (const uint32_t*)dB,
                                                                              d_nB, nB_max, strideB_rows, d_pairs, (uint4*)sc.a, (uint4*)sc.b);
-    static bool attr_set[16] = {};
-    if (!attr_set[device]) {
+    static std::atomic<bool> attr_set[64];  // per device, once: the attribute call is not free on the launch path
+    if (device >= 64 || !attr_set[device].load()) {
         ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
-        attr_set[device] = true;
+        if (device < 64) attr_set[device].store(true);
     }
     knn2_mma_kernel<<<dim3(ceil_div(nA_max, kMmaM), pairs), kMmaThreads, kMmaSmemBytes, st>>>(ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max,
                                                                                           strideB_rows, d_pairs, out_stride, d_idx, d_b1, d_b2);

@@ -269,3 +269,39 @@ def test_stereo_matches_bit_exact(w, h, nf, kind, seed):
     assert gkept == okept and okept > 100
     assert np.array_equal(gu[:n].view(np.uint32), ou.view(np.uint32))
     assert np.array_equal(gd[:n].view(np.uint32), od.view(np.uint32))
+
+
+def test_knn2_tensorcore_on_two_streams_at_once():
+    """Two agents' frontends share a GPU on separate streams: the tensor-core matcher keeps its expanded operands per
+    stream, so overlapping calls must not disturb each other."""
+    import torch
+    import ctypes as C
+    from multiagent_orb_slam2_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    n = 6000
+    data = []
+    for k in range(2):
+        B = synth.descriptors(n, 70 + k)
+        A = synth.descriptors_fast(n, 80 + k, B, 50)
+        data.append((torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)))
+
+    def run(backend, streams):
+        _lib.check(L.orbm_set_knn2_backend(backend))
+        outs = [[torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3)] for _ in range(2)]
+        torch.cuda.synchronize()
+        for rep in range(3):
+            for k in range(2):
+                A, B = data[k]
+                _lib.check(L.orbm_knn2_device(C.c_void_p(A.data_ptr()), n, C.c_void_p(B.data_ptr()), n, *[C.c_void_p(o.data_ptr()) for o in outs[k]],
+                                              C.c_void_p(streams[k].cuda_stream)))
+        torch.cuda.synchronize()
+        _lib.check(L.orbm_set_knn2_backend(0))
+        return [[o.cpu().numpy() for o in out] for out in outs]
+
+    s0, s1 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    want = run(1, [s0, s0])
+    got = run(2, [s0, s1])
+    for k in range(2):
+        for g, w in zip(got[k], want[k]):
+            assert np.array_equal(g, w)
