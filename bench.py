@@ -330,6 +330,18 @@ def run_b200(args):
         g1.record()
         barrier()
         mf_ms = max_over_ranks(g0.elapsed_time(g1)) / reps
+        # the same step with the POPC kernel (north star: "popc-bound uint4-vectorised kernel"), one repetition
+        from multiagent_orb_slam2_b200 import _lib as _orb_lib
+        _orb_lib.check(_orb_lib.lib().orbm_set_knn2_backend(1))
+        cm.match(local)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        cm.match(local)
+        h1.record()
+        barrier()
+        popc_ms = max_over_ranks(h0.elapsed_time(h1))
+        _orb_lib.check(_orb_lib.lib().orbm_set_knn2_backend(0))
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         mapfusion.exchange(local, rows)
@@ -343,6 +355,9 @@ def run_b200(args):
                 "exchange_ms": a0.elapsed_time(a1), "accepted_matches_rank0": accepted,
                 "frac_of_plain_popc_roofline": cmps / (mf_ms * 1e-3) / popc_roof,
                 "popc_roofline": "148 SM x 16 POPC/clk x 1.965 GHz / 8 POPC per cmp per GPU (measured 15.3/clk/SM)",
+                "popc_kernel": {"value": cmps / (popc_ms * 1e-3) / 1e9, "unit": "Gcmp/s", "ms_per_step": popc_ms,
+                                "frac_of_plain_popc_roofline": cmps / (popc_ms * 1e-3) / popc_roof,
+                                "what": "the same step with orbm_set_knn2_backend(1): knn2_kernel (carry-save popcount on the integer pipes)"},
                 # the kernel that runs at this size is the tcgen05 int8 one: 256 multiply-adds per comparison on +-1 bytes
                 "kernel": "knn2_mma_kernel (tcgen05.mma kind::i8, 128x128x256 tiles, top-2 out of TMEM)",
                 "tensor": {"achieved_int8_tops": cmps * 512 / (mf_ms * 1e-3) / 1e12 / world,
