@@ -218,21 +218,6 @@ struct Top2Packed {
     }
 };
 
-// running (256 - distance) of best / second and the index of the first best: 0 = distance 256 = "none yet"
-struct RowState {
-    int r1 = 0, r2 = 0, idx = -1;
-    __device__ __forceinline__ void tile(int k1, int k2, int col0) {
-        const int d1 = k1 >> 7, d2 = k2 >> 7;
-        if (d1 > r1) {
-            r2 = max(r1, d2);
-            r1 = d1;
-            idx = col0 + 127 - (k1 & 127);
-        } else {
-            r2 = max(r2, d1);
-        }
-    }
-};
-
 __global__ void __launch_bounds__(kMmaThreads, 2)
 knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const int* __restrict__ d_nA, int nA_max,
                 int strideA, const int* __restrict__ d_nB, int nB_max, int strideB, const int* __restrict__ d_pairs, int out_stride,
@@ -364,208 +349,6 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// ---- variant with the query tile in tensor memory ---------------------------------------------------------------------
-// The 128 x 128 tiles above are shared-memory-bandwidth bound: every MMA reads 4 KB of A and 4 KB of B from shared memory
-// in 64 tensor cycles while TMA writes the next tile. Here the query tile lives in TMEM (64 columns: lane = row, four int8
-// per 32-bit column) - written once per CTA by tcgen05.st straight from the packed descriptors - and the MMA takes it from
-// there (tcgen05.mma with a TMEM A operand), which halves the shared-memory reads. One CTA per SM (the accumulators and
-// the A tile need more than half of TMEM): a 6-deep B ring, 3 accumulators and 16 epilogue warps hide the latencies
-// that a second CTA hid before.
-constexpr int kTsStages = 6;
-constexpr int kTsAccs = 3;
-constexpr int kTsEpiWarps = 16;
-constexpr int kTsThreads = (2 + kTsEpiWarps) * 32;  // 576
-constexpr int kTsSmemBytes = kTsStages * kBStageBytes + 1024;
-constexpr int kTsACols = 64;                          // 128 rows x 256 int8
-
-__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint32_t (&r)[64]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
-        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(r[32]), "r"(r[33]),
-        "r"(r[34]), "r"(r[35]), "r"(r[36]), "r"(r[37]), "r"(r[38]), "r"(r[39]), "r"(r[40]), "r"(r[41]), "r"(r[42]), "r"(r[43]), "r"(r[44]),
-        "r"(r[45]), "r"(r[46]), "r"(r[47]), "r"(r[48]), "r"(r[49]), "r"(r[50]), "r"(r[51]), "r"(r[52]), "r"(r[53]), "r"(r[54]), "r"(r[55]),
-        "r"(r[56]), "r"(r[57]), "r"(r[58]), "r"(r[59]), "r"(r[60]), "r"(r[61]), "r"(r[62]), "r"(r[63])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// 32 lanes x 32 consecutive columns, packed two per register
-__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
-__global__ void __launch_bounds__(kTsThreads, 1)
-knn2_mma_ts_kernel(const uint32_t* __restrict__ dA, const __grid_constant__ CUtensorMap map_b, const int* __restrict__ d_nA, int nA_max,
-                   int strideA, const int* __restrict__ d_nB, int nB_max, int strideB, const int* __restrict__ d_pairs, int out_stride,
-                   int* __restrict__ out_idx, int* __restrict__ out_b1, int* __restrict__ out_b2) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_a, bar_full[kTsStages], bar_empty[kTsStages], bar_tfull[kTsAccs], bar_tempty[kTsAccs];
-    __shared__ uint32_t tmem_base_s;
-    __shared__ int s_r1[3][kMmaM], s_r2[3][kMmaM], s_ri[3][kMmaM];
-
-    const int p = blockIdx.y, mtile = blockIdx.x;
-    const int setA = d_pairs ? d_pairs[2 * p] : p, setB = d_pairs ? d_pairs[2 * p + 1] : p;
-    const int na = d_nA ? min(d_nA[setA], nA_max) : nA_max;
-    const int nb = d_nB ? min(d_nB[setB], nB_max) : nB_max;
-    const int row0 = mtile * kMmaM;
-    if (row0 >= na) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* o_idx = out_idx + (size_t)p * out_stride;
-    int* o_b1 = out_b1 + (size_t)p * out_stride;
-    int* o_b2 = out_b2 + (size_t)p * out_stride;
-    if (nb <= 0) {
-        for (int r = threadIdx.x; r < kMmaM; r += kTsThreads)
-            if (row0 + r < na) { o_idx[row0 + r] = -1; o_b1[row0 + r] = 256; o_b2[row0 + r] = 256; }
-        return;
-    }
-    const int ntiles = (nb + kTileN - 1) / kTileN;
-    uint8_t* sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-
-    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar_a, 4);
-        for (int s = 0; s < kTsStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-        for (int a = 0; a < kTsAccs; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], kTsEpiWarps); }
-        mbar_fence_init();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-    const uint32_t tmem_acc = tmem_base + kTsACols;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            const int brow = p * strideB;
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kTsStages;
-                if (t >= kTsStages) mbar_wait_or_trap(&bar_empty[s], ((t / kTsStages) & 1) ^ 1);
-                uint8_t* dst = sb + s * kBStageBytes;
-                mbar_expect_tx(&bar_full[s], kBStageBytes);
-                tma_load_2d(dst, &map_b, 0, brow + t * kTileN, &bar_full[s]);
-                tma_load_2d(dst + kTileN * 128, &map_b, 128, brow + t * kTileN, &bar_full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_i8(kMmaM, kTileN);
-            mbar_wait_or_trap(&bar_a, 0);   // the query tile is in tensor memory
-            tc_fence_after();
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kTsStages, a = t % kTsAccs;
-                if (t >= kTsAccs) mbar_wait_or_trap(&bar_tempty[a], ((t / kTsAccs) & 1) ^ 1);
-                mbar_wait_or_trap(&bar_full[s], (t / kTsStages) & 1);
-                tc_fence_after();
-                const uint32_t b_smem = smem_u32(sb + s * kBStageBytes);
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_i8_ts(tmem_acc + a * kTileN, tmem_base + (c * 4 + k) * 8, smem_desc_k_sw128(b_smem + c * (kTileN * 128) + k * 32), idesc,
-                                  (c | k) ? 1u : 0u);
-                }
-                tc_commit(&bar_empty[s]);
-                tc_commit(&bar_tfull[a]);
-            }
-        }
-    } else {
-        // ===== epilogue: 16 warps = 4 TMEM lane quarters x 4 column quarters of 32 =====
-        const int q = warp & 3, cq = (warp - 2) >> 2;
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        if (cq == 0) {
-            // this warp's 32 query rows: packed bits -> +-64 bytes -> tensor memory columns [0, 64)
-            uint32_t bits[8];
-            const bool have = row0 + row < na;
-            const uint32_t* src = dA + ((size_t)setA * strideA + row0 + row) * 8;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) bits[w] = have ? src[w] : 0u;
-            uint32_t e[64];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-#pragma unroll
-                for (int nib = 0; nib < 8; ++nib) {
-                    const uint32_t x = (bits[w] >> (4 * nib)) & 0xFu;
-                    const uint32_t t = (x * 0x00204081u) & 0x01010101u;
-                    e[w * 8 + nib] = 0xC0C0C0C0u ^ (t * 0x80u);  // bit 1 -> +64, bit 0 -> -64
-                }
-            }
-            tmem_st64(tmem_base + lane_base, e);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_a);
-        }
-        RowState st;
-        for (int t = 0; t < ntiles; ++t) {
-            const int a = t % kTsAccs;
-            mbar_wait_or_trap(&bar_tfull[a], (t / kTsAccs) & 1);
-            tc_fence_after();
-            const int col0 = t * kTileN + cq * 32;
-            const int valid = nb - col0;
-            uint32_t r[16];
-            tmem_ld32_pack16(tmem_acc + lane_base + a * kTileN + cq * 32, r);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[a]);
-            Top2Packed acc;
-            acc.reset();
-            auto bias = [](int i) { return (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16; };
-            if (valid >= 32) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
-            } else {
-                auto mask = [valid](int i) { return (2 * i < valid ? 0xFFFFu : 0u) | (2 * i + 1 < valid ? 0xFFFF0000u : 0u); };
-#pragma unroll
-                for (int i = 0; i < 16; i += 2)
-                    acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)) & mask(i), __vadd2(r[i + 1], bias(i + 1)) & mask(i + 1));
-            }
-            int k1, k2;
-            acc.reduce(k1, k2);
-            st.tile(k1, k2, col0);
-        }
-        if (cq > 0) { s_r1[cq - 1][row] = st.r1; s_r2[cq - 1][row] = st.r2; s_ri[cq - 1][row] = st.idx; }
-        asm volatile("bar.sync 1, %0;" ::"n"(kTsEpiWarps * 32) : "memory");
-        if (cq == 0 && row0 + row < na) {
-            int A1 = st.r1, A2 = st.r2, Ai = st.idx;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {  // merge the other column quarters: equal distances keep the smaller index
-                const int B1 = s_r1[c][row], B2 = s_r2[c][row], Bi = s_ri[c][row];
-                const int m2 = max(min(A1, B1), max(A2, B2));
-                if (B1 > A1) Ai = Bi;
-                else if (B1 == A1) Ai = (Ai < 0 || Bi < 0) ? max(Ai, Bi) : min(Ai, Bi);
-                A1 = max(A1, B1);
-                A2 = m2;
-            }
-            o_idx[row0 + row] = Ai;
-            o_b1[row0 + row] = 256 - A1;
-            o_b2[row0 + row] = 256 - A2;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
 // ---- debug: one tile, the raw dot products ----------------------------------------------------------------------
 __global__ void __launch_bounds__(128) mma_dot_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                            int32_t* __restrict__ out) {
@@ -641,7 +424,6 @@ namespace orb {
 // stream are ordered, so they can share buffers; calls on different streams (two agents' frontends on one GPU) must not.
 struct MmaScratch { uint8_t* a = nullptr; uint8_t* b = nullptr; size_t cap_a = 0, cap_b = 0; };
 static std::mutex g_mma_mutex;
-static std::atomic<int> g_mma_variant{0};  // 0: both operands from shared memory, 1: query tile in tensor memory
 static std::map<std::pair<int, cudaStream_t>, MmaScratch> g_mma_scratch;
 
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
@@ -684,16 +466,6 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
         ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
         if (device < 64) attr_set[device].store(true);
     }
-    if (g_mma_variant.load() == 1) {
-        static std::atomic<bool> ts_attr_set[64];
-        if (device >= 64 || !ts_attr_set[device].load()) {
-            ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
-            if (device < 64) ts_attr_set[device].store(true);
-        }
-        knn2_mma_ts_kernel<<<dim3(ceil_div(nA_max, kMmaM), pairs), kTsThreads, kTsSmemBytes, st>>>((const uint32_t*)dA, mb, d_nA, nA_max, strideA_rows,
-                                                                                               d_nB, nB_max, strideB_rows, d_pairs, out_stride, d_idx,
-                                                                                               d_b1, d_b2);
-    } else
     knn2_mma_kernel<<<dim3(ceil_div(nA_max, kMmaM), pairs), kMmaThreads, kMmaSmemBytes, st>>>(ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max,
                                                                                           strideB_rows, d_pairs, out_stride, d_idx, d_b1, d_b2);
     count_launch(2);
@@ -738,11 +510,4 @@ extern "C" int orbm_debug_mma_dot(int device, const uint8_t* A128, const uint8_t
     }
     cudaFree(d_bits); cudaFree(d_exp); cudaFree(d_out);
     return rc;
-}
-
-extern "C" int orbm_set_mma_variant(int variant) {
-    using namespace orb;
-    ORB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (A in shared memory) or 1 (A in tensor memory)");
-    g_mma_variant.store(variant);
-    return ORB_OK;
 }

@@ -12,8 +12,6 @@ vp = C.c_void_p
 L.orbm_knn2_mma_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
 dev = torch.device("cuda", 0)
 L.orbm_set_knn2_backend(1)  # orbm_knn2_device = the POPC kernel in this script
-if len(sys.argv) > 1:
-    L.orbm_set_mma_variant(int(sys.argv[1]))  # 1: query tile in tensor memory
 
 
 def run(fn, A, B):
