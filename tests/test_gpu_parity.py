@@ -305,3 +305,19 @@ def test_knn2_tensorcore_on_two_streams_at_once():
     for k in range(2):
         for g, w in zip(got[k], want[k]):
             assert np.array_equal(g, w)
+
+
+def test_tensorcore_tile_dot_products():
+    """The data path of the tensor-core matcher on one 128 x 256 tile: bit expansion, SWIZZLE_128B TMA loads, tcgen05.mma
+    kind::i8 and tcgen05.ld must reproduce dot = 256 - 2 * Hamming distance for every pair."""
+    import ctypes as C
+    from multiagent_orb_slam2_b200 import _lib
+    rng = np.random.default_rng(12)
+    A = rng.integers(0, 256, (128, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (256, 32), dtype=np.uint8)
+    B[5] = A[7]; B[200] = ~A[100]
+    out = np.zeros((128, 256), np.int32)
+    _lib.check(_lib.lib().orbm_debug_mma_dot(0, A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    ham = np.unpackbits(A[:, None, :] ^ B[None, :, :], axis=2).sum(2).astype(np.int32)
+    assert np.array_equal(out, 256 - 2 * ham)
+    assert out[7, 5] == 256 and out[100, 200] == -256
