@@ -352,33 +352,72 @@ int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, in
 }
 
 // ---- host-buffer wrappers: H2D, kernel, D2H, synchronise --------------------------------------
+// ORBmatcher is constructed on the stack at 13 call sites and called from the Tracking, LocalMapping, LoopClosing and
+// MapFusion threads concurrently: every calling thread keeps its own device arena (grow-only) and
+// its own stream, so a search costs copies + one launch, not five cudaMalloc / cudaFree pairs on the default stream.
+extern "C++" {
 namespace {
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        ORB_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16));
+struct HostCallWorkspace {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    uint8_t* base = nullptr;
+    size_t cap = 0, used = 0;
+    ~HostCallWorkspace() { release(); }
+    void release() {
+        if (device >= 0) {
+            cudaSetDevice(device);
+            if (base) cudaFree(base);
+            if (st) cudaStreamDestroy(st);
+        }
+        base = nullptr; st = nullptr; cap = 0; device = -1;
+    }
+    // make room for `bytes` on `dev`; pointers handed out before are invalid afterwards
+    int begin(int dev, size_t bytes) {
+        if (dev != device) {
+            release();
+            ORB_CUDA_TRY(cudaSetDevice(dev));
+            ORB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            device = dev;
+        } else {
+            ORB_CUDA_TRY(cudaSetDevice(dev));
+        }
+        if (bytes > cap) {
+            if (base) { cudaStreamSynchronize(st); cudaFree(base); base = nullptr; cap = 0; }
+            const size_t want = bytes + bytes / 2 + 4096;
+            ORB_CUDA_TRY(cudaMalloc(&base, want));
+            cap = want;
+        }
+        used = 0;
         return ORB_OK;
     }
+    template <class T> T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used += align_up(count * sizeof(T) + 1, 256);
+        return p;
+    }
+    static size_t need(size_t bytes) { return align_up(bytes + 1, 256); }
 };
+thread_local HostCallWorkspace tls_ws;
 }  // namespace
+}  // extern "C++"
 
 int orbm_knn2(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int32_t* idx, int32_t* best, int32_t* second) {
     ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
     if (nA == 0) return ORB_OK;
     ORB_REQUIRE(A && idx && best && second && (nB == 0 || B), "null pointer");
-    ORB_CUDA_TRY(cudaSetDevice(device));
-    DevBuf dA, dB, dO;
+    HostCallWorkspace& ws = tls_ws;
     int rc;
-    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dO.alloc((size_t)nA * 12))) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
-    if (nB) ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
-    int* o = (int*)dO.p;
-    if ((rc = orbm_knn2_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, nB, o, o + nA, o + 2 * (size_t)nA, 0))) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)nA * 12)))) return rc;
+    uint8_t* dA = ws.take<uint8_t>((size_t)nA * 32);
+    uint8_t* dB = ws.take<uint8_t>((size_t)nB * 32);
+    int* o = ws.take<int>((size_t)nA * 3);
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice, ws.st));
+    if (nB) ORB_CUDA_TRY(cudaMemcpyAsync(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice, ws.st));
+    if ((rc = orbm_knn2_device(dA, nA, dB, nB, o, o + nA, o + 2 * (size_t)nA, ws.st))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
     return ORB_OK;
 }
 
@@ -389,24 +428,25 @@ int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int 
     ORB_REQUIRE(A && B && offsets && cands && idx && best && second, "null pointer");
     const int total = offsets[nA];
     ORB_REQUIRE(total >= 0, "bad offsets");
-    ORB_CUDA_TRY(cudaSetDevice(device));
-    DevBuf dA, dB, dOf, dC, dO;
+    HostCallWorkspace& ws = tls_ws;
     int rc;
-    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dOf.alloc((size_t)(nA + 1) * 4)) ||
-        (rc = dC.alloc((size_t)total * 4)) || (rc = dO.alloc((size_t)nA * 12)))
+    if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)(nA + 1) * 4) + ws.need((size_t)total * 4) +
+                                   ws.need((size_t)nA * 12))))
         return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(dOf.p, offsets, (size_t)(nA + 1) * 4, cudaMemcpyHostToDevice, 0));
-    if (total) ORB_CUDA_TRY(cudaMemcpyAsync(dC.p, cands, (size_t)total * 4, cudaMemcpyHostToDevice, 0));
-    int* o = (int*)dO.p;
-    if ((rc = orbm_knn2_lists_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, (const int*)dOf.p, (const int*)dC.p, o,
-                                     o + nA, o + 2 * (size_t)nA, 0)))
-        return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    uint8_t* dA = ws.take<uint8_t>((size_t)nA * 32);
+    uint8_t* dB = ws.take<uint8_t>((size_t)nB * 32);
+    int* dOf = ws.take<int>((size_t)nA + 1);
+    int* dC = ws.take<int>((size_t)total);
+    int* o = ws.take<int>((size_t)nA * 3);
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dOf, offsets, (size_t)(nA + 1) * 4, cudaMemcpyHostToDevice, ws.st));
+    if (total) ORB_CUDA_TRY(cudaMemcpyAsync(dC, cands, (size_t)total * 4, cudaMemcpyHostToDevice, ws.st));
+    if ((rc = orbm_knn2_lists_device(dA, nA, dB, dOf, dC, o, o + nA, o + 2 * (size_t)nA, ws.st))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
     return ORB_OK;
 }
 
@@ -418,19 +458,23 @@ int orbm_list_distances(int device, const uint8_t* A, int nA, const uint8_t* B, 
     const int total = offsets[nA];
     ORB_REQUIRE(total >= 0, "bad offsets");
     if (total == 0) return ORB_OK;
-    ORB_CUDA_TRY(cudaSetDevice(device));
-    DevBuf dA, dB, dOf, dC, dO;
+    HostCallWorkspace& ws = tls_ws;
     int rc;
-    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dOf.alloc((size_t)(nA + 1) * 4)) ||
-        (rc = dC.alloc((size_t)total * 4)) || (rc = dO.alloc((size_t)total * 2)))
+    if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)(nA + 1) * 4) + ws.need((size_t)total * 4) +
+                                   ws.need((size_t)total * 2))))
         return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(dOf.p, offsets, (size_t)(nA + 1) * 4, cudaMemcpyHostToDevice, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(dC.p, cands, (size_t)total * 4, cudaMemcpyHostToDevice, 0));
-    if ((rc = orbm_list_distances_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, (const int*)dOf.p, (const int*)dC.p, (int16_t*)dO.p, 0))) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(out, dO.p, (size_t)total * 2, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    uint8_t* dA = ws.take<uint8_t>((size_t)nA * 32);
+    uint8_t* dB = ws.take<uint8_t>((size_t)nB * 32);
+    int* dOf = ws.take<int>((size_t)nA + 1);
+    int* dC = ws.take<int>((size_t)total);
+    int16_t* dO = ws.take<int16_t>((size_t)total);
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dOf, offsets, (size_t)(nA + 1) * 4, cudaMemcpyHostToDevice, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dC, cands, (size_t)total * 4, cudaMemcpyHostToDevice, ws.st));
+    if ((rc = orbm_list_distances_device(dA, nA, dB, dOf, dC, dO, ws.st))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(out, dO, (size_t)total * 2, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
     return ORB_OK;
 }
 
@@ -438,15 +482,17 @@ int orbm_distance_matrix(int device, const uint8_t* A, int nA, const uint8_t* B,
     ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
     if (nA == 0 || nB == 0) return ORB_OK;
     ORB_REQUIRE(A && B && out, "null pointer");
-    ORB_CUDA_TRY(cudaSetDevice(device));
-    DevBuf dA, dB, dO;
+    HostCallWorkspace& ws = tls_ws;
     int rc;
-    if ((rc = dA.alloc((size_t)nA * 32)) || (rc = dB.alloc((size_t)nB * 32)) || (rc = dO.alloc((size_t)nA * nB * 2))) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(dA.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, 0));
-    ORB_CUDA_TRY(cudaMemcpyAsync(dB.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, 0));
-    if ((rc = orbm_distance_matrix_device((const uint8_t*)dA.p, nA, (const uint8_t*)dB.p, nB, (int16_t*)dO.p, 0))) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(out, dO.p, (size_t)nA * nB * 2, cudaMemcpyDeviceToHost, 0));
-    ORB_CUDA_TRY(cudaStreamSynchronize(0));
+    if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)nA * nB * 2)))) return rc;
+    uint8_t* dA = ws.take<uint8_t>((size_t)nA * 32);
+    uint8_t* dB = ws.take<uint8_t>((size_t)nB * 32);
+    int16_t* dO = ws.take<int16_t>((size_t)nA * nB);
+    ORB_CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice, ws.st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice, ws.st));
+    if ((rc = orbm_distance_matrix_device(dA, nA, dB, nB, dO, ws.st))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(out, dO, (size_t)nA * nB * 2, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
     return ORB_OK;
 }
 

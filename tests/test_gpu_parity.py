@@ -321,3 +321,31 @@ def test_tensorcore_tile_dot_products():
     ham = np.unpackbits(A[:, None, :] ^ B[None, :, :], axis=2).sum(2).astype(np.int32)
     assert np.array_equal(out, 256 - 2 * ham)
     assert out[7, 5] == 256 and out[100, 200] == -256
+
+
+def test_host_wrappers_from_many_threads():
+    """ORBmatcher is called concurrently from the Tracking / LocalMapping / LoopClosing / MapFusion threads: the host-buffer
+    entry points keep a workspace and a stream per calling thread."""
+    import threading
+    B = synth.descriptors(1500, 21)
+    sets = [synth.descriptors_fast(900 + 50 * k, 30 + k, B, 50) for k in range(6)]
+    want = [O.knn2(a, B) for a in sets]
+    errors = []
+
+    def worker(k):
+        try:
+            m = ORBmatcher(0.75)
+            for rep in range(5):
+                gi, g1, g2 = m.knn2(sets[k], B)
+                D = m.distance_matrix(sets[k][:40], B[:60])
+                assert np.array_equal(gi, want[k][0]) and np.array_equal(g1, want[k][1]) and np.array_equal(g2, want[k][2])
+                assert D[3, 7] == O.hamming(sets[k][3], B[7])
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
