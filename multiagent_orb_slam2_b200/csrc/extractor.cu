@@ -78,6 +78,7 @@ struct orbx_extractor {
     DeviceBuffers db{};
     void* d_geom = nullptr; void* d_cells = nullptr; void* d_taps = nullptr; void* d_tiles = nullptr; void* d_pattern = nullptr;
     uint8_t* d_input = nullptr;  // staging for host frames: [max_batch][height][pitch0]
+    float* d_stereo = nullptr;   // outputs of the host-buffer stereo call (uRight, depth, sad, kept), allocated on first use
     size_t in_pitch = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
@@ -366,7 +367,7 @@ void orbx_destroy(orbx_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     void* ptrs[] = {h->d_geom, h->d_cells, h->d_taps, h->d_tiles, h->d_pattern, h->db.pyr, h->db.blur, h->db.slots, h->db.cell_counts,
-                    h->db.sortbuf, h->db.selected, h->db.sel_counts, h->db.kps, h->db.desc, h->db.counts, h->d_input};
+                    h->db.sortbuf, h->db.selected, h->db.sel_counts, h->db.kps, h->db.desc, h->db.counts, h->d_input, h->d_stereo};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     for (cudaEvent_t e : h->ev_stage) if (e) cudaEventDestroy(e);
@@ -579,8 +580,8 @@ int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf,
     ORB_REQUIRE(left && uRight && depth && kept, "null pointer");
     const int oc = left->hg.out_cap;
     ORB_CUDA_TRY(cudaSetDevice(left->device));
-    float* d = nullptr;
-    ORB_CUDA_TRY(cudaMalloc(&d, (size_t)oc * 12 + 16));
+    if (!left->d_stereo) ORB_CUDA_TRY(cudaMalloc(&left->d_stereo, (size_t)oc * 12 + 16));
+    float* d = left->d_stereo;
     float* d_u = d; float* d_d = d + oc; int* d_s = (int*)(d + 2 * (size_t)oc); int* d_k = d_s + oc;
     cudaStream_t st = left->stream;
     int rc = orbm_stereo_match_device(left, right, frame, mbf, mb, d_u, d_d, d_s, d_k, st);
@@ -592,7 +593,6 @@ int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf,
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { set_error("stereo copy failed: %s", cudaGetErrorString(e)); rc = ORB_ECUDA; }
     }
-    cudaFree(d);
     return rc;
 }
 
