@@ -236,7 +236,7 @@ __global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, cons
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
                     int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st);
 static std::atomic<int> g_knn2_backend{0};        // 0 = by problem size, 1 = POPC kernel, 2 = tensor-core kernel
-constexpr long long kMmaMinWork = 1ll << 24;      // comparisons per call from which the tensor-core path is used
+constexpr long long kMmaMinWork = 1ll << 19;      // comparisons per call from which the tensor-core path is used (measured break-even: ~700 x 700)
 
 static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB,
                        const int* d_nB, int nB_max, int strideB_rows, const int* d_pairs, int pairs, int* d_idx, int* d_b1,
