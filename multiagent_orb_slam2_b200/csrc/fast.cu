@@ -1,5 +1,7 @@
 // K3: FAST-9/16 detection per 30-px cell with per-cell threshold fallback and 3x3 non-maximum
-// suppression. One thread block per (cell, frame).
+// suppression. One WARP per cell; every warp walks a strided list of cells of one frame with the
+// next cell's tile already in flight (TMA, two tile buffers per warp), so there is no block barrier
+// anywhere and no wait for the tile after a warp's first cell.
 //
 // Replaces the cell loop of ComputeKeyPointsOctTree, /root/reference/src/ORBextractor.cc:789-829,
 // i.e. cv::FAST(cell + 6 px halo, iniThFAST, true) with the minThFAST retry when the cell comes back
@@ -9,22 +11,23 @@
 //   * scores exist only for the cell interior [3, tw-3) x [3, th-3); NMS compares against the
 //     thresholded score map of THIS cell (0 outside), strict '>' on all 8 neighbours.
 // Since the NMS test for a pixel with score s >= t reduces to "all neighbours < s", the local-maximum
-// flag is threshold independent; the ini/min decision is a block-wide count.
+// flag is threshold independent; the ini/min decision is a warp-wide count.
 //
-// Work is compacted between phases so that the expensive paths run on dense thread sets instead of
-// diverged warps (the first version spent ~310 instructions per pixel, 2/3 of them in diverged
-// slow paths):
-//   1. every interior pixel: 4-point rejection test (any arc of 9 contains ring pixel 0 or 8 and 4
-//      or 12)                                     -> survivors appended to a shared-memory list
-//   2. list entries: full 16-pixel arc test + exact score        -> score map, corner list
-//   3. corner list: 3x3 maximum test                              -> per-row bit masks
-//   4. masks -> row-major ordered slot list (reference order inside the cell).
+// Phases (all warp-synchronous, work compacted between them so that the expensive part runs on dense
+// lanes):
+//   1. every interior pixel, FOUR per lane from aligned 32-bit words of the tile: 4-point rejection
+//      test (any arc of 9 contains ring pixel 0 or 8 and 4 or 12) on packed 16-bit halves
+//      (PRMT unpack, VIMNMX.S16x2, VIADD.16x2)          -> survivor list (one shuffle scan per 128 px)
+//   2. survivors: the 16 ring pixels packed two per register (k, k+8), the 16 arc minima by two rounds
+//      of VIMNMX3.S16x2; corner <=> score >= minTh       -> score map, corner list (in place)
+//   3. corner list: 3x3 strict maximum                   -> per-row bit masks (all / >= iniTh)
+//   4. prefix over the mask words, then the corner list again: rank = offset + bits below -> the
+//      row-major ordered slot list (reference order inside the cell).
+#include <algorithm>
+
 #include "extract_kernels.cuh"
 
 namespace orb {
-
-constexpr int kFastThreads = 128;
-constexpr int kFastWarps = kFastThreads / 32;
 
 // ring pixel k at (dx,dy): OpenCV order, starting at (0,3) going through (3,0), (0,-3), (-3,0)
 __device__ __forceinline__ int ring_offset(int k, int tp) {
@@ -33,205 +36,259 @@ __device__ __forceinline__ int ring_offset(int k, int tp) {
     return dy[k] * tp + dx[k];
 }
 
-// full arc test at threshold th: 0 = no corner, 1 = bright arc (centre brighter than 9 contiguous ring
-// pixels by more than th), 2 = dark arc
-__device__ __forceinline__ int fast_arc_test(const uint8_t* __restrict__ p, int tp, int th) {
-    const int v = p[0];
-    const int lo = v - th, hi = v + th;
-    // sign bits shifted into the masks: one IADD + one funnel shift per comparison. The ring ends up
-    // in reverse bit order, which does not matter for circular contiguity.
-    uint32_t mb = 0, md = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int r = p[ring_offset(k, tp)];
-        mb = __funnelshift_l((uint32_t)(r - lo), mb, 1);  // r < lo
-        md = __funnelshift_l((uint32_t)(hi - r), md, 1);  // r > hi
-    }
-    auto has_arc9 = [](uint32_t m) {
-        m |= m << 16;
-        uint32_t a = m & (m >> 1);
-        a &= a >> 2;
-        a &= a >> 4;
-        a &= m >> 8;
-        return a != 0;
-    };
-    return has_arc9(mb) ? 1 : (has_arc9(md) ? 2 : 0);
+constexpr int kFastWarps = 4;
+constexpr int kFastThreads = kFastWarps * 32;
+constexpr int kFastMaxCellsPerWarp = 8;
+
+// per-warp shared memory: tile[2] | score | mask_ini | mask_all | offs | list
+struct FastLayout { int tile_bytes, mask_words, list_off, warp_bytes; };
+__host__ __device__ inline FastLayout fast_layout(int max_tw, int max_th, int tp) {
+    FastLayout f;
+    f.tile_bytes = max_th * tp;                      // multiple of 16 (tp is)
+    f.mask_words = 2 * max_th;                       // (row, 32-column half) entries
+    f.list_off = 3 * f.tile_bytes + (int)align_up((size_t)3 * f.mask_words * 4, 16);
+    const int npx = (max_tw > 6 && max_th > 6) ? (max_tw - 6) * (max_th - 6) : 0;
+    f.warp_bytes = (int)align_up((size_t)f.list_off + 2 * (size_t)npx + 16, 128);
+    return f;
 }
 
-// exact score of a known corner: max over the 16 arcs of the minimum margin on the corner's side, - 1
-// (the other side cannot hold a 9-arc at the same time, so it cannot win the maximum)
-__device__ __forceinline__ int fast_score_side(const uint8_t* __restrict__ p, int tp, bool dark) {
-    const int v = p[0];
-    int d[16];
+__device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
+
+// max over the 16 arcs of 9 contiguous ring pixels of the minimum margin on one side, from the ring
+// packed two pixels per register. sgn = +1: ring above the centre (margin r - v), -1: below (v - r).
+// Margins carry a bias of 256 so that both halves stay positive and one IMAD chain packs and
+// subtracts: D[k] = (256 + sgn (r[k] - v)) | (256 + sgn (r[k+8] - v)) << 16.
+__device__ __forceinline__ int fast_side_margin(const int (&r)[16], int v, int sgn) {
+    const uint32_t c0 = (uint32_t)(256 - sgn * v) * 0x10001u;
+    const int s16 = sgn * 65536;
+    uint32_t D[10];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { const int r = p[ring_offset(k, tp)]; d[k] = dark ? r - v : v - r; }
-    int m2[16], m4[16], best = 0;
+    for (int k = 0; k < 8; ++k) D[k] = (uint32_t)(r[k] * sgn + (r[k + 8] * s16 + (int)c0));
+    D[8] = swap16(D[0]); D[9] = swap16(D[1]);
+    uint32_t Q[14];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m2[k] = min(d[k], d[(k + 1) & 15]);
+    for (int k = 0; k < 8; ++k) Q[k] = __vimin3_s16x2(D[k], D[k + 1], D[k + 2]);  // min of 3 contiguous, arcs k and k+8
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+    for (int k = 0; k < 6; ++k) Q[8 + k] = swap16(Q[k]);
+    uint32_t R[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int m8 = min(m4[k], m4[(k + 4) & 15]);
-        best = max(best, min(m8, d[(k + 8) & 15]));
-    }
-    return best - 1;
+    for (int k = 0; k < 8; ++k) R[k] = __vimin3_s16x2(Q[k], Q[k + 3], Q[k + 6]);  // min of 9 contiguous
+    const uint32_t m = __vimax3_s16x2(__vimax3_s16x2(R[0], R[1], R[2]), __vimax3_s16x2(R[3], R[4], R[5]), __vmaxs2(R[6], R[7]));
+    return max((int)(m & 0xffffu), (int)(m >> 16)) - 256;
 }
 
-// Shared memory (dynamic): tile | score | masks | offsets | corner lists. The tile (fast_bw x max_th
-// bytes: the largest cell of the handle + 15 bytes, because the innermost TMA coordinate must be a
-// multiple of 16 bytes) arrives by one TMA box load per block; whatever lies beyond this cell's own
-// tw x th window is simply not looked at.
 __global__ void __launch_bounds__(kFastThreads)
 fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, const __grid_constant__ TmaMaps maps,
                   uint32_t* __restrict__ slots, int* __restrict__ cell_counts) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int max_th = g->max_th, tp = g->fast_bw;
-    uint8_t* tile = smem;
-    uint8_t* score = smem + (size_t)max_th * tp;
-    uint32_t* mask_ini = reinterpret_cast<uint32_t*>(score + (size_t)max_th * tp);  // [max_th][2]
-    uint32_t* mask_all = mask_ini + 2 * max_th;
-    int* offs = reinterpret_cast<int*>(mask_all + 2 * max_th);                      // [2*max_th + 1]
-    uint16_t* list1 = reinterpret_cast<uint16_t*>(offs + 2 * max_th + 2);           // survivors of the 4-point test
-    uint16_t* list2 = list1 + (size_t)max_th * tp;                                  // corners
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_cnt[kFastWarps], s_n2, s_total_ini;
-
-    const CellDesc c = cells[blockIdx.x];
-    const int frame = blockIdx.y;
-    const LevelGeom& L = g->lv[c.level];
+    __shared__ __align__(8) uint64_t bars[kFastWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tw = c.tw, th = c.th;
-    const int dw = tw - 6, dh = th - 6;  // interior (detection) size
-    int* count_out = cell_counts + (size_t)frame * g->ncells + blockIdx.x;
-    if (dw <= 0 || dh <= 0) {
-        if (threadIdx.x == 0) *count_out = 0;
-        return;
-    }
-    if (threadIdx.x == 0) {
-        s_n2 = 0; s_total_ini = 0;
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(&bar, (uint32_t)(max_th * tp));
-        tma_load_3d(tile, &maps.m[c.level], c.x0 & ~15, c.y0, frame, &bar);  // innermost TMA coordinate: 16-byte granular
-    }
-    {   // meanwhile: clear the score map and the masks
-        uint32_t* scorew = reinterpret_cast<uint32_t*>(score);
-        for (int i = threadIdx.x; i < (max_th * tp) >> 2; i += kFastThreads) scorew[i] = 0u;
-        for (int i = threadIdx.x; i < 4 * max_th; i += kFastThreads) mask_ini[i] = 0u;  // mask_ini + mask_all
-    }
-    __syncthreads();       // barrier init + cleared maps visible
-    mbar_wait(&bar, 0);    // tile landed
-
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int max_th = g->max_th, tp = g->fast_bw, tpw = tp >> 2;
+    const FastLayout lay = fast_layout(g->max_tw, max_th, tp);
+    const int T = lay.tile_bytes;
+    uint8_t* wbase = smem + (size_t)warp * lay.warp_bytes;
+    uint8_t* score = wbase + 2 * T;
+    uint32_t* mask_ini = reinterpret_cast<uint32_t*>(score + T);
+    uint32_t* mask_all = mask_ini + lay.mask_words;
+    uint32_t* offs = mask_all + lay.mask_words;
+    uint16_t* list = reinterpret_cast<uint16_t*>(wbase + lay.list_off);
+    const int frame = blockIdx.y, ncells = g->ncells;
+    const int stride = gridDim.x * kFastWarps;       // cells gw, gw + stride, ... belong to this warp
+    const int gw = blockIdx.x * kFastWarps + warp;
     const int minTh = g->minTh, iniTh = g->iniTh;
-    const int phase = c.x0 & 15;
-    const uint8_t* t0 = tile + phase;  // pixel (x, y) of the cell tile at t0[y * tp + x]
-    uint8_t* sc0 = score + phase;
+    if (gw >= ncells) return;
 
-    // ---- phase 1: 4-point rejection on every interior pixel ----------------------------------------
-    // branch-free test, incremental addressing, survivors appended to a list private to the warp
-    // (no atomics): warp w owns list1[w * seg .. (w+1) * seg)
-    const int seg = (max_th * tp) / kFastWarps;
-    uint16_t* mylist = list1 + warp * seg;
-    int cnt = 0;
-    for (int x0 = 3; x0 < tw - 3; x0 += 32) {  // one trip unless the cell is wider than 38 px
-        const bool xin = x0 + lane < tw - 3;
-        const int x = xin ? x0 + lane : tw - 4;  // idle lanes re-test the last column (no branch), masked below
-        const uint8_t* p = t0 + (3 + warp) * tp + x;
-        const int up = -3 * tp, dn = 3 * tp;
-        int at = (3 + warp) * tp + x;
-        for (int y = 3 + warp; y < th - 3; y += kFastWarps, p += kFastWarps * tp, at += kFastWarps * tp) {
-            const int v = p[0], lo = v - minTh, hi = v + minTh;
-            const int r0 = p[dn], r8 = p[up], r4 = p[3], r12 = p[-3];
-            const bool keep = xin & ((max(min(r0, r8), min(r4, r12)) < lo) | (min(max(r0, r8), max(r4, r12)) > hi));
-            const uint32_t ball = __ballot_sync(0xffffffffu, keep);
-            if (keep) mylist[cnt + __popc(ball & ((1u << lane) - 1))] = (uint16_t)at;
-            cnt += __popc(ball);
+    // one elected lane per warp owns the two mbarriers and issues the tile loads
+    auto issue = [&](int ci, int buf) {
+        const CellDesc c = cells[ci];
+        if (c.tw > 6 && c.th > 6) {
+            mbar_expect_tx(&bars[warp][buf], (uint32_t)T);
+            tma_load_3d(wbase + buf * T, &maps.m[c.level], c.x0 & ~15, c.y0, frame, &bars[warp][buf]);  // innermost TMA coordinate: 16-byte granular
         }
+    };
+    if (lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        mbar_fence_init();
+        issue(gw, 0);
     }
-    if (lane == 0) s_cnt[warp] = cnt;
-    __syncthreads();
+    uint32_t parity = 0;  // bit b: phase to wait for on buffer b
 
-    // ---- phase 2a: full 16-pixel arc test on the survivors -> corner list (bit 15 = dark side) -------
-    int c0 = s_cnt[0], c1 = s_cnt[1], c2 = s_cnt[2], c3 = s_cnt[3];
-    const int n1 = c0 + c1 + c2 + c3;
-    for (int i = threadIdx.x; i < n1; i += kFastThreads) {
-        int k = i, w = 0;
-        if (k >= c0) { k -= c0; w = 1; if (k >= c1) { k -= c1; w = 2; if (k >= c2) { k -= c2; w = 3; } } }
-        const int at = list1[w * seg + k];
-        const int side = fast_arc_test(t0 + at, tp, minTh);
-        if (side) list2[atomicAdd(&s_n2, 1)] = (uint16_t)(at | (side == 2 ? 0x8000 : 0));
-    }
-    __syncthreads();
-    // ---- phase 2b: exact score of the corners, dense -----------------------------------------------
-    const int n2 = s_n2;
-    for (int i = threadIdx.x; i < n2; i += kFastThreads) {
-        const int e = list2[i], at = e & 0x7fff;
-        sc0[at] = (uint8_t)fast_score_side(t0 + at, tp, (e & 0x8000) != 0);
-        list2[i] = (uint16_t)at;
-    }
-    __syncthreads();
+    for (int k = 0, ci = gw; ci < ncells; ++k, ci += stride) {
+        const int buf = k & 1;
+        __syncwarp();  // every lane is done with the previous cell (and with the buffer the next load overwrites)
+        if (lane == 0 && ci + stride < ncells) issue(ci + stride, buf ^ 1);
 
-    // ---- phase 3: 3x3 strict maximum on the corners -> bit masks per (row, 32-column chunk) --------
-    int my_ini = 0;
-    for (int i = threadIdx.x; i < n2; i += kFastThreads) {
-        const int at = list2[i];
-        const uint8_t* q = sc0 + at;
-        const int s = q[0];
-        const int m = max(max(max(q[-tp - 1], q[-tp]), max(q[-tp + 1], q[-1])), max(max(q[1], q[tp - 1]), max(q[tp], q[tp + 1])));
-        if (m < s) {
-            const int y = at / tp, x = at - y * tp;
-            const int e = (y - 3) * 2 + ((x - 3) >> 5);
-            const uint32_t bit = 1u << ((x - 3) & 31);
-            atomicOr(&mask_all[e], bit);
-            if (s >= iniTh) { atomicOr(&mask_ini[e], bit); ++my_ini; }
+        const CellDesc c = cells[ci];
+        const LevelGeom& L = g->lv[c.level];
+        const int tw = c.tw, th = c.th;
+        const int dw = tw - 6, dh = th - 6;  // interior (detection) size
+        int* count_out = cell_counts + (size_t)frame * ncells + ci;
+        if (dw <= 0 || dh <= 0) {
+            if (lane == 0) *count_out = 0;
+            continue;
         }
-    }
-    if (my_ini) atomicAdd(&s_total_ini, my_ini);
-    __syncthreads();
-    const uint32_t* mask = s_total_ini > 0 ? mask_ini : mask_all;  // minThFAST retry of an empty cell
+        {   // clear the score map and the masks (contiguous)
+            uint4* z = reinterpret_cast<uint4*>(score);
+            const int nz = (T + 2 * lay.mask_words * 4) >> 4;
+            for (int i = lane; i < nz; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+        mbar_wait(&bars[warp][buf], (parity >> buf) & 1u);
+        parity ^= 1u << buf;
 
-    // ---- phase 4: exclusive prefix over the entries in row-major order (warp 0), ordered write ------
-    const int nent = dh * 2;
-    if (warp == 0) {
-        int carry = 0;
-        for (int e0 = 0; e0 < nent; e0 += 32) {
-            const int e = e0 + lane;
-            const int cnt = e < nent ? __popc(mask[e]) : 0;
+        const uint8_t* tile = wbase + buf * T;  // pixel (x, y) of the cell tile at tile[y * tp + phase + x]
+        const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
+        const int phase = c.x0 & 15;
+
+        // ---- phase 1: 4-point rejection, four pixels (one aligned word) per lane ----------------------
+        const int bs = phase + 3, be = bs + dw;  // interior byte columns [bs, be) of a tile row
+        const int gfirst = bs >> 2, G = ((be - 1) >> 2) - gfirst + 1;
+        const int nitems = dh * G;
+        const uint32_t Ginv = (65536u + G - 1) / G;  // floor(i / G) == i * Ginv >> 16 for i * G < 65536
+        const uint32_t T1 = (uint32_t)(minTh + 1) * 0x10001u, T2 = ((uint32_t)(-minTh) & 0xffffu) * 0x10001u;
+        int n1 = 0;
+        for (int i0 = 0; i0 < nitems; i0 += 32) {
+            const bool act = i0 + lane < nitems;
+            const int i = act ? i0 + lane : nitems - 1;
+            const int row = (int)((uint32_t)i * Ginv >> 16), gg = i - row * G;
+            const int y = 3 + row, wcol = gfirst + gg;
+            const uint32_t* wp = tile32 + y * tpw + wcol;
+            const uint32_t C = wp[0], Lw = wp[-1], Rw = wp[1], U = wp[-3 * tpw], Dn = wp[3 * tpw];
+            const uint32_t W12 = __funnelshift_r(Lw, C, 8);   // ring pixel 12 (x - 3) of the four centres
+            const uint32_t W4 = __funnelshift_r(C, Rw, 24);   // ring pixel 4  (x + 3)
+            uint32_t hit[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t sel = h ? 0x4342u : 0x4140u;
+                const uint32_t c2 = __byte_perm(C, 0, sel), u2 = __byte_perm(U, 0, sel), d2 = __byte_perm(Dn, 0, sel);
+                const uint32_t l2 = __byte_perm(W12, 0, sel), r2 = __byte_perm(W4, 0, sel);
+                const uint32_t nc = ~c2;                       // -c - 1 in each half
+                const uint32_t kd = __vadd2(nc, T1);           // t - c
+                const uint32_t kb = __vadd2(nc, T2);           // -c - 1 - t
+                const uint32_t a = __vmaxs2(__vmins2(d2, u2), __vmins2(l2, r2));
+                const uint32_t b = __vmins2(__vmaxs2(d2, u2), __vmaxs2(l2, r2));
+                // sign bit of a half set  <=>  one of (0,8) and one of (4,12) below v - t, or above v + t
+                hit[h] = __vadd2(a, kd) | ~__vadd2(b, kb);
+            }
+            // survivors of this lane: pixel j at bit (15, 31, 14, 30)[j]; byte columns outside [bs, be) masked
+            const int bcol0 = wcol << 2;
+            const int lead = max(bs - bcol0, 0), trail = max(bcol0 + 4 - be, 0);
+            const uint32_t v4 = act ? ((0xfu << lead) & (0xfu >> trail)) : 0u;  // valid pixels, bit j
+            const uint32_t vw = (v4 & 1u) << 15 | (v4 & 2u) << 30 | (v4 & 4u) << 12 | (v4 & 8u) << 27;
+            const uint32_t kw = ((hit[0] & 0x80008000u) | ((hit[1] >> 1) & 0x40004000u)) & vw;
+            const int cnt = __popc(kw);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            if (e < nent) offs[e] = carry + inc - cnt;
+            uint16_t* dst = list + n1 + inc - cnt;
+            const uint32_t e0 = (uint32_t)(bcol0 | y << 7);
+            if (kw & 0x00008000u) *dst++ = (uint16_t)e0;
+            if (kw & 0x80000000u) *dst++ = (uint16_t)(e0 + 1);
+            if (kw & 0x00004000u) *dst++ = (uint16_t)(e0 + 2);
+            if (kw & 0x40000000u) *dst++ = (uint16_t)(e0 + 3);
+            n1 += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+
+        // ---- phase 2: exact score of the survivors on their possible side; corner <=> score >= minTh ----
+        int n2 = 0;
+        for (int i0 = 0; i0 < n1; i0 += 32) {
+            const bool act = i0 + lane < n1;
+            const int e = list[act ? i0 + lane : n1 - 1];
+            const int at = (e >> 7 & 127) * tp + (e & 127);
+            const uint8_t* p = tile + at;
+            const int v = p[0];
+            int r[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) r[q] = p[ring_offset(q, tp)];
+            // which side(s) can hold an arc of 9: one of (0,8) and one of (4,12) beyond the threshold
+            const bool fb = max(min(r[0], r[8]), min(r[4], r[12])) < v - minTh;
+            const bool fa = min(max(r[0], r[8]), max(r[4], r[12])) > v + minTh;
+            int s = fast_side_margin(r, v, fb ? -1 : 1) - 1;
+            if (__any_sync(0xffffffffu, fb & fa)) {  // both sides passed the 4-point test: rare
+                if (fb & fa) s = max(s, fast_side_margin(r, v, 1) - 1);
+            }
+            const bool corner = act & (s >= minTh);
+            __syncwarp();  // all entries of this step are read before the compacted list overwrites them
+            const uint32_t ball = __ballot_sync(0xffffffffu, corner);
+            if (corner) {
+                score[at] = (uint8_t)s;
+                list[n2 + __popc(ball & lt_mask)] = (uint16_t)e;
+            }
+            n2 += __popc(ball);
+        }
+        __syncwarp();
+
+        // ---- phase 3: 3x3 strict maximum on the corners -> bit masks per (row, 32-column half) ---------
+        int total_ini = 0;
+        for (int i0 = 0; i0 < n2; i0 += 32) {
+            const bool act = i0 + lane < n2;
+            const int e = list[act ? i0 + lane : n2 - 1];
+            const int y = e >> 7, x = (e & 127) - phase;
+            const uint8_t* q = score + y * tp + (e & 127);
+            const int s = q[0];
+            const int m = max(max(max(q[-tp - 1], q[-tp]), max(q[-tp + 1], q[-1])), max(max(q[1], q[tp - 1]), max(q[tp], q[tp + 1])));
+            const bool keep = act & (m < s);
+            const bool ini = keep & (s >= iniTh);
+            if (keep) {
+                const int w = (y - 3) * 2 + ((x - 3) >> 5);
+                const uint32_t bit = 1u << ((x - 3) & 31);
+                atomicOr(&mask_all[w], bit);
+                if (ini) atomicOr(&mask_ini[w], bit);
+            }
+            total_ini += __popc(__ballot_sync(0xffffffffu, ini));
+        }
+        __syncwarp();
+        const uint32_t* mask = total_ini > 0 ? mask_ini : mask_all;  // minThFAST retry of an empty cell
+
+        // ---- phase 4: exclusive prefix over the mask words in row-major order, ordered write ----------
+        const int nent = dh * 2;
+        int carry = 0;
+        for (int e0 = 0; e0 < nent; e0 += 32) {
+            const int w = e0 + lane;
+            const int cnt = w < nent ? __popc(mask[w]) : 0;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (w < nent) offs[w] = carry + inc - cnt;
             carry += __shfl_sync(0xffffffffu, inc, 31);
         }
         if (lane == 0) *count_out = min(carry, L.slot_cap);
-    }
-    __syncthreads();
-
-    uint32_t* out = slots + (size_t)frame * g->slot_words + L.slot_off + (size_t)c.ordinal * L.slot_cap;
-    for (int e = threadIdx.x; e < nent; e += kFastThreads) {
-        uint32_t m = mask[e];
-        int rank = offs[e];
-        const int y = 3 + (e >> 1), xb = 3 + (e & 1) * 32;
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int x = xb + b;
-            if (rank < L.slot_cap)
-                out[rank] = (uint32_t)(x + c.offx) | (uint32_t)(y + c.offy) << 12 | (uint32_t)sc0[y * tp + x] << 24;
-            ++rank;
+        __syncwarp();
+        uint32_t* out = slots + (size_t)frame * g->slot_words + L.slot_off + (size_t)c.ordinal * L.slot_cap;
+        for (int i = lane; i < n2; i += 32) {
+            const int e = list[i];
+            const int y = e >> 7, x = (e & 127) - phase;
+            const int w = (y - 3) * 2 + ((x - 3) >> 5);
+            const uint32_t bit = 1u << ((x - 3) & 31), mw = mask[w];
+            if (mw & bit) {
+                const int rank = offs[w] + __popc(mw & (bit - 1u));
+                if (rank < L.slot_cap)
+                    out[rank] = (uint32_t)(x + c.offx) | (uint32_t)(y + c.offy) << 12 | (uint32_t)score[y * tp + (e & 127)] << 24;
+            }
         }
     }
 }
 
-static size_t fast_smem_bytes(const Geometry& hg, int tp) {
-    const size_t px = (size_t)hg.max_th * tp;
-    return 2 * px + (size_t)hg.max_th * 4 * sizeof(uint32_t) + (2 * (size_t)hg.max_th + 2) * sizeof(int) + 2 * px * sizeof(uint16_t);
-}
-
 int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st) {
-    fast_cells_kernel<<<dim3(hg.ncells, n), kFastThreads, fast_smem_bytes(hg, hg.fast_bw), st>>>(db.geom, db.cells, maps, db.slots,
-                                                                                               db.cell_counts);
+    // list entries hold the byte column in 7 bits and the row in 7 bits
+    ORB_REQUIRE(hg.fast_bw <= 128 && hg.max_th <= 128 && hg.max_tw - 6 <= 64, "FAST cell larger than 64 x 122 pixels");
+    const FastLayout lay = fast_layout(hg.max_tw, hg.max_th, hg.fast_bw);
+    const size_t smem = (size_t)lay.warp_bytes * kFastWarps;
+    static int attr_bytes[64];  // per device: dynamic shared memory opted in so far
+    int dev = 0;
+    ORB_CUDA_TRY(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && dev < 64 && attr_bytes[dev] < (int)smem) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_bytes[dev] = (int)smem;
+    }
+    // cells per warp: as many as keeps every SM's warp slots (5 blocks of 4 warps) busy, at most 8
+    const long long warps_wanted = (long long)kNumSMs * 5 * kFastWarps;
+    int cpw = (int)std::min<long long>(kFastMaxCellsPerWarp, std::max<long long>(1, (long long)hg.ncells * n / warps_wanted));
+    const int blocks_x = ceil_div(ceil_div(hg.ncells, cpw), kFastWarps);
+    fast_cells_kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
