@@ -1,7 +1,8 @@
 // K3: FAST-9/16 detection per 30-px cell with per-cell threshold fallback and 3x3 non-maximum
-// suppression. One WARP per cell; every warp walks a strided list of cells of one frame with the
-// next cell's tile already in flight (TMA, two tile buffers per warp), so there is no block barrier
-// anywhere and no wait for the tile after a warp's first cell.
+// suppression. One WARP per cell; every warp walks a strided list of cells of one frame. A cell's
+// tile (TMA box load) is dead once its scores are known, so the next cell's load is issued at that
+// point and lands while the warp finishes phases 3-4: no block barrier anywhere, no wait for the
+// tile after a warp's first cell, and 6.6 KB of shared memory per warp (8 blocks of 4 warps per SM).
 //
 // Replaces the cell loop of ComputeKeyPointsOctTree, /root/reference/src/ORBextractor.cc:789-829,
 // i.e. cv::FAST(cell + 6 px halo, iniThFAST, true) with the minThFAST retry when the cell comes back
@@ -40,14 +41,17 @@ constexpr int kFastWarps = 4;
 constexpr int kFastThreads = kFastWarps * 32;
 constexpr int kFastMaxCellsPerWarp = 8;
 
-// per-warp shared memory: tile[2] | score | mask_ini | mask_all | offs | list
-struct FastLayout { int tile_bytes, mask_words, list_off, warp_bytes; };
+// per-warp shared memory: tile | score (interior + 1 px ring only) | mask_ini | mask_all | offs | list
+struct FastLayout { int tile_bytes, score_pitch, score_bytes, mask_words, mask_off, list_off, warp_bytes; };
 __host__ __device__ inline FastLayout fast_layout(int max_tw, int max_th, int tp) {
     FastLayout f;
     f.tile_bytes = max_th * tp;                      // multiple of 16 (tp is)
-    f.mask_words = 2 * max_th;                       // (row, 32-column half) entries
-    f.list_off = 3 * f.tile_bytes + (int)align_up((size_t)3 * f.mask_words * 4, 16);
-    const int npx = (max_tw > 6 && max_th > 6) ? (max_tw - 6) * (max_th - 6) : 0;
+    f.score_pitch = (int)align_up((size_t)max_tw - 4, 4);  // score of cell pixel (x, y) at [(y - 2) * pitch + x - 2]
+    f.score_bytes = (int)align_up((size_t)f.score_pitch * (max_th - 4), 16);
+    f.mask_words = 2 * (max_th - 6);                 // (row, 32-column half) entries
+    f.mask_off = f.tile_bytes + f.score_bytes;
+    f.list_off = f.mask_off + (int)align_up((size_t)3 * f.mask_words * 4, 16);
+    const int npx = (max_tw - 6) * (max_th - 6);
     f.warp_bytes = (int)align_up((size_t)f.list_off + 2 * (size_t)npx + 16, 128);
     return f;
 }
@@ -77,68 +81,67 @@ __device__ __forceinline__ int fast_side_margin(const int (&r)[16], int v, int s
     return max((int)(m & 0xffffu), (int)(m >> 16)) - 256;
 }
 
-__global__ void __launch_bounds__(kFastThreads)
+__global__ void __launch_bounds__(kFastThreads, 8)
 fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, const __grid_constant__ TmaMaps maps,
                   uint32_t* __restrict__ slots, int* __restrict__ cell_counts) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[kFastWarps][2];
+    __shared__ __align__(8) uint64_t bars[kFastWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int max_th = g->max_th, tp = g->fast_bw, tpw = tp >> 2;
     const FastLayout lay = fast_layout(g->max_tw, max_th, tp);
-    const int T = lay.tile_bytes;
+    const int T = lay.tile_bytes, sp = lay.score_pitch;
     uint8_t* wbase = smem + (size_t)warp * lay.warp_bytes;
-    uint8_t* score = wbase + 2 * T;
-    uint32_t* mask_ini = reinterpret_cast<uint32_t*>(score + T);
+    uint8_t* score = wbase + T;
+    uint32_t* mask_ini = reinterpret_cast<uint32_t*>(wbase + lay.mask_off);
     uint32_t* mask_all = mask_ini + lay.mask_words;
     uint32_t* offs = mask_all + lay.mask_words;
     uint16_t* list = reinterpret_cast<uint16_t*>(wbase + lay.list_off);
+    uint64_t* bar = &bars[warp];
     const int frame = blockIdx.y, ncells = g->ncells;
     const int stride = gridDim.x * kFastWarps;       // cells gw, gw + stride, ... belong to this warp
     const int gw = blockIdx.x * kFastWarps + warp;
     const int minTh = g->minTh, iniTh = g->iniTh;
     if (gw >= ncells) return;
 
-    // one elected lane per warp owns the two mbarriers and issues the tile loads
-    auto issue = [&](int ci, int buf) {
+    // one elected lane per warp owns the mbarrier and issues the tile loads. The tile is dead once a
+    // cell's scores are known, so the next cell's load is issued there and lands during phases 3-4.
+    auto issue = [&](int ci) {
+        if (ci >= ncells) return;
         const CellDesc c = cells[ci];
         if (c.tw > 6 && c.th > 6) {
-            mbar_expect_tx(&bars[warp][buf], (uint32_t)T);
-            tma_load_3d(wbase + buf * T, &maps.m[c.level], c.x0 & ~15, c.y0, frame, &bars[warp][buf]);  // innermost TMA coordinate: 16-byte granular
+            mbar_expect_tx(bar, (uint32_t)T);
+            tma_load_3d(wbase, &maps.m[c.level], c.x0 & ~15, c.y0, frame, bar);  // innermost TMA coordinate: 16-byte granular
         }
     };
     if (lane == 0) {
-        mbar_init(&bars[warp][0], 1);
-        mbar_init(&bars[warp][1], 1);
+        mbar_init(bar, 1);
         mbar_fence_init();
-        issue(gw, 0);
+        issue(gw);
     }
-    uint32_t parity = 0;  // bit b: phase to wait for on buffer b
+    uint32_t parity = 0;
 
-    for (int k = 0, ci = gw; ci < ncells; ++k, ci += stride) {
-        const int buf = k & 1;
-        __syncwarp();  // every lane is done with the previous cell (and with the buffer the next load overwrites)
-        if (lane == 0 && ci + stride < ncells) issue(ci + stride, buf ^ 1);
-
+    for (int ci = gw; ci < ncells; ci += stride) {
+        __syncwarp();  // every lane is done with the previous cell
         const CellDesc c = cells[ci];
         const LevelGeom& L = g->lv[c.level];
         const int tw = c.tw, th = c.th;
         const int dw = tw - 6, dh = th - 6;  // interior (detection) size
         int* count_out = cell_counts + (size_t)frame * ncells + ci;
         if (dw <= 0 || dh <= 0) {
-            if (lane == 0) *count_out = 0;
+            if (lane == 0) { *count_out = 0; issue(ci + stride); }
             continue;
         }
-        {   // clear the score map and the masks (contiguous)
+        {   // clear the score map and the masks
             uint4* z = reinterpret_cast<uint4*>(score);
-            const int nz = (T + 2 * lay.mask_words * 4) >> 4;
-            for (int i = lane; i < nz; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = lane; i < lay.score_bytes >> 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = lane; i < 2 * lay.mask_words; i += 32) mask_ini[i] = 0u;
         }
         __syncwarp();
-        mbar_wait(&bars[warp][buf], (parity >> buf) & 1u);
-        parity ^= 1u << buf;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
 
-        const uint8_t* tile = wbase + buf * T;  // pixel (x, y) of the cell tile at tile[y * tp + phase + x]
+        const uint8_t* tile = wbase;  // pixel (x, y) of the cell tile at tile[y * tp + phase + x]
         const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
         const int phase = c.x0 & 15;
 
@@ -214,12 +217,13 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             __syncwarp();  // all entries of this step are read before the compacted list overwrites them
             const uint32_t ball = __ballot_sync(0xffffffffu, corner);
             if (corner) {
-                score[at] = (uint8_t)s;
+                score[((e >> 7) - 2) * sp + (e & 127) - phase - 2] = (uint8_t)s;
                 list[n2 + __popc(ball & lt_mask)] = (uint16_t)e;
             }
             n2 += __popc(ball);
         }
-        __syncwarp();
+        __syncwarp();  // nobody reads the tile any more
+        if (lane == 0) issue(ci + stride);
 
         // ---- phase 3: 3x3 strict maximum on the corners -> bit masks per (row, 32-column half) ---------
         int total_ini = 0;
@@ -227,9 +231,9 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             const bool act = i0 + lane < n2;
             const int e = list[act ? i0 + lane : n2 - 1];
             const int y = e >> 7, x = (e & 127) - phase;
-            const uint8_t* q = score + y * tp + (e & 127);
+            const uint8_t* q = score + (y - 2) * sp + x - 2;
             const int s = q[0];
-            const int m = max(max(max(q[-tp - 1], q[-tp]), max(q[-tp + 1], q[-1])), max(max(q[1], q[tp - 1]), max(q[tp], q[tp + 1])));
+            const int m = max(max(max(q[-sp - 1], q[-sp]), max(q[-sp + 1], q[-1])), max(max(q[1], q[sp - 1]), max(q[sp], q[sp + 1])));
             const bool keep = act & (m < s);
             const bool ini = keep & (s >= iniTh);
             if (keep) {
@@ -266,7 +270,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             if (mw & bit) {
                 const int rank = offs[w] + __popc(mw & (bit - 1u));
                 if (rank < L.slot_cap)
-                    out[rank] = (uint32_t)(x + c.offx) | (uint32_t)(y + c.offy) << 12 | (uint32_t)score[y * tp + (e & 127)] << 24;
+                    out[rank] = (uint32_t)(x + c.offx) | (uint32_t)(y + c.offy) << 12 | (uint32_t)score[(y - 2) * sp + x - 2] << 24;
             }
         }
     }
@@ -284,8 +288,8 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps
         ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes[dev] = (int)smem;
     }
-    // cells per warp: as many as keeps every SM's warp slots (5 blocks of 4 warps) busy, at most 8
-    const long long warps_wanted = (long long)kNumSMs * 5 * kFastWarps;
+    // cells per warp: as many as keeps every SM's warp slots (8 blocks of 4 warps) busy, at most 8
+    const long long warps_wanted = (long long)kNumSMs * 8 * kFastWarps;
     int cpw = (int)std::min<long long>(kFastMaxCellsPerWarp, std::max<long long>(1, (long long)hg.ncells * n / warps_wanted));
     const int blocks_x = ceil_div(ceil_div(hg.ncells, cpw), kFastWarps);
     fast_cells_kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts);
