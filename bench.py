@@ -239,26 +239,30 @@ def run_b200(args):
     kp_per_frame = float(pin["counts"].numpy()[:B].mean())
     matches_per_frame = float((fe.match[:B].cpu().numpy() >= 0).sum() / B)
 
-    # ---- end to end through the host-buffer API ("e2e"): two agents' worth of buffers in flight ----
+    # ---- end to end through the host-buffer API ("e2e"): three agents' worth of buffers in flight, so that
+    # the upload of step i+1, the kernels of step i and the download of step i-1 overlap --------------------
     h_frames = torch.from_numpy(frames).pin_memory()
-    fes = [fe, AgentFrontend(W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B, nnratio=NNRATIO, th=TH)]
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    DEPTH = 3
+    fes = [fe] + [AgentFrontend(W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=B, nnratio=NNRATIO, th=TH)
+                  for _ in range(DEPTH - 1)]
+    streams = [torch.cuda.Stream(dev) for _ in range(DEPTH)]
     outs = [f.pinned_outputs() for f in fes]
 
     def e2e_step(i):
-        k = i & 1
+        k = i % DEPTH
         with torch.cuda.stream(streams[k]):
             fes[k].process_async(h_frames, outs[k])
 
-    for i in range(max(args.warmup, 2)):
+    for i in range(max(args.warmup, DEPTH)):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(i)
-        if i >= 1:
-            streams[(i - 1) & 1].synchronize()  # the host consumes step i-1's results while step i runs
-            _ = int(outs[(i - 1) & 1]["counts"][0])
+        if i >= DEPTH - 1:
+            j = (i - (DEPTH - 1)) % DEPTH
+            streams[j].synchronize()  # the host consumes an earlier step's results while the later ones run
+            _ = int(outs[j]["counts"][0])
     for s in streams:
         s.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
@@ -416,7 +420,7 @@ def run_b200(args):
                        "keypoints_per_frame": kp_per_frame, "matches_per_frame": matches_per_frame},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * fe.h2d_bytes_per_frame(),
                     "d2h_bytes_per_step": B * fe.d2h_bytes_per_frame(), "ms_per_step": e2e_ms / args.steps,
-                    "how": "pinned host frames -> orbx_upload_frames/extract_staged/orbm_knn2_batched/download, 2 buffers in flight"},
+                    "how": "pinned host frames -> orbx_upload_frames/extract_staged/orbm_knn2_batched/download, 3 buffers in flight"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mapfusion": mapf, "bow_transform": bow,
         }))
     if world > 1:

@@ -51,12 +51,12 @@ struct SlotInfo { int valid, level, x, y, response, dst; };
 __global__ void __launch_bounds__(kDescWarps * 32, 5)
 orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_t* __restrict__ pyr,
                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ selected,
-                       const int* __restrict__ sel_counts, const int8_t* __restrict__ pattern,
+                       const int* __restrict__ sel_counts, const float* __restrict__ pattern,
                        orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int* __restrict__ counts) {
     __shared__ float patf[1024];  // transposed: value (test t, component c) of byte `lane` at [(4t+c)*32 + lane]
     __shared__ SlotInfo info[kDescSlots];
     __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) patf[(i & 31) * 32 + (i >> 5)] = (float)pattern[i];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) patf[i] = pattern[i];
 
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

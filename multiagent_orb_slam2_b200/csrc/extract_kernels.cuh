@@ -78,7 +78,7 @@ struct DeviceBuffers {
     const CellDesc* cells;
     const LinTap* taps;
     const BlurTile* tiles;
-    const int8_t* pattern;  // 1024 x int8
+    const float* pattern;   // 1024 floats, transposed: [4 * test + component][descriptor byte]
     uint8_t* pyr;
     uint8_t* blur;
     uint32_t* slots;

@@ -211,18 +211,20 @@ int build_geometry(orbx_extractor* h) {
     int rc;
     if ((rc = dalloc(&h->d_geom, sizeof(Geometry))) || (rc = dalloc(&h->d_cells, cells.size() * sizeof(CellDesc))) ||
         (rc = dalloc(&h->d_taps, taps.size() * sizeof(LinTap))) || (rc = dalloc(&h->d_tiles, tiles.size() * sizeof(BlurTile))) ||
-        (rc = dalloc(&h->d_pattern, 1024)))
+        (rc = dalloc(&h->d_pattern, 1024 * sizeof(float))))
         return rc;
-    int8_t pat8[1024];
-    for (int i = 0; i < 1024; ++i) pat8[i] = (int8_t)kPatternInts[i];
+    // sampling pattern as floats, transposed for the describe kernel: value q = 4 * test + component of
+    // descriptor byte b at [q * 32 + b]
+    float patT[1024];
+    for (int i = 0; i < 1024; ++i) patT[(i & 31) * 32 + (i >> 5)] = (float)kPatternInts[i];
     ORB_CUDA_TRY(cudaMemcpy(h->d_geom, &g, sizeof(Geometry), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_taps, taps.data(), taps.size() * sizeof(LinTap), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice));
-    ORB_CUDA_TRY(cudaMemcpy(h->d_pattern, pat8, 1024, cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_pattern, patT, sizeof(patT), cudaMemcpyHostToDevice));
     DeviceBuffers& db = h->db;
     db.geom = (const Geometry*)h->d_geom; db.cells = (const CellDesc*)h->d_cells; db.taps = (const LinTap*)h->d_taps;
-    db.tiles = (const BlurTile*)h->d_tiles; db.pattern = (const int8_t*)h->d_pattern;
+    db.tiles = (const BlurTile*)h->d_tiles; db.pattern = (const float*)h->d_pattern;
     h->in_pitch = align_up((size_t)h->width, 128);
     if ((rc = dalloc((void**)&db.pyr, (size_t)B * g.pyr_bytes)) || (rc = dalloc((void**)&db.blur, (size_t)B * g.blur_bytes)) ||
         (rc = dalloc((void**)&db.slots, (size_t)B * g.slot_words * 4)) || (rc = dalloc((void**)&db.cell_counts, (size_t)B * g.ncells * 4)) ||
