@@ -253,12 +253,14 @@ def run_b200(args):
         with torch.cuda.stream(streams[k]):
             fes[k].process_async(h_frames, outs[k])
 
-    for i in range(max(args.warmup, DEPTH)):
+    for i in range(max(args.warmup, 2 * DEPTH)):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
+    marks = []
     for i in range(args.steps):
         e2e_step(i)
+        marks.append(time.perf_counter() - t0)
         if i >= DEPTH - 1:
             j = (i - (DEPTH - 1)) % DEPTH
             streams[j].synchronize()  # the host consumes an earlier step's results while the later ones run
@@ -266,6 +268,8 @@ def run_b200(args):
     for s in streams:
         s.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    if rank == 0:
+        sys.stderr.write("e2e enqueue times (ms): " + " ".join("%.2f" % (m * 1e3) for m in marks) + "\n")
     barrier()
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
