@@ -39,24 +39,34 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 constexpr int kDescWarps = 8;
 constexpr int kDescSlots = 32;  // keypoint slots per block
+// blurred window of a keypoint in shared memory: rows y-18..y+18, 40 bytes from the word at or left of x-18
+// (64-bit loads of a 48-byte window were tried: 43 KB of shared memory per block pushes the SM to its largest
+// carve-out and the kernel, which also lives on L1 hits, from 0.49 to 0.64 ms; cudaFuncAttributePreferredSharedMemoryCarveout
+// swept 40..100 %: the default choice is the best)
+constexpr int kPatchReach = 18, kPatchRows = 2 * kPatchReach + 1, kPatchRowWords = 10, kPatchWords = 372;
 
 struct SlotInfo { int valid, level, x, y, response, dst; };
 
 // grid (ceil(sel_words / 32), frames), block 256. Phases:
 //   0. thread i < 32 resolves slot i (level, position in the frame's output, packed candidate)
-//   A. every warp: intensity-centroid angle of 4 slots (lane = patch column, loop over rows)
-//   B. warp 0: lane i evaluates sin/cos (double, rounded once) for slot i - 32 keypoints per
+//   A. every warp: intensity-centroid moments of 4 slots (aligned word loads, IDP.4A against int8 coordinates)
+//   B. warp 0: lane i evaluates the angle and sin/cos (double, rounded once) for slot i - 32 keypoints per
 //      instruction stream instead of one
-//   C. every warp: rotated BRIEF of 4 slots (lane = output byte), keypoint record
+//   C. every warp: rotated BRIEF of 4 slots, two at a time, sampled from a shared-memory copy of the
+//      blurred 37 x 40 window (lane = output byte), keypoint record
 __global__ void __launch_bounds__(kDescWarps * 32, 5)
 orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_t* __restrict__ pyr,
                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ selected,
-                       const int* __restrict__ sel_counts, const float* __restrict__ pattern,
+                       const int* __restrict__ sel_counts, const float* __restrict__ pattern, const uint32_t* __restrict__ ic_table,
                        orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int* __restrict__ counts) {
     __shared__ float patf[1024];  // transposed: value (test t, component c) of byte `lane` at [(4t+c)*32 + lane]
     __shared__ SlotInfo info[kDescSlots];
     __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
+    __shared__ __align__(16) uint32_t patch[kDescWarps * 2 * kPatchWords];  // per warp: blurred windows of two keypoints
+    __shared__ int s_m10[kDescSlots], s_m01[kDescSlots];
+    __shared__ uint32_t ictab[kIcTableWords];  // [phase][u | v][item]
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) patf[i] = pattern[i];
+    for (int i = threadIdx.x; i < kIcTableWords; i += blockDim.x) ictab[i] = ic_table[i];
 
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,85 +96,130 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     }
     __syncthreads();
 
-    // ---- A: IC_Angle -----------------------------------------------------------------------------
+    // ---- A: IC_Angle moments ---------------------------------------------------------------------
+    // The 31 x 31 bounding box of the circular patch is read as aligned 32-bit words (9 per row, the left
+    // edge rounded down to a word), lane = (row, word) item; the table holds, per alignment phase and
+    // item, the u and v coordinates of the 4 bytes as int8 (0 outside the circle), so that two IDP.4A
+    // per word accumulate m10 = sum u I and m01 = sum v I (integer sums: same value as the reference's
+    // row-pair loop, whatever the order).
     for (int k = 0; k < kDescSlots / kDescWarps; ++k) {
         const int sidx = warp * (kDescSlots / kDescWarps) + k;
         const SlotInfo si = info[sidx];
         if (!si.valid) continue;
         int spitch;
         const uint8_t* img = level_ptr(*g, fs, pyr, frame, si.level, &spitch);
-        const uint8_t* center = img + (size_t)si.y * spitch + si.x;
+        const int xs = si.x - kHalfPatch;
+        const uint8_t* base = img + (size_t)(si.y - kHalfPatch) * spitch + (xs & ~3);
+        const uint32_t* tu = ictab + (xs & 3) * 2 * kIcItems;
         int m10 = 0, m01 = 0;
-        const int u = lane - kHalfPatch;
-        if (lane < 2 * kHalfPatch + 1) {
-            // the circular patch is symmetric under transposition: column u spans rows |v| <= umax[|u|]
-            const int vext = g->umax[u < 0 ? -u : u];
-            const uint8_t* col = center + u;
-            int vals[2 * kHalfPatch + 1];
 #pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-                const int av = v < 0 ? -v : v;
-                vals[v + kHalfPatch] = av <= vext ? (int)col[v * spitch] : 0;  // all loads in flight together
+        for (int s = 0; s < kIcItems / 32; ++s) {
+            const int i = s * 32 + lane;
+            const int r = i / kIcWordsPerRow, j = i - r * kIcWordsPerRow;
+            if (r < 2 * kHalfPatch + 1) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * spitch + 4 * j);
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(tu[i]));
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m01) : "r"(w), "r"(tu[kIcItems + i]));
             }
-            int colsum = 0;
-#pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) { colsum += vals[v + kHalfPatch]; m01 += v * vals[v + kHalfPatch]; }
-            m10 = u * colsum;
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-        if (lane == 0) s_angle[sidx] = fast_atan2_deg((float)m01, (float)m10);
+        m10 = __reduce_add_sync(0xffffffffu, m10);
+        m01 = __reduce_add_sync(0xffffffffu, m01);
+        if (lane == 0) { s_m10[sidx] = m10; s_m01[sidx] = m01; }
     }
     __syncthreads();
 
-    // ---- B: sin / cos, one keypoint per lane -------------------------------------------------------
+    // ---- B: angle, sin / cos, one keypoint per lane --------------------------------------------------
     if (warp == 0 && info[lane].valid) {
         const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-        const float rad = __fmul_rn(s_angle[lane], factorPI);
+        const float ang = fast_atan2_deg((float)s_m01[lane], (float)s_m10[lane]);
+        const float rad = __fmul_rn(ang, factorPI);
         double sn, cs;
         sincos((double)rad, &sn, &cs);
-        s_cos[lane] = (float)cs; s_sin[lane] = (float)sn;
+        s_angle[lane] = ang; s_cos[lane] = (float)cs; s_sin[lane] = (float)sn;
     }
     __syncthreads();
 
     // ---- C: rotated BRIEF + keypoint record ----------------------------------------------------------
-    for (int k = 0; k < kDescSlots / kDescWarps; ++k) {
-        const int sidx = warp * (kDescSlots / kDescWarps) + k;
-        const SlotInfo si = info[sidx];
-        if (!si.valid) continue;
-        const LevelGeom& L = g->lv[si.level];
-        const float a = s_cos[sidx], b = s_sin[sidx];
-        const uint8_t* bc = blur + (size_t)frame * g->blur_bytes + L.blur_off + (size_t)si.y * L.pitch + si.x;
-        const int bp = L.pitch;
+    // The 512 sample points of a keypoint lie within 18 px of it (pattern radius 18.4). Gathering them
+    // straight from global memory costs one L1 wavefront per image row touched by each of the 16 load
+    // instructions (~11 each: the kernel was bound by the L1 data pipe). Instead the warp copies the
+    // 37 x 40 byte window (left edge rounded down to a word) into shared memory with coalesced word
+    // loads and gathers there. Two keypoints are described per pass so that the pattern values are read
+    // once for both.
+    uint32_t* mypatch = patch + warp * 2 * kPatchWords;
+    for (int kk = 0; kk < kDescSlots / kDescWarps; kk += 2) {
+        const int sidx0 = warp * (kDescSlots / kDescWarps) + kk;
+        const SlotInfo si0 = info[sidx0], si1 = info[sidx0 + 1];
+        if (!si0.valid && !si1.valid) continue;
+        // (an invalid slot of the pair samples stale data around the window centre and stores nothing)
+        int off[2] = {kPatchReach * kPatchRowWords * 4 + kPatchReach, kPatchReach * kPatchRowWords * 4 + kPatchReach};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const SlotInfo& si = q ? si1 : si0;
+            if (!si.valid) continue;
+            const LevelGeom& L = g->lv[si.level];
+            const int xs = si.x - kPatchReach;
+            const uint8_t* src = blur + (size_t)frame * g->blur_bytes + L.blur_off + (size_t)(si.y - kPatchReach) * L.pitch + (xs & ~3);
+            const int bp = L.pitch;
+#pragma unroll
+            for (int s = 0; s < (kPatchRows * kPatchRowWords + 31) / 32; ++s) {
+                const int i = s * 32 + lane;
+                const int r = i / kPatchRowWords, j = i - r * kPatchRowWords;
+                if (i < kPatchRows * kPatchRowWords) mypatch[q * kPatchWords + i] = *reinterpret_cast<const uint32_t*>(src + r * bp + 4 * j);
+            }
+            off[q] = kPatchReach * (kPatchRowWords * 4) + kPatchReach + (xs & 3);
+        }
+        __syncwarp();
+        const uint8_t* p0 = reinterpret_cast<const uint8_t*>(mypatch) + off[0];
+        const uint8_t* p1 = reinterpret_cast<const uint8_t*>(mypatch + kPatchWords) + off[1];
+        const float a0 = si0.valid ? s_cos[sidx0] : 0.f, b0 = si0.valid ? s_sin[sidx0] : 0.f;  // s_cos / s_sin are unset for invalid slots
+        const float a1 = si1.valid ? s_cos[sidx0 + 1] : 0.f, b1 = si1.valid ? s_sin[sidx0 + 1] : 0.f;
         const float* pp = patf + lane;
-        int val = 0;
+        int val0 = 0, val1 = 0;
+        constexpr int kRow = kPatchRowWords * 4;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             const float x0 = pp[(4 * t) * 32], y0 = pp[(4 * t + 1) * 32], x1 = pp[(4 * t + 2) * 32], y1 = pp[(4 * t + 3) * 32];
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            val |= (int)(bc[r0 * bp + c0] < bc[r1 * bp + c1]) << t;
+            {
+                const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b0), __fmul_rn(y0, a0)));
+                const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a0), __fmul_rn(y0, b0)));
+                const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b0), __fmul_rn(y1, a0)));
+                const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a0), __fmul_rn(y1, b0)));
+                val0 |= (int)(p0[r0 * kRow + c0] < p0[r1 * kRow + c1]) << t;
+            }
+            {
+                const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b1), __fmul_rn(y0, a1)));
+                const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a1), __fmul_rn(y0, b1)));
+                const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b1), __fmul_rn(y1, a1)));
+                const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a1), __fmul_rn(y1, b1)));
+                val1 |= (int)(p1[r0 * kRow + c0] < p1[r1 * kRow + c1]) << t;
+            }
         }
-        desc[((size_t)frame * g->out_cap + si.dst) * 32 + lane] = (uint8_t)val;
-        if (lane == 0) {
-            orbx_keypoint kp;
-            // `pt *= scale` (1095-1101) is applied for level != 0 only; scale[0] == 1 makes it uniform
-            kp.x = __fmul_rn((float)si.x, L.scale);
-            kp.y = __fmul_rn((float)si.y, L.scale);
-            kp.size = (float)L.patch_size;
-            kp.angle = s_angle[sidx];
-            kp.response = (float)si.response;
-            kp.octave = si.level;
-            kps[(size_t)frame * g->out_cap + si.dst] = kp;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const SlotInfo& si = q ? si1 : si0;
+            if (!si.valid) continue;
+            const LevelGeom& L = g->lv[si.level];
+            desc[((size_t)frame * g->out_cap + si.dst) * 32 + lane] = (uint8_t)(q ? val1 : val0);
+            if (lane == 0) {
+                orbx_keypoint kp;
+                // `pt *= scale` (1095-1101) is applied for level != 0 only; scale[0] == 1 makes it uniform
+                kp.x = __fmul_rn((float)si.x, L.scale);
+                kp.y = __fmul_rn((float)si.y, L.scale);
+                kp.size = (float)L.patch_size;
+                kp.angle = s_angle[sidx0 + q];
+                kp.response = (float)si.response;
+                kp.octave = si.level;
+                kps[(size_t)frame * g->out_cap + si.dst] = kp;
+            }
         }
+        __syncwarp();  // the next pair overwrites the patches
     }
 }
 
 int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
     orient_describe_kernel<<<dim3(ceil_div(hg.sel_words, kDescSlots), n), kDescWarps * 32, 0, st>>>(
-        db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.kps, db.desc, db.counts);
+        db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.ic_table, db.kps, db.desc, db.counts);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

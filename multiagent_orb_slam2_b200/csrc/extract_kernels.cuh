@@ -23,6 +23,8 @@ constexpr int kEdgeThreshold = 19;
 constexpr int kMinBorder = kEdgeThreshold - 3;  // 16
 constexpr int kHalfPatch = 15;
 constexpr int kQtMaxDepth = 13;
+// IC_Angle by word loads: 31 rows x 9 words (31 + 3 alignment bytes) = 279 items, padded to 9 warp steps; 4 phases x (u, v)
+constexpr int kIcWordsPerRow = 9, kIcItems = 288, kIcTableWords = 4 * 2 * kIcItems;
 
 struct LevelGeom {
     int w, h, pitch;
@@ -78,6 +80,7 @@ struct DeviceBuffers {
     const CellDesc* cells;
     const LinTap* taps;
     const BlurTile* tiles;
+    const uint32_t* ic_table;  // kIcTableWords
     const float* pattern;   // 1024 floats, transposed: [4 * test + component][descriptor byte]
     uint8_t* pyr;
     uint8_t* blur;

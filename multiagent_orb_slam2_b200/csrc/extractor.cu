@@ -3,6 +3,7 @@
 // orchestration (operator(), 1043-1105) and the orbx_* C ABI.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -211,7 +212,7 @@ int build_geometry(orbx_extractor* h) {
     int rc;
     if ((rc = dalloc(&h->d_geom, sizeof(Geometry))) || (rc = dalloc(&h->d_cells, cells.size() * sizeof(CellDesc))) ||
         (rc = dalloc(&h->d_taps, taps.size() * sizeof(LinTap))) || (rc = dalloc(&h->d_tiles, tiles.size() * sizeof(BlurTile))) ||
-        (rc = dalloc(&h->d_pattern, 1024 * sizeof(float))))
+        (rc = dalloc(&h->d_pattern, 1024 * sizeof(float) + kIcTableWords * 4)))
         return rc;
     // sampling pattern as floats, transposed for the describe kernel: value q = 4 * test + component of
     // descriptor byte b at [q * 32 + b]
@@ -222,9 +223,29 @@ int build_geometry(orbx_extractor* h) {
     ORB_CUDA_TRY(cudaMemcpy(h->d_taps, taps.data(), taps.size() * sizeof(LinTap), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_pattern, patT, sizeof(patT), cudaMemcpyHostToDevice));
+    {   // IC_Angle coefficient words (describe.cu): for each alignment phase p of the patch's left edge, item
+        // i = row * 9 + word: the int8 u (then v) coordinates of the 4 bytes, 0 outside the circular patch
+        std::vector<uint32_t> tab(kIcTableWords, 0u);
+        for (int p = 0; p < 4; ++p)
+            for (int r = 0; r < 2 * kHalfPatch + 1; ++r)
+                for (int j = 0; j < kIcWordsPerRow; ++j) {
+                    uint32_t cu = 0, cv = 0;
+                    const int v = r - kHalfPatch;
+                    for (int k = 0; k < 4; ++k) {
+                        const int u = 4 * j + k - kHalfPatch - p;
+                        if (u < -kHalfPatch || u > kHalfPatch || std::abs(u) > g.umax[std::abs(v)]) continue;
+                        cu |= (uint32_t)(uint8_t)(int8_t)u << (8 * k);
+                        cv |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+                    }
+                    tab[(size_t)p * 2 * kIcItems + r * kIcWordsPerRow + j] = cu;
+                    tab[(size_t)p * 2 * kIcItems + kIcItems + r * kIcWordsPerRow + j] = cv;
+                }
+        ORB_CUDA_TRY(cudaMemcpy((uint8_t*)h->d_pattern + sizeof(patT), tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    }
     DeviceBuffers& db = h->db;
     db.geom = (const Geometry*)h->d_geom; db.cells = (const CellDesc*)h->d_cells; db.taps = (const LinTap*)h->d_taps;
     db.tiles = (const BlurTile*)h->d_tiles; db.pattern = (const float*)h->d_pattern;
+    db.ic_table = (const uint32_t*)((const uint8_t*)h->d_pattern + 1024 * sizeof(float));
     h->in_pitch = align_up((size_t)h->width, 128);
     if ((rc = dalloc((void**)&db.pyr, (size_t)B * g.pyr_bytes)) || (rc = dalloc((void**)&db.blur, (size_t)B * g.blur_bytes)) ||
         (rc = dalloc((void**)&db.slots, (size_t)B * g.slot_words * 4)) || (rc = dalloc((void**)&db.cell_counts, (size_t)B * g.ncells * 4)) ||

@@ -16,9 +16,9 @@
 //
 // Phases (all warp-synchronous, work compacted between them so that the expensive part runs on dense
 // lanes):
-//   1. every interior pixel, FOUR per lane from aligned 32-bit words of the tile: 4-point rejection
+//   1. every interior pixel, 2 rows x 4 per lane from aligned 32-bit words of the tile: 4-point rejection
 //      test (any arc of 9 contains ring pixel 0 or 8 and 4 or 12) on packed 16-bit halves
-//      (PRMT unpack, VIMNMX.S16x2, VIADD.16x2)          -> survivor list (one shuffle scan per 128 px)
+//      (PRMT unpack, VIMNMX.S16x2, VIADD.16x2)          -> survivor list (one shuffle scan per 256 px)
 //   2. survivors: the 16 ring pixels packed two per register (k, k+8), the 16 arc minima by two rounds
 //      of VIMNMX3.S16x2; corner <=> score >= minTh       -> score map, corner list (in place)
 //   3. corner list: 3x3 strict maximum                   -> per-row bit masks (all / >= iniTh)
@@ -145,20 +145,15 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
         const int phase = c.x0 & 15;
 
-        // ---- phase 1: 4-point rejection, four pixels (one aligned word) per lane ----------------------
+        // ---- phase 1: 4-point rejection, 2 rows x 4 pixels (two aligned words, one above the other) per lane ----
         const int bs = phase + 3, be = bs + dw;  // interior byte columns [bs, be) of a tile row
         const int gfirst = bs >> 2, G = ((be - 1) >> 2) - gfirst + 1;
-        const int nitems = dh * G;
+        const int nitems = ((dh + 1) >> 1) * G;
         const uint32_t Ginv = (65536u + G - 1) / G;  // floor(i / G) == i * Ginv >> 16 for i * G < 65536
         const uint32_t T1 = (uint32_t)(minTh + 1) * 0x10001u, T2 = ((uint32_t)(-minTh) & 0xffffu) * 0x10001u;
-        int n1 = 0;
-        for (int i0 = 0; i0 < nitems; i0 += 32) {
-            const bool act = i0 + lane < nitems;
-            const int i = act ? i0 + lane : nitems - 1;
-            const int row = (int)((uint32_t)i * Ginv >> 16), gg = i - row * G;
-            const int y = 3 + row, wcol = gfirst + gg;
-            const uint32_t* wp = tile32 + y * tpw + wcol;
-            const uint32_t C = wp[0], Lw = wp[-1], Rw = wp[1], U = wp[-3 * tpw], Dn = wp[3 * tpw];
+        // sign bits of the result's halves: pixel j at bit (15, 31, 14, 30)[j] set  <=>  one of ring pixels
+        // (0,8) and one of (4,12) lie below v - t, or both above v + t
+        auto hit4 = [&](uint32_t C, uint32_t U, uint32_t Dn, uint32_t Lw, uint32_t Rw) {
             const uint32_t W12 = __funnelshift_r(Lw, C, 8);   // ring pixel 12 (x - 3) of the four centres
             const uint32_t W4 = __funnelshift_r(C, Rw, 24);   // ring pixel 4  (x + 3)
             uint32_t hit[2];
@@ -172,25 +167,38 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
                 const uint32_t kb = __vadd2(nc, T2);           // -c - 1 - t
                 const uint32_t a = __vmaxs2(__vmins2(d2, u2), __vmins2(l2, r2));
                 const uint32_t b = __vmins2(__vmaxs2(d2, u2), __vmaxs2(l2, r2));
-                // sign bit of a half set  <=>  one of (0,8) and one of (4,12) below v - t, or above v + t
                 hit[h] = __vadd2(a, kd) | ~__vadd2(b, kb);
             }
-            // survivors of this lane: pixel j at bit (15, 31, 14, 30)[j]; byte columns outside [bs, be) masked
+            return (hit[0] & 0x80008000u) | ((hit[1] >> 1) & 0x40004000u);
+        };
+        int n1 = 0;
+        for (int i0 = 0; i0 < nitems; i0 += 32) {
+            const bool act = i0 + lane < nitems;
+            const int i = act ? i0 + lane : nitems - 1;
+            const int rp = (int)((uint32_t)i * Ginv >> 16), gg = i - rp * G;
+            const int y = 3 + 2 * rp, wcol = gfirst + gg;
+            const uint32_t* wp = tile32 + y * tpw + wcol;
+            // byte columns outside [bs, be) masked; the second row may lie below the interior
             const int bcol0 = wcol << 2;
             const int lead = max(bs - bcol0, 0), trail = max(bcol0 + 4 - be, 0);
             const uint32_t v4 = act ? ((0xfu << lead) & (0xfu >> trail)) : 0u;  // valid pixels, bit j
             const uint32_t vw = (v4 & 1u) << 15 | (v4 & 2u) << 30 | (v4 & 4u) << 12 | (v4 & 8u) << 27;
-            const uint32_t kw = ((hit[0] & 0x80008000u) | ((hit[1] >> 1) & 0x40004000u)) & vw;
-            const int cnt = __popc(kw);
+            const uint32_t kw0 = hit4(wp[0], wp[-3 * tpw], wp[3 * tpw], wp[-1], wp[1]) & vw;
+            const uint32_t kw1 = hit4(wp[tpw], wp[-2 * tpw], wp[4 * tpw], wp[tpw - 1], wp[tpw + 1]) & (y + 1 < th - 3 ? vw : 0u);
+            const int cnt = __popc(kw0) + __popc(kw1);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
             uint16_t* dst = list + n1 + inc - cnt;
-            const uint32_t e0 = (uint32_t)(bcol0 | y << 7);
-            if (kw & 0x00008000u) *dst++ = (uint16_t)e0;
-            if (kw & 0x80000000u) *dst++ = (uint16_t)(e0 + 1);
-            if (kw & 0x00004000u) *dst++ = (uint16_t)(e0 + 2);
-            if (kw & 0x40000000u) *dst++ = (uint16_t)(e0 + 3);
+            const uint32_t e0 = (uint32_t)(bcol0 | y << 7), e1 = e0 + 128u;
+            if (kw0 & 0x00008000u) *dst++ = (uint16_t)e0;
+            if (kw0 & 0x80000000u) *dst++ = (uint16_t)(e0 + 1);
+            if (kw0 & 0x00004000u) *dst++ = (uint16_t)(e0 + 2);
+            if (kw0 & 0x40000000u) *dst++ = (uint16_t)(e0 + 3);
+            if (kw1 & 0x00008000u) *dst++ = (uint16_t)e1;
+            if (kw1 & 0x80000000u) *dst++ = (uint16_t)(e1 + 1);
+            if (kw1 & 0x00004000u) *dst++ = (uint16_t)(e1 + 2);
+            if (kw1 & 0x40000000u) *dst++ = (uint16_t)(e1 + 3);
             n1 += __shfl_sync(0xffffffffu, inc, 31);
         }
         __syncwarp();
