@@ -11,11 +11,14 @@
 namespace orb {
 
 // ------------------------------------------------------------------------------------------------
-// resize: one block = one 128 x 32 output tile. The source window of the tile arrives in shared
-// memory by one TMA box load (rs_bw x rs_bh bytes, zero fill beyond the level - never read); while
-// it is in flight each thread fetches the column taps of its 4 output columns and the row taps of
-// its 4 output rows into registers.
-constexpr int kRsTW = 128, kRsTH = 32;
+// resize: one block = one 128 x 64 output tile, one warp = 8 consecutive output rows of it, one lane =
+// 4 output columns. The source window of the tile arrives in shared memory by one TMA box load
+// (rs_bw x rs_bh bytes, zero fill beyond the level - never read); while it is in flight each thread
+// fetches the column taps of its 4 columns and the row taps of its 8 rows into registers.
+// The horizontal pass of a source row is kept for the next output row: consecutive output rows share
+// a source row (the second tap of row y is the first tap of row y+1 unless the scale skips a row), so
+// a warp interpolates ~1.2 source rows per output row instead of 2. Row decisions are warp-uniform.
+constexpr int kRsTW = 128, kRsTH = 64, kRsRowsPerWarp = 8;
 
 __global__ void __launch_bounds__(256)
 resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, const __grid_constant__ TmaMaps maps,
@@ -41,53 +44,74 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
     }
     // all table reads of this thread, issued while the window is in flight
     const int q = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int x0 = X0 + 4 * q;
-    LinTap tcol[4], trow[kRsTH / 8];
+    const int x0 = X0 + 4 * q, yw = Y0 + kRsRowsPerWarp * rg;
+    // a LinTap is 8 bytes (source index | two 16-bit weights): one 64-bit load each
+    uint2 tcol[4], trow[kRsRowsPerWarp];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tcol[k] = tx[min(x0 + k, L.w - 1)];
+    for (int k = 0; k < 4; ++k) tcol[k] = reinterpret_cast<const uint2*>(tx)[min(x0 + k, L.w - 1)];
 #pragma unroll
-    for (int rr = 0; rr < kRsTH / 8; ++rr) trow[rr] = ty[min(Y0 + rg + 8 * rr, L.h - 1)];
+    for (int rr = 0; rr < kRsRowsPerWarp; ++rr) trow[rr] = reinterpret_cast<const uint2*>(ty)[min(yw + rr, L.h - 1)];
     __syncthreads();
     mbar_wait(&bar, 0);
 
     if (x0 >= L.w) return;
-    // Per thread constants of its 4 columns: the source bytes (sx, sx+1) of all four lie within 12
-    // bytes of the word-aligned base (scale <= 1.8), i.e. in 3 words w0 w1 w2 of a window row. For
-    // column k a byte permute picks its two taps out of (w0,w1) or (w1,w2); one IDP.2A applies the two
-    // 11-bit weights (u16 pair) to the two pixels (u8 pair).
-    const int wbase = (tcol[0].ofs - sx_lo) & ~3;
+    // Per thread constants of its 4 columns: the source bytes (sx, sx+1) of all four lie within 8 bytes
+    // of column 0's first tap (scale < 2), i.e. in 3 words w0 w1 w2 of a window row. Two funnel shifts
+    // bring those 8 bytes to (u0, u1); for column k one byte permute picks its two taps and one IDP.2A
+    // applies the two 11-bit weights (u16 pair) to the two pixels (u8 pair).
+    const int o0 = (int)tcol[0].x - sx_lo;
+    uint32_t wofs = (uint32_t)(o0 & ~3), shbits = (uint32_t)(o0 & 3) * 8u;
     uint32_t sel[4], coef[4];
-    bool hi[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int o = tcol[k].ofs - sx_lo - wbase;  // 0..10
-        hi[k] = o >= 7;                        // second tap beyond byte 7: use the (w1,w2) pair
-        o -= hi[k] ? 4 : 0;
-        sel[k] = (uint32_t)o | (uint32_t)(o + 1) << 4 | 0x4400u;  // bytes: tap0, tap1, 0, 0  (4 = a zero byte... see below)
-        coef[k] = (uint32_t)(uint16_t)tcol[k].c0 | (uint32_t)(uint16_t)tcol[k].c1 << 16;
+        const uint32_t d = tcol[k].x - tcol[0].x;  // 0..6
+        sel[k] = d | (d + 1) << 4 | 0x4400u;       // only the two low bytes of the permute result are used by IDP.2A (lo variant)
+        coef[k] = tcol[k].y;                        // c0 | c1 << 16
+        asm volatile("" : "+r"(sel[k]));            // keep in a register (ptxas re-derived it in every row otherwise)
     }
+    asm volatile("" : "+r"(wofs), "+r"(shbits));
+    // horizontal pass of window row s for the 4 columns, already shifted right by 4 as the vertical pass wants it
+    auto horiz = [&](int s, uint32_t (&h)[4]) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(win + (uint32_t)(s - sy_lo) * (uint32_t)bw + wofs);
+        const uint32_t a0 = r[0], a1 = r[1], a2 = r[2];
+        const uint32_t u0 = __funnelshift_r(a0, a1, shbits), u1 = __funnelshift_r(a1, a2, shbits);
 #pragma unroll
-    for (int rr = 0; rr < kRsTH / 8; ++rr) {
-        const int y = Y0 + rg + 8 * rr;
-        if (y >= L.h) break;
-        const LinTap t = trow[rr];
-        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(win + (size_t)(t.ofs - sy_lo) * bw + wbase);
-        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(win + (size_t)(min(t.ofs + 1, S.h - 1) - sy_lo) * bw + wbase);
-        const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2], c0 = r1[0], c1 = r1[1], c2 = r1[2];
-        const int b0 = t.c0, b1 = t.c1;
+        for (int k = 0; k < 4; ++k) h[k] = __dp2a_lo(coef[k], __byte_perm(u0, u1, sel[k]), 0u) >> 4;
+    };
+    int crow = -1;
+    uint32_t hc[4] = {0, 0, 0, 0};  // cached horizontal pass: source row and values
+    uint8_t* drow = dst + (size_t)yw * L.pitch + x0;
+    const int dpitch = L.pitch, sh_max = S.h - 1, nrows = min(kRsRowsPerWarp, L.h - yw);
+#pragma unroll
+    for (int rr = 0; rr < kRsRowsPerWarp; ++rr) {
+        if (rr >= nrows) break;
+        const int s0 = (int)trow[rr].x, s1 = min(s0 + 1, sh_max);
+        uint32_t h0[4], h1[4];
+        if (s0 == crow) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h0[k] = hc[k];
+        } else {
+            horiz(s0, h0);
+        }
+        if (s1 == s0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h1[k] = h0[k];
+        } else {
+            horiz(s1, h1);
+        }
+        crow = s1;
+        // (b * h) >> 16 as the high word of (b << 16) * h: weights are 0..2048, h < 2^15
+        const uint32_t b0 = trow[rr].y << 16, b1 = trow[rr].y & 0xffff0000u;
         uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            // only the two low bytes of the permute result are used by IDP.2A (lo variant)
-            const uint32_t p0 = hi[k] ? __byte_perm(a1, a2, sel[k]) : __byte_perm(a0, a1, sel[k]);
-            const uint32_t p1 = hi[k] ? __byte_perm(c1, c2, sel[k]) : __byte_perm(c0, c1, sel[k]);
-            const int h0 = (int)__dp2a_lo(coef[k], p0, 0u);
-            const int h1 = (int)__dp2a_lo(coef[k], p1, 0u);
-            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            packed |= (uint32_t)(v & 0xff) << (8 * k);
+            hc[k] = h1[k];
+            const uint32_t v = (__umulhi(b0, h0[k]) + __umulhi(b1, h1[k]) + 2u) >> 2;
+            packed |= (v & 0xffu) << (8 * k);
         }
         // rows are 128-byte pitched and x0 is a multiple of 4: aligned 32-bit store (pitch slack absorbs the tail)
-        *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x0) = packed;
+        *reinterpret_cast<uint32_t*>(drow) = packed;
+        drow += dpitch;
     }
 }
 
