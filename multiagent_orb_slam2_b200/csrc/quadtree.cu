@@ -28,7 +28,6 @@ struct QtShared {
     int warp_tmp[32];
     int carry;
     int bcast[4];
-    int hist[256];
     int wcount[kQtWarps][256];
 };
 
@@ -38,6 +37,20 @@ struct QtShared {
 __device__ int block_exclusive_scan(const int* in, int* out, int len, QtShared& sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __syncthreads();  // inputs written by other warps are visible
+    if (len <= kQtThreads) {  // the node lists: one element per thread, two short parallel stages
+        const int v = (int)threadIdx.x < len ? in[threadIdx.x] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sh.warp_tmp[warp] = inc;
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kQtWarps; ++w) { const int t = sh.warp_tmp[w]; total += t; off += w < warp ? t : 0; }
+        if ((int)threadIdx.x < len) out[threadIdx.x] = off + inc - v;
+        __syncthreads();  // out[] visible; warp_tmp free for the next scan
+        return total;
+    }
     if (len <= 32 * 32) {
         if (warp == 0) {
             const int per = (len + 31) >> 5, lo = lane * per, hi = min(lo + per, len);
@@ -102,59 +115,61 @@ __device__ __forceinline__ uint32_t qt_path_key(int x, int y, int H, float rootW
 
 // LSD radix sort of (key, val) pairs, 8 bits per pass; result ends in (kA, vA) or (kB, vB): returns
 // 0 / 1 accordingly. Buffers are global (L2 resident) so any candidate count fits.
+// Every warp owns one contiguous chunk of the input and walks it twice per pass (count, scatter) with
+// warp-level synchronisation only; the block meets 4 times per pass (the earlier tile-by-tile version
+// met 3 times per 256 elements). Stable: chunks are ordered by warp, a chunk is walked in order.
 __device__ int block_radix_sort(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32_t* vB, int n, int key_bits, QtShared& sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kQtWarps * 256; i += kQtThreads) (&sh.wcount[0][0])[i] = 0;
+    const int per = ((n + kQtThreads - 1) / kQtThreads) * 32;  // elements per warp, a multiple of 32
+    const int lo = min(warp * per, n), hi = min(lo + per, n);
+    const uint32_t lt = (1u << lane) - 1u;
     int flip = 0;
     for (int shift = 0; shift < key_bits; shift += 8) {
         const uint32_t* ki = flip ? kB : kA; const uint32_t* vi = flip ? vB : vA;
         uint32_t* ko = flip ? kA : kB;       uint32_t* vo = flip ? vA : vB;
-        if (threadIdx.x < 256) sh.hist[threadIdx.x] = 0;
+        for (int i = threadIdx.x; i < kQtWarps * 256; i += kQtThreads) (&sh.wcount[0][0])[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += kQtThreads) atomicAdd(&sh.hist[(ki[i] >> shift) & 255], 1);
-        __syncthreads();
-        // exclusive scan of the 256 bins (warps 0..7), result back into hist
-        {
-            int v = 0, inc = 0;
-            if (threadIdx.x < 256) {
-                v = sh.hist[threadIdx.x];
-                inc = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                if (lane == 31) sh.warp_tmp[warp] = inc;
-            }
-            __syncthreads();
-            if (threadIdx.x < 256) {
-                int off = 0;
-                for (int w = 0; w < warp; ++w) off += sh.warp_tmp[w];
-                sh.hist[threadIdx.x] = off + inc - v;
-            }
-            __syncthreads();
+        // digit counts of this warp's chunk
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < hi;
+            const uint32_t digit = valid ? (ki[i] >> shift) & 255u : 0x100u + lane;  // invalid lanes never group
+            const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+            if (valid && (peers & lt) == 0) sh.wcount[warp][digit] += __popc(peers);
+            __syncwarp();
         }
-        for (int base = 0; base < n; base += kQtThreads) {
-            const int i = base + threadIdx.x;
-            const bool valid = i < n;
+        __syncthreads();
+        // thread d: total of digit d, exclusive scan over the digits, then the start of every warp's run
+        {
+            int c[kQtWarps], v = 0;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) { c[w] = sh.wcount[w][threadIdx.x]; v += c[w]; }
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) sh.warp_tmp[warp] = inc;
+            __syncthreads();
+            int run = inc - v;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) run += w < warp ? sh.warp_tmp[w] : 0;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) { sh.wcount[w][threadIdx.x] = run; run += c[w]; }
+        }
+        __syncthreads();
+        // scatter: wcount[warp][digit] is the running cursor of this warp's run of that digit
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < hi;
             uint32_t k = 0, v = 0;
             if (valid) { k = ki[i]; v = vi[i]; }
-            const uint32_t digit = valid ? (k >> shift) & 255u : 0x100u + lane;  // invalid lanes never group
+            const uint32_t digit = valid ? (k >> shift) & 255u : 0x100u + lane;
             const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-            const int rank = __popc(peers & ((1u << lane) - 1));
-            const bool leader = valid && rank == 0;
-            if (leader) sh.wcount[warp][digit] = __popc(peers);
-            __syncthreads();
-            if (threadIdx.x < 256) {  // per digit: offsets of the warps of this tile, advance the bin base
-                int run = sh.hist[threadIdx.x];
-#pragma unroll 8
-                for (int w = 0; w < kQtWarps; ++w) {
-                    const int c = sh.wcount[w][threadIdx.x];
-                    if (c) { sh.wcount[w][threadIdx.x] = run; run += c; }  // untouched entries stay 0
-                }
-                sh.hist[threadIdx.x] = run;
-            }
-            __syncthreads();
-            if (valid) { const int pos = sh.wcount[warp][digit] + rank; ko[pos] = k; vo[pos] = v; }
+            const int rank = __popc(peers & lt);
+            int pos = 0;
+            if (valid) pos = sh.wcount[warp][digit] + rank;
             __syncwarp();
-            if (leader) sh.wcount[warp][digit] = 0;
+            if (valid && rank == 0) sh.wcount[warp][digit] += __popc(peers);
+            if (valid) { ko[pos] = k; vo[pos] = v; }
             __syncwarp();
         }
         flip ^= 1;
@@ -379,10 +394,15 @@ quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slo
     int* offs = nodemem;  // sel_cap*14 ints >= cell_count always holds for sane settings (checked on host)
     const int total = block_exclusive_scan(counts, offs, L.cell_count, sh);
     __syncthreads();
-    for (int c = warp; c < L.cell_count; c += kQtWarps) {
-        const int n = counts[c], o = offs[c];
-        const uint32_t* s = lslots + (size_t)c * L.slot_cap;
-        for (int k = lane; k < n; k += 32) cand[o + k] = s[k];
+    // 8 lanes per cell (a cell holds ~10 candidates): 4 cells of a warp have their dependent count -> slot
+    // loads in flight together
+    for (int c0 = warp * 4; c0 < L.cell_count; c0 += kQtWarps * 4) {
+        const int c = c0 + (lane >> 3);
+        if (c < L.cell_count) {
+            const int n = counts[c], o = offs[c];
+            const uint32_t* s = lslots + (size_t)c * L.slot_cap;
+            for (int k = lane & 7; k < n; k += 8) cand[o + k] = s[k];
+        }
     }
     __syncthreads();
     quadtree_select(cand, total, L.quota, L.nRoots, L.rootW, L.h - 2 * kMinBorder, L.key_depth, scratch,
