@@ -96,6 +96,8 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     }
     __syncthreads();
 
+    constexpr int kIcRows = 2 * kHalfPatch + 1;
+    const int ic_lr = lane / kIcWordsPerRow, ic_lj = lane - ic_lr * kIcWordsPerRow;
     // ---- A: IC_Angle moments ---------------------------------------------------------------------
     // The 31 x 31 bounding box of the circular patch is read as aligned 32-bit words (9 per row, the left
     // edge rounded down to a word), lane = (row, word) item; the table holds, per alignment phase and
@@ -110,17 +112,23 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
         const uint8_t* img = level_ptr(*g, fs, pyr, frame, si.level, &spitch);
         const int xs = si.x - kHalfPatch;
         const uint8_t* base = img + (size_t)(si.y - kHalfPatch) * spitch + (xs & ~3);
-        const uint32_t* tu = ictab + (xs & 3) * 2 * kIcItems;
+        const uint32_t* tu = ictab + (xs & 3) * 2 * kIcItems + lane;
         int m10 = 0, m01 = 0;
+        // 3 rows (27 words) per warp step: item 27 s + lane, its word at a fixed per-lane offset + s * 3 rows
+        const uint8_t* wp = base + ic_lr * spitch + 4 * ic_lj;
+        const int step = 3 * spitch;
+        // all loads first (unconditional: the idle lanes' addresses are inside the image too), so that they
+        // are in flight together
+        constexpr int kSteps = (kIcRows * kIcWordsPerRow + 26) / 27;
+        uint32_t w[kSteps];
 #pragma unroll
-        for (int s = 0; s < kIcItems / 32; ++s) {
-            const int i = s * 32 + lane;
-            const int r = i / kIcWordsPerRow, j = i - r * kIcWordsPerRow;
-            if (r < 2 * kHalfPatch + 1) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * spitch + 4 * j);
-                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(tu[i]));
-                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m01) : "r"(w), "r"(tu[kIcItems + i]));
-            }
+        for (int s = 0; s < kSteps; ++s) w[s] = *reinterpret_cast<const uint32_t*>(wp + s * step);
+#pragma unroll
+        for (int s = 0; s < kSteps; ++s) {
+            const bool on = lane < 27 && 27 * s + lane < kIcRows * kIcWordsPerRow;
+            const uint32_t cu = on ? tu[27 * s] : 0u, cv = on ? tu[kIcItems + 27 * s] : 0u;
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w[s]), "r"(cu));
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m01) : "r"(w[s]), "r"(cv));
         }
         m10 = __reduce_add_sync(0xffffffffu, m10);
         m01 = __reduce_add_sync(0xffffffffu, m01);
@@ -147,6 +155,7 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     // loads and gathers there. Two keypoints are described per pass so that the pattern values are read
     // once for both.
     uint32_t* mypatch = patch + warp * 2 * kPatchWords;
+    const int pt_lr = lane / kPatchRowWords, pt_lj = lane - pt_lr * kPatchRowWords;
     for (int kk = 0; kk < kDescSlots / kDescWarps; kk += 2) {
         const int sidx0 = warp * (kDescSlots / kDescWarps) + kk;
         const SlotInfo si0 = info[sidx0], si1 = info[sidx0 + 1];
@@ -160,13 +169,18 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
             const LevelGeom& L = g->lv[si.level];
             const int xs = si.x - kPatchReach;
             const uint8_t* src = blur + (size_t)frame * g->blur_bytes + L.blur_off + (size_t)(si.y - kPatchReach) * L.pitch + (xs & ~3);
-            const int bp = L.pitch;
+            // 3 rows (30 words) per warp step: word 30 s + lane of the window, at a fixed per-lane offset + s * 3 rows
+            const uint8_t* wp = src + pt_lr * L.pitch + 4 * pt_lj;
+            const int step = 3 * L.pitch;
+            uint32_t* d = mypatch + q * kPatchWords + lane;
+            constexpr int kSteps = (kPatchRows * kPatchRowWords + 29) / 30;
+            uint32_t w[kSteps];  // unconditional loads, all in flight
 #pragma unroll
-            for (int s = 0; s < (kPatchRows * kPatchRowWords + 31) / 32; ++s) {
-                const int i = s * 32 + lane;
-                const int r = i / kPatchRowWords, j = i - r * kPatchRowWords;
-                if (i < kPatchRows * kPatchRowWords) mypatch[q * kPatchWords + i] = *reinterpret_cast<const uint32_t*>(src + r * bp + 4 * j);
-            }
+            for (int s = 0; s < kSteps; ++s)  // the last step's rows are clamped to the window: rows below it may lie outside the slab
+                w[s] = *reinterpret_cast<const uint32_t*>(s + 1 < kSteps ? wp + s * step : src + min(3 * s + pt_lr, kPatchRows - 1) * L.pitch + 4 * pt_lj);
+#pragma unroll
+            for (int s = 0; s < kSteps; ++s)
+                if (lane < 30 && 30 * s + lane < kPatchRows * kPatchRowWords) d[30 * s] = w[s];
             off[q] = kPatchReach * (kPatchRowWords * 4) + kPatchReach + (xs & 3);
         }
         __syncwarp();
@@ -175,24 +189,24 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
         const float a0 = si0.valid ? s_cos[sidx0] : 0.f, b0 = si0.valid ? s_sin[sidx0] : 0.f;  // s_cos / s_sin are unset for invalid slots
         const float a1 = si1.valid ? s_cos[sidx0 + 1] : 0.f, b1 = si1.valid ? s_sin[sidx0 + 1] : 0.f;
         const float* pp = patf + lane;
-        int val0 = 0, val1 = 0;
+        uint32_t val0 = 0, val1 = 0;  // bits enter at the bottom, test 7 first: sign of I(p0) - I(p1) by one funnel shift
         constexpr int kRow = kPatchRowWords * 4;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
+        for (int t = 7; t >= 0; --t) {
             const float x0 = pp[(4 * t) * 32], y0 = pp[(4 * t + 1) * 32], x1 = pp[(4 * t + 2) * 32], y1 = pp[(4 * t + 3) * 32];
             {
                 const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b0), __fmul_rn(y0, a0)));
                 const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a0), __fmul_rn(y0, b0)));
                 const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b0), __fmul_rn(y1, a0)));
                 const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a0), __fmul_rn(y1, b0)));
-                val0 |= (int)(p0[r0 * kRow + c0] < p0[r1 * kRow + c1]) << t;
+                val0 = __funnelshift_l((uint32_t)((int)p0[r0 * kRow + c0] - (int)p0[r1 * kRow + c1]), val0, 1);
             }
             {
                 const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b1), __fmul_rn(y0, a1)));
                 const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a1), __fmul_rn(y0, b1)));
                 const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b1), __fmul_rn(y1, a1)));
                 const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a1), __fmul_rn(y1, b1)));
-                val1 |= (int)(p1[r0 * kRow + c0] < p1[r1 * kRow + c1]) << t;
+                val1 = __funnelshift_l((uint32_t)((int)p1[r0 * kRow + c0] - (int)p1[r1 * kRow + c1]), val1, 1);
             }
         }
 #pragma unroll
