@@ -148,7 +148,10 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         // ---- phase 1: 4-point rejection, 2 rows x 4 pixels (two aligned words, one above the other) per lane ----
         const int bs = phase + 3, be = bs + dw;  // interior byte columns [bs, be) of a tile row
         const int gfirst = bs >> 2, G = ((be - 1) >> 2) - gfirst + 1;
-        const int nitems = ((dh + 1) >> 1) * G;
+        // rows are taken in bands of 8: row pair rp = 4 * band + q holds rows 8 * band + q and 8 * band + q + 4, so that the
+        // four pairs a warp step touches with one load instruction lie in consecutive rows (2-way instead of 4-way bank
+        // conflicts at the tile's 16-word pitch)
+        const int nitems = ((dh + 7) >> 3) * 4 * G;
         const uint32_t Ginv = (65536u + G - 1) / G;  // floor(i / G) == i * Ginv >> 16 for i * G < 65536
         const uint32_t T1 = (uint32_t)(minTh + 1) * 0x10001u, T2 = ((uint32_t)(-minTh) & 0xffffu) * 0x10001u;
         // sign bits of the result's halves: pixel j at bit (15, 31, 14, 30)[j] set  <=>  one of ring pixels
@@ -176,21 +179,21 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             const bool act = i0 + lane < nitems;
             const int i = act ? i0 + lane : nitems - 1;
             const int rp = (int)((uint32_t)i * Ginv >> 16), gg = i - rp * G;
-            const int y = 3 + 2 * rp, wcol = gfirst + gg;
+            const int y = 3 + 8 * (rp >> 2) + (rp & 3), wcol = gfirst + gg;
             const uint32_t* wp = tile32 + y * tpw + wcol;
-            // byte columns outside [bs, be) masked; the second row may lie below the interior
+            // byte columns outside [bs, be) masked; either row may lie below the interior
             const int bcol0 = wcol << 2;
             const int lead = max(bs - bcol0, 0), trail = max(bcol0 + 4 - be, 0);
             const uint32_t v4 = act ? ((0xfu << lead) & (0xfu >> trail)) : 0u;  // valid pixels, bit j
             const uint32_t vw = (v4 & 1u) << 15 | (v4 & 2u) << 30 | (v4 & 4u) << 12 | (v4 & 8u) << 27;
-            const uint32_t kw0 = hit4(wp[0], wp[-3 * tpw], wp[3 * tpw], wp[-1], wp[1]) & vw;
-            const uint32_t kw1 = hit4(wp[tpw], wp[-2 * tpw], wp[4 * tpw], wp[tpw - 1], wp[tpw + 1]) & (y + 1 < th - 3 ? vw : 0u);
+            const uint32_t kw0 = hit4(wp[0], wp[-3 * tpw], wp[3 * tpw], wp[-1], wp[1]) & (y < th - 3 ? vw : 0u);
+            const uint32_t kw1 = hit4(wp[4 * tpw], wp[tpw], wp[7 * tpw], wp[4 * tpw - 1], wp[4 * tpw + 1]) & (y + 4 < th - 3 ? vw : 0u);
             const int cnt = __popc(kw0) + __popc(kw1);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
             uint16_t* dst = list + n1 + inc - cnt;
-            const uint32_t e0 = (uint32_t)(bcol0 | y << 7), e1 = e0 + 128u;
+            const uint32_t e0 = (uint32_t)(bcol0 | y << 7), e1 = e0 + 4u * 128u;
             if (kw0 & 0x00008000u) *dst++ = (uint16_t)e0;
             if (kw0 & 0x80000000u) *dst++ = (uint16_t)(e0 + 1);
             if (kw0 & 0x00004000u) *dst++ = (uint16_t)(e0 + 2);
