@@ -20,8 +20,9 @@
 //      test (any arc of 9 contains ring pixel 0 or 8 and 4 or 12) on packed 16-bit halves
 //      (PRMT unpack, VIMNMX.S16x2, VIADD.16x2)          -> survivor list (one shuffle scan per 256 px)
 //   2. survivors: the 16 ring pixels packed two per register (k, k+8), the 16 arc minima by two rounds
-//      of VIMNMX3.S16x2; corner <=> score >= minTh       -> score map, corner list (in place)
-//   3. corner list: 3x3 strict maximum                   -> per-row bit masks (all / >= iniTh)
+//      of VIMNMX3.S16x2; corner <=> score >= threshold   -> score map, corner list (in place)
+//   3. corner list: 3x3 strict maximum                   -> per-row bit mask
+//   (1-3 run at iniThFAST; a cell that comes back empty repeats them at minThFAST on the same tile)
 //   4. prefix over the mask words, then the corner list again: rank = offset + bits below -> the
 //      row-major ordered slot list (reference order inside the cell).
 #include <algorithm>
@@ -41,7 +42,7 @@ constexpr int kFastWarps = 4;
 constexpr int kFastThreads = kFastWarps * 32;
 constexpr int kFastMaxCellsPerWarp = 8;
 
-// per-warp shared memory: tile | score (interior + 1 px ring only) | mask_ini | mask_all | offs | list
+// per-warp shared memory: tile | score (interior + 1 px ring only) | mask | offs | list
 struct FastLayout { int tile_bytes, score_pitch, score_bytes, mask_words, mask_off, list_off, warp_bytes; };
 __host__ __device__ inline FastLayout fast_layout(int max_tw, int max_th, int tp) {
     FastLayout f;
@@ -50,7 +51,7 @@ __host__ __device__ inline FastLayout fast_layout(int max_tw, int max_th, int tp
     f.score_bytes = (int)align_up((size_t)f.score_pitch * (max_th - 4), 16);
     f.mask_words = 2 * (max_th - 6);                 // (row, 32-column half) entries
     f.mask_off = f.tile_bytes + f.score_bytes;
-    f.list_off = f.mask_off + (int)align_up((size_t)3 * f.mask_words * 4, 16);
+    f.list_off = f.mask_off + (int)align_up((size_t)2 * f.mask_words * 4, 16);
     const int npx = (max_tw - 6) * (max_th - 6);
     f.warp_bytes = (int)align_up((size_t)f.list_off + 2 * (size_t)npx + 16, 128);
     return f;
@@ -93,9 +94,8 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     const int T = lay.tile_bytes, sp = lay.score_pitch;
     uint8_t* wbase = smem + (size_t)warp * lay.warp_bytes;
     uint8_t* score = wbase + T;
-    uint32_t* mask_ini = reinterpret_cast<uint32_t*>(wbase + lay.mask_off);
-    uint32_t* mask_all = mask_ini + lay.mask_words;
-    uint32_t* offs = mask_all + lay.mask_words;
+    uint32_t* mask = reinterpret_cast<uint32_t*>(wbase + lay.mask_off);
+    uint32_t* offs = mask + lay.mask_words;
     uint16_t* list = reinterpret_cast<uint16_t*>(wbase + lay.list_off);
     uint64_t* bar = &bars[warp];
     const int frame = blockIdx.y, ncells = g->ncells;
@@ -135,7 +135,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         {   // clear the score map and the masks
             uint4* z = reinterpret_cast<uint4*>(score);
             for (int i = lane; i < lay.score_bytes >> 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = lane; i < 2 * lay.mask_words; i += 32) mask_ini[i] = 0u;
+            for (int i = lane; i < lay.mask_words; i += 32) mask[i] = 0u;
         }
         __syncwarp();
         mbar_wait(bar, parity);
@@ -153,7 +153,14 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         // conflicts at the tile's 16-word pitch)
         const int nitems = ((dh + 7) >> 3) * 4 * G;
         const uint32_t Ginv = (65536u + G - 1) / G;  // floor(i / G) == i * Ginv >> 16 for i * G < 65536
-        const uint32_t T1 = (uint32_t)(minTh + 1) * 0x10001u, T2 = ((uint32_t)(-minTh) & 0xffffu) * 0x10001u;
+        // The reference runs cv::FAST at iniThFAST and, only when the cell comes back empty, again at minThFAST
+        // (809-816). Same here: at iniTh far fewer pixels survive the rejection test and reach phases 2-3, and
+        // the local-maximum test does not depend on the threshold (header), so pass 0 yields exactly the
+        // iniTh result; an empty cell repeats phases 1-3 at minTh on the same tile.
+        int n2 = 0;
+        for (int pass = 0;; ++pass) {
+        const int thr = pass ? minTh : iniTh;
+        const uint32_t T1 = (uint32_t)(thr + 1) * 0x10001u, T2 = ((uint32_t)(-thr) & 0xffffu) * 0x10001u;
         // sign bits of the result's halves: pixel j at bit (15, 31, 14, 30)[j] set  <=>  one of ring pixels
         // (0,8) and one of (4,12) lie below v - t, or both above v + t
         auto hit4 = [&](uint32_t C, uint32_t U, uint32_t Dn, uint32_t Lw, uint32_t Rw) {
@@ -206,8 +213,8 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         }
         __syncwarp();
 
-        // ---- phase 2: exact score of the survivors on their possible side; corner <=> score >= minTh ----
-        int n2 = 0;
+        // ---- phase 2: exact score of the survivors on their possible side; corner <=> score >= thr ----
+        n2 = 0;
         for (int i0 = 0; i0 < n1; i0 += 32) {
             const bool act = i0 + lane < n1;
             const int e = list[act ? i0 + lane : n1 - 1];
@@ -218,13 +225,13 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
 #pragma unroll
             for (int q = 0; q < 16; ++q) r[q] = p[ring_offset(q, tp)];
             // which side(s) can hold an arc of 9: one of (0,8) and one of (4,12) beyond the threshold
-            const bool fb = max(min(r[0], r[8]), min(r[4], r[12])) < v - minTh;
-            const bool fa = min(max(r[0], r[8]), max(r[4], r[12])) > v + minTh;
+            const bool fb = max(min(r[0], r[8]), min(r[4], r[12])) < v - thr;
+            const bool fa = min(max(r[0], r[8]), max(r[4], r[12])) > v + thr;
             int s = fast_side_margin(r, v, fb ? -1 : 1) - 1;
             if (__any_sync(0xffffffffu, fb & fa)) {  // both sides passed the 4-point test: rare
                 if (fb & fa) s = max(s, fast_side_margin(r, v, 1) - 1);
             }
-            const bool corner = act & (s >= minTh);
+            const bool corner = act & (s >= thr);
             __syncwarp();  // all entries of this step are read before the compacted list overwrites them
             const uint32_t ball = __ballot_sync(0xffffffffu, corner);
             if (corner) {
@@ -233,11 +240,10 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             }
             n2 += __popc(ball);
         }
-        __syncwarp();  // nobody reads the tile any more
-        if (lane == 0) issue(ci + stride);
+        __syncwarp();
 
-        // ---- phase 3: 3x3 strict maximum on the corners -> bit masks per (row, 32-column half) ---------
-        int total_ini = 0;
+        // ---- phase 3: 3x3 strict maximum on the corners -> bit mask per (row, 32-column half) ----------
+        int total = 0;
         for (int i0 = 0; i0 < n2; i0 += 32) {
             const bool act = i0 + lane < n2;
             const int e = list[act ? i0 + lane : n2 - 1];
@@ -246,17 +252,13 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             const int s = q[0];
             const int m = max(max(max(q[-sp - 1], q[-sp]), max(q[-sp + 1], q[-1])), max(max(q[1], q[sp - 1]), max(q[sp], q[sp + 1])));
             const bool keep = act & (m < s);
-            const bool ini = keep & (s >= iniTh);
-            if (keep) {
-                const int w = (y - 3) * 2 + ((x - 3) >> 5);
-                const uint32_t bit = 1u << ((x - 3) & 31);
-                atomicOr(&mask_all[w], bit);
-                if (ini) atomicOr(&mask_ini[w], bit);
-            }
-            total_ini += __popc(__ballot_sync(0xffffffffu, ini));
+            if (keep) atomicOr(&mask[(y - 3) * 2 + ((x - 3) >> 5)], 1u << ((x - 3) & 31));
+            total += __popc(__ballot_sync(0xffffffffu, keep));
         }
-        __syncwarp();
-        const uint32_t* mask = total_ini > 0 ? mask_ini : mask_all;  // minThFAST retry of an empty cell
+        if (total > 0 || pass == 1 || iniTh <= minTh) break;  // minThFAST retry of an empty cell
+        }
+        __syncwarp();  // nobody reads the tile any more
+        if (lane == 0) issue(ci + stride);
 
         // ---- phase 4: exclusive prefix over the mask words in row-major order, ordered write ----------
         const int nent = dh * 2;
