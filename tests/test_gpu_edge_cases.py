@@ -92,3 +92,31 @@ def test_other_image_geometries(w, h, nf):
     ok, od = O.OracleExtractor(nf, 1.2, 8, 20, 7)(img)
     got = np.stack([gk["x"], gk["y"], gk["size"], gk["angle"], gk["response"], gk["octave"].astype(np.float32)], 1)
     assert len(gk) == len(ok) and np.array_equal(got.view(np.uint32), ok.view(np.uint32)) and np.array_equal(gd, od)
+
+
+def _plateau_image(w, h, seed):
+    """2x2-replicated noise: neighbouring pixels with EQUAL FAST scores, so that cells exist whose corners at
+    iniThFAST all lose the strict 3x3 maximum test (the cell is then empty and is redone at minThFAST)."""
+    rng = np.random.default_rng(seed)
+    small = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+    return np.ascontiguousarray(np.kron(small, np.ones((2, 2), np.uint8))[:h, :w])
+
+
+@pytest.mark.parametrize("ini,mn", [(20, 7), (12, 12), (60, 5), (120, 1), (254, 1)])
+@pytest.mark.parametrize("kind", ["blocks", "blurnoise", "plateau", "flat"])
+def test_fast_thresholds_and_empty_cell_retry(ini, mn, kind):
+    """The FAST kernel runs every cell at iniThFAST and repeats it at minThFAST only when it comes back empty
+    (src/ORBextractor.cc:809-816): candidates of every level, keypoints and descriptors against the oracle for
+    thresholds that make the retry rare, frequent, universal, or a no-op (ini == min)."""
+    w, h = 640, 480
+    img = _plateau_image(w, h, 5) if kind == "plateau" else synth.image(kind, w, h, 5)
+    o = O.OracleExtractor(1000, 1.2, 8, ini, mn)
+    ok, od = o(img)
+    g = ORBextractor(1000, 1.2, 8, ini, mn)
+    gk, gd = g(img)
+    for l in range(8):
+        assert np.array_equal(g.candidates(l), o.level(l)["cand"]), "FAST candidates level %d" % l
+    got = np.stack([gk["x"], gk["y"], gk["size"], gk["angle"], gk["response"], gk["octave"].astype(np.float32)], 1)
+    assert len(gk) == len(ok)
+    if len(ok):
+        assert np.array_equal(got.view(np.uint32), ok.view(np.uint32)) and np.array_equal(gd, od)
