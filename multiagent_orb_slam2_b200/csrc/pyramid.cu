@@ -135,6 +135,7 @@ int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMa
 //          the rounding constant; 4 columns per thread, sliding window down the tile.
 // ~14 instructions per pixel instead of ~120 for the straightforward byte-wise version.
 constexpr int kBlurTW = 128, kBlurTH = 58, kBlurInRows = 64, kBlurInWords = 40;  // 160-byte TMA box rows
+constexpr int kBlurHsvPitch = kBlurTW + 4;  // +4 words: rows of a partial tile's flattened items fall into different banks
 constexpr int kBlurLead = 16;  // bytes left of the tile in the box: innermost TMA coordinate is 16-byte granular (3 needed)
 
 __device__ __forceinline__ int reflect101(int p, int n) {
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256)
 blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, const __grid_constant__ TmaMaps maps,
             uint8_t* __restrict__ blur) {
     __shared__ __align__(128) uint32_t in_w[kBlurInRows][kBlurInWords];
-    __shared__ __align__(16) uint32_t hsv[kBlurInRows / 2][kBlurTW];
+    __shared__ __align__(16) uint32_t hsv[kBlurInRows / 2][kBlurHsvPitch];
     __shared__ __align__(8) uint64_t bar;
     const BlurTile t = tiles[blockIdx.x];
     const int frame = blockIdx.y;
@@ -187,10 +188,15 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
         }
     }
 
+    // Partial tiles (right column / bottom row of a level) only enumerate what lies inside the level: nq column
+    // quads and nrp input row pairs; items are flattened so that whole warps drop out instead of lanes.
+    const int nq = min(kBlurTW / 4, (L.w - X0 + 3) >> 2);
+    const int nrp = min(kBlurInRows / 2, (min(kBlurTH, L.h - Y0) + 6 + 1) >> 1);  // output rows + 6 halo rows, in pairs
+    const uint32_t qinv = (65536u + nq - 1) / nq;  // floor(i / nq) == i * qinv >> 16 for i * nq < 65536
     // horizontal pass: item = (row pair, column quad)
     constexpr uint32_t kLo = 18u | 34u << 8 | 48u << 16 | 56u << 24, kHi = 48u | 34u << 8 | 18u << 16;
-    for (int it = tid; it < (kBlurInRows / 2) * (kBlurTW / 4); it += 256) {
-        const int pr = it >> 5, k = it & 31;
+    for (int it = tid; it < nrp * nq; it += 256) {
+        const int pr = (int)((uint32_t)it * qinv >> 16), k = it - pr * nq;
         uint32_t h[2][4];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
@@ -214,9 +220,9 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
     // the pair rows m..m+3
     constexpr uint32_t e0 = 18u | 34u << 8, e1 = 48u | 56u << 8, e2 = 48u | 34u << 8, e3 = 18u;       // even row 2m
     constexpr uint32_t o0 = 18u << 8, o1 = 34u | 48u << 8, o2 = 56u | 48u << 8, o3 = 34u | 18u << 8;  // odd row 2m+1
-    const int quad = tid & 31, seg = tid >> 5;
+    const int seg = (int)((uint32_t)tid * qinv >> 16), quad = tid - seg * nq;  // (tid / nq, tid % nq): 8 segments of 4 row pairs
     const int x = X0 + 4 * quad;
-    if (x < L.w) {
+    if (seg < 8 && Y0 + 8 * seg < L.h) {
         const int m0 = seg * 4;
         uint4 p0 = *reinterpret_cast<const uint4*>(&hsv[m0][4 * quad]);
         uint4 p1 = *reinterpret_cast<const uint4*>(&hsv[m0 + 1][4 * quad]);
