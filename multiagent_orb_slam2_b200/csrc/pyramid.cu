@@ -17,7 +17,8 @@ namespace orb {
 // fetches the column taps of its 4 columns and the row taps of its 8 rows into registers.
 // The horizontal pass of a source row is kept for the next output row: consecutive output rows share
 // a source row (the second tap of row y is the first tap of row y+1 unless the scale skips a row), so
-// a warp interpolates ~1.2 source rows per output row instead of 2. Row decisions are warp-uniform.
+// a warp interpolates ~1.2 source rows per output row instead of 2. Row decisions are warp-uniform
+// (except in the narrow tiles of a level's last column, see below).
 constexpr int kRsTW = 128, kRsTH = 64, kRsRowsPerWarp = 8;
 
 __global__ void __launch_bounds__(256)
@@ -43,8 +44,15 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
         tma_load_3d(win, &maps.m[level - 1], sx_lo, sy_lo, frame, &bar);
     }
     // all table reads of this thread, issued while the window is in flight
-    const int q = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int x0 = X0 + 4 * q, yw = Y0 + kRsRowsPerWarp * rg;
+    // A tile of the level's last column may hold only a few column quads: its warps then put 2 or 4 row groups
+    // side by side (16 or 8 lanes per row, each lane group a contiguous run of 4 or 2 rows) instead of running
+    // 8 rows with most lanes idle.
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int nqv = min(32, (L.w - X0 + 3) >> 2);
+    const int lpr_log = nqv <= 8 ? 3 : nqv <= 16 ? 4 : 5;         // lanes per row: 8, 16 or 32
+    const int rpg = kRsRowsPerWarp >> (5 - lpr_log);                // rows per lane group: 2, 4 or 8
+    const int q = lane & ((1 << lpr_log) - 1);
+    const int x0 = X0 + 4 * q, yw = Y0 + kRsRowsPerWarp * rg + (lane >> lpr_log) * rpg;
     // a LinTap is 8 bytes (source index | two 16-bit weights): one 64-bit load each
     uint2 tcol[4], trow[kRsRowsPerWarp];
 #pragma unroll
@@ -81,7 +89,7 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
     int crow = -1;
     uint32_t hc[4] = {0, 0, 0, 0};  // cached horizontal pass: source row and values
     uint8_t* drow = dst + (size_t)yw * L.pitch + x0;
-    const int dpitch = L.pitch, sh_max = S.h - 1, nrows = min(kRsRowsPerWarp, L.h - yw);
+    const int dpitch = L.pitch, sh_max = S.h - 1, nrows = min(rpg, L.h - yw);
 #pragma unroll
     for (int rr = 0; rr < kRsRowsPerWarp; ++rr) {
         if (rr >= nrows) break;
