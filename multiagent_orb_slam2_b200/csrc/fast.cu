@@ -16,9 +16,10 @@
 //
 // Phases (all warp-synchronous, work compacted between them so that the expensive part runs on dense
 // lanes):
-//   1. every interior pixel, 2 rows x 4 per lane from aligned 32-bit words of the tile: 4-point rejection
-//      test (any arc of 9 contains ring pixel 0 or 8 and 4 or 12) on packed 16-bit halves
-//      (PRMT unpack, VIMNMX.S16x2, VIADD.16x2)          -> survivor list (one shuffle scan per 256 px)
+//   1. every interior pixel, 2 rows x 4 per lane from aligned 32-bit words of the tile: rejection test (any arc
+//      of 9 contains ring pixel 0 or 8 and 4 or 12: one of each pair must differ from the centre by more than
+//      the threshold) on the four bytes of a word at once (VABSDIFF4 + SWAR compare)
+//                                                        -> survivor list (one shuffle scan per 256 px)
 //   2. survivors: the 16 ring pixels packed two per register (k, k+8), the 16 arc minima by two rounds
 //      of VIMNMX3.S16x2; corner <=> score >= threshold   -> score map, corner list (in place)
 //   3. corner list: 3x3 strict maximum                   -> per-row bit mask
@@ -160,26 +161,20 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         int n2 = 0;
         for (int pass = 0;; ++pass) {
         const int thr = pass ? minTh : iniTh;
-        const uint32_t T1 = (uint32_t)(thr + 1) * 0x10001u, T2 = ((uint32_t)(-thr) & 0xffffu) * 0x10001u;
-        // sign bits of the result's halves: pixel j at bit (15, 31, 14, 30)[j] set  <=>  one of ring pixels
-        // (0,8) and one of (4,12) lie below v - t, or both above v + t
+        // Rejection test on four pixels at once, bytes in place (no unpacking): a pixel survives when one of ring
+        // pixels (0,8) AND one of (4,12) differ from it by more than thr, whatever the sign. That is slightly weaker
+        // than the signed 4-point test (measured: 9.2 % instead of 7.6 % of the pixels survive at thr 20) but costs
+        // 19 instead of 47 instructions per word: VABSDIFF4 and, per difference, |d| > thr as the top bit of
+        // ((d & 0x7f) + 127 - thr) | d. Phase 2 decides exactly. (thr > 126: everything survives.)
+        const uint32_t Kthr = (uint32_t)max(127 - thr, 0) * 0x01010101u, Kall = thr > 126 ? 0x80808080u : 0u;
         auto hit4 = [&](uint32_t C, uint32_t U, uint32_t Dn, uint32_t Lw, uint32_t Rw) {
             const uint32_t W12 = __funnelshift_r(Lw, C, 8);   // ring pixel 12 (x - 3) of the four centres
             const uint32_t W4 = __funnelshift_r(C, Rw, 24);   // ring pixel 4  (x + 3)
-            uint32_t hit[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t sel = h ? 0x4342u : 0x4140u;
-                const uint32_t c2 = __byte_perm(C, 0, sel), u2 = __byte_perm(U, 0, sel), d2 = __byte_perm(Dn, 0, sel);
-                const uint32_t l2 = __byte_perm(W12, 0, sel), r2 = __byte_perm(W4, 0, sel);
-                const uint32_t nc = ~c2;                       // -c - 1 in each half
-                const uint32_t kd = __vadd2(nc, T1);           // t - c
-                const uint32_t kb = __vadd2(nc, T2);           // -c - 1 - t
-                const uint32_t a = __vmaxs2(__vmins2(d2, u2), __vmins2(l2, r2));
-                const uint32_t b = __vmins2(__vmaxs2(d2, u2), __vmaxs2(l2, r2));
-                hit[h] = __vadd2(a, kd) | ~__vadd2(b, kb);
-            }
-            return (hit[0] & 0x80008000u) | ((hit[1] >> 1) & 0x40004000u);
+            const uint32_t a = __vabsdiffu4(C, U), b = __vabsdiffu4(C, Dn), c = __vabsdiffu4(C, W12), d = __vabsdiffu4(C, W4);
+            const uint32_t qa = (a & 0x7f7f7f7fu) + Kthr, qb = (b & 0x7f7f7f7fu) + Kthr;
+            const uint32_t qc = (c & 0x7f7f7f7fu) + Kthr, qd = (d & 0x7f7f7f7fu) + Kthr;
+            const uint32_t v = qa | a | qb | b, h = qc | c | qd | d;
+            return ((v & h) | Kall) & 0x80808080u;  // pixel j at bit 8 j + 7
         };
         int n1 = 0;
         for (int i0 = 0; i0 < nitems; i0 += 32) {
@@ -191,8 +186,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             // byte columns outside [bs, be) masked; either row may lie below the interior
             const int bcol0 = wcol << 2;
             const int lead = max(bs - bcol0, 0), trail = max(bcol0 + 4 - be, 0);
-            const uint32_t v4 = act ? ((0xfu << lead) & (0xfu >> trail)) : 0u;  // valid pixels, bit j
-            const uint32_t vw = (v4 & 1u) << 15 | (v4 & 2u) << 30 | (v4 & 4u) << 12 | (v4 & 8u) << 27;
+            const uint32_t vw = (0x80808080u << (8 * lead)) & (0x80808080u >> (8 * trail)) & (act ? 0xffffffffu : 0u);
             const uint32_t kw0 = hit4(wp[0], wp[-3 * tpw], wp[3 * tpw], wp[-1], wp[1]) & (y < th - 3 ? vw : 0u);
             const uint32_t kw1 = hit4(wp[4 * tpw], wp[tpw], wp[7 * tpw], wp[4 * tpw - 1], wp[4 * tpw + 1]) & (y + 4 < th - 3 ? vw : 0u);
             const int cnt = __popc(kw0) + __popc(kw1);
@@ -201,14 +195,14 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
             uint16_t* dst = list + n1 + inc - cnt;
             const uint32_t e0 = (uint32_t)(bcol0 | y << 7), e1 = e0 + 4u * 128u;
-            if (kw0 & 0x00008000u) *dst++ = (uint16_t)e0;
-            if (kw0 & 0x80000000u) *dst++ = (uint16_t)(e0 + 1);
-            if (kw0 & 0x00004000u) *dst++ = (uint16_t)(e0 + 2);
-            if (kw0 & 0x40000000u) *dst++ = (uint16_t)(e0 + 3);
-            if (kw1 & 0x00008000u) *dst++ = (uint16_t)e1;
-            if (kw1 & 0x80000000u) *dst++ = (uint16_t)(e1 + 1);
-            if (kw1 & 0x00004000u) *dst++ = (uint16_t)(e1 + 2);
-            if (kw1 & 0x40000000u) *dst++ = (uint16_t)(e1 + 3);
+            if (kw0 & 0x00000080u) *dst++ = (uint16_t)e0;
+            if (kw0 & 0x00008000u) *dst++ = (uint16_t)(e0 + 1);
+            if (kw0 & 0x00800000u) *dst++ = (uint16_t)(e0 + 2);
+            if (kw0 & 0x80000000u) *dst++ = (uint16_t)(e0 + 3);
+            if (kw1 & 0x00000080u) *dst++ = (uint16_t)e1;
+            if (kw1 & 0x00008000u) *dst++ = (uint16_t)(e1 + 1);
+            if (kw1 & 0x00800000u) *dst++ = (uint16_t)(e1 + 2);
+            if (kw1 & 0x80000000u) *dst++ = (uint16_t)(e1 + 3);
             n1 += __shfl_sync(0xffffffffu, inc, 31);
         }
         __syncwarp();
