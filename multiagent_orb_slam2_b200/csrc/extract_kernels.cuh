@@ -51,6 +51,7 @@ struct CellDesc {
     int16_t offx, offy;             // j*wCell, i*hCell added to cell-local keypoints
     int16_t pad;
     int32_t ordinal;                // position among the level's active cells (row-major)
+    uint32_t ginv;                  // ceil(65536 / G), G = aligned 4-byte groups covering the interior columns (fast.cu)
 };
 
 struct LinTap { int ofs; short c0, c1; };  // cv::resize INTER_LINEAR tap: source index + 2048-scaled weights

@@ -177,6 +177,11 @@ int build_geometry(orbx_extractor* h) {
                 CellDesc cd{};
                 cd.level = (int16_t)l; cd.x0 = (int16_t)x0; cd.y0 = (int16_t)y0; cd.tw = (int16_t)(x1 - x0); cd.th = (int16_t)(y1 - y0);
                 cd.offx = (int16_t)(j * L.wCell); cd.offy = (int16_t)(i * L.hCell); cd.ordinal = ord++;
+                {   // FAST phase 1 walks the interior columns in aligned 4-byte groups of the tile row (tile byte 0 = x0 & ~15)
+                    const int bs = (x0 & 15) + 3, be = bs + (x1 - x0) - 6;
+                    const int G = be > bs ? ((be - 1) >> 2) - (bs >> 2) + 1 : 1;
+                    cd.ginv = (65536u + G - 1) / G;
+                }
                 cells.push_back(cd);
                 g.max_tw = std::max(g.max_tw, (int)cd.tw); g.max_th = std::max(g.max_th, (int)cd.th);
             }

@@ -128,6 +128,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         const LevelGeom& L = g->lv[c.level];
         const int tw = c.tw, th = c.th;
         const int dw = tw - 6, dh = th - 6;  // interior (detection) size
+        const int wsh = dw > 32 ? 1 : 0;     // mask words per interior row: 1 or 2
         int* count_out = cell_counts + (size_t)frame * ncells + ci;
         if (dw <= 0 || dh <= 0) {
             if (lane == 0) { *count_out = 0; issue(ci + stride); }
@@ -153,7 +154,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         // four pairs a warp step touches with one load instruction lie in consecutive rows (2-way instead of 4-way bank
         // conflicts at the tile's 16-word pitch)
         const int nitems = ((dh + 7) >> 3) * 4 * G;
-        const uint32_t Ginv = (65536u + G - 1) / G;  // floor(i / G) == i * Ginv >> 16 for i * G < 65536
+        const uint32_t Ginv = c.ginv;  // ceil(65536 / G), from the host: floor(i / G) == i * Ginv >> 16 for i * G < 65536
         // The reference runs cv::FAST at iniThFAST and, only when the cell comes back empty, again at minThFAST
         // (809-816). Same here: at iniTh far fewer pixels survive the rejection test and reach phases 2-3, and
         // the local-maximum test does not depend on the threshold (header), so pass 0 yields exactly the
@@ -246,7 +247,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             const int s = q[0];
             const int m = max(max(max(q[-sp - 1], q[-sp]), max(q[-sp + 1], q[-1])), max(max(q[1], q[sp - 1]), max(q[sp], q[sp + 1])));
             const bool keep = act & (m < s);
-            if (keep) atomicOr(&mask[(y - 3) * 2 + ((x - 3) >> 5)], 1u << ((x - 3) & 31));
+            if (keep) atomicOr(&mask[((y - 3) << wsh) + ((x - 3) >> 5)], 1u << ((x - 3) & 31));
             total += __popc(__ballot_sync(0xffffffffu, keep));
         }
         if (total > 0 || pass == 1 || iniTh <= minTh) break;  // minThFAST retry of an empty cell
@@ -255,7 +256,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         if (lane == 0) issue(ci + stride);
 
         // ---- phase 4: exclusive prefix over the mask words in row-major order, ordered write ----------
-        const int nent = dh * 2;
+        const int nent = dh << wsh;
         int carry = 0;
         for (int e0 = 0; e0 < nent; e0 += 32) {
             const int w = e0 + lane;
@@ -272,7 +273,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         for (int i = lane; i < n2; i += 32) {
             const int e = list[i];
             const int y = e >> 7, x = (e & 127) - phase;
-            const int w = (y - 3) * 2 + ((x - 3) >> 5);
+            const int w = ((y - 3) << wsh) + ((x - 3) >> 5);
             const uint32_t bit = 1u << ((x - 3) & 31), mw = mask[w];
             if (mw & bit) {
                 const int rank = offs[w] + __popc(mw & (bit - 1u));
