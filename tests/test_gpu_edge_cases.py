@@ -120,3 +120,37 @@ def test_fast_thresholds_and_empty_cell_retry(ini, mn, kind):
     assert len(gk) == len(ok)
     if len(ok):
         assert np.array_equal(got.view(np.uint32), ok.view(np.uint32)) and np.array_equal(gd, od)
+
+
+def test_three_frontends_in_flight_share_one_compute_stream():
+    """The end-to-end pipeline of bench.py: three agents' buffers in flight on three streams, their kernels
+    serialised on the GPU's shared compute stream (frontend.py). Every step's results must equal those of
+    the same frames processed alone."""
+    import torch
+    from multiagent_orb_slam2_b200.frontend import AgentFrontend
+    sets = []
+    for k in range(3):
+        frames = []
+        for s in range(2):
+            a, b, _ = synth.shifted_pair("blocks", 640, 480, 10 * k + s)
+            frames += [a, b]
+        sets.append(torch.from_numpy(np.stack(frames)).pin_memory())
+    fes = [AgentFrontend(640, 480, max_batch=4) for _ in range(3)]
+    ref = []
+    for k in range(3):
+        kps, desc, counts, match = fes[k].process(sets[k])
+        ref.append((kps.copy(), desc.copy(), counts.copy(), match.copy()))
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = [f.pinned_outputs() for f in fes]
+    for rep in range(4):
+        for k in range(3):
+            with torch.cuda.stream(streams[k]):
+                fes[k].process_async(sets[(k + rep) % 3], outs[k])
+        for k in range(3):
+            streams[k].synchronize()
+            rk, rd, rc, rm = ref[(k + rep) % 3]
+            assert np.array_equal(outs[k]["counts"].numpy()[:4], rc)
+            for i in range(4):
+                c = rc[i]
+                assert np.array_equal(outs[k]["desc"].numpy()[i, :c], rd[i, :c])
+                assert np.array_equal(outs[k]["match"].numpy()[i, :c], rm[i, :c])
