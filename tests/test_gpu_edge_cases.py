@@ -154,3 +154,21 @@ def test_three_frontends_in_flight_share_one_compute_stream():
                 c = rc[i]
                 assert np.array_equal(outs[k]["desc"].numpy()[i, :c], rd[i, :c])
                 assert np.array_equal(outs[k]["match"].numpy()[i, :c], rm[i, :c])
+
+
+@pytest.mark.parametrize("w,h,nl", [(91, 91, 1), (95, 150, 2), (150, 93, 2)])
+def test_single_large_cell_levels(w, h, nl):
+    """Levels only 59..63 px wide inside the border are ONE cell of up to 63 px (nCols = int(width / 30) = 1 needs
+    width < 60; 2 cells of 30..44 px otherwise): the largest FAST tiles there are, more than 48 KB of shared memory
+    per block and two mask words per row."""
+    img = synth.image("blocks", w, h, 3)
+    o = O.OracleExtractor(300, 1.2, nl, 20, 7)
+    ok, od = o(img)
+    g = ORBextractor(300, 1.2, nl, 20, 7)
+    gk, gd = g(img)
+    for l in range(nl):
+        assert np.array_equal(g.candidates(l), o.level(l)["cand"]), "FAST candidates level %d" % l
+    got = np.stack([gk["x"], gk["y"], gk["size"], gk["angle"], gk["response"], gk["octave"].astype(np.float32)], 1)
+    assert len(gk) == len(ok)
+    if len(ok):
+        assert np.array_equal(got.view(np.uint32), ok.view(np.uint32)) and np.array_equal(gd, od)
