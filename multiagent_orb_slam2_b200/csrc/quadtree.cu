@@ -207,19 +207,29 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
     __syncthreads();
     int root_bits = 0;
     while ((1 << root_bits) < nRoots) ++root_bits;
-    const int flip = block_radix_sort(kA, vA, kB, vB, n, 2 * depth + root_bits, sh);
-    const uint32_t* sk = flip ? kB : kA;  // re-pointed to shared memory on the fast path
-    const uint32_t* sv = flip ? vB : vA;
     // Fast path (the usual case): sorted keys and a per-element selection word live in shared memory, so
-    // the binary searches of the list simulation and the per-node maximum never leave the SM.
+    // the binary searches of the list simulation and the per-node maximum never leave the SM. The second
+    // buffer pair of the sort IS that shared memory: with the usual three 8-bit passes the sorted set ends
+    // there (global -> shared -> global -> shared) and only every other pass touches L2.
     const bool fast = n <= kQtSmemKeys;
     uint32_t* skey = reinterpret_cast<uint32_t*>(nodemem + 14 * sel_cap);
     uint32_t* comb = skey + kQtSmemKeys;  // response << 24 | (0xffffff - candidate index): max = best, earliest on ties
+    if (fast) { kB = skey; vB = comb; }
+    const int flip = block_radix_sort(kA, vA, kB, vB, n, 2 * depth + root_bits, sh);
+    const uint32_t* sk = flip ? kB : kA;
+    const uint32_t* sv = flip ? vB : vA;
     if (fast) {
-        for (int i = threadIdx.x; i < n; i += kQtThreads) {
-            const uint32_t c = sv[i];
-            skey[i] = sk[i];
-            comb[i] = (cand[c] >> 24) << 24 | (0xffffffu - c);
+        if (flip) {  // already in shared memory: turn the candidate indices into selection words in place
+            for (int i = threadIdx.x; i < n; i += kQtThreads) {
+                const uint32_t c = comb[i];
+                comb[i] = (cand[c] >> 24) << 24 | (0xffffffu - c);
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += kQtThreads) {
+                const uint32_t c = sv[i];
+                skey[i] = sk[i];
+                comb[i] = (cand[c] >> 24) << 24 | (0xffffffu - c);
+            }
         }
         __syncthreads();
         sk = skey;
