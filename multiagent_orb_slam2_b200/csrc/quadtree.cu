@@ -399,17 +399,18 @@ quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slo
     const uint32_t* lslots = slots + (size_t)frame * g->slot_words + L.slot_off;
 
     // stitch the cells' lists in row-major cell order (789-829): offsets = scan of counts.
-    // nodemem is free until quadtree_select: use it for the offsets when it is large enough,
-    // else fall back to a serial prefix inside each warp's walk.
-    int* offs = nodemem;  // sel_cap*14 ints >= cell_count always holds for sane settings (checked on host)
-    const int total = block_exclusive_scan(counts, offs, L.cell_count, sh);
+    // nodemem is free until quadtree_select: cell counts (one coalesced pass) and their offsets live there
+    // (14 * max_cap ints >= 2 * cell_count, sized on the host)
+    int* offs = nodemem;
+    int* cnt_s = nodemem + L.cell_count;
+    for (int c = threadIdx.x; c < L.cell_count; c += kQtThreads) cnt_s[c] = counts[c];
+    const int total = block_exclusive_scan(cnt_s, offs, L.cell_count, sh);
     __syncthreads();
-    // 8 lanes per cell (a cell holds ~10 candidates): 4 cells of a warp have their dependent count -> slot
-    // loads in flight together
+    // 8 lanes per cell (a cell holds ~10 candidates): the slot loads of 4 cells per warp are in flight together
     for (int c0 = warp * 4; c0 < L.cell_count; c0 += kQtWarps * 4) {
         const int c = c0 + (lane >> 3);
         if (c < L.cell_count) {
-            const int n = counts[c], o = offs[c];
+            const int n = cnt_s[c], o = offs[c];
             const uint32_t* s = lslots + (size_t)c * L.slot_cap;
             for (int k = lane & 7; k < n; k += 8) cand[o + k] = s[k];
         }
@@ -444,7 +445,7 @@ static int qt_configure(size_t need) {
 
 int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStream_t st) {
     int max_cap = 0;
-    for (int l = 0; l < hg.nlevels; ++l) max_cap = max(max_cap, max(hg.lv[l].sel_cap, ceil_div(hg.lv[l].cell_count, 14) + 1));
+    for (int l = 0; l < hg.nlevels; ++l) max_cap = max(max_cap, max(hg.lv[l].sel_cap, ceil_div(2 * hg.lv[l].cell_count, 14) + 1));
     const size_t smem = qt_smem_bytes(max_cap);
     int rc = qt_configure(smem);
     if (rc) return rc;
