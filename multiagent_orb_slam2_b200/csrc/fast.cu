@@ -83,6 +83,10 @@ __device__ __forceinline__ int fast_side_margin(const int (&r)[16], int v, int s
     return max((int)(m & 0xffffu), (int)(m >> 16)) - 256;
 }
 
+// TP: the tile's row pitch in bytes when it is known at compile time (64 for every cell up to 49 px wide: all
+// standard camera settings), 0 = read it from the geometry. A constant pitch turns the ring offsets and row
+// strides into immediates.
+template <int TP>
 __global__ void __launch_bounds__(kFastThreads, 8)
 fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, const __grid_constant__ TmaMaps maps,
                   uint32_t* __restrict__ slots, int* __restrict__ cell_counts) {
@@ -90,7 +94,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     __shared__ __align__(8) uint64_t bars[kFastWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const int max_th = g->max_th, tp = g->fast_bw, tpw = tp >> 2;
+    const int max_th = g->max_th, tp = TP ? TP : g->fast_bw, tpw = tp >> 2;
     const FastLayout lay = fast_layout(g->max_tw, max_th, tp);
     const int T = lay.tile_bytes, sp = lay.score_pitch;
     uint8_t* wbase = smem + (size_t)warp * lay.warp_bytes;
@@ -292,15 +296,17 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps
     static int attr_bytes[64];  // per device: dynamic shared memory opted in so far
     int dev = 0;
     ORB_CUDA_TRY(cudaGetDevice(&dev));
+    auto kernel = hg.fast_bw == 64 ? fast_cells_kernel<64> : fast_cells_kernel<0>;
     if (smem > 48 * 1024 && dev < 64 && attr_bytes[dev] < (int)smem) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes[dev] = (int)smem;
     }
     // cells per warp: as many as keeps every SM's warp slots (8 blocks of 4 warps) busy, at most 8
     const long long warps_wanted = (long long)kNumSMs * 8 * kFastWarps;
     int cpw = (int)std::min<long long>(kFastMaxCellsPerWarp, std::max<long long>(1, (long long)hg.ncells * n / warps_wanted));
     const int blocks_x = ceil_div(ceil_div(hg.ncells, cpw), kFastWarps);
-    fast_cells_kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts);
+    kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
