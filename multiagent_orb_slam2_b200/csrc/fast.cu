@@ -2,7 +2,9 @@
 // suppression. One WARP per cell; every warp walks a strided list of cells of one frame. A cell's
 // tile (TMA box load) is dead once its scores are known, so the next cell's load is issued at that
 // point and lands while the warp finishes phases 3-4: no block barrier anywhere, no wait for the
-// tile after a warp's first cell, and 6.6 KB of shared memory per warp (8 blocks of 4 warps per SM).
+// tile after a warp's first cell, and 6.4 KB of shared memory per warp. A block is ONE warp (measured at B=512:
+// 0.765 ms against 0.797 / 0.814 / 0.860 ms with 2 / 4 / 8 warps per block - a block's slots free up as soon
+// as its own cells are done).
 //
 // Replaces the cell loop of ComputeKeyPointsOctTree, /root/reference/src/ORBextractor.cc:789-829,
 // i.e. cv::FAST(cell + 6 px halo, iniThFAST, true) with the minThFAST retry when the cell comes back
@@ -39,7 +41,7 @@ __device__ __forceinline__ int ring_offset(int k, int tp) {
     return dy[k] * tp + dx[k];
 }
 
-constexpr int kFastWarps = 4;
+constexpr int kFastWarps = 1;
 constexpr int kFastThreads = kFastWarps * 32;
 constexpr int kFastMaxCellsPerWarp = 8;
 
@@ -87,7 +89,7 @@ __device__ __forceinline__ int fast_side_margin(const int (&r)[16], int v, int s
 // standard camera settings), 0 = read it from the geometry. A constant pitch turns the ring offsets and row
 // strides into immediates.
 template <int TP>
-__global__ void __launch_bounds__(kFastThreads, 8)
+__global__ void __launch_bounds__(kFastThreads, 32 / kFastWarps)
 fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, const __grid_constant__ TmaMaps maps,
                   uint32_t* __restrict__ slots, int* __restrict__ cell_counts) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -302,8 +304,8 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps
         ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_bytes[dev] = (int)smem;
     }
-    // cells per warp: as many as keeps every SM's warp slots (8 blocks of 4 warps) busy, at most 8
-    const long long warps_wanted = (long long)kNumSMs * 8 * kFastWarps;
+    // cells per warp: as many as keeps every SM's warp slots (about 30 one-warp blocks) busy, at most 8
+    const long long warps_wanted = (long long)kNumSMs * 32;
     int cpw = (int)std::min<long long>(kFastMaxCellsPerWarp, std::max<long long>(1, (long long)hg.ncells * n / warps_wanted));
     const int blocks_x = ceil_div(ceil_div(hg.ncells, cpw), kFastWarps);
     kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts);
