@@ -137,7 +137,7 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     __syncthreads();
 
     // ---- B: angle, sin / cos, one keypoint per lane --------------------------------------------------
-    if (warp == 0 && info[lane].valid) {
+    if (warp == 0 && lane < kDescSlots && info[lane].valid) {
         const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
         const float ang = fast_atan2_deg((float)s_m01[lane], (float)s_m10[lane]);
         const float rad = __fmul_rn(ang, factorPI);
