@@ -206,7 +206,7 @@ int build_geometry(orbx_extractor* h) {
     // the innermost TMA coordinate is 16-byte granular: boxes carry up to 15 lead-in bytes
     g.fast_bw = (int)align_up((size_t)g.max_tw + 15, 16);
     g.rs_bw = (int)align_up((size_t)ceil(128.0 * sf) + 2 + 15 + 12, 16);  // + 3-word read window of the last column quad
-    g.rs_bh = (int)ceil(64.0 * sf) + 3;  // kRsTH output rows (pyramid.cu)
+    g.rs_bh = (int)ceil(32.0 * sf) + 3;  // kRsTH output rows (pyramid.cu)
     if (g.fast_bw > 256 || g.max_th > 256 || g.rs_bw > 256) { set_error("scale factor / cell size too large for the TMA tile boxes"); return ORB_EINVAL; }
     g.pyr_bytes = std::max<size_t>(pyr, 256); g.blur_bytes = blur; g.slot_words = slot; g.cand_words = slot;
     g.sel_words = sel; g.out_cap = sel;
