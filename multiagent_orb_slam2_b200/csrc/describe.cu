@@ -50,8 +50,8 @@ struct SlotInfo { int valid, level, x, y, response, dst; };
 // grid (ceil(sel_words / 32), frames), block 256. Phases:
 //   0. thread i < 32 resolves slot i (level, position in the frame's output, packed candidate)
 //   A. every warp: intensity-centroid moments of 4 slots (aligned word loads, IDP.4A against int8 coordinates)
-//   B. warp 0: lane i evaluates the angle and sin/cos (double, rounded once) for slot i - 32 keypoints per
-//      instruction stream instead of one
+//   B. every warp: lanes 0-3 evaluate the angle and sin/cos (double, rounded once) of the warp's own 4 slots;
+//      after the table fill no block barrier separates the phases
 //   C. every warp: rotated BRIEF of 4 slots, two at a time, sampled from a shared-memory copy of the
 //      blurred 37 x 40 window (lane = output byte), keypoint record
 __global__ void __launch_bounds__(kDescWarps * 32, 5)
@@ -134,18 +134,22 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
         m01 = __reduce_add_sync(0xffffffffu, m01);
         if (lane == 0) { s_m10[sidx] = m10; s_m01[sidx] = m01; }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- B: angle, sin / cos, one keypoint per lane --------------------------------------------------
-    if (warp == 0 && lane < kDescSlots && info[lane].valid) {
-        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-        const float ang = fast_atan2_deg((float)s_m01[lane], (float)s_m10[lane]);
-        const float rad = __fmul_rn(ang, factorPI);
-        double sn, cs;
-        sincos((double)rad, &sn, &cs);
-        s_angle[lane] = ang; s_cos[lane] = (float)cs; s_sin[lane] = (float)sn;
+    // ---- B: angle, sin / cos: every warp for its own slots, one keypoint per lane (no block barrier between
+    // the phases: a warp runs A, B, C for its 4 keypoints on its own) ------------------------------------
+    if (lane < kDescSlots / kDescWarps) {
+        const int sl = warp * (kDescSlots / kDescWarps) + lane;
+        if (info[sl].valid) {
+            const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+            const float ang = fast_atan2_deg((float)s_m01[sl], (float)s_m10[sl]);
+            const float rad = __fmul_rn(ang, factorPI);
+            double sn, cs;
+            sincos((double)rad, &sn, &cs);
+            s_angle[sl] = ang; s_cos[sl] = (float)cs; s_sin[sl] = (float)sn;
+        }
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- C: rotated BRIEF + keypoint record ----------------------------------------------------------
     // The 512 sample points of a keypoint lie within 18 px of it (pattern radius 18.4). Gathering them
