@@ -306,7 +306,7 @@ def run_b200(args):
         cmp_per_step = float((pin["counts"].numpy()[:B].astype(np.float64) * np.roll(pin["counts"].numpy()[:B], -1)).sum())
         per_stage["hamming_knn2"] = {"ms": match_ms, "gcmp_per_s": cmp_per_step / (match_ms * 1e-3) / 1e9}
         a = per_stage[STAGES[dom]]
-        # DRAM bytes per frame of each kernel from `ncu --set full` (profiles/r01_ncu_full_s3e_summary.md, B=64:
+        # DRAM bytes per frame of each kernel from `ncu --set full` (profiles/r01_ncu_full_s3f_summary.md, B=64:
         # dram__bytes_read.sum + dram__bytes_write.sum per launch / 64; FAST also at B=512: 561 MB / 512), scaled to
         # this launch's B frames
         ncu_traffic_per_frame = {"pyramid_resize": 1.05e6, "gaussian_blur": 1.52e6, "fast_cells": 1.10e6, "quadtree": 0.135e6,
@@ -316,8 +316,8 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": a["alg_bytes_per_frame"] * B,
                 "peak_source": pk_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "note": "the dominant kernel (FAST) is bound by instruction issue and the shared-memory pipe, not by HBM (ncu at "
-                        "B=512: 80 % of issue slots, 72 % of shared-memory wavefront peak, 50 thread instructions per pixel, DRAM "
-                        "8 %); its DRAM traffic equals its algorithmic bytes. The HBM-streaming stages are pyramid_resize and "
+                        "B=512: 80 % of issue slots, 78 % of shared-memory wavefront peak, 46 thread instructions per pixel, DRAM "
+                        "9 %); its DRAM traffic equals its algorithmic bytes. The HBM-streaming stages are pyramid_resize and "
                         "gaussian_blur (see stages)",
                 "stages": per_stage}
 
