@@ -52,7 +52,7 @@ __host__ __device__ inline FastLayout fast_layout(int max_tw, int max_th, int tp
     f.tile_bytes = max_th * tp;                      // multiple of 16 (tp is)
     f.score_pitch = (int)align_up((size_t)max_tw - 4, 4);  // score of cell pixel (x, y) at [(y - 2) * pitch + x - 2]
     f.score_bytes = (int)align_up((size_t)f.score_pitch * (max_th - 4), 16);
-    f.mask_words = 2 * (max_th - 6);                 // (row, 32-column half) entries
+    f.mask_words = (max_tw - 6 > 32 ? 2 : 1) * (max_th - 6);  // one word per interior row and 32 columns
     f.mask_off = f.tile_bytes + f.score_bytes;
     f.list_off = f.mask_off + (int)align_up((size_t)2 * f.mask_words * 4, 16);
     const int npx = (max_tw - 6) * (max_th - 6);
