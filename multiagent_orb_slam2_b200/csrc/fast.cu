@@ -29,6 +29,7 @@
 //   4. prefix over the mask words, then the corner list again: rank = offset + bits below -> the
 //      row-major ordered slot list (reference order inside the cell).
 #include <algorithm>
+#include <atomic>
 
 #include "extract_kernels.cuh"
 
@@ -295,7 +296,7 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps
     ORB_REQUIRE(hg.fast_bw <= 128 && hg.max_th <= 128 && hg.max_tw - 6 <= 64, "FAST cell larger than 64 x 122 pixels");
     const FastLayout lay = fast_layout(hg.max_tw, hg.max_th, hg.fast_bw);
     const size_t smem = (size_t)lay.warp_bytes * kFastWarps;
-    static int attr_bytes[64];  // per device: dynamic shared memory opted in so far
+    static std::atomic<int> attr_bytes[64];  // per device: dynamic shared memory opted in so far (a racing second call only repeats the attribute set)
     int dev = 0;
     ORB_CUDA_TRY(cudaGetDevice(&dev));
     auto kernel = hg.fast_bw == 64 ? fast_cells_kernel<64> : fast_cells_kernel<0>;
