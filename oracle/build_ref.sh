@@ -58,4 +58,15 @@ extern "C" void refm_three_maxima(const int* sizes, int L, int* out3) {
 }
 POST
 } | g++ -std=c++14 -O3 -march=x86-64-v3 -fPIC -shared -w -I"$here/shim" -x c++ - -o "$here/_ref/libref_matcher_bits.so"
+#   libref_slam.so           the reference's matcher and map data model, UNMODIFIED: src/ORBmatcher.cc, Frame.cc, KeyFrame.cc,
+#                            MapPoint.cc, Map.cc, KeyFrameDatabase.cc, ORBextractor.cc + the vendored DBoW2, against the
+#                            stand-in (float cv::Mat expressions pinned to cv2) + ref_slam_wrap.cc. The extractor inside uses
+#                            the canonical node-size tie-break like libref_orb_canonical.so. Eigen / g2o / Pangolin are not
+#                            needed: Converter.h is the only header that pulls them (see shim/slam_preamble.h).
+g++ -std=c++14 -O2 -march=x86-64-v3 -ffp-contract=off -fPIC -shared -w -pthread \
+    -include "$here/shim/canonical_sort.h" -include "$here/shim/slam_preamble.h" -I"$here/shim" -I"$ref/include" -I"$ref" \
+    "$ref/src/ORBmatcher.cc" "$ref/src/Frame.cc" "$ref/src/KeyFrame.cc" "$ref/src/MapPoint.cc" "$ref/src/Map.cc" \
+    "$ref/src/KeyFrameDatabase.cc" "$ref/src/ORBextractor.cc" \
+    "$dbow/DBoW2/FORB.cpp" "$dbow/DBoW2/BowVector.cpp" "$dbow/DBoW2/FeatureVector.cpp" "$dbow/DBoW2/ScoringObject.cpp" \
+    "$dbow/DUtils/Random.cpp" "$dbow/DUtils/Timestamp.cpp" "$here/ref_slam_wrap.cc" -o "$here/_ref/libref_slam.so"
 echo "build_ref: built $(ls "$here/_ref" | tr '\n' ' ')"
