@@ -224,11 +224,14 @@ class OracleFrame:
     64 x 48 grid (AssignFeaturesToGrid src/Frame.cc:230-245, GetFeaturesInArea 327-380)."""
     COLS, ROWS = 64, 48
 
-    def __init__(self, kps6, desc, width, height):
+    def __init__(self, kps6, desc, width, height, bounds=None):
+        """kps6: the UNDISTORTED keypoints (mvKeysUn); bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY) of image_bounds() when the
+        camera has distortion, else the image rectangle (src/Frame.cc:436-464)."""
         self.kps, self.desc = kps6, desc
-        self.minX, self.minY = np.float32(0), np.float32(0)
-        self.wInv = np.float32(self.COLS) / np.float32(width)
-        self.hInv = np.float32(self.ROWS) / np.float32(height)
+        b = (0, width, 0, height) if bounds is None else bounds
+        self.minX, self.minY = np.float32(b[0]), np.float32(b[2])
+        self.wInv = np.float32(self.COLS) / np.float32(np.float32(b[1]) - np.float32(b[0]))
+        self.hInv = np.float32(self.ROWS) / np.float32(np.float32(b[3]) - np.float32(b[2]))
         self.grid = [[[] for _ in range(self.ROWS)] for _ in range(self.COLS)]
         for i in range(len(kps6)):
             # C round(): half away from zero
@@ -263,6 +266,55 @@ class OracleFrame:
                     if abs(np.float32(self.kps[j, 0] - x)) < r and abs(np.float32(self.kps[j, 1] - y)) < r:
                         out.append(j)
         return out
+
+
+def undistort_points(pts, K, dist):
+    """cv::undistortPoints(pts, pts, K, dist, noArray(), K) as Frame::UndistortKeyPoints calls it (src/Frame.cc:404-434):
+    5 fixed-point iterations of the distortion model in double, re-projection with K, result stored as float
+    (pinned bit-exactly to cv2 4.13 in tests/test_oracle_vs_cv2.py)."""
+    pts = np.asarray(pts, np.float32).reshape(-1, 2)
+    K = np.asarray(K, np.float32).reshape(3, 3).astype(np.float64)
+    k = np.zeros(12); d = np.asarray(dist, np.float32).astype(np.float64).ravel(); k[:len(d)] = d
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    ifx, ify = 1.0 / fx, 1.0 / fy
+    out = np.empty_like(pts)
+    for i in range(len(pts)):
+        x0 = (float(pts[i, 0]) - cx) * ifx; y0 = (float(pts[i, 1]) - cy) * ify
+        x, y = x0, y0
+        for _ in range(5):
+            r2 = x * x + y * y
+            icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+            if icdist < 0:
+                x, y = x0, y0
+                break
+            dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2
+            dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2
+            x = (x0 - dx) * icdist; y = (y0 - dy) * icdist
+        out[i, 0] = np.float32(fx * x + cx); out[i, 1] = np.float32(fy * y + cy)
+    return out
+
+
+def image_bounds(width, height, K, dist):
+    """Frame::ComputeImageBounds, src/Frame.cc:436-464: (mnMinX, mnMaxX, mnMinY, mnMaxY) as floats."""
+    f = np.float32
+    if np.float32(np.asarray(dist).ravel()[0]) == 0:
+        return np.array([0, width, 0, height], f)
+    c = undistort_points(np.array([[0, 0], [width, 0], [0, height], [width, height]], f), K, dist)
+    return np.array([min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])], f)
+
+
+def stereo_from_rgbd(kps, un, depth, mbf):
+    """Frame::ComputeStereoFromRGBD, src/Frame.cc:643-664: depth sampled at the truncated RAW keypoint position, the right
+    coordinate from the UNDISTORTED x."""
+    f = np.float32
+    n = len(kps)
+    ur, dz = np.full(n, -1, f), np.full(n, -1, f)
+    for i in range(n):
+        d = depth[int(kps[i, 1]), int(kps[i, 0])]
+        if d > 0:
+            dz[i] = d
+            ur[i] = f(f(un[i, 0]) - f(f(mbf) / f(d)))
+    return ur, dz
 
 
 def three_maxima(sizes):

@@ -64,13 +64,13 @@ class World:
                                       C.c_float(th_depth), width, height, C.c_float(scale_factor), nlevels, _p(T))
 
     def frame_images(self, kind, img, K4, imgR=None, depth=None, dist=(0, 0, 0, 0), bf=40.0, th_depth=35.0, nfeatures=1000,
-                     scale_factor=1.2, nlevels=8, ini=20, mn=7, sys=0):
+                     scale_factor=1.2, nlevels=8, ini=20, mn=7, sys=0, mb_before=0.0):
         img = np.ascontiguousarray(img, np.uint8); h, w = img.shape
         r = None if imgR is None else np.ascontiguousarray(imgR, np.uint8)
         dm = None if depth is None else _f(depth)
         d = _f(dist)
         return self.L.rs_frame_images(self.h, sys, kind, _p(img), _p(r), _p(dm), w, h, _p(_f(K4)), _p(d), len(d), C.c_float(bf),
-                                      C.c_float(th_depth), nfeatures, C.c_float(scale_factor), nlevels, ini, mn)
+                                      C.c_float(th_depth), nfeatures, C.c_float(scale_factor), nlevels, ini, mn, C.c_float(mb_before))
 
     def frame_n(self, f):
         return self.L.rs_frame_n(self.h, f)

@@ -8,9 +8,11 @@
 // KeyFrames and MapPoints. System* is only ever a map key in the reference (MapPoint::mbTrackInView[pSystem] ...), so
 // small integers stand in for it. slam_preamble.h (force-included) turns `private` into `public` for the reference
 // headers so that members can be filled from arrays; no reference line is changed.
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <new>
 #include <set>
 #include <vector>
 
@@ -144,7 +146,7 @@ int rs_frame_arrays(void* h, int sys, int n, const float* kps6, const uint8_t* d
 // depth = float image). The extractor(s) are the reference's ORBextractor.
 int rs_frame_images(void* h, int sys, int kind, const uint8_t* img, const uint8_t* imgR, const float* depth, int width, int height,
                     const float* K4, const float* dist, int ndist, float bf, float th_depth, int nfeatures, float scale_factor,
-                    int nlevels, int ini_th, int min_th) {
+                    int nlevels, int ini_th, int min_th, float mb_before) {
     World* w = (World*)h;
     ORBextractor* exL = new ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th);
     ORBextractor* exR = kind == 1 ? new ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th) : nullptr;
@@ -158,7 +160,14 @@ int rs_frame_images(void* h, int sys, int kind, const uint8_t* img, const uint8_
     if (kind == 0) F = new Frame(sys_token(sys), im, ts, exL, &w->voc, K, D, bf, th_depth);
     else if (kind == 1) {
         cv::Mat imr(height, width, CV_8U, (void*)imgR, (size_t)width);
-        F = new Frame(sys_token(sys), im, imr, ts, exL, exR, &w->voc, K, D, bf, th_depth);
+        // The stereo constructor runs ComputeStereoMatches (which reads mb: minZ = mb, maxD = mbf/minZ, src/Frame.cc:489-491)
+        // BEFORE it assigns mb = mbf/fx (src/Frame.cc:114), and no initialiser touches mb: the reference matches with whatever
+        // the object's memory held - in the running system the previous frame's baseline. The object is therefore built in
+        // memory that already holds `mb_before`, which makes that quirk an explicit input.
+        void* mem = ::operator new(sizeof(Frame));
+        std::memset(mem, 0, sizeof(Frame));
+        *reinterpret_cast<float*>(static_cast<char*>(mem) + offsetof(Frame, mb)) = mb_before;
+        F = new (mem) Frame(sys_token(sys), im, imr, ts, exL, exR, &w->voc, K, D, bf, th_depth);
     } else {
         cv::Mat dm(height, width, CV_32F, (void*)depth, (size_t)width * 4);
         F = new Frame(sys_token(sys), im, dm, ts, exL, &w->voc, K, D, bf, th_depth);

@@ -210,7 +210,9 @@ struct MatExpr {
                     m.at<float>(y, x) = r;
                 }
         } else {
-            assert(a.mtype == CV_32F && b.mtype == CV_32F);
+            // a transposed SECOND operand (A*B.t()) takes another OpenCV kernel that is not modelled: no compiled reference
+            // file uses it, so it is refused rather than guessed
+            if (a.mtype != CV_32F || b.mtype != CV_32F || (flags & cvprim::GEMM_B_T)) { std::cerr << "cvshim: unsupported gemm form\n"; std::abort(); }
             const int mr = (flags & cvprim::GEMM_A_T) ? a.cols : a.rows, nc = (flags & cvprim::GEMM_B_T) ? b.rows : b.cols;
             m.create(mr, nc, CV_32F);
             cvprim::gemm32f((const float*)a.data, a.rows, a.cols, a.step / 4, (const float*)b.data, b.rows, b.cols, b.step / 4, alpha,

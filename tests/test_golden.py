@@ -55,3 +55,23 @@ def test_cuda_knn2_reproduces_golden():
     z = np.load(os.path.join(GOLD, "knn2_500x700.npz"))
     idx, d1, d2 = ORBmatcher().knn2(z["A"], z["B"])
     assert np.array_equal(idx, z["idx"]) and np.array_equal(d1, z["best"]) and np.array_equal(d2, z["second"])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_oracle_reproduces_guided_reference_golden(seed):
+    """tests/golden/guided_reference_seed*.npz: the nine guided searches + Frame::isInFrustum as computed by the reference's
+    own ORBmatcher.cc / Frame.cc (oracle/_ref/libref_slam.so) - the oracle restatements must reproduce them."""
+    import guided_scenario as G
+    z = np.load(os.path.join(GOLD, "guided_reference_seed%d.npz" % seed))
+    views, shift, scale = G.extract_pair_cpu(seed)
+    assert np.array_equal(views[0][0].view(np.uint32), z["k0"].view(np.uint32)) and tuple(z["shift"]) == tuple(shift)
+    sc = G.make_scenario(seed, views, shift, scale)
+    want = G.oracle_results(sc)
+    for i in range(16):
+        assert np.array_equal(want[i], z["r%02d" % i]), G.NAMES[i]
+    for i in range(5):
+        assert np.array_equal(want[19 + i], z["t%02d" % i]), G.NAMES[19 + i]
+    fr, alive = sc["frustum"], sc["frustum"]["alive"].astype(bool)
+    assert np.array_equal(z["frustum"][:, 0] != 0, alive)
+    for col, key in ((1, "u"), (2, "v"), (3, "ur"), (5, "view_cos")):
+        assert np.array_equal(z["frustum"][alive, col].view(np.uint32), fr[key][alive].view(np.uint32)), key

@@ -76,6 +76,18 @@ def run_case(tmp, seed, exe=None, views=None):
     assert len(got) == len(want) == len(NAMES)
     for name, g, w in zip(NAMES, got, want):
         assert np.array_equal(g, w), (name, g[:20], w[:20])
+    # ... and against what the reference's OWN ORBmatcher produced on this scenario (tests/golden/guided_reference_seed*.npz,
+    # frozen by tools/make_golden.py from oracle/_ref/libref_slam.so). Search 7, Fuse(KF, vpMapPoints), edits the map graph
+    # through MapPoint::Replace / AddObservation; the driver's stand-in graph types only log those calls, so its slot map is
+    # compared with the oracle above and the reference's graph state with the oracle in test_oracle_vs_reference_matcher.py.
+    gold = os.path.join(ROOT, "tests", "golden", "guided_reference_seed%d.npz" % seed)
+    if os.path.exists(gold):
+        z = np.load(gold)
+        assert np.array_equal(z["k0"].view(np.uint32), sc["k"][0].view(np.uint32)) and np.array_equal(z["k1"].view(np.uint32), sc["k"][1].view(np.uint32))
+        ref = [z["r%02d" % i] for i in range(16)] + [None] * 3 + [z["t%02d" % i] for i in range(5)]
+        for name, g, r in zip(NAMES, got, ref):
+            if r is not None:
+                assert np.array_equal(g, r), ("vs reference golden", name, g[:20], r[:20])
     return dict(zip(NAMES, want))
 
 

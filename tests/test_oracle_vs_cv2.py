@@ -80,3 +80,33 @@ def test_fast_atan2_matches_cv2():
 def test_round_half_even_matches_cvround():
     for v in [0.5, 1.5, 2.5, -0.5, -1.5, 3.4999, 17.5, -17.5]:
         assert O.lib().orc_round(v) == int(np.rint(np.float32(v)))
+
+
+# ---- the float cv::Mat arithmetic of the stand-in the reference's matcher / Frame code is compiled against -------------
+def test_shim_matrix_expressions_match_cv2():
+    """oracle/cvprim_mat.h (used by oracle/shim's MatExpr model): gemm in the shapes the reference uses - Rcw*P+tcw,
+    -R.t()*t, s*R products, 4x4 poses - cv::norm, and cv::undistortPoints with the TUM1 / 4-coefficient distortions."""
+    import ref_slam as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref_slam.so not built")
+    rng = np.random.default_rng(0)
+    f = np.float32
+    for _ in range(2000):
+        A = rng.normal(0, 1, (3, 3)).astype(f); x = rng.normal(0, 5, (3, 1)).astype(f); t = rng.normal(0, 2, (3, 1)).astype(f)
+        B = rng.normal(0, 1, (3, 3)).astype(f)
+        assert np.array_equal(cv2.gemm(A, x, 1.0, t, 1.0), R.gemm32f(A, x, 1.0, t, 1.0))
+        assert np.array_equal(cv2.gemm(A, t, -1.0, None, 0.0, flags=cv2.GEMM_1_T), R.gemm32f(A, t, -1.0, None, 0.0, 1))
+        assert np.array_equal(cv2.gemm(A, B, 1.0, None, 0.0), R.gemm32f(A, B))
+        assert np.array_equal(cv2.gemm(A, x, -1.0, None, 0.0), R.gemm32f(A, x, -1.0))
+        T = rng.normal(0, 1, (4, 4)).astype(f); c = rng.normal(0, 1, (4, 1)).astype(f)
+        assert np.array_equal(cv2.gemm(T, c, 1.0, None, 0.0), R.gemm32f(T, c))
+        assert np.array_equal(cv2.gemm(T, T.copy(), 1.0, None, 0.0), R.gemm32f(T, T))
+        assert R.norm_l2(x) == cv2.norm(x)
+    K = np.array([[517.306408, 0, 318.643040], [0, 516.469215, 255.313989], [0, 0, 1]], f)
+    pts = np.stack([rng.uniform(-5, 645, 4000), rng.uniform(-5, 485, 4000)], 1).astype(f)
+    pts[:4] = [[0, 0], [640, 0], [0, 480], [640, 480]]
+    for d in ([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], [0.1, 0, 0, 0]):
+        d = np.array(d, f)
+        want = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, d, None, K).reshape(-1, 2)
+        assert np.array_equal(R.undistort_points(pts, K, d).view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(O.undistort_points(pts[:300], K, d).view(np.uint32), want[:300].view(np.uint32))

@@ -9,6 +9,7 @@ import pytest
 import guided_scenario as G
 import oracle_lib as O
 import ref_slam as R
+from guided_reference import RefScene, fuse_graph_model, reference_results
 from multiagent_orb_slam2_b200 import synth
 
 pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_slam.so not built (reference tree absent)")
@@ -18,144 +19,6 @@ W, H = G.W, G.H
 
 def bits(a):
     return np.ascontiguousarray(a, f32).view(np.uint32)
-
-
-class RefScene:
-    """The scenario of guided_scenario.make_scenario as the reference's own objects: two Frames / KeyFrames with poses,
-    associations and feature vectors, and the map points with their descriptors, normals, distance ranges, observation
-    counts and bad flags."""
-
-    def __init__(self, sc, kf_views=(0, 1)):
-        cam = sc["cam"]
-        self.sc = sc
-        w = self.w = R.World()
-        K4 = [cam["fx"], cam["fy"], cam["cx"], cam["cy"]]
-        self.f = [w.frame_arrays(sc["k"][v], sc["d"][v], K4, W, H, uright=sc["uright"][v], bf=float(cam["bf"]), Tcw=sc["T"][v]) for v in range(2)]
-        self.kf = [w.keyframe(self.f[v]) if v in kf_views else None for v in range(2)]
-        ref = self.kf[kf_views[0]]
-        nmp = len(sc["pos"])
-        for i in range(nmp):
-            m = w.mappoint(sc["pos"][i], ref)
-            assert m == i
-            w.mp_set(m, desc=sc["mdesc"][i], normal=sc["nrm"][i], min_max=(sc["min_d"][i], sc["max_d"][i]), n_obs=sc["nobs"][i], bad=sc["bad"][i])
-        for v in range(2):
-            w.frame_set_featvec(self.f[v], sc["fv"][v])
-            if self.kf[v] is not None:
-                w.kf_set_featvec(self.kf[v], sc["fv"][v])
-
-    def hold(self, v, frame=True, kf=True, observe=False):
-        """view v's keypoints hold the scenario's associations (Frame::mvpMapPoints / KeyFrame::mvpMapPoints)."""
-        a = self.sc["assoc"][v]
-        if frame:
-            self.w.frame_set_mappoints(self.f[v], a)
-        if kf and self.kf[v] is not None:
-            self.w.kf_set_mappoints(self.kf[v], a)
-            if observe:
-                for idx in np.flatnonzero(a >= 0):
-                    self.w.mp_set_observation(int(a[idx]), self.kf[v], int(idx))
-
-
-def reference_results(sc):
-    """The list guided_scenario.oracle_results produces, computed by the reference's ORBmatcher on the reference's objects."""
-    TH = G.TH
-    nmp = len(sc["pos"])
-    assoc0, assoc1 = sc["assoc"]
-    res = []
-    # 1. a-10: Frame::isInFrustum for every point, then SearchByProjection(F, vpMapPoints, th)
-    s = RefScene(sc); s.hold(1)
-    fr = np.stack([s.w.is_in_frustum(s.f[1], m, 0.5) for m in range(nmp)])
-    nm = s.w.search_by_projection_local(s.f[1], np.arange(nmp), float(TH[0]), 0.8)
-    res += [[nm], s.w.frame_get_mappoints(s.f[1])]
-    frustum = fr
-    # 2. a-11 stereo / mono
-    for mono in (False, True):
-        s = RefScene(sc); s.hold(0); s.hold(1)
-        s.w.frame_set_outliers(s.f[0], sc["outlier0"])
-        nm = s.w.search_by_projection_last(s.f[1], s.f[0], float(TH[1]), mono, 0.9, True)
-        res += [[nm], s.w.frame_get_mappoints(s.f[1])]
-    # 3. a-12 (Cur, KF, sAlreadyFound, th, ORBdist)
-    s = RefScene(sc); s.hold(0); s.hold(1)
-    nm = s.w.search_by_projection_kf(s.f[1], s.kf[0], np.flatnonzero(sc["found"]), float(TH[2]), 64, 0.9, True)
-    res += [[nm], s.w.frame_get_mappoints(s.f[1])]
-    # 4. a-12 (KF, Scw, vpPoints, vpMatched, th)
-    s = RefScene(sc); s.hold(1)
-    nm, matched = s.w.search_by_projection_sim3(s.kf[1], sc["Scw"], np.arange(nmp), assoc1, int(TH[3]))
-    res += [[nm], matched]
-    # 5. a-13 (KF, F)
-    s = RefScene(sc); s.hold(0)
-    nm, out = s.w.search_by_bow_kf_f(s.kf[0], s.f[1], 0.75, True)
-    res += [[nm], out]
-    # 6. a-14
-    for only in (False, True):
-        s = RefScene(sc); s.hold(0); s.hold(1)
-        pairs = s.w.search_for_triangulation(s.kf[0], s.kf[1], sc["F12"], only, 0.6, False)
-        res += [[len(pairs)], np.array(pairs, np.int32).reshape(-1)]
-    # 7. Fuse(KF, vpMapPoints, th): compared through the graph state it leaves (see test below)
-    s = RefScene(sc); s.hold(1, observe=True)
-    nf = s.w.fuse(s.kf[1], np.arange(nmp), float(TH[4]))
-    state = [s.w.mp_get(m) for m in range(nmp)]
-    fuse = dict(n=nf, held=s.w.kf_get_mappoints(s.kf[1], len(assoc1)), bad=np.array([x["bad"] for x in state]),
-                nobs=np.array([x["n_obs"] for x in state]), replaced=np.array([s.w.mp_replaced(m) for m in range(nmp)]))
-    # 8. Fuse(KF, Scw, vpPoints, th, vpReplacePoint)
-    s = RefScene(sc); s.hold(1, observe=True)
-    nf, repl = s.w.fuse_sim3(s.kf[1], sc["Scw"], np.arange(nmp), float(TH[5]))
-    res8 = [[nf], repl, s.w.kf_get_mappoints(s.kf[1], len(assoc1))]
-    # 9. SearchBySim3 (vbAlreadyMatched2 comes from MapPoint::GetIndexInKeyFrame: the points need their observations)
-    s = RefScene(sc); s.hold(0); s.hold(1, observe=True)
-    n0 = len(assoc0)
-    m12 = np.full(n0, -1, np.int32)
-    where1 = {int(m): j for j, m in enumerate(assoc1) if m >= 0}
-    for i in range(0, n0, 17):
-        if assoc0[i] >= 0 and int(assoc0[i]) in where1:
-            m12[i] = assoc0[i]
-    sim = sc["sim"]
-    nf, mm = s.w.search_by_sim3(s.kf[0], s.kf[1], m12, float(sim[0]), sim[1:10], sim[10:13], float(TH[6]))
-    res9 = [[nf], mm]
-    return [np.asarray(r, np.int32) for r in res], fuse, [np.asarray(r, np.int32) for r in res8 + res9], frustum
-
-
-def fuse_graph_model(sc, best):
-    """What the reference's graph calls inside Fuse(KF, vpMapPoints, th) (src/ORBmatcher.cc:950-969) do to the scene of
-    RefScene.hold(1, observe=True), where every map point is observed by at most the target keyframe:
-    MapPoint::AddObservation (+2 observations on a stereo keypoint, src/MapPoint.cc:102-113), KeyFrame::AddMapPoint,
-    MapPoint::Replace (src/MapPoint.cc:181-221: the replaced point turns bad and hands its keyframe slot over)."""
-    assoc1 = sc["assoc"][1]
-    held, nob, bad = assoc1.copy(), sc["nobs"].copy(), sc["bad"].copy()
-    nmp = len(sc["pos"])
-    replaced = np.full(nmp, -1, np.int32)
-    observed_at = {int(m): int(j) for j, m in enumerate(assoc1) if m >= 0}   # mObservations[kf1]
-    stereo = sc["uright"][1] >= 0
-    nf = 0
-
-    def replace(this, by):   # this->Replace(by)
-        bad[this] = True
-        replaced[this] = by
-        if this in observed_at:
-            j = observed_at.pop(this)
-            if by not in observed_at:
-                held[j] = by
-                observed_at[by] = j
-                nob[by] += 2 if stereo[j] else 1
-            else:
-                held[j] = -1
-
-    for i in range(nmp):
-        if best[i] < 0:
-            continue
-        j = int(best[i])
-        other = int(held[j])
-        if other >= 0:
-            if not bad[other]:
-                if nob[other] > nob[i]:
-                    replace(i, other)
-                else:
-                    replace(other, i)
-        else:
-            observed_at[i] = j
-            nob[i] += 2 if stereo[j] else 1
-            held[j] = i
-        nf += 1
-    return dict(n=nf, held=held, bad=bad, nobs=nob, replaced=replaced)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
@@ -200,3 +63,225 @@ def test_oracle_equals_reference_guided_searches(seed):
     for key, least in [("a10 n", 100), ("a11 stereo n", 50), ("a11 mono n", 50), ("a12 cur-kf n", 50), ("a12 kf-scw n", 30), ("bow n", 50),
                        ("tri n", 10), ("fuse n", 30), ("fuse-scw n", 30), ("sim3 n", 10)]:
         assert counts[key][0] >= least, (key, counts[key][0])
+
+
+# ---- Frame frontend: constructors on images, grid, GetFeaturesInArea, UndistortKeyPoints, stereo, RGB-D ---------------
+TUM1 = dict(K=[517.306408, 516.469215, 318.643040, 255.313989], dist=[0.262383, -0.953104, -0.005358, 0.002628, 1.163314])  # TUM1.yaml
+KITTI = dict(K=[718.856, 718.856, 607.1928, 185.2157], bf=386.1448)                                                        # KITTI00-02.yaml
+
+
+def _keys6(fr):
+    return fr["kps"]
+
+
+@pytest.mark.parametrize("kind,seed", [("blocks", 3), ("blurnoise", 4)])
+def test_mono_frame_constructor_grid_and_features_in_area(kind, seed):
+    """Frame(mono) on an image (src/Frame.cc:174-228): keypoints / descriptors == oracle extractor, the 64 x 48 grid ==
+    OracleFrame's, GetFeaturesInArea == features_in_area (same indices, same order) incl. the level filters."""
+    img = synth.image(kind, W, H, seed)
+    w = R.World()
+    f = w.frame_images(0, img, TUM1["K"])
+    got = w.frame_get(f)
+    k, d = O.OracleExtractor(1000, 1.2, 8, 20, 7)(img)
+    assert np.array_equal(bits(got["kps"]), bits(k)) and np.array_equal(got["desc"], d)
+    assert np.array_equal(bits(got["un"]), bits(k[:, :2]))            # no distortion: mvKeysUn = mvKeys
+    assert np.all(got["uright"] == -1) and np.all(got["depth"] == -1)
+    F = O.OracleFrame(k, d, W, H)
+    counts, items = w.frame_grid(f)
+    want_items = [i for ix in range(64) for iy in range(48) for i in F.grid[ix][iy]]
+    assert counts.tolist() == [[len(F.grid[ix][iy]) for iy in range(48)] for ix in range(64)]
+    assert items.tolist() == want_items and len(want_items) > 900
+    rng = np.random.default_rng(seed)
+    nonempty = 0
+    for _ in range(300):
+        x, y = f32(rng.uniform(-30, W + 30)), f32(rng.uniform(-30, H + 30))
+        r = f32(rng.choice([3.0, 7.5, 15.0, 40.0, 100.0, 700.0]))
+        lo, hi = [(-1, -1), (0, 0), (2, 3), (0, 4), (3, -1), (-1, 2)][rng.integers(0, 6)]
+        a = w.frame_features_in_area(f, x, y, r, lo, hi)
+        assert a == F.features_in_area(x, y, r, lo, hi)
+        nonempty += len(a) > 0
+    assert nonempty > 100
+    # KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:589-628): same cells, no level filter
+    kf = w.keyframe(f)
+    for _ in range(100):
+        x, y, r = f32(rng.uniform(0, W)), f32(rng.uniform(0, H)), f32(rng.choice([4.0, 20.0, 90.0]))
+        assert w.kf_features_in_area(kf, x, y, r) == F.features_in_area(x, y, r)
+
+
+def test_undistort_keypoints_and_image_bounds_with_tum1_distortion():
+    """Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:404-464) with the TUM1 distortion: the reference run on
+    the cv2-pinned undistortPoints stand-in == oracle restatement == cv2 itself; the grid then uses the undistorted
+    bounds."""
+    cv2 = pytest.importorskip("cv2")
+    img = synth.image("blocks", W, H, 5)
+    w = R.World()
+    f = w.frame_images(0, img, TUM1["K"], dist=TUM1["dist"])
+    got = w.frame_get(f)
+    k, d = O.OracleExtractor(1000, 1.2, 8, 20, 7)(img)
+    K = np.array([[TUM1["K"][0], 0, TUM1["K"][2]], [0, TUM1["K"][1], TUM1["K"][3]], [0, 0, 1]], f32)
+    dist = np.array(TUM1["dist"], f32)
+    un = O.undistort_points(k[:, :2], K, dist)
+    assert np.array_equal(bits(got["un"]), bits(un))
+    assert np.array_equal(bits(un), bits(cv2.undistortPoints(k[:, :2].reshape(-1, 1, 2).copy(), K, dist, None, K).reshape(-1, 2)))
+    assert np.abs(un - k[:, :2]).max() > 1.0                           # the distortion is not a no-op
+    b = w.frame_bounds(f)
+    want = O.image_bounds(W, H, K, dist)
+    assert np.array_equal(bits(b[:4]), bits(want))
+    Fo = O.OracleFrame(np.concatenate([un, k[:, 2:]], 1), d, W, H, bounds=want)
+    counts, items = w.frame_grid(f)
+    assert items.tolist() == [i for ix in range(64) for iy in range(48) for i in Fo.grid[ix][iy]]
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        x, y, r = f32(rng.uniform(-20, W + 20)), f32(rng.uniform(-20, H + 20)), f32(rng.choice([5.0, 30.0, 120.0]))
+        assert w.frame_features_in_area(f, x, y, r, 0, 3) == Fo.features_in_area(x, y, r, 0, 3)
+
+
+@pytest.mark.parametrize("wd,ht,nf,kind,seed", [(1241, 376, 2000, "blocks", 0), (752, 480, 1200, "blocks", 1), (640, 480, 1000, "blurnoise", 2)])
+def test_stereo_frame_constructor_equals_oracle(wd, ht, nf, kind, seed):
+    """Frame(stereo) (src/Frame.cc:61-117): two extractor threads + ComputeStereoMatches (466-640). mvuRight / mvDepth bit
+    patterns == oracle stereo_match (which the CUDA stereo kernel is tested against)."""
+    left, right = synth.stereo_pair(kind, wd, ht, seed)
+    mbf, fx = f32(KITTI["bf"]), f32(KITTI["K"][0])
+    mb = f32(mbf / fx)
+    w = R.World()
+    f = w.frame_images(1, left, KITTI["K"], imgR=right, bf=float(mbf), nfeatures=nf, mb_before=float(mb))
+    got = w.frame_get(f)
+    oL, oR = O.OracleExtractor(nf, 1.2, 8, 20, 7), O.OracleExtractor(nf, 1.2, 8, 20, 7)
+    kL, dL = oL(left)
+    oR(right)
+    ou, od, kept = O.stereo_match(oL, oR, mbf, mb)
+    assert np.array_equal(bits(got["kps"]), bits(kL)) and np.array_equal(got["desc"], dL)
+    assert np.array_equal(bits(got["uright"]), bits(ou)) and np.array_equal(bits(got["depth"]), bits(od))
+    assert kept == int((got["depth"] > 0).sum()) and kept > 100
+
+
+def test_rgbd_frame_constructor_equals_restatement():
+    """Frame(RGB-D) (src/Frame.cc:119-172) -> ComputeStereoFromRGBD (643-664), with distortion so that kp and kpU differ."""
+    rng = np.random.default_rng(4)
+    img = synth.image("blocks", W, H, 90)
+    depth = rng.uniform(0.3, 8.0, (H, W)).astype(f32)
+    depth[rng.random((H, W)) < 0.2] = 0.0
+    depth[rng.random((H, W)) < 0.02] = -1.0
+    for dist in ([0, 0, 0, 0], TUM1["dist"]):
+        w = R.World()
+        f = w.frame_images(2, img, TUM1["K"], depth=depth, dist=dist, bf=40.0)
+        got = w.frame_get(f)
+        ur, dz = O.stereo_from_rgbd(got["kps"], got["un"], depth, 40.0)
+        assert np.array_equal(bits(got["uright"]), bits(ur)) and np.array_equal(bits(got["depth"]), bits(dz))
+        assert 0.6 < (dz > 0).mean() < 0.9
+
+
+# ---- the two searches that are not part of the guided scenario -------------------------------------------------------
+@pytest.mark.parametrize("seed,window,ratio,ori", [(0, 100, 0.9, True), (1, 30, 0.9, True), (2, 100, 0.7, False), (3, 10, 0.9, True)])
+def test_oracle_equals_reference_search_for_initialization(seed, window, ratio, ori):
+    views, _, _ = G.extract_pair_cpu(seed + 20)
+    (k0, d0), (k1, d1) = views
+    w = R.World()
+    f0, f1 = (w.frame_arrays(k, d, TUM1["K"], W, H) for k, d in views)
+    F0, F1 = O.OracleFrame(k0, d0, W, H), O.OracleFrame(k1, d1, W, H)
+    prev = k0[:, :2].copy()
+    for _ in range(2):   # the second call starts from the updated vbPrevMatched, like consecutive initialisation attempts
+        want_prev = prev.copy()
+        wn, wm = O.search_for_initialization(F0, F1, want_prev, window, ratio, ori)
+        gn, gm, got_prev = w.search_for_initialization(f0, f1, prev, window, ratio, ori)
+        assert gn == wn and np.array_equal(gm, wm) and np.array_equal(bits(got_prev), bits(want_prev))
+        prev = want_prev
+    assert wn > (20 if window >= 30 else 3)
+
+
+@pytest.mark.parametrize("seed,ratio,ori", [(0, 0.75, True), (1, 0.75, False), (2, 0.9, True)])
+def test_oracle_equals_reference_search_by_bow_kf_kf(seed, ratio, ori):
+    """SearchByBoW(KF1, KF2) (src/ORBmatcher.cc:524-657), the matcher of MapFusion::ComputeSim3 / CovisibilityDiscovery
+    (src/MapFusion.cc:275, 849)."""
+    views, shift, scale = G.extract_pair_cpu(seed + 30)
+    sc = G.make_scenario(seed + 30, views, shift, scale)
+    s = RefScene(sc); s.hold(0); s.hold(1)
+    assoc0, assoc1 = sc["assoc"]
+    gn, gm = s.w.search_by_bow_kf_kf(s.kf[0], s.kf[1], len(assoc0), ratio, ori)
+    v0 = (assoc0 >= 0) & ~sc["bad"][np.maximum(assoc0, 0)]
+    v1 = (assoc1 >= 0) & ~sc["bad"][np.maximum(assoc1, 0)]
+    wn, wm = O.search_by_bow_kf_kf(sc["d"][0], sc["fv"][0], v0, sc["k"][0][:, 3], sc["d"][1], sc["fv"][1], v1, sc["k"][1][:, 3], ratio, ori)
+    assert gn == wn and np.array_equal(gm, np.where(wm >= 0, assoc1[np.maximum(wm, 0)], -1))
+    assert wn >= 10
+
+
+def test_oracle_equals_reference_distinctive_descriptor():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:246-311). The reference walks its observations in
+    std::map<KeyFrame*, size_t> order, i.e. by heap address; ties between medians are therefore allocator dependent, so
+    the check is: the chosen descriptor attains the least median, and equals the oracle's choice when that is unique."""
+    rng = np.random.default_rng(7)
+    w = R.World()
+    kfs, descs = [], []
+    base = synth.descriptors(1, 3)[0]
+    for i in range(12):
+        n = 3
+        k = np.zeros((n, 6), f32); k[:, 0] = 100 + 10 * np.arange(n); k[:, 1] = 100; k[:, 2] = 31
+        b = np.unpackbits(np.tile(base, (n, 1)), axis=1)
+        for r in range(n):
+            b[r, rng.choice(256, rng.integers(0, 60), replace=False)] ^= 1
+        d = np.packbits(b, axis=1)
+        kfs.append(w.keyframe(w.frame_arrays(k, d, TUM1["K"], W, H)))
+        descs.append(d)
+    unique = 0
+    for n_obs in (1, 2, 3, 4, 7, 12):
+        m = w.mappoint([0, 0, 5], kfs[0])
+        rows = []
+        for j in range(n_obs):
+            idx = int(rng.integers(0, 3))
+            w.observe(m, kfs[j], idx)
+            rows.append(descs[j][idx])
+        w.mp_compute_distinctive(m)
+        got = w.mp_get(m)["desc"]
+        rows = np.array(rows)
+        med = [sorted(0 if a == b2 else O.hamming(rows[a], rows[b2]) for b2 in range(n_obs))[int(0.5 * (n_obs - 1))] for a in range(n_obs)]
+        winners = [a for a in range(n_obs) if med[a] == min(med)]
+        assert any(np.array_equal(got, rows[a]) for a in winners)
+        if len(winners) == 1:
+            assert np.array_equal(got, rows[O.distinctive_descriptor(rows)])
+            unique += 1
+    assert unique >= 3
+
+
+# ---- KeyFrameDatabase (SURVEY section 8f-4) ----------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,n_kf", [(0, 400), (1, 120)])
+def test_oracle_equals_reference_keyframe_database(tmp_path, seed, n_kf):
+    """KeyFrameDatabase::add / erase / DetectLoopCandidates (src/KeyFrameDatabase.cc:40-197) on the reference's own
+    KeyFrame covisibility graph, against oracle_lib.detect_loop_candidates (which the CUDA database is tested against)."""
+    from test_kfdb import bow_vectors
+    rng = np.random.default_rng(seed)
+    voc = synth.vocabulary(10, 4, seed=3)
+    path = str(tmp_path / "voc.txt")
+    synth.write_vocabulary_text(path, voc)
+    w = R.World(path)
+    n_words = 10 ** 4
+    vecs, _ = bow_vectors(rng, n_kf + 6, n_words)
+    k1 = np.array([[50, 50, 31, 0, 20, 0]], f32); d1 = np.zeros((1, 32), np.uint8)
+    kfs = []
+    for ids, wt in vecs:
+        kf = w.keyframe(w.frame_arrays(k1, d1, TUM1["K"], W, H))
+        w.kf_set_bowvec(kf, ids, wt)
+        kfs.append(kf)
+    for kf in kfs[:n_kf]:
+        w.db_add(kf)
+    alive = np.ones(n_kf, bool)
+    for slot in rng.choice(n_kf, n_kf // 20, replace=False):
+        w.db_erase(int(slot)); alive[slot] = False
+    neigh = {}
+    for s in range(n_kf):
+        nb = [int(x) for x in rng.choice(np.delete(np.arange(n_kf), s), 10, replace=False)]
+        neigh[s] = nb
+        for rank, b in enumerate(nb):
+            w.kf_add_connection(s, b, 100 - rank)          # distinct weights: GetBestCovisibilityKeyFrames order = nb
+    hits = 0
+    for qi in range(n_kf, n_kf + 6):
+        q_ids, q_w = vecs[qi]
+        connected = set(int(x) for x in rng.choice(n_kf, 15, replace=False))
+        for c in connected:
+            w.kf_add_connection(qi, c, 20)
+        scores = sorted((O.l1_score(q_ids, q_w, *vecs[s]) for s in range(n_kf)), reverse=True)
+        min_score = 0.5 * float(scores[max(3, n_kf // 50)])
+        want = O.detect_loop_candidates(vecs[:n_kf], alive, q_ids, q_w, min_score, connected, lambda s: neigh[s])
+        got = w.db_detect_loop_candidates(qi, min_score)
+        assert got == want
+        hits += len(want) > 0
+    assert hits >= 4

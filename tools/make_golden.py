@@ -11,6 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402
 from multiagent_orb_slam2_b200 import synth  # noqa: E402
 
@@ -41,3 +42,22 @@ B[350] = B[3]
 idx, d1, d2 = O.knn2(A, B)
 np.savez_compressed(os.path.join(out, "knn2_500x700.npz"), A=A, B=B, idx=idx, best=d1, second=d2)
 print("knn2 fixture written")
+
+# The nine guided searches + Frame::isInFrustum of the reference's OWN ORBmatcher.cc / Frame.cc / KeyFrame.cc / MapPoint.cc
+# (oracle/_ref/libref_slam.so, compiled unmodified) on the scenario of tests/guided_scenario.py: the GPU box compares the
+# C++ facade with these.
+import guided_reference as GR  # noqa: E402
+import guided_scenario as G  # noqa: E402
+import ref_slam  # noqa: E402
+
+assert ref_slam.available(), "build oracle/_ref first (oracle/build_ref.sh)"
+for seed in (0, 1):
+    views, shift, scale = G.extract_pair_cpu(seed)
+    sc = G.make_scenario(seed, views, shift, scale)
+    res, fuse, tail, frustum = GR.reference_results(sc)
+    arrays = {"r%02d" % i: a for i, a in enumerate(res)}
+    arrays.update({"t%02d" % i: a for i, a in enumerate(tail)})
+    arrays.update({"fuse_" + k: np.asarray(v) for k, v in fuse.items()})
+    np.savez_compressed(os.path.join(out, "guided_reference_seed%d.npz" % seed), frustum=frustum, k0=views[0][0], k1=views[1][0],
+                        shift=np.array(shift), **arrays)
+    print("guided reference fixture", seed, [int(a[0]) for a in res[::2]])
