@@ -11,9 +11,16 @@ from . import _lib
 
 
 class DeviceFrameGrid:
-    def __init__(self, extractor, frame=0, min_x=0.0, min_y=0.0, max_x=None, max_y=None):
+    def __init__(self, extractor, frame=0, min_x=0.0, min_y=0.0, max_x=None, max_y=None, stream=None):
         """extractor: an ORBextractor whose last call produced `frame`; bounds default to the image
-        (mnMinX.. of an undistorted / rectified camera, src/Frame.cc:457-462)."""
+        (mnMinX.. of an undistorted / rectified camera, src/Frame.cc:457-462).
+
+        Stream ordering: the grid is built on `stream` (a raw cudaStream_t / torch.cuda.Stream; default: torch's current
+        stream on the extractor's device - never the legacy NULL stream, which the library's non-blocking streams are not
+        ordered against). The extraction that produced the keypoints must already be ordered before that stream: the
+        synchronous ORBextractor calls are; after an asynchronous launch (frontend.process_async) pass the stream the
+        extraction ran on, or make `stream` wait on its event first. Queries issued on any other stream wait for the
+        build through an event recorded here."""
         self.L = _lib.lib()
         self.ex = extractor
         h, w = extractor._shape
@@ -26,8 +33,24 @@ class DeviceFrameGrid:
         g = C.c_void_p()
         _lib.check(self.L.orbm_grid_create(extractor.device, cap, C.byref(g)))
         self._g = g
-        _lib.check(self.L.orbm_grid_build_device(g, C.c_void_p(self.d_kps), C.c_void_p(self.d_count), float(min_x), float(min_y),
-                                                 float(w if max_x is None else max_x), float(h if max_y is None else max_y), None))
+        with torch.cuda.device(self.dev):
+            if stream is None:
+                ts = torch.cuda.current_stream(self.dev)
+            elif isinstance(stream, torch.cuda.Stream):
+                ts = stream
+            else:
+                ts = torch.cuda.ExternalStream(int(stream), device=self.dev)
+            _lib.check(self.L.orbm_grid_build_device(g, C.c_void_p(self.d_kps), C.c_void_p(self.d_count), float(min_x), float(min_y),
+                                                     float(w if max_x is None else max_x), float(h if max_y is None else max_y),
+                                                     C.c_void_p(ts.cuda_stream)))
+            self._built = torch.cuda.Event()
+            self._built.record(ts)
+
+    def _query_stream(self):
+        """torch's current stream, ordered after the grid build."""
+        st = torch.cuda.current_stream(self.dev)
+        st.wait_event(self._built)
+        return C.c_void_p(st.cuda_stream)
 
     def close(self):
         if getattr(self, "_g", None):
@@ -51,7 +74,7 @@ class DeviceFrameGrid:
         tmin, tmax = t(min_level, np.int32), t(max_level, np.int32)
         out = [torch.empty(n, dtype=torch.int32, device=self.dev) for _ in range(5)]
         p = lambda z: C.c_void_p(z.data_ptr())
-        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        st = self._query_stream()
         _lib.check(self.L.orbm_window_knn2_device(self._g, C.c_void_p(self.d_desc), p(q), n, p(tx), p(ty), p(tr), p(tmin), p(tmax),
                                                   p(out[0]), p(out[1]), p(out[2]), p(out[3]), p(out[4]), st))
         torch.cuda.synchronize(self.dev)
@@ -67,7 +90,7 @@ class DeviceFrameGrid:
         tmin, tmax = t(min_level, np.int32), t(max_level, np.int32)
         cap = cap or 64 * n
         p = lambda z: C.c_void_p(z.data_ptr())
-        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        st = self._query_stream()
         while True:
             offs = torch.empty(n + 1, dtype=torch.int32, device=self.dev)
             cands = torch.empty(cap, dtype=torch.int32, device=self.dev)

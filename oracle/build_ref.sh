@@ -69,4 +69,18 @@ g++ -std=c++14 -O2 -march=x86-64-v3 -ffp-contract=off -fPIC -shared -w -pthread 
     "$ref/src/KeyFrameDatabase.cc" "$ref/src/ORBextractor.cc" \
     "$dbow/DBoW2/FORB.cpp" "$dbow/DBoW2/BowVector.cpp" "$dbow/DBoW2/FeatureVector.cpp" "$dbow/DBoW2/ScoringObject.cpp" \
     "$dbow/DUtils/Random.cpp" "$dbow/DUtils/Timestamp.cpp" "$here/ref_slam_wrap.cc" -o "$here/_ref/libref_slam.so"
+#   real_types_test         tests/cpp/real_types_test.cc: the PRODUCT's C++ facade templates (include/orbslam2_b200/ORBmatcher.h)
+#                            instantiated on the reference's own Frame / KeyFrame / MapPoint classes, beside the reference's
+#                            ORBmatcher on identical objects. Needs the reference headers, so it is built here and travels
+#                            to the GPU box as a binary; run by tests/test_gpu_real_types.py.
+repo="$(cd "$here/.." && pwd)"
+if [ -f "$repo/multiagent_orb_slam2_b200/lib/liborb_b200.so" ]; then
+  g++ -std=c++14 -O2 -march=x86-64-v3 -ffp-contract=off -w -pthread \
+      -include "$here/shim/slam_preamble.h" -I"$here/shim" -I"$ref/include" -I"$ref" -I"$repo/include" \
+      "$repo/tests/cpp/real_types_test.cc" -o "$here/_ref/real_types_test" \
+      -L"$here/_ref" -lref_slam -L"$repo/multiagent_orb_slam2_b200/lib" -lorb_b200 \
+      -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../multiagent_orb_slam2_b200/lib'
+else
+  echo "build_ref: liborb_b200.so not built yet, skipping real_types_test" >&2
+fi
 echo "build_ref: built $(ls "$here/_ref" | tr '\n' ' ')"

@@ -228,6 +228,12 @@ int rs_kf_features_in_area(void* h, int k, float x, float y, float r, int* out, 
     return (int)v.size();
 }
 
+// raw object pointers, for tests/cpp/real_types_test.cc (the product's facade templates instantiated on these types)
+void* rs_frame_ptr(void* h, int f) { return ((World*)h)->frames[f]; }
+void* rs_kf_ptr(void* h, int k) { return ((World*)h)->kfs[k]; }
+void* rs_mp_ptr(void* h, int m) { return ((World*)h)->mps[m]; }
+int rs_mp_id(void* h, void* p) { return ((World*)h)->id_of((MapPoint*)p); }
+
 // ---- bag of words ----------------------------------------------------------------------------------------------
 static int dump_bow(const DBoW2::BowVector& bv, const DBoW2::FeatureVector& fv, int* word_ids, double* word_w, int* node_ids,
                     int* node_off, int* feat, int* n_nodes) {

@@ -30,11 +30,12 @@ def test_facade_headers_compile(tmp_path):
 def oracle_init_search(a, b, nf, window):
     o = O.OracleExtractor(2 * nf, 1.2, 8, 20, 7)
     ka, da = o(a)
+    lvl3_a = o.level(3)["img"].copy()   # the oracle object holds frame b's pyramid after the next call
     kb, db = o(b)
     F1, F2 = O.OracleFrame(ka, da, a.shape[1], a.shape[0]), O.OracleFrame(kb, db, a.shape[1], a.shape[0])
     prev = ka[:, :2].copy()
     nm, m12 = O.search_for_initialization(F1, F2, prev, window, 0.9, True)
-    return o, ka, da, kb, db, nm, m12, prev
+    return lvl3_a, ka, da, kb, db, nm, m12, prev
 
 
 @pytest.mark.gpu
@@ -45,7 +46,7 @@ def test_cpp_facade_matches_oracle(tmp_path):
     pa, pb, out = [str(tmp_path / n) for n in ("a.raw", "b.raw", "out.bin")]
     a.tofile(pa); b.tofile(pb)
     print(subprocess.check_output([exe, str(w), str(h), pa, pb, out, str(nf)], text=True))
-    o, ka, da, kb, db, nm, m12, _ = oracle_init_search(a, b, nf, 100)
+    lvl3_a, ka, da, kb, db, nm, m12, _ = oracle_init_search(a, b, nf, 100)
     buf = open(out, "rb").read()
     pos = 0
 
@@ -62,7 +63,8 @@ def test_cpp_facade_matches_oracle(tmp_path):
         assert np.array_equal(take(np.uint8, 32 * n).reshape(n, 32), od)
         if k == 0:
             pw, ph = take(np.int32, 2)
-            assert np.array_equal(take(np.uint8, pw * ph).reshape(ph, pw), o.level(3)["img"]) or True  # oracle holds frame b now
+            assert (ph, pw) == lvl3_a.shape
+            assert np.array_equal(take(np.uint8, pw * ph).reshape(ph, pw), lvl3_a)   # mvImagePyramid[3] of frame a through the facade
     assert int(take(np.int32, 1)[0]) == nm
     n1 = int(take(np.int32, 1)[0])
     assert np.array_equal(take(np.int32, n1), m12)
@@ -222,3 +224,40 @@ def test_search_by_projection_frame_mappoints_matches_oracle(seed, th):
     gnm, gas = ORBmatcher(0.8).SearchByProjection_Frame_MapPoints(DeviceFrameGrid(ex_b), kb["octave"], uright, occupied, scale, mp, th)
     assert gnm == onm and np.array_equal(gas, oas)
     assert onm > 100
+
+
+@pytest.mark.gpu
+def test_device_grid_built_and_queried_on_a_side_stream_right_after_process_async():
+    """The grid build and the window queries run on torch's current stream (never the legacy NULL stream, which the
+    library's non-blocking streams are not ordered against): built under a side stream immediately after an asynchronous
+    frontend launch - no host synchronisation in between - the candidate lists must still be those of the finished
+    extraction; queries from a third stream wait for the build through its event."""
+    import torch
+    from multiagent_orb_slam2_b200.device_grid import DeviceFrameGrid
+    from multiagent_orb_slam2_b200.frontend import AgentFrontend
+    w, h = 640, 480
+    frames = []
+    for s in range(4):
+        a, b, _ = synth.shifted_pair("blocks", w, h, s + 60)
+        frames += [a, b]
+    imgs = torch.from_numpy(np.stack(frames)).pin_memory()
+    fe = AgentFrontend(w, h, max_batch=8)
+    o = O.OracleExtractor()
+    side, third = torch.cuda.Stream(), torch.cuda.Stream()
+    for rep in range(3):   # repeated so that a missing dependency would race against a busy device
+        with torch.cuda.stream(side):
+            fe.process_async(imgs)
+            grid = DeviceFrameGrid(fe.ex, frame=5)
+        k5, d5 = o(frames[5])
+        k4, d4 = o(frames[4])
+        qx, qy = k4[:, 0], k4[:, 1]
+        r = np.full(len(k4), 20.0, np.float32)
+        with torch.cuda.stream(third):
+            gi, g1, g2, _, _ = grid.window_knn2(d4, qx, qy, r)
+        F = O.OracleFrame(k5, d5, w, h)
+        for i in range(0, len(k4), 7):
+            cand = F.features_in_area(qx[i], qy[i], r[i])
+            ds = [O.hamming(d4[i], d5[j]) for j in cand]
+            want = (cand[int(np.argmin(ds))], min(ds)) if cand else (-1, 256)
+            assert (gi[i], g1[i]) == want, (rep, i)
+        grid.close()
