@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from guided_scenario import H, TH, W, f32, make_scenario, oracle_results
+from guided_scenario import H, NAMES, TH, W, f32, make_scenario, oracle_results
 from multiagent_orb_slam2_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
