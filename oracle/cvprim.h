@@ -94,24 +94,41 @@ static const int kGauss7[7] = {18, 34, 48, 56, 48, 34, 18};
 
 static inline void gaussian7x7_u8(const uint8_t* src, int w, int h, size_t sstride,
                                   uint8_t* dst, size_t dstride) {
-    std::vector<uint16_t> hbuf((size_t)w * h);
+    // horizontal pass into 16-bit rows (sum <= 255*256 fits), reflected indices only in the 3-pixel margins;
+    // vertical pass accumulates whole rows (tap-major), which the compiler vectorises
+    static thread_local std::vector<uint16_t> hbuf;
+    static thread_local std::vector<uint32_t> acc;
+    hbuf.resize((size_t)w * h);
+    acc.resize(w);
+    uint16_t* const hb = hbuf.data();   // thread_local: hoisted out of the loops
+    uint32_t* const ac = acc.data();
     for (int y = 0; y < h; ++y) {
         const uint8_t* p = src + (size_t)y * sstride;
-        for (int x = 0; x < w; ++x) {
+        uint16_t* o = hb + (size_t)y * w;
+        const int x_lo = w < 7 ? w : 3, x_hi = w < 7 ? w : w - 3;
+        for (int x = 0; x < x_lo; ++x) {
             int s = 0;
             for (int k = 0; k < 7; ++k) s += kGauss7[k] * p[reflect101(x + k - 3, w)];
-            hbuf[(size_t)y * w + x] = (uint16_t)s;
+            o[x] = (uint16_t)s;
+        }
+        for (int x = x_lo; x < x_hi; ++x)
+            o[x] = (uint16_t)(18 * (p[x - 3] + p[x + 3]) + 34 * (p[x - 2] + p[x + 2]) + 48 * (p[x - 1] + p[x + 1]) + 56 * p[x]);
+        for (int x = x_hi > x_lo ? x_hi : x_lo; x < w; ++x) {
+            int s = 0;
+            for (int k = 0; k < 7; ++k) s += kGauss7[k] * p[reflect101(x + k - 3, w)];
+            o[x] = (uint16_t)s;
         }
     }
     for (int y = 0; y < h; ++y) {
-        uint8_t* o = dst + (size_t)y * dstride;
-        const uint16_t* rows[7];
-        for (int k = 0; k < 7; ++k) rows[k] = &hbuf[(size_t)reflect101(y + k - 3, h) * w];
-        for (int x = 0; x < w; ++x) {
-            uint32_t s = 32768u;
-            for (int k = 0; k < 7; ++k) s += (uint32_t)kGauss7[k] * rows[k][x];
-            o[x] = (uint8_t)(s >> 16);
+        uint32_t* a = ac;
+        for (int x = 0; x < w; ++x) a[x] = 32768u;
+        for (int k = 0; k < 7; ++k) {
+            const uint16_t* r = hb + (size_t)reflect101(y + k - 3, h) * w;
+            const uint32_t c = (uint32_t)kGauss7[k];
+            for (int x = 0; x < w; ++x) a[x] += c * r[x];
         }
+        uint8_t* o = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x) o[x] = (uint8_t)(a[x] >> 16);
     }
 }
 
@@ -140,20 +157,27 @@ static const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1,
 // Largest threshold t (minus nothing) for which the pixel is a FAST-9 corner is score:
 // corner at threshold th  <=>  fast_score >= th. Returns -1 when no arc has a positive margin.
 static inline int fast_score(const uint8_t* p, size_t stride) {
-    int d[16];
+    int d[25];
     const int v = p[0];
     for (int k = 0; k < 16; ++k) d[k] = v - p[(std::ptrdiff_t)kRingDy[k] * (std::ptrdiff_t)stride + kRingDx[k]];
+    for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
+    // the arcs starting at k and k+1 share the 8 values d[k+1..k+8]: one pass over the even k covers all 16 arcs
     int best = 0;
-    for (int k = 0; k < 16; ++k) {
-        int mn = d[k], mx = d[k];
-        for (int j = 1; j < 9; ++j) {
-            const int e = d[(k + j) & 15];
+    for (int k = 0; k < 16; k += 2) {
+        int mn = d[k + 1], mx = d[k + 1];
+        for (int j = 2; j <= 8; ++j) {
+            const int e = d[k + j];
             mn = e < mn ? e : mn;
             mx = e > mx ? e : mx;
         }
         // all brighter-than-ring by mn, or all darker-than-ring by -mx
-        if (mn > best) best = mn;
-        if (-mx > best) best = -mx;
+        const int a = d[k], b = d[k + 9];
+        const int mn0 = a < mn ? a : mn, mn1 = b < mn ? b : mn;
+        const int mx0 = a > mx ? a : mx, mx1 = b > mx ? b : mx;
+        if (mn0 > best) best = mn0;
+        if (mn1 > best) best = mn1;
+        if (-mx0 > best) best = -mx0;
+        if (-mx1 > best) best = -mx1;
     }
     return best - 1;
 }
@@ -163,25 +187,65 @@ struct FastKp { int x, y, score; };
 // cv::FAST(img, kps, threshold, true) on a w x h image: corners with score >= threshold in the
 // interior [3,w-3)x[3,h-3), kept iff strictly greater than all 8 neighbours of the thresholded
 // score map (0 outside the interior / for non-corners). Output row-major.
+// Like OpenCV's FAST_t<16> the pixel is first put through the cheap necessary condition - an arc of 9 contiguous ring
+// pixels contains one pixel of every opposite pair (k, k+8), so for a corner at threshold t every pair must hold a pixel
+// brighter than v+t, or every pair one darker than v-t; pairs (0,8), (4,12), (2,10), (6,14) are tested - and only the
+// survivors (a few per cent) get the exact 16-arc score. The result is identical to scoring every pixel.
 static inline void fast9_nms(const uint8_t* img, int w, int h, size_t stride, int threshold,
                              std::vector<FastKp>& out) {
     out.clear();
     if (w < 7 || h < 7) return;
-    std::vector<int> sc((size_t)w * h, 0);
-    for (int y = 3; y < h - 3; ++y)
-        for (int x = 3; x < w - 3; ++x) {
-            const int s = fast_score(img + (size_t)y * stride + x, stride);
-            sc[(size_t)y * w + x] = s >= threshold ? s : 0;
+    static thread_local std::vector<int> sc;
+    sc.assign((size_t)w * h, 0);
+    int* const scp = sc.data();   // thread_local objects are reached through a call in a shared library: hoist
+    const std::ptrdiff_t st = (std::ptrdiff_t)stride;
+    const std::ptrdiff_t o0 = 3 * st, o8 = -3 * st, o4 = 3, o12 = -3, o2 = 2 * st + 2, o10 = -2 * st - 2, o6 = -2 * st + 2, o14 = 2 * st - 2;
+    static thread_local std::vector<uint8_t> weak;
+    weak.resize(w);
+    uint8_t* const wk = weak.data();
+    for (int y = 3; y < h - 3; ++y) {
+        const uint8_t* row = img + (size_t)y * stride;
+        int* srow = scp + (size_t)y * w;
+        // row-wide weak form of the first two pair tests (|v - p| > t for one pixel of the pair, either sign): a
+        // superset of the survivors, written so that the compiler vectorises it
+        {
+            const uint8_t *r0 = row + o0, *r8 = row + o8;
+            uint8_t* m = wk;
+            for (int x = 3; x < w - 3; ++x) {
+                const int v = row[x];
+                const int d0 = v - r0[x], d8 = v - r8[x], d4 = v - row[x + 3], d12 = v - row[x - 3];
+                const int a0 = d0 < 0 ? -d0 : d0, a8 = d8 < 0 ? -d8 : d8, a4 = d4 < 0 ? -d4 : d4, a12 = d12 < 0 ? -d12 : d12;
+                m[x] = (uint8_t)(((a0 > threshold) | (a8 > threshold)) & ((a4 > threshold) | (a12 > threshold)));
+            }
         }
+        for (int x = 3; x < w - 3; ++x) {
+            if (!wk[x]) continue;
+            const uint8_t* p = row + x;
+            const int hi = p[0] + threshold, lo = p[0] - threshold;
+            const int a = p[o0], b = p[o8];
+            int bright = (a > hi) | (b > hi), dark = (a < lo) | (b < lo);
+            const int c = p[o4], d = p[o12];
+            bright &= (c > hi) | (d > hi); dark &= (c < lo) | (d < lo);
+            if (!(bright | dark)) continue;
+            const int e = p[o2], f = p[o10];
+            bright &= (e > hi) | (f > hi); dark &= (e < lo) | (f < lo);
+            if (!(bright | dark)) continue;
+            const int g = p[o6], i = p[o14];
+            bright &= (g > hi) | (i > hi); dark &= (g < lo) | (i < lo);
+            if (!(bright | dark)) continue;
+            const int s = fast_score(p, stride);
+            if (s >= threshold) srow[x] = s;
+        }
+    }
     for (int y = 3; y < h - 3; ++y)
         for (int x = 3; x < w - 3; ++x) {
-            const int s = sc[(size_t)y * w + x];
+            const int s = scp[(size_t)y * w + x];
             if (s <= 0) continue;
             bool mx = true;
             for (int dy = -1; dy <= 1 && mx; ++dy)
                 for (int dx = -1; dx <= 1; ++dx) {
                     if (!dx && !dy) continue;
-                    if (sc[(size_t)(y + dy) * w + x + dx] >= s) { mx = false; break; }
+                    if (scp[(size_t)(y + dy) * w + x + dx] >= s) { mx = false; break; }
                 }
             if (mx) out.push_back({x, y, s});
         }
