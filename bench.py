@@ -188,11 +188,16 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    nccl_log = None
     if world > 1:
-        # keep NCCL's version banner / logging off stdout: the contract is ONE JSON line
-        os.environ.pop("NCCL_DEBUG", None)
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # NCCL's own log (communicator size, transport) is evidence of the N-rank run: INIT lines at INFO level, kept off
+        # stdout (the contract is ONE JSON line there): every rank logs to a file, rank 0 echoes its file to stderr
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        nccl_log = os.path.join(tempfile.gettempdir(), "orb_bench_nccl_%d_rank%d.log" % (os.getppid(), rank))
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()   # creates the communicator now, so that its INIT lines are in the log
     B = args.batch
     L = _lib.lib()
 
@@ -322,60 +327,102 @@ def run_b200(args):
                 "stages": per_stage}
 
     # ---- MapFusion cross-map matching (BASELINE config 5): G Hamming cmp/s over all ranks ------------------
+    # orbm_knn2_allgather (csrc/xmap.cu): the exchange is peer loads over NVLink inside the operand expansion, no collective
+    # library call on the data path; one map per rank (2 maps at N=1), and a second leg with 2 maps whose query rows are
+    # split over all N ranks.
     mapf = None
     if not args.no_mapfusion:
         from multiagent_orb_slam2_b200 import mapfusion, synth
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
         rows = args.map_rows
-        n_maps = max(2, world)
-        mine = [m for m in range(n_maps) if mapfusion.owner_of_map(m, world) == rank]
         base = synth.descriptors(rows, 4242)
-        local = [torch.from_numpy(synth.descriptors_fast(rows, 5000 + m, base, 60)).to(dev) for m in mine]
-        cm = mapfusion.CrossMapMatcher(rows, 0.75)
-        cm.match(local)  # warm-up (NCCL channels, kernel load)
-        barrier()
-        reps = 5
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(reps):
-            res, _cnt = cm.match(local)
-        g1.record()
-        barrier()
-        mf_ms = max_over_ranks(g0.elapsed_time(g1)) / reps
-        # the same step with the POPC kernel (north star: "popc-bound uint4-vectorised kernel"), one repetition
-        from multiagent_orb_slam2_b200 import _lib as _orb_lib
-        _orb_lib.check(_orb_lib.lib().orbm_set_knn2_backend(1))
-        cm.match(local)
-        barrier()
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        h0.record()
-        cm.match(local)
-        h1.record()
-        barrier()
-        popc_ms = max_over_ranks(h0.elapsed_time(h1))
-        _orb_lib.check(_orb_lib.lib().orbm_set_knn2_backend(0))
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        mapfusion.exchange(local, rows)
-        a1.record()
-        torch.cuda.synchronize(dev)
-        cmps = float(n_maps * (n_maps - 1)) * rows * rows
-        accepted = int(sum(int((v[3][:rows] >= 0).sum()) for v in res.values()))
         popc_roof = 148 * 16 * 1.965e9 / 8 * world
-        mapf = {"metric": "G Hamming cmp/s, cross-map brute force + ratio test", "value": cmps / (mf_ms * 1e-3) / 1e9, "unit": "Gcmp/s",
-                "maps": n_maps, "rows_per_map": rows, "directed_pairs": n_maps * (n_maps - 1), "ms_per_step": mf_ms,
-                "exchange_ms": a0.elapsed_time(a1), "accepted_matches_rank0": accepted,
-                "frac_of_plain_popc_roofline": cmps / (mf_ms * 1e-3) / popc_roof,
-                "popc_roofline": "148 SM x 16 POPC/clk x 1.965 GHz / 8 POPC per cmp per GPU (measured 15.3/clk/SM)",
-                "popc_kernel": {"value": cmps / (popc_ms * 1e-3) / 1e9, "unit": "Gcmp/s", "ms_per_step": popc_ms,
-                                "frac_of_plain_popc_roofline": cmps / (popc_ms * 1e-3) / popc_roof,
-                                "what": "the same step with orbm_set_knn2_backend(1): knn2_kernel (carry-save popcount on the integer pipes)"},
-                # the kernel that runs at this size is the tcgen05 int8 one: 256 multiply-adds per comparison on +-1 bytes
-                "kernel": "knn2_mma_kernel (tcgen05.mma kind::i8, 128x128x256 tiles, top-2 out of TMEM)",
-                "tensor": {"achieved_int8_tops": cmps * 512 / (mf_ms * 1e-3) / 1e12 / world,
-                           "peak_int8_tops_per_gpu": 2 * peaks()[0].get("bf16_tflops", 2250.0),
-                           "frac": cmps * 512 / (mf_ms * 1e-3) / 1e12 / world / (2 * peaks()[0].get("bf16_tflops", 2250.0)),
-                           "peak_source": "2 x the measured dense bf16 cuBLAS figure of MEASURED_PEAKS.json (int8 = 2 x bf16 on sm_100a; 2 x 2250 nominal if absent)"}}
-        del local, res, cm
+
+        def xmap_leg(n_maps, reps):
+            cm = mapfusion.CrossMapMatcher(rows, n_maps, 0.75)
+            host = {m: synth.descriptors_fast(rows, 5000 + m, base, 60) for m in cm.owned}
+            local = [torch.from_numpy(host[m]).to(dev) for m in cm.owned]
+            rpm = [rows] * n_maps
+            cm.match(local, rpm)  # warm-up (peer mappings, kernel load)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(reps):
+                res, _r = cm.match(local, rpm)
+            g1.record()
+            barrier()
+            ms = max_over_ranks(g0.elapsed_time(g1)) / reps
+            # parity outside the timed region: sampled rows of every pair this rank owns against the oracle (needs every
+            # database map on the host: regenerate it from its seed)
+            import oracle_lib as O
+            checked = 0
+            rng = np.random.default_rng(rank)
+            for (a, b), (idx, d1, d2, _m) in res.items():
+                sample = np.sort(rng.choice(rows, 64, replace=False))
+                dbm = host[b] if b in host else synth.descriptors_fast(rows, 5000 + b, base, 60)
+                oi, o1, o2 = O.knn2(host[a][sample], dbm)
+                ok = (np.array_equal(idx.cpu().numpy()[sample], oi) and np.array_equal(d1.cpu().numpy()[sample], o1)
+                      and np.array_equal(d2.cpu().numpy()[sample], o2))
+                if not ok:
+                    raise SystemExit("bench.py: cross-map result of pair (%d, %d) differs from the oracle on rank %d" % (a, b, rank))
+                checked += len(sample)
+            accepted = int(sum(int((v[3] >= 0).sum()) for v in res.values()))
+            tot = torch.tensor([checked, accepted], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(tot)
+            launches_step = None
+            cm.close()
+            cmps = float(n_maps * (n_maps - 1)) * rows * rows
+            return {"maps": n_maps, "rows_per_map": rows, "directed_pairs": n_maps * (n_maps - 1), "ms_per_step": ms,
+                    "value": cmps / (ms * 1e-3) / 1e9, "unit": "Gcmp/s", "parity_rows_checked": int(tot[0].item()),
+                    "accepted_matches": int(tot[1].item())}, cmps
+
+        n_maps = max(2, world)
+        leg, cmps = xmap_leg(n_maps, 5)
+        mf_ms = leg["ms_per_step"]
+        # the same step with the POPC kernel (north star: "popc-bound uint4-vectorised kernel") on ONE GPU-resident pair list
+        popc = None
+        if rank == 0:
+            from multiagent_orb_slam2_b200 import _lib as _orb_lib
+            LL = _orb_lib.lib()
+            a_set = torch.from_numpy(synth.descriptors_fast(rows, 5000, base, 60)).to(dev)
+            b_set = torch.from_numpy(synth.descriptors_fast(rows, 5001, base, 60)).to(dev)
+            o3 = [torch.empty(rows, dtype=torch.int32, device=dev) for _ in range(3)]
+            stp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _orb_lib.check(LL.orbm_set_knn2_backend(1))
+            run = lambda: _orb_lib.check(LL.orbm_knn2_device(C.c_void_p(a_set.data_ptr()), rows, C.c_void_p(b_set.data_ptr()), rows,
+                                                             *[C.c_void_p(o.data_ptr()) for o in o3], stp))
+            run()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            run()
+            h1.record()
+            torch.cuda.synchronize(dev)
+            _orb_lib.check(LL.orbm_set_knn2_backend(0))
+            pms = h0.elapsed_time(h1)
+            popc = {"value": float(rows) * rows / (pms * 1e-3) / 1e9, "unit": "Gcmp/s per GPU", "ms_per_pair": pms,
+                    "frac_of_plain_popc_roofline": float(rows) * rows / (pms * 1e-3) / (popc_roof / world),
+                    "what": "one 200k x 200k pair with the POPC kernel pinned (orb_b200_debug.h): knn2_kernel, carry-save popcount on the integer pipes"}
+            del a_set, b_set, o3
+        barrier()
+        split = None
+        if world > 2:
+            split, _ = xmap_leg(2, 5)   # fewer maps than GPUs: query rows of the 2 maps split over all ranks
+            split["what"] = "2 maps on %d GPUs: the 128-row query tiles of both pairs dealt evenly to all ranks" % world
+        int8_peak = peaks()[0].get("int8_tops_measured")
+        int8_src = "measured: bare tcgen05.mma kind::i8 issue loop, tools/microbench/utcimma_peak.cu (profiles/)"
+        if not int8_peak:
+            int8_peak = 2 * peaks()[0].get("bf16_tflops", 2250.0)
+            int8_src = "2 x the measured dense bf16 cuBLAS figure of MEASURED_PEAKS.json (int8 = 2 x bf16 on sm_100a; 2 x 2250 nominal if absent)"
+        mapf = dict(leg)
+        mapf.update({"metric": "G Hamming cmp/s, cross-map brute force + ratio test",
+                     "exchange": "fused: peer loads over NVLink inside the operand-expansion kernel (orbm_knn2_allgather), no collective call",
+                     "frac_of_plain_popc_roofline": cmps / (mf_ms * 1e-3) / popc_roof,
+                     "popc_roofline": "148 SM x 16 POPC/clk x 1.965 GHz / 8 POPC per cmp per GPU (measured 15.3/clk/SM)",
+                     "popc_kernel": popc, "fewer_maps_than_gpus": split,
+                     "kernel": "knn2_mma_kernel (tcgen05.mma kind::i8, 128x128x256 tiles, top-2 out of TMEM)",
+                     "tensor": {"achieved_int8_tops": cmps * 512 / (mf_ms * 1e-3) / 1e12 / world, "peak_int8_tops_per_gpu": int8_peak,
+                                "frac": cmps * 512 / (mf_ms * 1e-3) / 1e12 / world / int8_peak, "peak_source": int8_src}})
 
     # ---- DBoW2 vocabulary transform of the batch's descriptors (Frame::ComputeBoW), rank 0 -----
     bow = None
@@ -432,6 +479,10 @@ def run_b200(args):
         }))
     if world > 1:
         dist.destroy_process_group()
+        if rank == 0 and nccl_log and os.path.exists(nccl_log):
+            lines = [l.rstrip() for l in open(nccl_log, errors="replace")]
+            keep = [l for l in lines if "nranks" in l or "NCCL version" in l or "comm 0x" in l][:12]
+            sys.stderr.write("NCCL log (rank 0, %s):\n" % nccl_log + "\n".join(keep or lines[:12]) + "\n")
 
 
 def main():

@@ -108,42 +108,15 @@ int orbx_download_results(orbx_handle h, int n, orbx_keypoint* kps, uint8_t* des
 int orbx_pyramid_level_device(orbx_handle h, int frame, int level, const uint8_t** d_ptr, size_t* pitch);
 int orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride);
 
-/* Stage taps used by the parity tests (not needed by a SLAM caller): the blurred level
- * (src/ORBextractor.cc:1085-1086) and the FAST candidates of a level in the reference's order
- * (cell row-major, then row-major inside the cell; x,y in level coordinates; 789-829). */
-int orbx_debug_blurred_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride);
-int orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xys /* [cap][3] */, int cap, int* n_out);
-
-/* Measurement hooks (bench.py): with stage timing on, the pipeline runs its stages back to back on
- * ONE stream with CUDA events in between; orbx_stage_times returns the device milliseconds of
- * {resize chain, blur, FAST, quadtree, orient+describe} of the last call, orbx_algorithmic_bytes the
- * per-frame algorithmic HBM bytes of the same stages. */
-#define ORBX_NUM_STAGES 5
-int orbx_set_stage_timing(orbx_handle h, int enable);
-int orbx_stage_times(orbx_handle h, float* ms /* [ORBX_NUM_STAGES] */);
-int orbx_algorithmic_bytes(orbx_handle h, double* bytes /* [ORBX_NUM_STAGES] */);
-
-/* Stand-alone stages on host buffers (parity tests / micro-benchmarks). */
-int orbx_debug_quadtree(int device, const int32_t* xs, const int32_t* ys, const int32_t* scores, int n,
-                        int minX, int maxX, int minY, int maxY, int N, int32_t* out_idx, int cap, int* n_out);
-
 /* ------------------------------------------------------------------------------------------
  * Matcher primitives. Replace the DescriptorDistance loops of ORBmatcher (src/ORBmatcher.cc:1649-1665
  * called from 102, 216, 387, 444, 586, 738, 944, 1074, 1214, 1294, 1419, 1548; src/Frame.cc:541).
  * Descriptors are 32 bytes, rows contiguous. Selection rule of every reference search: strict '<'
  * updates in iteration order => (two smallest distances, index of the FIRST minimum); both
- * distances start at 256; idx = -1 when no candidate is closer than 256. */
-
-/* The brute-force searches below have two implementations with identical results: the POPC kernel (csrc/hamming.cu) and the
- * tensor-core kernel (csrc/hamming_mma.cu: +-1 int8 expansion, tcgen05.mma kind::i8, top-2 epilogue out of TMEM), chosen by
- * problem size. backend: 0 = automatic (default), 1 = POPC only, 2 = tensor cores only (tests and measurements). */
-int orbm_set_knn2_backend(int backend);
-/* The tensor-core implementation called directly (one query set against one database set), whatever the size. */
-int orbm_knn2_mma_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best,
-                         int32_t* d_second, void* stream);
-/* Debug tap of its data path: the +-1 dot products (= 256 - 2 * distance) of 128 x 256 host descriptors through the bit
- * expansion, the SWIZZLE_128B TMA loads, tcgen05.mma kind::i8 and tcgen05.ld; out = int32 [128][256]. */
-int orbm_debug_mma_dot(int device, const uint8_t* A128, const uint8_t* B256, int32_t* out);
+ * distances start at 256; idx = -1 when no candidate is closer than 256.
+ * The brute-force searches have two implementations with identical results - the POPC kernel (csrc/hamming.cu) and the
+ * tensor-core kernel (csrc/hamming_mma.cu: +-1 int8 expansion, tcgen05.mma kind::i8, top-2 epilogue out of TMEM) -
+ * chosen by problem size; orb_b200_debug.h can pin one of them for the calling thread (tests, measurements). */
 
 /* Brute force: every row of A against every row of B (SearchByBoW inner loop with the gate removed,
  * src/ORBmatcher.cc:566-598; BASELINE configs 3 and 5). */
@@ -203,6 +176,42 @@ int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf,
  * MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:246-311). */
 int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int16_t* d_out, void* stream);
 int orbm_distance_matrix(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int16_t* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-map matching over the GPUs of one node (BASELINE config 5; SURVEY.md section 8b "orbm_hamming_knn2_allgather", 8e).
+ * Replaces, for whole maps, what MapFusion::ComputeSim3 / CovisibilityDiscovery do keyframe by keyframe through
+ * ORBmatcher::SearchByBoW(KF, KF) (src/MapFusion.cc:275, 849 -> src/ORBmatcher.cc:524-657): every descriptor of map a
+ * against every descriptor of map b != a, (first-minimum index, best, second) per query row.
+ * n_maps maps live on `world` ranks (GPUs): map m on rank m % world (its slot-th map there, slot = m / world). The
+ * exchange is part of the call: no collective library runs on the data path. Every rank owns a window of device memory
+ * that its peers map (CUDA IPC between processes, peer access inside one process); a rank reads the packed descriptor
+ * sets it needs straight out of the owners' windows over NVLink inside the kernel that expands them into the tensor-core
+ * operands, and writes results into the window of the query map's owner. The directed pairs are cut into 128-row query
+ * tiles and dealt evenly to the ranks, so fewer maps than GPUs still keep every GPU busy (query-row split); a row's
+ * result is always computed over the whole database in canonical order, i.e. it is identical to the single-GPU result.
+ * Protocol per step (one orbm_knn2_allgather call on EVERY rank, same n_maps / rows_per_map everywhere): publish owned sets
+ * (release flag) -> acquire peers' flags as their sets are first needed -> match -> release "done" into every window ->
+ * owners acquire all contributors. Waits are bounded (seconds) and trap rather than hang.
+ *   orbm_xmap_create       window + operand scratch for maps of up to rows_cap descriptors
+ *   orbm_xmap_ipc_handle   64 opaque bytes (cudaIpcMemHandle_t) to hand to the other processes by any host transport
+ *   orbm_xmap_attach_ipc   handles of all ranks, rank order (own entry ignored); multi-process
+ *   orbm_xmap_attach_local contexts of all ranks created in THIS process (one thread driving several GPUs, as the
+ *                          reference's single-process MultiAgentServer would); enables peer access
+ *   orbm_knn2_allgather    d_sets[k] = device pointer to the k-th map this rank owns (rows_per_map[rank + k*world] x 32 B);
+ *                          rows_per_map = host array of all n_maps counts; only enqueues on `stream`
+ *   orbm_xmap_result       device pointers (valid after the stream has finished the step) to idx / best / second of pair
+ *                          (map_a, map_b), rows_per_map[map_a] entries each, on the rank that owns map_a
+ *   orbm_xmap_plan         host only: the (a, b, first tile, end tile) chunks of `rank` - the split itself, for tests */
+#define ORBM_XMAP_HANDLE_BYTES 64
+typedef struct orbm_xmap* orbm_xmap_t;
+int orbm_xmap_create(int device, int rank, int world, int n_maps, int rows_cap, orbm_xmap_t* out);
+void orbm_xmap_destroy(orbm_xmap_t x);
+int orbm_xmap_ipc_handle(orbm_xmap_t x, void* handle64);
+int orbm_xmap_attach_ipc(orbm_xmap_t x, const void* handles /* world x ORBM_XMAP_HANDLE_BYTES */);
+int orbm_xmap_attach_local(orbm_xmap_t* ctxs, int world);
+int orbm_knn2_allgather(orbm_xmap_t x, const uint8_t* const* d_sets, const int32_t* rows_per_map, void* stream);
+int orbm_xmap_result(orbm_xmap_t x, int map_a, int map_b, const int32_t** d_idx, const int32_t** d_best, const int32_t** d_second);
+int orbm_xmap_plan(int n_maps, const int32_t* rows_per_map, int world, int rank, int32_t* chunks /* [cap][4] */, int cap, int* n_chunks);
 
 /* ------------------------------------------------------------------------------------------
  * Device-resident Frame grid + windowed search. orbm_grid_build_device replaces

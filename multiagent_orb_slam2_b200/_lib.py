@@ -85,6 +85,13 @@ def lib():
         "orbdb_query": [vp, vp, vp, i32, vp, vp, vp, i32],
         "orbdb_query_device": [vp, vp, vp, i32, vp, vp, vp, vp],
         "orbm_stereo_from_rgbd_device": [i32, vp, vp, i32, vp, i32, i32, C.c_size_t, f32, vp, vp, vp],
+        "orbm_xmap_create": [i32, i32, i32, i32, i32, C.POINTER(vp)],
+        "orbm_xmap_ipc_handle": [vp, vp],
+        "orbm_xmap_attach_ipc": [vp, vp],
+        "orbm_xmap_attach_local": [vp, i32],
+        "orbm_knn2_allgather": [vp, vp, vp, vp],
+        "orbm_xmap_result": [vp, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
+        "orbm_xmap_plan": [i32, vp, i32, i32, vp, i32, C.POINTER(i32)],
         "orbm_project_points_device": [i32, vp, i32, f32, f32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sigs.items():
@@ -101,6 +108,8 @@ def lib():
     L.orbv_destroy.restype = None
     L.orbx_destroy.argtypes = [vp]
     L.orbx_destroy.restype = None
+    L.orbm_xmap_destroy.argtypes = [vp]
+    L.orbm_xmap_destroy.restype = None
     _lib = L
     return L
 
@@ -112,8 +121,11 @@ def check(rc, allow=()):
 
 
 def exported_symbols():
-    """Names declared in include/orb_b200.h (parsed), for the load/export test."""
+    """Names declared in include/orb_b200.h and include/orb_b200_debug.h (parsed), for the load/export test."""
     import re
-    hdr = open(os.path.join(HERE, "..", "include", "orb_b200.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(orb[a-z]*_[a-z0-9_]+)\s*\(", hdr)))
+    names = set()
+    for h in ("orb_b200.h", "orb_b200_debug.h"):
+        hdr = open(os.path.join(HERE, "..", "include", h)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        names |= set(re.findall(r"\b(orb[a-z]*_[a-z0-9_]+)\s*\(", hdr))
+    return sorted(names)

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "liborb_b200.so")
-SOURCES = ["runtime.cu", "hamming.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "extractor.cu", "stereo.cu", "bow.cu", "grid.cu", "project.cu", "kfdb.cu", "hamming_mma.cu"]
+SOURCES = ["runtime.cu", "hamming.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "extractor.cu", "stereo.cu", "bow.cu", "grid.cu", "project.cu", "kfdb.cu", "hamming_mma.cu", "xmap.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--fmad=false", "-cudart", "static"]
 
@@ -21,7 +21,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "orb_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "orb_b200.h"), os.path.join(HERE, "..", "include", "orb_b200_debug.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

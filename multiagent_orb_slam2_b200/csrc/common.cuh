@@ -5,6 +5,7 @@
 #include <cstdio>
 
 #include "../../include/orb_b200.h"
+#include "../../include/orb_b200_debug.h"
 
 namespace orb {
 

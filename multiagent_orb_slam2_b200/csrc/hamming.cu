@@ -235,7 +235,7 @@ __global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, cons
 // ---- host launcher ----------------------------------------------------------------------------
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
                     int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st);
-static std::atomic<int> g_knn2_backend{0};        // 0 = by problem size, 1 = POPC kernel, 2 = tensor-core kernel
+static thread_local int t_knn2_backend = 0;        // per calling thread: 0 = by problem size, 1 = POPC kernel, 2 = tensor-core kernel
 constexpr long long kMmaMinWork = 1ll << 19;      // comparisons per call from which the tensor-core path is used (measured break-even: ~700 x 700)
 
 static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB,
@@ -244,7 +244,7 @@ static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strid
     if (pairs <= 0 || nA_max <= 0) return ORB_OK;
     // large problems go to the tensor cores (hamming_mma.cu): same results, several times the POPC pipe's throughput
     const long long work = (long long)pairs * nA_max * nB_max;
-    const int backend = g_knn2_backend.load();
+    const int backend = t_knn2_backend;
     if (nB_max > 0 && (backend == 2 || (backend == 0 && work >= kMmaMinWork && nB_max >= 64)))
         return launch_knn2_mma(dA, d_nA, nA_max, strideA_rows, dB, d_nB, nB_max, strideB_rows, d_pairs, pairs, strideA_rows, d_idx, d_b1, d_b2, st);
     // pick the slice count so that the grid covers the machine about twice
@@ -274,7 +274,7 @@ extern "C" {
 
 int orbm_set_knn2_backend(int backend) {
     ORB_REQUIRE(backend >= 0 && backend <= 2, "backend must be 0 (auto), 1 (POPC) or 2 (tensor cores)");
-    g_knn2_backend.store(backend);
+    t_knn2_backend = backend;
     return ORB_OK;
 }
 

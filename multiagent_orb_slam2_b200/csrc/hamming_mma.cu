@@ -475,6 +475,55 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
 
 }  // namespace orb
 
+namespace orb {
+// ---- building blocks for the cross-map context (xmap.cu): operands already expanded by the caller --------------------
+int mma_encode_operand_map(CUtensorMap* out, const void* base, long long rows, bool query_side) {
+    return encode_expanded_map(out, base, rows, query_side ? kMmaM : kTileN);
+}
+// rows [0, n_rows) of a packed 32-byte descriptor array (which may live in a PEER GPU's memory: the loads then travel over
+// NVLink) -> 256 int8 per row, +-64 (query operand) or +-1 (database operand), into local memory
+__global__ void __launch_bounds__(256) expand_rows_kernel(const uint32_t* __restrict__ src, int n_words, uint32_t neg, uint32_t flip,
+                                                          uint4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint32_t w = src[i];
+    uint32_t o[8];
+#pragma unroll
+    for (int nib = 0; nib < 8; ++nib) {
+        const uint32_t x = (w >> (4 * nib)) & 0xFu;
+        const uint32_t t = (x * 0x00204081u) & 0x01010101u;
+        o[nib] = neg ^ (t * flip);
+    }
+    out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+int mma_expand_rows(const uint8_t* packed, int n_rows, bool query_side, uint8_t* out, cudaStream_t st) {
+    if (n_rows <= 0) return ORB_OK;
+    expand_rows_kernel<<<ceil_div(n_rows * 8, 256), 256, 0, st>>>((const uint32_t*)packed, n_rows * 8, query_side ? 0xC0C0C0C0u : 0xFFFFFFFFu,
+                                                                  query_side ? 0x80u : 0xFEu, (uint4*)out);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+// one query block (na rows, expanded, starting at row 0 of map_a) against one database (nb rows of map_b); the three
+// output arrays may point into a peer GPU's memory
+int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, int na, int nb, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st) {
+    if (na <= 0) return ORB_OK;
+    int device = 0;
+    ORB_CUDA_TRY(cudaGetDevice(&device));
+    static std::atomic<bool> attr_set[64];
+    if (device >= 64 || !attr_set[device].load()) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
+        if (device < 64) attr_set[device].store(true);
+    }
+    knn2_mma_kernel<<<dim3(ceil_div(na, kMmaM), 1), kMmaThreads, kMmaSmemBytes, st>>>(map_a, map_b, nullptr, na, na, nullptr, nb, nb, nullptr, na,
+                                                                                    d_idx, d_b1, d_b2);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+}  // namespace orb
+
 // Debug / experiment entry: the tensor-core matcher on one pair of device arrays.
 extern "C" int orbm_knn2_mma_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best, int32_t* d_second,
                                     void* stream) {
