@@ -31,15 +31,19 @@ sys.path.insert(0, ROOT)
 W, H, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
 NNRATIO, TH = 0.9, 50
 METRIC = "frames/s ORB extract+match @640x480,1000kp"
+WORKLOAD = "640x480 gray, 1000 kp, 8 levels, scale 1.2, FAST 20/7; frame-to-frame brute-force match (ratio 0.9, TH_LOW 50)"
 STAGES = ["pyramid_resize", "gaussian_blur", "fast_cells", "quadtree", "orient_describe"]
+DISTINCT_FRAMES = 64
 
 
-def make_frames(n, seed0):
-    """n synthetic 640x480 frames: consecutive frames are shifted/re-noised copies (real matches)."""
+def make_frames(n, seed0, w=W, h=H, distinct=DISTINCT_FRAMES):
+    """n synthetic frames: `distinct` different ones (distinct/2 scenes x 2 views; consecutive frames are shifted /
+    re-noised copies, i.e. real matches), tiled to n. The data-dependent stages (FAST survivors, empty-cell retries,
+    quadtree depth) therefore see 64 different inputs per batch."""
     from multiagent_orb_slam2_b200 import synth
     base = []
-    for s in range(8):  # 8 distinct scenes x 2 views, tiled to n frames (generation is CPU heavy)
-        a, b, _ = synth.shifted_pair("blocks", W, H, seed0 + s)
+    for s in range(max(1, min(distinct, n) // 2)):
+        a, b, _ = synth.shifted_pair("blocks", w, h, seed0 + s)
         base += [a, b]
     reps = (n + len(base) - 1) // len(base)
     return np.ascontiguousarray(np.stack((base * reps)[:n]))
@@ -146,6 +150,187 @@ def cpu_reference_run(frames, threads):
     return time.perf_counter() - t0, kind
 
 
+def cv2_primitive_bound(frame, reps=5):
+    """Single-thread lower bound of the extraction's OpenCV primitives through cv2: the 7 resizes,
+    the per-cell FAST calls (incl. ~815 Python call overheads) and the 8 Gaussian blurs of one 640x480 frame; no quadtree,
+    orientation or descriptors. None when cv2 is not importable."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    scale = [np.float32(1.0)]
+    for _ in range(1, NLEVELS):
+        scale.append(np.float32(scale[-1] * np.float32(SCALE)))
+
+    def once():
+        lv = [frame]
+        for l in range(1, NLEVELS):
+            inv = np.float32(1.0) / scale[l]
+            sz = (int(np.rint(np.float32(W) * inv)), int(np.rint(np.float32(H) * inv)))
+            lv.append(cv2.resize(lv[-1], sz, interpolation=cv2.INTER_LINEAR))
+        fast_ini = cv2.FastFeatureDetector_create(INI_TH, True)
+        fast_min = cv2.FastFeatureDetector_create(MIN_TH, True)
+        ncand = 0
+        for im in lv:
+            hh, ww = im.shape
+            minb, maxx, maxy = 16, ww - 16, hh - 16
+            ncols, nrows = max(1, (maxx - minb) // 30), max(1, (maxy - minb) // 30)
+            wc, hc = -(-(maxx - minb) // ncols), -(-(maxy - minb) // nrows)
+            for i in range(nrows):
+                y0 = minb + i * hc
+                if y0 >= maxy - 3:
+                    continue
+                y1 = min(y0 + hc + 6, maxy)
+                for j in range(ncols):
+                    x0 = minb + j * wc
+                    if x0 >= maxx - 6:
+                        continue
+                    x1 = min(x0 + wc + 6, maxx)
+                    k = fast_ini.detect(im[y0:y1, x0:x1])
+                    if not k:
+                        k = fast_min.detect(im[y0:y1, x0:x1])
+                    ncand += len(k)
+        for im in lv:
+            cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        return ncand
+
+    once()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ncand = once()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    return {"ms_per_frame_1_thread": ms, "frames_per_s_1_thread": 1e3 / ms, "fast_candidates": int(ncand),
+            "what": "cv2 %s primitives only (7 resizes, per-cell FAST with Python call overhead, 8 blurs), 1 thread" % cv2.__version__}
+
+# ------------------------------------------------------------------------------------------------------
+def extra_config_legs(args, dev, local_rank):
+    """The other named configurations of BASELINE.json (rank 0, N=1): C2 KITTI-shape stereo (2 x 1241x376, 2000 kp, extract
+    L+R + Frame::ComputeStereoMatches on the device), C3 EuRoC-shape 752x480 batched 64 frames/launch with full
+    frame-to-frame matching, and the drop-in's real operating point: one frame per call through the C++ facade."""
+    import ctypes as C
+    import torch
+    from multiagent_orb_slam2_b200 import _lib, synth
+    from multiagent_orb_slam2_b200.extractor import ORBextractor
+    from multiagent_orb_slam2_b200.frontend import AgentFrontend
+    L = _lib.lib()
+    pk, _ = peaks()
+    out = {}
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    def stage_times(ex, d_frames, n):
+        _lib.check(L.orbx_set_stage_timing(ex._h, 1))
+        ms = (C.c_float * len(STAGES))()
+        acc = np.zeros(len(STAGES))
+        for _ in range(3):
+            ex.extract_device(d_frames.data_ptr(), d_frames.stride(1), d_frames.stride(0), n, st)
+            _lib.check(L.orbx_stage_times(ex._h, ms))
+            acc += np.array(list(ms))
+        _lib.check(L.orbx_set_stage_timing(ex._h, 0))
+        alg = (C.c_double * len(STAGES))()
+        _lib.check(L.orbx_algorithmic_bytes(ex._h, alg))
+        return {name: {"ms": acc[i] / 3, "alg_bytes_per_frame": alg[i],
+                       "frac_hbm": (alg[i] * n / (acc[i] / 3 * 1e-3) / 1e9 / pk["hbm_gbs"]) if acc[i] > 0 else 0.0} for i, name in enumerate(STAGES)}
+
+    # ---- C2: KITTI-shape stereo ------------------------------------------------------------------------------------
+    KW, KH, KN, KB = 1241, 376, 2000, 64
+    pairs = [synth.stereo_pair("blocks", KW, KH, 700 + s) for s in range(32)]
+    left = np.ascontiguousarray(np.stack([p[0] for p in pairs] * (KB // 32)))
+    right = np.ascontiguousarray(np.stack([p[1] for p in pairs] * (KB // 32)))
+    exl = ORBextractor(KN, SCALE, NLEVELS, INI_TH, MIN_TH, KW, KH, device=local_rank, max_batch=KB)
+    exr = ORBextractor(KN, SCALE, NLEVELS, INI_TH, MIN_TH, KW, KH, device=local_rank, max_batch=KB)
+    dl, dr = torch.from_numpy(left).to(dev), torch.from_numpy(right).to(dev)
+    cap = exl.cap
+    ur = torch.empty((KB, cap), dtype=torch.float32, device=dev); dz = torch.empty_like(ur)
+    sad = torch.empty((KB, cap), dtype=torch.int32, device=dev); kept = torch.zeros(KB, dtype=torch.int32, device=dev)
+    mbf, mb = 386.1448, 386.1448 / 718.856
+
+    def stereo_step():
+        exl.extract_device(dl.data_ptr(), dl.stride(1), dl.stride(0), KB, st)
+        exr.extract_device(dr.data_ptr(), dr.stride(1), dr.stride(0), KB, st)
+        _lib.check(L.orbm_stereo_match_batch_device(exl._h, exr._h, KB, mbf, mb, C.c_void_p(ur.data_ptr()), C.c_void_p(dz.data_ptr()),
+                                                    C.c_void_p(sad.data_ptr()), C.c_void_p(kept.data_ptr()), cap, C.c_void_p(st)))
+
+    ms = timed(stereo_step, 5)
+    ms_extract = timed(lambda: (exl.extract_device(dl.data_ptr(), dl.stride(1), dl.stride(0), KB, st),
+                                exr.extract_device(dr.data_ptr(), dr.stride(1), dr.stride(0), KB, st)), 5)
+    # end to end through the host-buffer calls: both images up, keypoints / descriptors / stereo coordinates down
+    t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        exl.extract_batch(left); exr.extract_batch(right)
+        u = np.empty(cap, np.float32); d = np.empty(cap, np.float32); k = C.c_int()
+        for f in range(KB):
+            _lib.check(L.orbm_stereo_match(exl._h, exr._h, f, mbf, mb, u.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), cap, C.byref(k)))
+    e2e_s = (time.perf_counter() - t0) / reps
+    out["kitti_stereo"] = {"workload": "KITTI-shape stereo 1241x376 left/right, 2000 kp per image, 8 levels, stereo Hamming matching + SAD refinement",
+                           "stereo_pairs_per_step": KB, "distinct_pairs": 32, "ms_per_step": ms, "value": KB / (ms * 1e-3), "unit": "stereo frames/s",
+                           "ms_extract_LR": ms_extract, "ms_stereo_match": ms - ms_extract, "matched_per_frame": float(kept.float().mean().item()),
+                           "e2e": {"value": KB / e2e_s, "unit": "stereo frames/s", "how": "orbx_extract_batch (L, R) + orbm_stereo_match per frame, host buffers, synchronous",
+                                   "h2d_bytes_per_step": 2 * KB * KW * KH, "d2h_bytes_per_step": KB * (2 * cap * 60 + cap * 8)},
+                           "stages_left": stage_times(exl, dl, KB)}
+    del exl, exr, dl, dr, ur, dz, sad, kept
+
+    # ---- C3: EuRoC-shape, 64 frames per launch, full frame-to-frame matching -----------------------------------------
+    EW, EH, EN, EB = 752, 480, 1200, 64
+    frames = make_frames(EB, 900, EW, EH)
+    fe = AgentFrontend(EW, EH, EN, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank, max_batch=EB, nnratio=NNRATIO, th=TH)
+    d_frames = torch.from_numpy(frames).to(dev)
+    ms = timed(lambda: fe.process_device(d_frames), 10)
+    ms_match = timed(lambda: fe.match_consecutive(EB), 10)
+    h_frames = torch.from_numpy(frames).pin_memory()
+    o = fe.pinned_outputs()
+    fe.process_async(h_frames, o); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        fe.process_async(h_frames, o)
+        torch.cuda.current_stream(dev).synchronize()
+        _ = int(o["counts"].numpy()[:EB].sum())
+    e2e_s = (time.perf_counter() - t0) / 10
+    out["euroc_b64"] = {"workload": "EuRoC-shape 752x480, 64 frames per launch, 1200 kp, full frame-to-frame matching (ratio 0.9, TH_LOW 50)",
+                        "frames_per_step": EB, "ms_per_step": ms, "value": EB / (ms * 1e-3), "unit": "frames/s", "ms_matching": ms_match,
+                        "keypoints_per_frame": float(o["counts"].numpy()[:EB].mean()),
+                        "e2e": {"value": EB / e2e_s, "unit": "frames/s", "how": "one buffer, upload -> kernels -> download, synchronised every step",
+                                "h2d_bytes_per_step": EB * EW * EH, "d2h_bytes_per_step": EB * fe.d2h_bytes_per_frame()},
+                        "stages": stage_times(fe.ex, d_frames, EB)}
+    del fe, d_frames
+
+    # ---- the drop-in's operating point: batch 1 through the C++ facade --------------------------------------------------
+    try:
+        exe = os.path.join(ROOT, "multiagent_orb_slam2_b200", "lib", "bench_single_frame")
+        src = os.path.join(ROOT, "tools", "bench", "single_frame.cc")
+        lib = os.path.join(ROOT, "multiagent_orb_slam2_b200", "lib")
+        if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+            subprocess.check_call(["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "include"), src, "-o", exe, "-L" + lib, "-lorb_b200",
+                                   "-Wl,-rpath," + lib])
+        with tempfile.NamedTemporaryFile(suffix=".raw", delete=False) as f:
+            make_frames(16, 300).tofile(f)
+            raw = f.name
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+        js = subprocess.check_output([exe, str(W), str(H), raw, "16", str(NFEAT), "200"], text=True, env=env, timeout=300)
+        os.unlink(raw)
+        sf = json.loads(js)
+        sf["what"] = ("C++ facade ORB_SLAM2::ORBextractor::operator() on ONE 640x480 host image per call (median of 200 calls, wall clock incl. "
+                      "H2D, kernels, D2H and the vector<cv::KeyPoint> fill); SearchForInitialization on a 2 x nFeatures frame pair")
+        sf["frames_per_s_single_stream"] = 1e6 / sf["extract_us"]
+        out["single_frame"] = sf
+    except Exception as e:  # the headline must not depend on a host compiler being present
+        out["single_frame"] = {"unavailable": repr(e)[:300]}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -167,8 +352,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "640x480 gray, 1000 kp, 8 levels, scale 1.2, FAST 20/7; frame-to-frame brute-force match", "sample": what},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what},
+        "config": {"workload": WORKLOAD, "sample": what},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what,
+                         "ms_per_frame_per_thread": 1e3 * cores / v, "cv2_bound": cv2_primitive_bound(frames[0])},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -198,6 +384,21 @@ def run_b200(args):
         os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()   # creates the communicator now, so that its INIT lines are in the log
+    comm = None
+    if world > 1 and rank == 0:
+        nr = None
+        try:
+            import re
+            for line in open(nccl_log, errors="replace"):
+                m = re.search(r"nranks (\d+)", line)
+                if m:
+                    nr = int(m.group(1))
+                    break
+        except Exception:
+            pass
+        comm = {"backend": "nccl", "world_size": world, "nranks_in_nccl_log": nr,
+                "data_path": "extraction / matching: none (replicas); cross-map: peer loads + flags over NVLink (orbm_knn2_allgather); NCCL "
+                             "carries the timing all-reduce, the barriers and the 64-byte window handles only"}
     B = args.batch
     L = _lib.lib()
 
@@ -253,6 +454,13 @@ def run_b200(args):
     streams = [torch.cuda.Stream(dev) for _ in range(DEPTH)]
     outs = [f.pinned_outputs() for f in fes]
 
+    def consume(out):
+        """What the facade's operator() does with a finished step on the host (src/ORBextractor.cc:1072-1101 fills
+        vector<cv::KeyPoint>): every frame's count read, its keypoint records and matches walked once."""
+        cnt = out["counts"].numpy()[:B]
+        kp = out["kps"].numpy()[:B].view(np.float32).reshape(B, -1, 6)
+        return int(cnt.sum()), float(kp[:, :, 4].sum()), int((out["match"].numpy()[:B] >= 0).sum())
+
     def e2e_step(i):
         k = i % DEPTH
         with torch.cuda.stream(streams[k]):
@@ -269,7 +477,7 @@ def run_b200(args):
         if i >= DEPTH - 1:
             j = (i - (DEPTH - 1)) % DEPTH
             streams[j].synchronize()  # the host consumes an earlier step's results while the later ones run
-            _ = int(outs[j]["counts"][0])
+            consume(outs[j])
     for s in streams:
         s.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
@@ -449,6 +657,10 @@ def run_b200(args):
                "features_per_launch": nfeat, "ms_per_launch": bms, "hamming_per_feature": 60}
         del voc
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = extra_config_legs(args, dev, local_rank)
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------
@@ -460,22 +672,24 @@ def run_b200(args):
         cpu_reference_run(cf[:cores], cores)
         dt, kind = cpu_reference_run(cf, cores)
         cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": kind,
-               "sample": "%d frames extract+match on %d host threads (%.1f s)" % (sample, cores, dt)}
+               "sample": "%d frames extract+match on %d host threads (%.1f s)" % (sample, cores, dt),
+               "ms_per_frame_per_thread": 1e3 * cores * dt / sample, "cv2_bound": cv2_primitive_bound(cf[0])}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "640x480 gray, 1000 kp, 8 levels, scale 1.2, FAST 20/7; frame-to-frame brute-force match (ratio 0.9, TH_LOW 50)",
-                       "frames_per_step_per_gpu": B, "agents": world, "parallelism": "one agent stream per GPU, no collective",
+            "config": {"workload": WORKLOAD,
+                       "frames_per_step_per_gpu": B, "distinct_frames_per_batch": min(DISTINCT_FRAMES, B), "agents": world, "parallelism": "one agent stream per GPU, no collective",
                        "host_cpus_per_rank": numa,
                        "l2": "inputs larger than L2 (%d MB of frames per step)" % (B * W * H // 2**20),
                        "keypoints_per_frame": kp_per_frame, "matches_per_frame": matches_per_frame},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * fe.h2d_bytes_per_frame(),
                     "d2h_bytes_per_step": B * fe.d2h_bytes_per_frame(), "ms_per_step": e2e_ms / args.steps,
                     "how": "pinned host frames -> orbx_upload_frames/extract_staged/orbm_knn2_batched/download, 3 buffers in flight"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mapfusion": mapf, "bow_transform": bow,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mapfusion": mapf, "bow_transform": bow, "other_configs": other,
+            "comm": comm,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -495,6 +709,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mapfusion", action="store_true", help="skip the cross-map Hamming leg")
     ap.add_argument("--no-bow", action="store_true", help="skip the vocabulary transform leg")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the KITTI-stereo / EuRoC-B64 / single-frame legs")
     ap.add_argument("--map-rows", type=int, default=200000, help="descriptors per map in the cross-map leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

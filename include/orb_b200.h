@@ -171,6 +171,10 @@ int orbm_stereo_match_device(orbx_handle left, orbx_handle right, int frame, flo
                              float* d_depth, int32_t* d_sad, int32_t* d_kept, void* stream);
 int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf, float mb, float* uRight,
                       float* depth, int cap, int* kept);
+/* The same for frames 0 .. n_frames-1 of the last (batched) calls of both handles in ONE launch pair (BASELINE config 2
+ * as a batch): outputs [n_frames][out_stride] (out_stride >= orbx_max_keypoints(left)), d_kept[n_frames]. */
+int orbm_stereo_match_batch_device(orbx_handle left, orbx_handle right, int n_frames, float mbf, float mb, float* d_uRight,
+                                   float* d_depth, int32_t* d_sad, int32_t* d_kept, int out_stride, void* stream);
 
 /* Full distance matrix (nA x nB, int16) for the ordered greedy resolve of the stateful searches and for
  * MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:246-311). */

@@ -65,6 +65,7 @@ def lib():
         "orbm_list_distances": [i32, vp, i32, vp, i32, vp, vp, vp],
         "orbm_ratio_filter_device": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
         "orbm_stereo_match_device": [vp, vp, i32, f32, f32, vp, vp, vp, vp, vp],
+        "orbm_stereo_match_batch_device": [vp, vp, i32, f32, f32, vp, vp, vp, vp, i32, vp],
         "orbm_stereo_match": [vp, vp, i32, f32, f32, vp, vp, i32, C.POINTER(i32)],
         "orbm_grid_create": [i32, i32, C.POINTER(vp)],
         "orbm_grid_build_device": [vp, vp, vp, f32, f32, f32, f32, vp],

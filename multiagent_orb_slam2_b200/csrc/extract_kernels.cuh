@@ -104,8 +104,8 @@ struct StereoSide {  // one image of a stereo pair: geometry, pyramid and extrac
     const int* count;
     int frame;
 };
-int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, float mbf, float mb, float* d_uRight, float* d_depth, int* d_sad,
-                  int* d_kept, cudaStream_t st);
+int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, int n_frames, int out_stride, float mbf, float mb, float* d_uRight,
+                  float* d_depth, int* d_sad, int* d_kept, cudaStream_t st);
 
 // launchers (each enqueues on `st`; n = frames in this call)
 int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int level, int n, cudaStream_t st);

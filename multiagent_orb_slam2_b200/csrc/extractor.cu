@@ -600,8 +600,22 @@ int orbm_stereo_match_device(orbx_handle left, orbx_handle right, int frame, flo
     ORB_REQUIRE(frame >= 0 && frame < left->last_n && frame < right->last_n, "frame was not extracted by both handles");
     ORB_REQUIRE(mb > 0 && mbf > 0, "baseline must be positive");
     ORB_CUDA_TRY(cudaSetDevice(left->device));
-    return launch_stereo(stereo_side(left, frame), stereo_side(right, frame), left->hg.out_cap, mbf, mb, d_uRight, d_depth, d_sad, d_kept,
-                         (cudaStream_t)stream);
+    return launch_stereo(stereo_side(left, frame), stereo_side(right, frame), left->hg.out_cap, 1, left->hg.out_cap, mbf, mb, d_uRight, d_depth,
+                         d_sad, d_kept, (cudaStream_t)stream);
+}
+
+int orbm_stereo_match_batch_device(orbx_handle left, orbx_handle right, int n_frames, float mbf, float mb, float* d_uRight, float* d_depth,
+                                   int32_t* d_sad, int32_t* d_kept, int out_stride, void* stream) {
+    ORB_REQUIRE(left && right && d_uRight && d_depth && d_sad && d_kept, "null pointer");
+    ORB_REQUIRE(left->device == right->device && left->width == right->width && left->height == right->height &&
+                    left->cfg.nlevels == right->cfg.nlevels && left->cfg.scale_factor == right->cfg.scale_factor,
+                "left / right extractors must share device, image size and pyramid settings");
+    ORB_REQUIRE(n_frames >= 1 && n_frames <= left->last_n && n_frames <= right->last_n, "more frames than both handles extracted");
+    ORB_REQUIRE(out_stride >= left->hg.out_cap, "out_stride must be at least orbx_max_keypoints(left)");
+    ORB_REQUIRE(mb > 0 && mbf > 0, "baseline must be positive");
+    ORB_CUDA_TRY(cudaSetDevice(left->device));
+    return launch_stereo(stereo_side(left, 0), stereo_side(right, 0), left->hg.out_cap, n_frames, out_stride, mbf, mb, d_uRight, d_depth, d_sad,
+                         d_kept, (cudaStream_t)stream);
 }
 
 int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf, float mb, float* uRight, float* depth, int cap, int* kept) {

@@ -505,6 +505,16 @@ int mma_expand_rows(const uint8_t* packed, int n_rows, bool query_side, uint8_t*
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }
+// Loads the kernels of this file on the current device NOW. With CUDA's lazy module loading the first launch of a kernel
+// loads its code, which can synchronise with work already running on that device; a rank whose stream is parked in a flag
+// wait (xmap.cu) while the host is still enqueueing that rank's first matcher launch would then deadlock.
+int mma_preload_kernels() {
+    cudaFuncAttributes fa;
+    ORB_CUDA_TRY(cudaFuncGetAttributes(&fa, expand_rows_kernel));
+    ORB_CUDA_TRY(cudaFuncGetAttributes(&fa, knn2_mma_kernel));
+    ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
+    return ORB_OK;
+}
 // one query block (na rows, expanded, starting at row 0 of map_a) against one database (nb rows of map_b); the three
 // output arrays may point into a peer GPU's memory
 int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, int na, int nb, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st) {

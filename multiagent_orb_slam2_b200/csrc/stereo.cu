@@ -27,10 +27,16 @@ __device__ __forceinline__ int st_reflect(int p, int n) {
 
 __global__ void __launch_bounds__(kStWarps * 32)
 stereo_match_kernel(StereoSide Ls, StereoSide Rs, float mbf, float mb, float* __restrict__ uRight, float* __restrict__ depth,
-                    int* __restrict__ sad) {
+                    int* __restrict__ sad, int out_stride) {
     __shared__ uint8_t sL[kStWarps][128], sR[kStWarps][11 * 21 + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int iL = blockIdx.x * kStWarps + warp;
+    // blockIdx.y = frame of the batch, relative to the first one (Ls.frame / Rs.frame)
+    const int fr = blockIdx.y;
+    Ls.frame += fr; Rs.frame += fr;
+    Ls.kps += (size_t)fr * Ls.g->out_cap; Ls.desc += (size_t)fr * Ls.g->out_cap * 32; Ls.count += fr;
+    Rs.kps += (size_t)fr * Rs.g->out_cap; Rs.desc += (size_t)fr * Rs.g->out_cap * 32; Rs.count += fr;
+    uRight += (size_t)fr * out_stride; depth += (size_t)fr * out_stride; sad += (size_t)fr * out_stride;
     const int nL = min(*Ls.count, Ls.g->out_cap), nR = min(*Rs.count, Rs.g->out_cap);
     if (iL >= nL) return;
     const orbx_keypoint kL = Ls.kps[iL];
@@ -112,51 +118,66 @@ stereo_match_kernel(StereoSide Ls, StereoSide Rs, float mbf, float mb, float* __
     }
 }
 
-// single block: median of (sad, index) pairs by rank counting, then the 1.5*1.4*median rejection
+// Median of the patch distances and the 1.5*1.4*median rejection (src/Frame.cc:625-639), one block per frame. The
+// reference sorts (distance, index) pairs and takes element m/2: found here by a radix select over the distances (they are
+// below 2^17: 121 pixels x 2 x 255) - 17 block-wide counting passes instead of n^2 rank comparisons - the distances staying
+// in global memory (L2), so there is no shared-memory limit on the number of keypoints.
 __global__ void __launch_bounds__(1024)
 stereo_median_filter_kernel(const int* __restrict__ count, int cap, float* __restrict__ uRight, float* __restrict__ depth,
-                            int* __restrict__ sad, int* __restrict__ kept) {
-    extern __shared__ int s_sad[];  // [cap]
-    __shared__ int s_m, s_median;
+                            int* __restrict__ sad, int* __restrict__ kept, int out_stride) {
+    __shared__ int s_cnt[2], s_m;
+    const int fr = blockIdx.x;
+    count += fr; kept += fr;
+    uRight += (size_t)fr * out_stride; depth += (size_t)fr * out_stride; sad += (size_t)fr * out_stride;
     const int n = min(*count, cap);
-    if (threadIdx.x == 0) { s_m = 0; s_median = -1; }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s_sad[i] = sad[i];
+    if (threadIdx.x == 0) s_m = 0;
     __syncthreads();
     int mine = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += s_sad[i] >= 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += sad[i] >= 0;
     if (mine) atomicAdd(&s_m, mine);
     __syncthreads();
     const int m = s_m;
     if (m == 0) { if (threadIdx.x == 0) *kept = 0; return; }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int d = s_sad[i];
-        if (d < 0) continue;
-        int rank = 0;
-        for (int j = 0; j < n; ++j) { const int e = s_sad[j]; rank += e >= 0 && (e < d || (e == d && j < i)); }
-        if (rank == m / 2) s_median = d;
+    // the (m/2)-th smallest distance (0-based; equal distances are interchangeable for the value)
+    int prefix = 0, k = m / 2;
+    for (int bit = 17; bit >= 0; --bit) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt[0] = 0;
+        __syncthreads();
+        int zeros = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int d = sad[i];
+            if (d >= 0 && (d >> (bit + 1)) == (prefix >> (bit + 1)) && !((d >> bit) & 1)) ++zeros;
+        }
+        if (zeros) atomicAdd(&s_cnt[0], zeros);
+        __syncthreads();
+        const int z = s_cnt[0];
+        if (k >= z) { k -= z; prefix |= 1 << bit; }
     }
-    __syncthreads();
-    const float thDist = __fmul_rn(1.5f * 1.4f, (float)s_median);
-    int k = 0;
+    const float thDist = __fmul_rn(1.5f * 1.4f, (float)prefix);
+    int good = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int d = s_sad[i];
+        const int d = sad[i];
         if (d < 0) continue;
-        if ((float)d < thDist) ++k;
+        if ((float)d < thDist) ++good;
         else { uRight[i] = -1.0f; depth[i] = -1.0f; }
     }
+    __syncthreads();
     if (threadIdx.x == 0) s_m = 0;
     __syncthreads();
-    if (k) atomicAdd(&s_m, k);
+    if (good) atomicAdd(&s_m, good);
     __syncthreads();
     if (threadIdx.x == 0) *kept = s_m;
 }
 
-int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, float mbf, float mb, float* d_uRight, float* d_depth, int* d_sad,
-                  int* d_kept, cudaStream_t st) {
-    stereo_match_kernel<<<ceil_div(capL, kStWarps), kStWarps * 32, 0, st>>>(L, R, mbf, mb, d_uRight, d_depth, d_sad);
+// n_frames consecutive frames of both handles, starting at L.frame / R.frame; outputs [n_frames][out_stride]
+int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, int n_frames, int out_stride, float mbf, float mb, float* d_uRight,
+                  float* d_depth, int* d_sad, int* d_kept, cudaStream_t st) {
+    ORB_REQUIRE(n_frames >= 1 && n_frames <= 65535, "1..65535 frames per stereo call");
+    stereo_match_kernel<<<dim3(ceil_div(capL, kStWarps), n_frames), kStWarps * 32, 0, st>>>(L, R, mbf, mb, d_uRight, d_depth, d_sad, out_stride);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
-    stereo_median_filter_kernel<<<1, 1024, (size_t)capL * sizeof(int), st>>>(L.count, capL, d_uRight, d_depth, d_sad, d_kept);
+    stereo_median_filter_kernel<<<n_frames, 1024, 0, st>>>(L.count, capL, d_uRight, d_depth, d_sad, d_kept, out_stride);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

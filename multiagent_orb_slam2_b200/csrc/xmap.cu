@@ -35,6 +35,7 @@ namespace orb {
 int mma_encode_operand_map(CUtensorMap* out, const void* base, long long rows, bool query_side);
 int mma_expand_rows(const uint8_t* packed, int n_rows, bool query_side, uint8_t* out, cudaStream_t st);
 int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, int na, int nb, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st);
+int mma_preload_kernels();
 
 constexpr int kXmapMaxWorld = 16, kXmapMaxSlots = 8, kXmapCtrlBytes = 4096, kXmapTile = 128;
 struct XmapCtrl {
@@ -192,7 +193,13 @@ int orbm_xmap_create(int device, int rank, int world, int n_maps, int rows_cap, 
     if ((e = cudaMalloc(&x->d_ptrs, orbm_xmap::kPtrSlots * sizeof(void*))) != cudaSuccess) return fail("cudaMalloc(flags)", e);
     if ((e = cudaMallocHost(&x->h_ptrs, orbm_xmap::kPtrSlots * sizeof(void*))) != cudaSuccess) return fail("cudaMallocHost(flags)", e);
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail("cudaDeviceSynchronize", e);
-    int rc = mma_encode_operand_map(&x->map_a, x->scr_a, (long long)x->res_rows, true);
+    // every kernel of the step is loaded while the device is idle (see mma_preload_kernels)
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, xmap_wait_kernel)) != cudaSuccess) return fail("cudaFuncGetAttributes", e);
+    if ((e = cudaFuncGetAttributes(&fa, xmap_signal_kernel)) != cudaSuccess) return fail("cudaFuncGetAttributes", e);
+    int rc = mma_preload_kernels();
+    if (rc != ORB_OK) { cudaFree(x->window); cudaFree(x->scr_a); cudaFree(x->scr_b); cudaFree(x->d_ptrs); cudaFreeHost(x->h_ptrs); delete x; return rc; }
+    rc = mma_encode_operand_map(&x->map_a, x->scr_a, (long long)x->res_rows, true);
     if (rc == ORB_OK) rc = mma_encode_operand_map(&x->map_b, x->scr_b, (long long)x->res_rows, false);
     if (rc != ORB_OK) { fail("tensor map", cudaSuccess); return rc; }
     x->peer[rank] = x->window;

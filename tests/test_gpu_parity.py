@@ -349,3 +349,38 @@ def test_host_wrappers_from_many_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_stereo_batch_equals_single_frames_and_oracle():
+    """orbm_stereo_match_batch_device (all frames of a batched L / R extraction in one launch pair) against the per-frame
+    call and the oracle."""
+    import ctypes as C
+    import torch
+    from multiagent_orb_slam2_b200 import _lib
+    from multiagent_orb_slam2_b200.extractor import compute_stereo_matches
+    w, h, nf, B = 752, 480, 1200, 5
+    pairs = [synth.stereo_pair("blocks", w, h, 20 + s) for s in range(B)]
+    left, right = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    mbf, fx = np.float32(386.1448), np.float32(718.856)
+    mb = np.float32(mbf / fx)
+    gL, gR = ORBextractor(nf, 1.2, 8, 20, 7, w, h, max_batch=B), ORBextractor(nf, 1.2, 8, 20, 7, w, h, max_batch=B)
+    kL, _, cL = gL.extract_batch(left)
+    gR.extract_batch(right)
+    cap = gL.cap
+    L = _lib.lib()
+    ur = torch.full((B, cap + 3), -7.0, dtype=torch.float32, device="cuda"); dz = torch.full_like(ur, -7.0)
+    sad = torch.zeros((B, cap + 3), dtype=torch.int32, device="cuda"); kept = torch.zeros(B, dtype=torch.int32, device="cuda")
+    _lib.check(L.orbm_stereo_match_batch_device(gL._h, gR._h, B, float(mbf), float(mb), C.c_void_p(ur.data_ptr()), C.c_void_p(dz.data_ptr()),
+                                                C.c_void_p(sad.data_ptr()), C.c_void_p(kept.data_ptr()), cap + 3, None))
+    torch.cuda.synchronize()
+    for f in range(B):
+        su, sd, sk = compute_stereo_matches(gL, gR, mbf, mb, frame=f)
+        n = int(cL[f])
+        assert int(kept[f]) == sk and sk > 100
+        assert np.array_equal(ur[f, :n].cpu().numpy().view(np.uint32), su[:n].view(np.uint32))
+        assert np.array_equal(dz[f, :n].cpu().numpy().view(np.uint32), sd[:n].view(np.uint32))
+        if f in (0, B - 1):
+            oL, oR = O.OracleExtractor(nf, 1.2, 8, 20, 7), O.OracleExtractor(nf, 1.2, 8, 20, 7)
+            oL(left[f]); oR(right[f])
+            ou, od, ok = O.stereo_match(oL, oR, mbf, mb)
+            assert ok == sk and np.array_equal(su[:n].view(np.uint32), ou.view(np.uint32)) and np.array_equal(sd[:n].view(np.uint32), od.view(np.uint32))
