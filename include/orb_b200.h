@@ -222,7 +222,9 @@ int orbm_xmap_plan(int n_maps, const int32_t* rows_per_map, int world, int rank,
  * Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:230-245, 382-392) on the keypoints an extractor left on the
  * device (bounds = mnMinX, mnMinY, mnMaxX, mnMaxY); orbm_window_knn2_device replaces Frame::GetFeaturesInArea
  * (src/Frame.cc:327-380) fused with the best / second loop that consumes it (e.g. src/ORBmatcher.cc:84-116): query q
- * = (x, y, r, minLevel, maxLevel, descriptor row q of d_queries); candidates are visited in the reference's order
+ * = (x, y, r, minLevel, maxLevel, descriptor row q of d_queries); the grid and the window tests use the coordinates of the
+ * keypoint array given to orbm_grid_build_device - for a distorted camera pass mvKeysUn (orbm_undistort_keypoints_device)
+ * and the bounds of orbm_image_bounds; candidates are visited in the reference's order
  * (cell column, cell row, insertion), so ties resolve identically. Outputs also carry the octaves of best and second
  * (src/ORBmatcher.cc:119-122). Stateless form; capacity < 2^20 keypoints per frame. */
 typedef struct orbm_grid* orbm_grid_handle;
@@ -269,11 +271,23 @@ int orbm_project_points_device(int device, const orbm_camera* cam, int mode, flo
                                int32_t* d_level, float* d_view_cos, float* d_radius, int32_t* d_min_level,
                                int32_t* d_max_level, void* stream);
 
+/* Frame::UndistortKeyPoints (src/Frame.cc:404-434): mvKeysUn for the keypoints an extractor left on the device (d_kps,
+ * d_count, cap of orbx_device_results) - cv::undistortPoints(pts, pts, mK, mDistCoef, noArray(), mK) in OpenCV's double
+ * arithmetic (5 iterations), x / y replaced, the other fields copied; a zero first coefficient is the reference's
+ * "mvKeysUn = mvKeys" shortcut. dist_coef (HOST) = k1 k2 p1 p2 [k3 [k4 k5 k6]]. The result array is what
+ * orbm_grid_build_device, the window searches and orbm_stereo_from_rgbd_device take for a distorted camera.
+ * orbm_image_bounds (host only) is Frame::ComputeImageBounds (436-464): bounds4 = mnMinX, mnMaxX, mnMinY, mnMaxY. */
+int orbm_undistort_keypoints_device(int device, const orbx_keypoint* d_kps, const int32_t* d_count, int cap, float fx, float fy, float cx,
+                                    float cy, const float* dist_coef, int n_dist, orbx_keypoint* d_kps_un, void* stream);
+int orbm_image_bounds(int width, int height, float fx, float fy, float cx, float cy, const float* dist_coef, int n_dist, float* bounds4);
+
 /* Frame::ComputeStereoFromRGBD (src/Frame.cc:643-664) for the keypoints an extractor left on the device
- * (orbx_device_results: d_kps, d_count, cap): depth image (float, device, stride in bytes) sampled at the truncated
- * keypoint position; d_depth[i] = d and d_uRight[i] = x - mbf/d when d > 0, else -1 (also for i >= count). */
-int orbm_stereo_from_rgbd_device(int device, const orbx_keypoint* d_kps, const int32_t* d_count, int cap, const float* d_depth_image,
-                                 int width, int height, size_t stride_bytes, float mbf, float* d_uRight, float* d_depth, void* stream);
+ * (orbx_device_results: d_kps, d_count, cap): depth image (float, device, stride in bytes) sampled at the truncated RAW
+ * keypoint position (mvKeys); d_depth[i] = d and d_uRight[i] = xU - mbf/d when d > 0, else -1 (also for i >= count), xU
+ * taken from d_kps_un (mvKeysUn, orbm_undistort_keypoints_device) or from d_kps when d_kps_un is NULL (no distortion). */
+int orbm_stereo_from_rgbd_device(int device, const orbx_keypoint* d_kps, const orbx_keypoint* d_kps_un, const int32_t* d_count, int cap,
+                                 const float* d_depth_image, int width, int height, size_t stride_bytes, float mbf, float* d_uRight,
+                                 float* d_depth, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Vocabulary tree descent (the step right after extraction): replaces the per-feature

@@ -85,7 +85,9 @@ def lib():
         "orbdb_size": [vp],
         "orbdb_query": [vp, vp, vp, i32, vp, vp, vp, i32],
         "orbdb_query_device": [vp, vp, vp, i32, vp, vp, vp, vp],
-        "orbm_stereo_from_rgbd_device": [i32, vp, vp, i32, vp, i32, i32, C.c_size_t, f32, vp, vp, vp],
+        "orbm_stereo_from_rgbd_device": [i32, vp, vp, vp, i32, vp, i32, i32, C.c_size_t, f32, vp, vp, vp],
+        "orbm_undistort_keypoints_device": [i32, vp, vp, i32, f32, f32, f32, f32, vp, i32, vp, vp],
+        "orbm_image_bounds": [i32, i32, f32, f32, f32, f32, vp, i32, vp],
         "orbm_xmap_create": [i32, i32, i32, i32, i32, C.POINTER(vp)],
         "orbm_xmap_ipc_handle": [vp, vp],
         "orbm_xmap_attach_ipc": [vp, vp],

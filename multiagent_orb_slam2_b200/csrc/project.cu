@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) project_points_kernel(const ProjectParams
 
 // Frame::ComputeStereoFromRGBD (/root/reference/src/Frame.cc:643-664): the depth image sampled at the (truncated) keypoint
 // position gives mvDepth, and mvuRight = x - mbf/depth, for the keypoints an extractor left on the device.
-__global__ void __launch_bounds__(256) stereo_from_rgbd_kernel(const orbx_keypoint* __restrict__ kps, const int32_t* __restrict__ count, int cap,
+__global__ void __launch_bounds__(256) stereo_from_rgbd_kernel(const orbx_keypoint* __restrict__ kps, const orbx_keypoint* __restrict__ kps_un, const int32_t* __restrict__ count, int cap,
                                                                const float* __restrict__ depth_img, int width, int height, size_t pitch_floats,
                                                                float mbf, float* __restrict__ uright, float* __restrict__ depth) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) stereo_from_rgbd_kernel(const orbx_keypoi
             const float d = depth_img[(size_t)v * pitch_floats + u];
             if (d > 0) {
                 dz = d;
-                ur = __fsub_rn(kp.x, __fdiv_rn(mbf, d));
+                ur = __fsub_rn(kps_un ? kps_un[i].x : kp.x, __fdiv_rn(mbf, d));   // kpU.pt.x - mbf/d (src/Frame.cc:661)
             }
         }
     }
@@ -110,7 +110,80 @@ __global__ void __launch_bounds__(256) stereo_from_rgbd_kernel(const orbx_keypoi
     depth[i] = dz;
 }
 
+// Frame::UndistortKeyPoints (src/Frame.cc:404-434) -> cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK): normalise with
+// K, 5 fixed-point iterations of the distortion model (k1 k2 p1 p2 k3 k4 k5 k6; the thin-prism terms are zero for ORB-SLAM2's
+// 4 / 5 coefficient calibrations), re-project with K - all in double like OpenCV, result stored as float. The build uses
+// --fmad=false, so no product is fused: identical to oracle/cvprim_mat.h (pinned to cv2 4.13) bit for bit.
+struct UndistortParams { double fx, fy, cx, cy, ifx, ify, k[8]; };
+__device__ __host__ inline void undistort_point(const UndistortParams& p, float xin, float yin, float* xo, float* yo) {
+    const double x0 = ((double)xin - p.cx) * p.ifx, y0 = ((double)yin - p.cy) * p.ify;
+    double x = x0, y = y0;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((p.k[7] * r2 + p.k[6]) * r2 + p.k[5]) * r2) / (1 + ((p.k[4] * r2 + p.k[1]) * r2 + p.k[0]) * r2);
+        if (icdist < 0) { x = x0; y = y0; break; }
+        const double dx = 2 * p.k[2] * x * y + p.k[3] * (r2 + 2 * x * x);
+        const double dy = p.k[2] * (r2 + 2 * y * y) + 2 * p.k[3] * x * y;
+        x = (x0 - dx) * icdist;
+        y = (y0 - dy) * icdist;
+    }
+    *xo = (float)(p.fx * x + p.cx);
+    *yo = (float)(p.fy * y + p.cy);
+}
+__global__ void __launch_bounds__(256) undistort_keypoints_kernel(UndistortParams p, const orbx_keypoint* __restrict__ kps,
+                                                                  const int* __restrict__ count, int cap, orbx_keypoint* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(*count, cap)) return;
+    orbx_keypoint kp = kps[i];
+    undistort_point(p, kp.x, kp.y, &kp.x, &kp.y);
+    out[i] = kp;
+}
+static int make_undistort_params(float fx, float fy, float cx, float cy, const float* dist, int n_dist, UndistortParams* p) {
+    ORB_REQUIRE(dist && (n_dist == 4 || n_dist == 5 || n_dist == 8), "distortion coefficients: 4 (k1 k2 p1 p2), 5 (+ k3) or 8 (+ k4 k5 k6)");
+    ORB_REQUIRE(fx != 0 && fy != 0, "zero focal length");
+    p->fx = fx; p->fy = fy; p->cx = cx; p->cy = cy;
+    p->ifx = 1.0 / p->fx; p->ify = 1.0 / p->fy;
+    for (int i = 0; i < 8; ++i) p->k[i] = i < n_dist ? (double)dist[i] : 0.0;
+    return ORB_OK;
+}
+
 }  // namespace orb
+
+extern "C" int orbm_undistort_keypoints_device(int device, const orbx_keypoint* d_kps, const int32_t* d_count, int cap, float fx, float fy, float cx,
+                                               float cy, const float* dist_coef, int n_dist, orbx_keypoint* d_kps_un, void* stream) {
+    using namespace orb;
+    ORB_REQUIRE(d_kps && d_count && d_kps_un && cap > 0, "bad arguments");
+    UndistortParams p;
+    const int rc = make_undistort_params(fx, fy, cx, cy, dist_coef, n_dist, &p);
+    if (rc != ORB_OK) return rc;
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    if (dist_coef[0] == 0.0f) {   // mDistCoef.at<float>(0) == 0.0: mvKeysUn = mvKeys (src/Frame.cc:406-410)
+        ORB_CUDA_TRY(cudaMemcpyAsync(d_kps_un, d_kps, (size_t)cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return ORB_OK;
+    }
+    undistort_keypoints_kernel<<<ceil_div(cap, 256), 256, 0, (cudaStream_t)stream>>>(p, d_kps, d_count, cap, d_kps_un);
+    count_launch();
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+// Frame::ComputeImageBounds (src/Frame.cc:436-464), host only: the four image corners through the same arithmetic.
+extern "C" int orbm_image_bounds(int width, int height, float fx, float fy, float cx, float cy, const float* dist_coef, int n_dist, float* bounds4) {
+    using namespace orb;
+    ORB_REQUIRE(bounds4 && width > 0 && height > 0, "bad arguments");
+    UndistortParams p;
+    const int rc = make_undistort_params(fx, fy, cx, cy, dist_coef, n_dist, &p);
+    if (rc != ORB_OK) return rc;
+    if (dist_coef[0] == 0.0f) { bounds4[0] = 0.0f; bounds4[1] = (float)width; bounds4[2] = 0.0f; bounds4[3] = (float)height; return ORB_OK; }
+    const float cxs[4] = {0.f, (float)width, 0.f, (float)width}, cys[4] = {0.f, 0.f, (float)height, (float)height};
+    float ux[4], uy[4];
+    for (int i = 0; i < 4; ++i) undistort_point(p, cxs[i], cys[i], &ux[i], &uy[i]);
+    bounds4[0] = ux[0] < ux[2] ? ux[0] : ux[2];   // mnMinX = min(corner0.x, corner2.x)
+    bounds4[1] = ux[1] > ux[3] ? ux[1] : ux[3];   // mnMaxX
+    bounds4[2] = uy[0] < uy[1] ? uy[0] : uy[1];   // mnMinY
+    bounds4[3] = uy[2] > uy[3] ? uy[2] : uy[3];   // mnMaxY
+    return ORB_OK;
+}
 
 extern "C" int orbm_project_points_device(int device, const orbm_camera* cam, int mode, float viewing_cos_limit, float th,
                                           const float* d_world_pos, const float* d_normal, const float* d_max_distance,
@@ -138,13 +211,14 @@ extern "C" int orbm_project_points_device(int device, const orbm_camera* cam, in
     return ORB_OK;
 }
 
-extern "C" int orbm_stereo_from_rgbd_device(int device, const orbx_keypoint* d_kps, const int32_t* d_count, int cap, const float* d_depth_image,
-                                            int width, int height, size_t stride_bytes, float mbf, float* d_uRight, float* d_depth, void* stream) {
+extern "C" int orbm_stereo_from_rgbd_device(int device, const orbx_keypoint* d_kps, const orbx_keypoint* d_kps_un, const int32_t* d_count, int cap,
+                                            const float* d_depth_image, int width, int height, size_t stride_bytes, float mbf, float* d_uRight,
+                                            float* d_depth, void* stream) {
     using namespace orb;
     ORB_REQUIRE(d_kps && d_count && d_depth_image && d_uRight && d_depth, "null pointer");
     ORB_REQUIRE(cap > 0 && width > 0 && height > 0 && stride_bytes >= (size_t)width * 4 && stride_bytes % 4 == 0, "bad geometry");
     ORB_CUDA_TRY(cudaSetDevice(device));
-    stereo_from_rgbd_kernel<<<ceil_div(cap, 256), 256, 0, (cudaStream_t)stream>>>(d_kps, d_count, cap, d_depth_image, width, height,
+    stereo_from_rgbd_kernel<<<ceil_div(cap, 256), 256, 0, (cudaStream_t)stream>>>(d_kps, d_kps_un, d_count, cap, d_depth_image, width, height,
                                                                                  stride_bytes / 4, mbf, d_uRight, d_depth);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());

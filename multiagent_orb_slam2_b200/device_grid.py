@@ -11,9 +11,14 @@ from . import _lib
 
 
 class DeviceFrameGrid:
-    def __init__(self, extractor, frame=0, min_x=0.0, min_y=0.0, max_x=None, max_y=None, stream=None):
+    def __init__(self, extractor, frame=0, min_x=0.0, min_y=0.0, max_x=None, max_y=None, stream=None, K=None, dist_coef=None):
         """extractor: an ORBextractor whose last call produced `frame`; bounds default to the image
         (mnMinX.. of an undistorted / rectified camera, src/Frame.cc:457-462).
+
+        Distorted cameras (TUM RGB-D, EuRoC mono): pass K = (fx, fy, cx, cy) and dist_coef = (k1, k2, p1, p2[, k3]). The grid
+        is then built over mvKeysUn (Frame::UndistortKeyPoints on the device, self.d_kps_un) inside the undistorted image
+        bounds (Frame::ComputeImageBounds), exactly like the reference's Frame; without them the raw keypoints are used,
+        which is only right for a camera without distortion.
 
         Stream ordering: the grid is built on `stream` (a raw cudaStream_t / torch.cuda.Stream; default: torch's current
         stream on the extractor's device - never the legacy NULL stream, which the library's non-blocking streams are not
@@ -33,6 +38,8 @@ class DeviceFrameGrid:
         g = C.c_void_p()
         _lib.check(self.L.orbm_grid_create(extractor.device, cap, C.byref(g)))
         self._g = g
+        self.d_kps_un = self.d_kps
+        self.bounds = (float(min_x), float(w if max_x is None else max_x), float(min_y), float(h if max_y is None else max_y))
         with torch.cuda.device(self.dev):
             if stream is None:
                 ts = torch.cuda.current_stream(self.dev)
@@ -40,9 +47,22 @@ class DeviceFrameGrid:
                 ts = stream
             else:
                 ts = torch.cuda.ExternalStream(int(stream), device=self.dev)
-            _lib.check(self.L.orbm_grid_build_device(g, C.c_void_p(self.d_kps), C.c_void_p(self.d_count), float(min_x), float(min_y),
-                                                     float(w if max_x is None else max_x), float(h if max_y is None else max_y),
-                                                     C.c_void_p(ts.cuda_stream)))
+            if dist_coef is not None and float(np.float32(dist_coef[0])) != 0.0:
+                if K is None:
+                    raise ValueError("dist_coef needs the camera matrix K = (fx, fy, cx, cy)")
+                d = np.ascontiguousarray(dist_coef, np.float32)
+                fx, fy, cx, cy = (float(np.float32(v)) for v in K)
+                b = np.zeros(4, np.float32)
+                _lib.check(self.L.orbm_image_bounds(w, h, fx, fy, cx, cy, d.ctypes.data_as(C.c_void_p), len(d), b.ctypes.data_as(C.c_void_p)))
+                self.bounds = tuple(float(v) for v in b)
+                with torch.cuda.stream(ts):
+                    self._un = torch.empty(cap * 24, dtype=torch.uint8, device=self.dev)
+                self.d_kps_un = self._un.data_ptr()
+                _lib.check(self.L.orbm_undistort_keypoints_device(extractor.device, C.c_void_p(self.d_kps), C.c_void_p(self.d_count), cap, fx, fy,
+                                                                  cx, cy, d.ctypes.data_as(C.c_void_p), len(d), C.c_void_p(self.d_kps_un),
+                                                                  C.c_void_p(ts.cuda_stream)))
+            _lib.check(self.L.orbm_grid_build_device(g, C.c_void_p(self.d_kps_un), C.c_void_p(self.d_count), self.bounds[0], self.bounds[2],
+                                                     self.bounds[1], self.bounds[3], C.c_void_p(ts.cuda_stream)))
             self._built = torch.cuda.Event()
             self._built.record(ts)
 
@@ -51,6 +71,13 @@ class DeviceFrameGrid:
         st = torch.cuda.current_stream(self.dev)
         st.wait_event(self._built)
         return C.c_void_p(st.cuda_stream)
+
+    def undistorted_keypoints(self, n):
+        """mvKeysUn of the frame as a structured host array (first n keypoints)."""
+        from .extractor import KP_DTYPE
+        torch.cuda.synchronize(self.dev)
+        view = _raw_device_bytes(self.d_kps_un, n * 24, self.dev)
+        return view.cpu().numpy().view(KP_DTYPE)
 
     def close(self):
         if getattr(self, "_g", None):
@@ -105,3 +132,12 @@ class DeviceFrameGrid:
             break
         torch.cuda.synchronize(self.dev)
         return offs.cpu().numpy(), cands[:total.value].cpu().numpy(), dist[:total.value].cpu().numpy()
+
+
+def _raw_device_bytes(ptr, nbytes, dev):
+    class _Ext:
+        pass
+    e = _Ext()
+    e.__cuda_array_interface__ = {"shape": (max(nbytes, 1),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    with torch.cuda.device(dev):
+        return torch.as_tensor(e, device=dev)[:nbytes]

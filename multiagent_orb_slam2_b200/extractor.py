@@ -165,10 +165,12 @@ def compute_stereo_matches(left, right, mbf, mb, frame=0):
     return u, d, kept.value
 
 
-def compute_stereo_from_rgbd(ex, depth_image, mbf, frame=0):
+def compute_stereo_from_rgbd(ex, depth_image, mbf, frame=0, d_kps_un=None):
     """Frame::ComputeStereoFromRGBD (/root/reference/src/Frame.cc:643-664) on the device-resident keypoints of the last call
     of `ex`: depth_image float32 H x W (metres, already scaled by mDepthMapFactor as in Tracking::GrabImageRGBD).
-    Returns (mvuRight, mvDepth) over the frame's keypoints."""
+    d_kps_un: device pointer to mvKeysUn of the frame (DeviceFrameGrid(..., K=, dist_coef=).d_kps_un) for a distorted camera -
+    the depth is sampled at the raw position, the right coordinate uses the undistorted x. Returns (mvuRight, mvDepth) over
+    the frame's keypoints."""
     import torch
     L = _lib.lib()
     kp, _, cn, cap = ex.device_results()
@@ -176,7 +178,8 @@ def compute_stereo_from_rgbd(ex, depth_image, mbf, frame=0):
     img = torch.as_tensor(np.ascontiguousarray(depth_image, np.float32)).to(dev)
     u = torch.empty(cap, dtype=torch.float32, device=dev); d = torch.empty(cap, dtype=torch.float32, device=dev)
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(L.orbm_stereo_from_rgbd_device(ex.device, C.c_void_p(kp + frame * cap * 24), C.c_void_p(cn + frame * 4), cap,
+    _lib.check(L.orbm_stereo_from_rgbd_device(ex.device, C.c_void_p(kp + frame * cap * 24), C.c_void_p(d_kps_un) if d_kps_un else None,
+                                              C.c_void_p(cn + frame * 4), cap,
                                               C.c_void_p(img.data_ptr()), img.shape[1], img.shape[0], img.shape[1] * 4, float(mbf),
                                               C.c_void_p(u.data_ptr()), C.c_void_p(d.data_ptr()), st))
     torch.cuda.synchronize(dev)

@@ -71,3 +71,21 @@ def test_three_maxima_and_descriptor_distance_host_helpers():
     assert ORBmatcher.ComputeThreeMaxima([0, 30, 3, 2] + [0] * 26) == (1, 2, -1)
     assert ORBmatcher.ComputeThreeMaxima([5, 30, 3, 2] + [0] * 26) == (1, 0, 2)
     assert ORBmatcher.ComputeThreeMaxima([0] * 30) == (-1, -1, -1)
+
+
+def test_image_bounds_host_entry_equals_oracle():
+    """orbm_image_bounds (Frame::ComputeImageBounds, src/Frame.cc:436-464) is host arithmetic: checked here without a GPU
+    against the oracle restatement (pinned to cv2.undistortPoints and to the reference's Frame constructor)."""
+    import oracle_lib as O
+    L = _lib.lib()
+    f32 = np.float32
+    for K4, dist in [([517.306408, 516.469215, 318.643040, 255.313989], [0.262383, -0.953104, -0.005358, 0.002628, 1.163314]),
+                     ([458.654, 457.296, 367.215, 248.375], [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]),
+                     ([500.0, 500.0, 320.0, 240.0], [0.0, 0.0, 0.0, 0.0])]:
+        for w, h in ((640, 480), (752, 480)):
+            d = np.array(dist, f32)
+            b = np.zeros(4, f32)
+            assert L.orbm_image_bounds(w, h, *[float(f32(v)) for v in K4], d.ctypes.data_as(C.c_void_p), len(d), b.ctypes.data_as(C.c_void_p)) == _lib.ORB_OK
+            Km = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], f32)
+            assert np.array_equal(b.view(np.uint32), O.image_bounds(w, h, Km, d).view(np.uint32)), (K4, w, h)
+    assert L.orbm_image_bounds(640, 480, 500.0, 500.0, 320.0, 240.0, d.ctypes.data_as(C.c_void_p), 3, b.ctypes.data_as(C.c_void_p)) == _lib.ORB_EINVAL

@@ -130,3 +130,53 @@ def test_stereo_from_rgbd_matches_restatement():
             want_u[i] = f32(k["x"][i] - f32(mbf / d))
     assert np.array_equal(dz.view(np.uint32), want_d.view(np.uint32)) and np.array_equal(ur.view(np.uint32), want_u.view(np.uint32))
     assert 0.6 < (want_d[:n] > 0).mean() < 0.9
+
+
+def test_undistort_keypoints_grid_and_rgbd_with_tum1_distortion():
+    """SURVEY section 8f-2 with a distorted camera (TUM1.yaml): Frame::UndistortKeyPoints / ComputeImageBounds on the device ==
+    oracle restatement (itself pinned to cv2 and to the reference's Frame constructor, tests/test_oracle_vs_reference_matcher.py);
+    the device grid then buckets mvKeysUn inside the undistorted bounds, and ComputeStereoFromRGBD uses the undistorted x."""
+    from multiagent_orb_slam2_b200.device_grid import DeviceFrameGrid
+    from multiagent_orb_slam2_b200.extractor import compute_stereo_from_rgbd
+    K4 = [517.306408, 516.469215, 318.643040, 255.313989]
+    dist = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], f32)
+    Km = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], f32)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    k, d = ex(synth.image("blocks", W, H, 91))
+    n = len(k)
+    grid = DeviceFrameGrid(ex, K=K4, dist_coef=dist)
+    un = grid.undistorted_keypoints(n)
+    want = O.undistort_points(np.stack([k["x"], k["y"]], 1), Km, dist)
+    assert np.array_equal(np.stack([un["x"], un["y"]], 1).view(np.uint32), want.view(np.uint32))
+    for fld in ("size", "angle", "response", "octave"):
+        assert np.array_equal(un[fld], k[fld])
+    assert np.abs(want - np.stack([k["x"], k["y"]], 1)).max() > 1.0
+    bounds = O.image_bounds(W, H, Km, dist)
+    assert np.array_equal(np.array(grid.bounds, f32).view(np.uint32), bounds.view(np.uint32))
+    # window search over the undistorted grid == oracle frame with mvKeysUn and the undistorted bounds
+    okun = np.stack([un["x"], un["y"], k["size"], k["angle"], k["response"], k["octave"].astype(f32)], 1)
+    F = O.OracleFrame(okun, d, W, H, bounds=bounds)
+    rng = np.random.default_rng(2)
+    nq = 300
+    qx, qy = rng.uniform(bounds[0] - 5, bounds[1] + 5, nq).astype(f32), rng.uniform(bounds[2] - 5, bounds[3] + 5, nq).astype(f32)
+    r = rng.choice([5.0, 20.0, 60.0], nq).astype(f32)
+    qd = d[rng.integers(0, n, nq)]
+    gi, g1, g2, _, _ = grid.window_knn2(qd, qx, qy, r, 0, 4)
+    hits = 0
+    for i in range(nq):
+        cand = F.features_in_area(qx[i], qy[i], r[i], 0, 4)
+        ds = [O.hamming(qd[i], d[j]) for j in cand]
+        wantq = (cand[int(np.argmin(ds))], min(ds)) if cand else (-1, 256)
+        assert (gi[i], g1[i]) == wantq, i
+        hits += len(cand) > 0
+    assert hits > 100
+    # RGB-D: depth at the raw position, right coordinate from the undistorted x
+    depth = rng.uniform(0.3, 8.0, (H, W)).astype(f32)
+    depth[rng.random((H, W)) < 0.2] = 0.0
+    ur, dz = compute_stereo_from_rgbd(ex, depth, 40.0, d_kps_un=grid.d_kps_un)
+    kp6 = np.stack([k["x"], k["y"]], 1)
+    wu, wd = O.stereo_from_rgbd(kp6, want, depth, 40.0)
+    assert np.array_equal(ur[:n].view(np.uint32), wu.view(np.uint32)) and np.array_equal(dz[:n].view(np.uint32), wd.view(np.uint32))
+    # zero distortion: mvKeysUn = mvKeys, bounds = image
+    g0 = DeviceFrameGrid(ex, K=K4, dist_coef=[0, 0, 0, 0])
+    assert g0.d_kps_un == g0.d_kps and g0.bounds == (0.0, float(W), 0.0, float(H))
