@@ -114,6 +114,65 @@ private:
     std::vector<int16_t> dist_;
 };
 
+// Running nearest / second-nearest of one candidate scan. Every search of the reference keeps them with strict '<' updates
+// in visiting order, so the nearest is the FIRST minimum and a tie with it becomes the second; an
+// optional tag (the candidate's pyramid level) travels with each of the two.
+struct NearestTwo {
+    int d1, d2, arg, tag1, tag2;
+    explicit NearestTwo(int start) : d1(start), d2(start), arg(-1), tag1(-1), tag2(-1) {}
+    void visit(int d, size_t index, int tag = -1) {
+        if (d < d1) { d2 = d1; tag2 = tag1; d1 = d; tag1 = tag; arg = (int)index; }
+        else if (d < d2) { d2 = d; tag2 = tag; }
+    }
+    bool passes_ratio(float ratio) const { return static_cast<float>(d1) < ratio * static_cast<float>(d2); }
+};
+struct Nearest {
+    int d, arg;
+    explicit Nearest(int start) : d(start), arg(-1) {}
+    void visit(int dist, size_t index) { if (dist < d) { d = dist; arg = (int)index; } }
+};
+
+// The orientation-consistency filter shared by seven searches: every accepted match votes with the angle difference of its
+// two keypoints into one of 30 bins; afterwards only the matches of the three fullest bins survive (second / third bin only
+// if they hold at least a tenth of the fullest). bin = round(rot / 30) with rot in [0, 360): the reference's arithmetic,
+// which only ever fills bins 0..12 (src/ORBmatcher.cc:240-250, 1603-1644) - kept as it is.
+class OrientationVote {
+public:
+    enum { kBins = 30 };
+    static int bin_of(float angle1, float angle2) {
+        float rot = angle1 - angle2;
+        if (rot < 0.0) rot += 360.0f;
+        const int bin = (int)std::round(rot * (1.0f / kBins));
+        return bin == kBins ? 0 : bin;
+    }
+    void cast(float angle1, float angle2, int token) { votes_[bin_of(angle1, angle2)].push_back(token); }
+    // the three dominant bins (-1 = none), exactly ComputeThreeMaxima
+    void dominant(int& first, int& second, int& third) const {
+        int m1 = 0, m2 = 0, m3 = 0;
+        first = second = third = -1;
+        for (int b = 0; b < kBins; ++b) {
+            const int n = (int)votes_[b].size();
+            if (n > m1) { m3 = m2; m2 = m1; m1 = n; third = second; second = first; first = b; }
+            else if (n > m2) { m3 = m2; m2 = n; third = second; second = b; }
+            else if (n > m3) { m3 = n; third = b; }
+        }
+        if (m2 < 0.1f * (float)m1) { second = -1; third = -1; }
+        else if (m3 < 0.1f * (float)m1) third = -1;
+    }
+    // calls drop(token) for every vote outside the dominant bins; drop returns how many matches that removed (0 or 1)
+    template <class Drop> int prune(Drop drop) const {
+        int a, b, c, removed = 0;
+        dominant(a, b, c);
+        for (int i = 0; i < kBins; ++i) {
+            if (i == a || i == b || i == c) continue;
+            for (size_t j = 0; j < votes_[i].size(); ++j) removed += drop(votes_[i][j]);
+        }
+        return removed;
+    }
+private:
+    std::vector<int> votes_[kBins];
+};
+
 }  // namespace b200_detail
 
 class ORBmatcher {
@@ -135,11 +194,9 @@ public:
     int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10) {
         int nmatches = 0;
         vnMatches12 = std::vector<int>(F1.mvKeysUn.size(), -1);
-        std::vector<int> rotHist[HISTO_LENGTH];
-        for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
-        const float factor = 1.0f / HISTO_LENGTH;
-        std::vector<int> vMatchedDistance(F2.mvKeysUn.size(), INT_MAX);
-        std::vector<int> vnMatches21(F2.mvKeysUn.size(), -1);
+        b200_detail::OrientationVote vote;
+        std::vector<int> claimed_at(F2.mvKeysUn.size(), INT_MAX);   // distance at which a keypoint of F2 is currently matched
+        std::vector<int> owner(F2.mvKeysUn.size(), -1);             // ... and by which keypoint of F1
 
         // 1. host: gate. Candidate lists in the reference's iteration order, CSR.
         const size_t n1 = F1.mvKeysUn.size();
@@ -161,41 +218,19 @@ public:
         // 3. host: the reference's ordered resolve (src/ORBmatcher.cc:434-488)
         for (size_t i1 = 0; i1 < n1; i1++) {
             if (offsets[i1] == offsets[i1 + 1]) continue;
-            int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
-            for (int k = offsets[i1]; k < offsets[i1 + 1]; ++k) {
-                const int i2 = cands[k], d = dist[k];
-                if (vMatchedDistance[i2] <= d) continue;
-                if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
-                else if (d < bestDist2) bestDist2 = d;
-            }
-            if (bestDist <= TH_LOW) {
-                if (bestDist < (float)bestDist2 * mfNNratio) {
-                    if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
-                    vnMatches12[i1] = bestIdx2;
-                    vnMatches21[bestIdx2] = (int)i1;
-                    vMatchedDistance[bestIdx2] = bestDist;
-                    nmatches++;
-                    if (mbCheckOrientation) {
-                        float rot = F1.mvKeysUn[i1].angle - F2.mvKeysUn[bestIdx2].angle;
-                        if (rot < 0.0) rot += 360.0f;
-                        int bin = (int)std::round(rot * factor);
-                        if (bin == HISTO_LENGTH) bin = 0;
-                        rotHist[bin].push_back((int)i1);
-                    }
-                }
-            }
+            b200_detail::NearestTwo nn(INT_MAX);
+            for (int k = offsets[i1]; k < offsets[i1 + 1]; ++k)
+                if (claimed_at[cands[k]] > dist[k]) nn.visit(dist[k], (size_t)cands[k]);   // a closer earlier claim hides the candidate
+            if (nn.d1 > TH_LOW || !nn.passes_ratio(mfNNratio)) continue;
+            if (owner[nn.arg] >= 0) { vnMatches12[owner[nn.arg]] = -1; nmatches--; }      // take the keypoint over
+            vnMatches12[i1] = nn.arg;
+            owner[nn.arg] = (int)i1;
+            claimed_at[nn.arg] = nn.d1;
+            nmatches++;
+            if (mbCheckOrientation) vote.cast(F1.mvKeysUn[i1].angle, F2.mvKeysUn[nn.arg].angle, (int)i1);
         }
-        if (mbCheckOrientation) {
-            int ind1 = -1, ind2 = -1, ind3 = -1;
-            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
-            for (int i = 0; i < HISTO_LENGTH; i++) {
-                if (i == ind1 || i == ind2 || i == ind3) continue;
-                for (size_t j = 0; j < rotHist[i].size(); j++) {
-                    const int idx1 = rotHist[i][j];
-                    if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
-                }
-            }
-        }
+        if (mbCheckOrientation)
+            nmatches -= vote.prune([&](int i1) { if (vnMatches12[i1] < 0) return 0; vnMatches12[i1] = -1; return 1; });
         for (size_t i1 = 0; i1 < vnMatches12.size(); i1++)
             if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2.mvKeysUn[vnMatches12[i1]].pt;
         return nmatches;
@@ -219,10 +254,8 @@ public:
         const cv::Mat& Descriptors2 = pKF2->mDescriptors;
 
         vpMatches12 = std::vector<MapPointT*>(vpMapPoints1.size(), static_cast<MapPointT*>(NULL));
-        std::vector<bool> vbMatched2(vpMapPoints2.size(), false);
-        std::vector<int> rotHist[HISTO_LENGTH];
-        for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
-        const float factor = 1.0f / HISTO_LENGTH;
+        std::vector<bool> taken2(vpMapPoints2.size(), false);
+        b200_detail::OrientationVote vote;
         int nmatches = 0;
 
         // 1. host: merge walk (552-634) -> CSR of (idx1 occurrence) x (features of the same node in KF2)
@@ -255,39 +288,20 @@ public:
             MapPointT* pMP1 = vpMapPoints1[idx1];
             if (!pMP1) continue;
             if (pMP1->isBad()) continue;
-            int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+            b200_detail::NearestTwo nn(256);
             for (int k = offsets[q]; k < offsets[q + 1]; ++k) {
                 const size_t idx2 = (size_t)cands[k];
                 MapPointT* pMP2 = vpMapPoints2[idx2];
-                if (vbMatched2[idx2] || !pMP2) continue;
-                if (pMP2->isBad()) continue;
-                const int d = dist[k];
-                if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdx2 = (int)idx2; }
-                else if (d < bestDist2) bestDist2 = d;
+                if (taken2[idx2] || !pMP2 || pMP2->isBad()) continue;
+                nn.visit(dist[k], idx2);
             }
-            if (bestDist1 < TH_LOW) {
-                if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
-                    vpMatches12[idx1] = vpMapPoints2[bestIdx2];
-                    vbMatched2[bestIdx2] = true;
-                    if (mbCheckOrientation) {
-                        float rot = vKeysUn1[idx1].angle - vKeysUn2[bestIdx2].angle;
-                        if (rot < 0.0) rot += 360.0f;
-                        int bin = (int)std::round(rot * factor);
-                        if (bin == HISTO_LENGTH) bin = 0;
-                        rotHist[bin].push_back((int)idx1);
-                    }
-                    nmatches++;
-                }
-            }
+            if (nn.d1 >= TH_LOW || !nn.passes_ratio(mfNNratio)) continue;   // strictly below TH_LOW here (600)
+            vpMatches12[idx1] = vpMapPoints2[nn.arg];
+            taken2[nn.arg] = true;
+            if (mbCheckOrientation) vote.cast(vKeysUn1[idx1].angle, vKeysUn2[nn.arg].angle, (int)idx1);
+            nmatches++;
         }
-        if (mbCheckOrientation) {
-            int ind1 = -1, ind2 = -1, ind3 = -1;
-            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
-            for (int i = 0; i < HISTO_LENGTH; i++) {
-                if (i == ind1 || i == ind2 || i == ind3) continue;
-                for (size_t j = 0; j < rotHist[i].size(); j++) { vpMatches12[rotHist[i][j]] = static_cast<MapPointT*>(NULL); nmatches--; }
-            }
-        }
+        if (mbCheckOrientation) nmatches -= vote.prune([&](int idx1) { vpMatches12[idx1] = static_cast<MapPointT*>(NULL); return 1; });
         return nmatches;
     }
 
@@ -327,7 +341,7 @@ public:
         int nmatches = 0;
         for (size_t n = 0; n < queries.size(); ++n) {
             const Query& q = queries[n];
-            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            b200_detail::NearestTwo nn(256);
             for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
                 const size_t idx = pairs.cand(k);
                 if (F.mvpMapPoints[idx] && F.mvpMapPoints[idx]->Observations() > 0) continue;
@@ -335,21 +349,13 @@ public:
                     const float er = fabs(q.mp->mTrackProjXR[pSystem] - F.mvuRight[idx]);
                     if (er > q.radius) continue;
                 }
-                const int dist = pairs.dist(k);
-                if (dist < bestDist) {
-                    bestDist2 = bestDist; bestDist = dist;
-                    bestLevel2 = bestLevel; bestLevel = F.mvKeysUn[idx].octave;
-                    bestIdx = (int)idx;
-                } else if (dist < bestDist2) {
-                    bestLevel2 = F.mvKeysUn[idx].octave;
-                    bestDist2 = dist;
-                }
+                nn.visit(pairs.dist(k), idx, F.mvKeysUn[idx].octave);
             }
-            if (bestDist <= TH_HIGH) {  // ratio to the second match only when both are at the same scale level
-                if (bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2) continue;
-                F.mvpMapPoints[bestIdx] = q.mp;
-                nmatches++;
-            }
+            if (nn.d1 > TH_HIGH) continue;
+            // the ratio to the second match counts only when both sit on the same pyramid level (119-122)
+            if (nn.tag1 == nn.tag2 && nn.d1 > mfNNratio * nn.d2) continue;
+            F.mvpMapPoints[nn.arg] = q.mp;
+            nmatches++;
         }
         return nmatches;
     }
@@ -395,10 +401,10 @@ public:
         pairs.run(CurrentFrame.mDescriptors);
 
         int nmatches = 0;
-        std::vector<int> rotHist[HISTO_LENGTH];
+        OrientationVote vote;
         for (size_t n = 0; n < queries.size(); ++n) {
             const Query& q = queries[n];
-            int bestDist = 256, bestIdx2 = -1;
+            Nearest nn(256);
             for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
                 const size_t i2 = pairs.cand(k);
                 if (CurrentFrame.mvpMapPoints[i2] && CurrentFrame.mvpMapPoints[i2]->Observations() > 0) continue;
@@ -406,22 +412,14 @@ public:
                     const float er = fabs(q.ur - CurrentFrame.mvuRight[i2]);
                     if (er > q.radius) continue;
                 }
-                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx2 = (int)i2; }
+                nn.visit(pairs.dist(k), i2);
             }
-            if (bestDist <= TH_HIGH) {
-                CurrentFrame.mvpMapPoints[bestIdx2] = q.mp;
-                nmatches++;
-                if (mbCheckOrientation) rotHist[RotationBin(LastFrame.mvKeysUn[q.i].angle, CurrentFrame.mvKeysUn[bestIdx2].angle)].push_back(bestIdx2);
-            }
+            if (nn.d > TH_HIGH) continue;
+            CurrentFrame.mvpMapPoints[nn.arg] = q.mp;
+            nmatches++;
+            if (mbCheckOrientation) vote.cast(LastFrame.mvKeysUn[q.i].angle, CurrentFrame.mvKeysUn[nn.arg].angle, nn.arg);
         }
-        if (mbCheckOrientation) {
-            int ind1 = -1, ind2 = -1, ind3 = -1;
-            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
-            for (int i = 0; i < HISTO_LENGTH; i++) {
-                if (i == ind1 || i == ind2 || i == ind3) continue;
-                for (size_t j = 0; j < rotHist[i].size(); j++) { CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPointPtr>(NULL); nmatches--; }
-            }
-        }
+        if (mbCheckOrientation) nmatches -= vote.prune([&](int i2) { CurrentFrame.mvpMapPoints[i2] = static_cast<MapPointPtr>(NULL); return 1; });
         return nmatches;
     }
 
@@ -461,29 +459,18 @@ public:
         pairs.run(CurrentFrame.mDescriptors);
 
         int nmatches = 0;
-        std::vector<int> rotHist[HISTO_LENGTH];
+        OrientationVote vote;
         for (size_t n = 0; n < queries.size(); ++n) {
             const Query& q = queries[n];
-            int bestDist = 256, bestIdx2 = -1;
-            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
-                const size_t i2 = pairs.cand(k);
-                if (CurrentFrame.mvpMapPoints[i2]) continue;
-                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx2 = (int)i2; }
-            }
-            if (bestDist <= ORBdist) {
-                CurrentFrame.mvpMapPoints[bestIdx2] = q.mp;
-                nmatches++;
-                if (mbCheckOrientation) rotHist[RotationBin(pKF->mvKeysUn[q.i].angle, CurrentFrame.mvKeysUn[bestIdx2].angle)].push_back(bestIdx2);
-            }
+            Nearest nn(256);
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k)
+                if (!CurrentFrame.mvpMapPoints[pairs.cand(k)]) nn.visit(pairs.dist(k), pairs.cand(k));
+            if (nn.d > ORBdist) continue;
+            CurrentFrame.mvpMapPoints[nn.arg] = q.mp;
+            nmatches++;
+            if (mbCheckOrientation) vote.cast(pKF->mvKeysUn[q.i].angle, CurrentFrame.mvKeysUn[nn.arg].angle, nn.arg);
         }
-        if (mbCheckOrientation) {
-            int ind1 = -1, ind2 = -1, ind3 = -1;
-            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
-            for (int i = 0; i < HISTO_LENGTH; i++) {
-                if (i == ind1 || i == ind2 || i == ind3) continue;
-                for (size_t j = 0; j < rotHist[i].size(); j++) { CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPointT*>(NULL); nmatches--; }
-            }
-        }
+        if (mbCheckOrientation) nmatches -= vote.prune([&](int i2) { CurrentFrame.mvpMapPoints[i2] = static_cast<MapPointT*>(NULL); return 1; });
         return nmatches;
     }
 
@@ -526,13 +513,10 @@ public:
         int nmatches = 0;
         for (size_t n = 0; n < queries.size(); ++n) {
             const Query& q = queries[n];
-            int bestDist = 256, bestIdx = -1;
-            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
-                const size_t idx = pairs.cand(k);
-                if (vpMatched[idx]) continue;
-                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx = (int)idx; }
-            }
-            if (bestDist <= TH_LOW) { vpMatched[bestIdx] = q.mp; nmatches++; }
+            Nearest nn(256);
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k)
+                if (!vpMatched[pairs.cand(k)]) nn.visit(pairs.dist(k), pairs.cand(k));
+            if (nn.d <= TH_LOW) { vpMatched[nn.arg] = q.mp; nmatches++; }
         }
         return nmatches;
     }
@@ -566,31 +550,18 @@ public:
         pairs.run(F.mDescriptors);
 
         int nmatches = 0;
-        std::vector<int> rotHist[HISTO_LENGTH];
+        b200_detail::OrientationVote vote;
         for (size_t n = 0; n < queries.size(); ++n) {
             const Query& q = queries[n];
-            int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
-            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
-                const size_t realIdxF = pairs.cand(k);
-                if (vpMapPointMatches[realIdxF]) continue;
-                const int dist = pairs.dist(k);
-                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = (int)realIdxF; }
-                else if (dist < bestDist2) bestDist2 = dist;
-            }
-            if (bestDist1 <= TH_LOW && static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
-                vpMapPointMatches[bestIdxF] = q.mp;
-                if (mbCheckOrientation) rotHist[RotationBin(pKF->mvKeysUn[q.idxKF].angle, F.mvKeys[bestIdxF].angle)].push_back(bestIdxF);
-                nmatches++;
-            }
+            b200_detail::NearestTwo nn(256);
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k)
+                if (!vpMapPointMatches[pairs.cand(k)]) nn.visit(pairs.dist(k), pairs.cand(k));
+            if (nn.d1 > TH_LOW || !nn.passes_ratio(mfNNratio)) continue;
+            vpMapPointMatches[nn.arg] = q.mp;
+            if (mbCheckOrientation) vote.cast(pKF->mvKeysUn[q.idxKF].angle, F.mvKeys[nn.arg].angle, nn.arg);   // F.mvKeys, not Un (235)
+            nmatches++;
         }
-        if (mbCheckOrientation) {
-            int ind1 = -1, ind2 = -1, ind3 = -1;
-            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
-            for (int i = 0; i < HISTO_LENGTH; i++) {
-                if (i == ind1 || i == ind2 || i == ind3) continue;
-                for (size_t j = 0; j < rotHist[i].size(); j++) { vpMapPointMatches[rotHist[i][j]] = static_cast<MapPointT*>(NULL); nmatches--; }
-            }
-        }
+        if (mbCheckOrientation) nmatches -= vote.prune([&](int iF) { vpMapPointMatches[iF] = static_cast<MapPointT*>(NULL); return 1; });
         return nmatches;
     }
 
@@ -637,41 +608,35 @@ public:
         pairs.run(pKF2->mDescriptors);
 
         int nmatches = 0;
-        std::vector<int> vMatches12(pKF1->N, -1);
-        std::vector<int> rotHist[HISTO_LENGTH];
+        std::vector<int> partner(pKF1->N, -1);
+        OrientationVote vote;
         for (size_t n = 0; n < queries.size(); ++n) {
             const Query& q = queries[n];
             const cv::KeyPoint& kp1 = pKF1->mvKeysUn[q.idx1];
-            int bestDist = TH_LOW, bestIdx2 = -1;
+            // not the strict rule here: a candidate as close as the current choice replaces it (`dist > bestDist` skips, 740),
+            // provided it passes the geometric gates - so the LAST minimum among the admissible candidates wins
+            int limit = TH_LOW, chosen = -1;
             for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) {
                 const size_t idx2 = pairs.cand(k);
                 const int dist = pairs.dist(k);
-                if (dist > TH_LOW || dist > bestDist) continue;
+                if (dist > limit) continue;
                 const cv::KeyPoint& kp2 = pKF2->mvKeysUn[idx2];
                 if (!q.stereo1 && !(pKF2->mvuRight[idx2] >= 0)) {  // too close to the epipole: skip
                     const float distex = subf(ex, kp2.pt.x), distey = subf(ey, kp2.pt.y);
                     if (addf(mulf(distex, distex), mulf(distey, distey)) < 100 * pKF2->mvScaleFactors[kp2.octave]) continue;
                 }
-                if (CheckDistEpipolarLine(kp1, kp2, F12, pKF2)) { bestIdx2 = (int)idx2; bestDist = dist; }
+                if (CheckDistEpipolarLine(kp1, kp2, F12, pKF2)) { chosen = (int)idx2; limit = dist; }
             }
-            if (bestIdx2 >= 0) {
-                vMatches12[q.idx1] = bestIdx2;
-                nmatches++;
-                if (mbCheckOrientation) rotHist[RotationBin(kp1.angle, pKF2->mvKeysUn[bestIdx2].angle)].push_back((int)q.idx1);
-            }
+            if (chosen < 0) continue;
+            partner[q.idx1] = chosen;
+            nmatches++;
+            if (mbCheckOrientation) vote.cast(kp1.angle, pKF2->mvKeysUn[chosen].angle, (int)q.idx1);
         }
-        if (mbCheckOrientation) {
-            int ind1 = -1, ind2 = -1, ind3 = -1;
-            ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
-            for (int i = 0; i < HISTO_LENGTH; i++) {
-                if (i == ind1 || i == ind2 || i == ind3) continue;
-                for (size_t j = 0; j < rotHist[i].size(); j++) { vMatches12[rotHist[i][j]] = -1; nmatches--; }
-            }
-        }
+        if (mbCheckOrientation) nmatches -= vote.prune([&](int idx1) { partner[idx1] = -1; return 1; });
         vMatchedPairs.clear();
         vMatchedPairs.reserve(nmatches);
-        for (size_t i = 0; i < vMatches12.size(); i++)
-            if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
+        for (size_t i = 0; i < partner.size(); i++)
+            if (partner[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)partner[i]));
         return nmatches;
     }
 
@@ -731,10 +696,10 @@ public:
         for (size_t n = 0; n < queries.size(); ++n) {
             MapPointT* pMP = queries[n].mp;
             if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;  // earlier replacements of this call may have changed it
-            int bestDist = 256, bestIdx = -1;
-            for (int k = pairs.begin(queries[n].q); k < pairs.end(queries[n].q); ++k)
-                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx = (int)pairs.cand(k); }
-            if (bestDist <= TH_LOW) {  // replace if the keypoint already has a MapPoint, otherwise add the measurement
+            Nearest nn(256);
+            for (int k = pairs.begin(queries[n].q); k < pairs.end(queries[n].q); ++k) nn.visit(pairs.dist(k), pairs.cand(k));
+            const int bestIdx = nn.arg;
+            if (nn.d <= TH_LOW) {  // replace if the keypoint already has a MapPoint, otherwise add the measurement
                 MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx);
                 if (pMPinKF) {
                     if (!pMPinKF->isBad()) {
@@ -788,10 +753,10 @@ public:
         int nFused = 0;
         for (size_t n = 0; n < queries.size(); ++n) {
             const Query& q = queries[n];
-            int bestDist = INT_MAX, bestIdx = -1;
-            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k)
-                if (pairs.dist(k) < bestDist) { bestDist = pairs.dist(k); bestIdx = (int)pairs.cand(k); }
-            if (bestDist <= TH_LOW) {
+            Nearest nn(INT_MAX);
+            for (int k = pairs.begin(q.q); k < pairs.end(q.q); ++k) nn.visit(pairs.dist(k), pairs.cand(k));
+            const int bestIdx = nn.arg;
+            if (nn.d <= TH_LOW) {
                 MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx);
                 if (pMPinKF) {
                     if (!pMPinKF->isBad()) vpReplacePoint[q.iMP] = pMPinKF;

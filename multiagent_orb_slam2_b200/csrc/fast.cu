@@ -21,7 +21,7 @@
 //   1. every interior pixel, 2 rows x 4 per lane from aligned 32-bit words of the tile: rejection test (any arc
 //      of 9 contains ring pixel 0 or 8 and 4 or 12: one of each pair must differ from the centre by more than
 //      the threshold) on the four bytes of a word at once (VABSDIFF4 + SWAR compare)
-//                                                        -> survivor list (one shuffle scan per 256 px)
+//      -> list of words with survivors (ballot + one store; all-flat warp steps skip half of the test) -> survivor list
 //   2. survivors: the 16 ring pixels packed two per register (k, k+8), the 16 arc minima by two rounds
 //      of VIMNMX3.S16x2; corner <=> score >= threshold   -> score map, corner list (in place)
 //   3. corner list: 3x3 strict maximum                   -> per-row bit mask
@@ -53,6 +53,9 @@ __host__ __device__ inline FastLayout fast_layout(int max_tw, int max_th, int tp
     f.tile_bytes = max_th * tp;                      // multiple of 16 (tp is)
     f.score_pitch = (int)align_up((size_t)max_tw - 4, 4);  // score of cell pixel (x, y) at [(y - 2) * pitch + x - 2]
     f.score_bytes = (int)align_up((size_t)f.score_pitch * (max_th - 4), 16);
+    // the same region first holds phase 1a's word list: 4 bytes per (row, aligned 4-pixel group) item, rows in bands of 8
+    const int wl_bytes = ((max_th - 6 + 7) >> 3) * 8 * (((max_tw - 6 + 3) >> 2) + 1) * 4;
+    if (wl_bytes > f.score_bytes) f.score_bytes = (int)align_up((size_t)wl_bytes, 16);
     f.mask_words = (max_tw - 6 > 32 ? 2 : 1) * (max_th - 6);  // one word per interior row and 32 columns
     f.mask_off = f.tile_bytes + f.score_bytes;
     f.list_off = f.mask_off + (int)align_up((size_t)2 * f.mask_words * 4, 16);
@@ -141,11 +144,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             if (lane == 0) { *count_out = 0; issue(ci + stride); }
             continue;
         }
-        {   // clear the score map and the masks
-            uint4* z = reinterpret_cast<uint4*>(score);
-            for (int i = lane; i < lay.score_bytes >> 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = lane; i < lay.mask_words; i += 32) mask[i] = 0u;
-        }
+        for (int i = lane; i < lay.mask_words; i += 32) mask[i] = 0u;   // (the score map is cleared after phase 1)
         __syncwarp();
         mbar_wait(bar, parity);
         parity ^= 1u;
@@ -175,16 +174,23 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
         // 19 instead of 47 instructions per word: VABSDIFF4 and, per difference, |d| > thr as the top bit of
         // ((d & 0x7f) + 127 - thr) | d. Phase 2 decides exactly. (thr > 126: everything survives.)
         const uint32_t Kthr = (uint32_t)max(127 - thr, 0) * 0x01010101u, Kall = thr > 126 ? 0x80808080u : 0u;
-        auto hit4 = [&](uint32_t C, uint32_t U, uint32_t Dn, uint32_t Lw, uint32_t Rw) {
+        // vertical half (ring pixels 0 and 8) and horizontal half (4 and 12) of the test; pixel j of the word at bit 8 j + 7
+        auto vert4 = [&](uint32_t C, uint32_t U, uint32_t Dn) {
+            const uint32_t a = __vabsdiffu4(C, U), b = __vabsdiffu4(C, Dn);
+            return ((((a & 0x7f7f7f7fu) + Kthr) | a | ((b & 0x7f7f7f7fu) + Kthr) | b) | Kall) & 0x80808080u;
+        };
+        auto horz4 = [&](uint32_t C, uint32_t Lw, uint32_t Rw) {
             const uint32_t W12 = __funnelshift_r(Lw, C, 8);   // ring pixel 12 (x - 3) of the four centres
             const uint32_t W4 = __funnelshift_r(C, Rw, 24);   // ring pixel 4  (x + 3)
-            const uint32_t a = __vabsdiffu4(C, U), b = __vabsdiffu4(C, Dn), c = __vabsdiffu4(C, W12), d = __vabsdiffu4(C, W4);
-            const uint32_t qa = (a & 0x7f7f7f7fu) + Kthr, qb = (b & 0x7f7f7f7fu) + Kthr;
-            const uint32_t qc = (c & 0x7f7f7f7fu) + Kthr, qd = (d & 0x7f7f7f7fu) + Kthr;
-            const uint32_t v = qa | a | qb | b, h = qc | c | qd | d;
-            return ((v & h) | Kall) & 0x80808080u;  // pixel j at bit 8 j + 7
+            const uint32_t c = __vabsdiffu4(C, W12), d = __vabsdiffu4(C, W4);
+            return ((((c & 0x7f7f7f7fu) + Kthr) | c | ((d & 0x7f7f7f7fu) + Kthr) | d) | Kall) & 0x80808080u;
         };
-        int n1 = 0;
+        // ---- phase 1a: words with at least one survivor -> word list (in the score region, dead until phase 2) ----
+        // entry = hit bits (8 j + 7) | byte column of the word (bits 0-6) | row << 8 (bits 8-14): one ballot and one
+        // predicated store per row instead of a scan and four stores; a warp step whose 256 pixels all fail the vertical
+        // half (flat image regions) skips the horizontal half
+        uint32_t* wl = reinterpret_cast<uint32_t*>(score);
+        int nw = 0;
         for (int i0 = 0; i0 < nitems; i0 += 32) {
             const bool act = i0 + lane < nitems;
             const int i = act ? i0 + lane : nitems - 1;
@@ -195,23 +201,40 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
             const int bcol0 = wcol << 2;
             const int lead = max(bs - bcol0, 0), trail = max(bcol0 + 4 - be, 0);
             const uint32_t vw = (0x80808080u << (8 * lead)) & (0x80808080u >> (8 * trail)) & (act ? 0xffffffffu : 0u);
-            const uint32_t kw0 = hit4(wp[0], wp[-3 * tpw], wp[3 * tpw], wp[-1], wp[1]) & (y < th - 3 ? vw : 0u);
-            const uint32_t kw1 = hit4(wp[4 * tpw], wp[tpw], wp[7 * tpw], wp[4 * tpw - 1], wp[4 * tpw + 1]) & (y + 4 < th - 3 ? vw : 0u);
-            const int cnt = __popc(kw0) + __popc(kw1);
+            const uint32_t C0 = wp[0], C1 = wp[4 * tpw];
+            uint32_t kw0 = vert4(C0, wp[-3 * tpw], wp[3 * tpw]) & (y < th - 3 ? vw : 0u);
+            uint32_t kw1 = vert4(C1, wp[tpw], wp[7 * tpw]) & (y + 4 < th - 3 ? vw : 0u);
+            if (!__any_sync(0xffffffffu, (kw0 | kw1) != 0u)) continue;
+            kw0 &= horz4(C0, wp[-1], wp[1]);
+            kw1 &= horz4(C1, wp[4 * tpw - 1], wp[4 * tpw + 1]);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, kw0 != 0u), b1 = __ballot_sync(0xffffffffu, kw1 != 0u);
+            const uint32_t pos = (uint32_t)(bcol0 | y << 8);
+            if (kw0) wl[nw + __popc(b0 & lt_mask)] = kw0 | pos;
+            nw += __popc(b0);
+            if (kw1) wl[nw + __popc(b1 & lt_mask)] = kw1 | (pos + (4u << 8));
+            nw += __popc(b1);
+        }
+        __syncwarp();
+        // ---- phase 1b: word list -> pixel list (byte column | row << 7), one scan per 32 surviving words ----
+        int n1 = 0;
+        for (int i0 = 0; i0 < nw; i0 += 32) {
+            const uint32_t w = i0 + lane < nw ? wl[i0 + lane] : 0u;
+            const int cnt = __popc(w & 0x80808080u);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
             uint16_t* dst = list + n1 + inc - cnt;
-            const uint32_t e0 = (uint32_t)(bcol0 | y << 7), e1 = e0 + 4u * 128u;
-            if (kw0 & 0x00000080u) *dst++ = (uint16_t)e0;
-            if (kw0 & 0x00008000u) *dst++ = (uint16_t)(e0 + 1);
-            if (kw0 & 0x00800000u) *dst++ = (uint16_t)(e0 + 2);
-            if (kw0 & 0x80000000u) *dst++ = (uint16_t)(e0 + 3);
-            if (kw1 & 0x00000080u) *dst++ = (uint16_t)e1;
-            if (kw1 & 0x00008000u) *dst++ = (uint16_t)(e1 + 1);
-            if (kw1 & 0x00800000u) *dst++ = (uint16_t)(e1 + 2);
-            if (kw1 & 0x80000000u) *dst++ = (uint16_t)(e1 + 3);
+            const uint32_t e = (w & 127u) | ((w >> 8) & 127u) << 7;
+            if (w & 0x00000080u) *dst++ = (uint16_t)e;
+            if (w & 0x00008000u) *dst++ = (uint16_t)(e + 1);
+            if (w & 0x00800000u) *dst++ = (uint16_t)(e + 2);
+            if (w & 0x80000000u) *dst++ = (uint16_t)(e + 3);
             n1 += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        {   // the word list is dead: the region becomes the (zeroed) score map
+            uint4* z = reinterpret_cast<uint4*>(score);
+            for (int i = lane; i < lay.score_bytes >> 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncwarp();
 
