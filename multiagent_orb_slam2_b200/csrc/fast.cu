@@ -323,10 +323,10 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps
     int dev = 0;
     ORB_CUDA_TRY(cudaGetDevice(&dev));
     auto kernel = hg.fast_bw == 64 ? fast_cells_kernel<64> : fast_cells_kernel<0>;
-    if (smem > 48 * 1024 && dev < 64 && attr_bytes[dev] < (int)smem) {
+    if (smem > 48 * 1024 && (dev >= 64 || attr_bytes[dev] < (int)smem)) {   // device indices beyond the cache: always opt in
         ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ORB_CUDA_TRY(cudaFuncSetAttribute(fast_cells_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_bytes[dev] = (int)smem;
+        if (dev < 64) attr_bytes[dev] = (int)smem;
     }
     // cells per warp: as many as keeps every SM's warp slots (about 30 one-warp blocks) busy, at most 8
     const long long warps_wanted = (long long)kNumSMs * 32;

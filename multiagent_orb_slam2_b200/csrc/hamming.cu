@@ -247,6 +247,7 @@ static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strid
     const int backend = t_knn2_backend;
     if (nB_max > 0 && (backend == 2 || (backend == 0 && work >= kMmaMinWork && nB_max >= 64)))
         return launch_knn2_mma(dA, d_nA, nA_max, strideA_rows, dB, d_nB, nB_max, strideB_rows, d_pairs, pairs, strideA_rows, d_idx, d_b1, d_b2, st);
+    ORB_REQUIRE(pairs <= 65535, "more than 65535 set pairs in one call");   // grid.z
     // pick the slice count so that the grid covers the machine about twice
     int S = 1;
     while (S < 8 && ceil_div(nA_max, kKnnThreads / S) * pairs < 2 * kNumSMs) S *= 2;
