@@ -121,6 +121,27 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def measured_int8_peak():
+    """Dense int8 tensor-core peak of this GPU: a bare tcgen05.mma kind::i8 issue loop with both operands in shared memory
+    (tools/microbench/utcimma_peak.cu) run live when its binary is there, else the value recorded under profiles/, else
+    2 x the measured bf16 cuBLAS figure."""
+    exe = os.path.join(ROOT, "tools", "microbench", "utcimma_peak")
+    try:
+        if os.path.exists(exe):
+            for line in subprocess.check_output([exe], text=True, timeout=120).splitlines():
+                if "int8_tops_measured" in line:
+                    return json.loads(line)["int8_tops_measured"], "measured live: bare tcgen05.mma kind::i8 issue loop (tools/microbench/utcimma_peak.cu)"
+    except Exception:
+        pass
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r02_utcimma_peak.log")):
+            if "int8_tops_measured" in line:
+                return json.loads(line)["int8_tops_measured"], "profiles/r02_utcimma_peak.log (bare tcgen05.mma kind::i8 issue loop on a B200 of this pool)"
+    except Exception:
+        pass
+    return 2 * peaks()[0].get("bf16_tflops", 2250.0), "2 x the measured dense bf16 cuBLAS figure of MEASURED_PEAKS.json"
+
+
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_run(frames, threads):
     """Reference CPU path on `frames`: extraction with the reference's own ORBextractor.cc
@@ -485,6 +506,20 @@ def run_b200(args):
         sys.stderr.write("e2e enqueue times (ms): " + " ".join("%.2f" % (m * 1e3) for m in marks) + "\n")
     barrier()
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    # the floor of the end-to-end number on this box: the same pinned frames copied host -> device and nothing else, all
+    # ranks at once (they share the host's PCIe switches / memory controllers), max over ranks
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_tmp = torch.empty_like(d_frames)
+    for _ in range(2):
+        d_tmp.copy_(h_frames, non_blocking=True)
+    barrier()
+    f0.record()
+    for _ in range(8):
+        d_tmp.copy_(h_frames, non_blocking=True)
+    f1.record()
+    barrier()
+    h2d_floor_ms = max_over_ranks(f0.elapsed_time(f1)) / 8
+    del d_tmp
 
     # ---- per-stage device time of the dominant kernels (roofline), rank 0 -----------------------------
     roof = None
@@ -617,11 +652,7 @@ def run_b200(args):
         if world > 2:
             split, _ = xmap_leg(2, 5)   # fewer maps than GPUs: query rows of the 2 maps split over all ranks
             split["what"] = "2 maps on %d GPUs: the 128-row query tiles of both pairs dealt evenly to all ranks" % world
-        int8_peak = peaks()[0].get("int8_tops_measured")
-        int8_src = "measured: bare tcgen05.mma kind::i8 issue loop, tools/microbench/utcimma_peak.cu (profiles/)"
-        if not int8_peak:
-            int8_peak = 2 * peaks()[0].get("bf16_tflops", 2250.0)
-            int8_src = "2 x the measured dense bf16 cuBLAS figure of MEASURED_PEAKS.json (int8 = 2 x bf16 on sm_100a; 2 x 2250 nominal if absent)"
+        int8_peak, int8_src = measured_int8_peak()
         mapf = dict(leg)
         mapf.update({"metric": "G Hamming cmp/s, cross-map brute force + ratio test",
                      "exchange": "fused: peer loads over NVLink inside the operand-expansion kernel (orbm_knn2_allgather), no collective call",
@@ -687,6 +718,9 @@ def run_b200(args):
                        "keypoints_per_frame": kp_per_frame, "matches_per_frame": matches_per_frame},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * fe.h2d_bytes_per_frame(),
                     "d2h_bytes_per_step": B * fe.d2h_bytes_per_frame(), "ms_per_step": e2e_ms / args.steps,
+                    "h2d_floor_ms": h2d_floor_ms, "h2d_floor_gbs_per_rank": B * fe.h2d_bytes_per_frame() / (h2d_floor_ms * 1e-3) / 1e9,
+                    "h2d_floor_note": "pure pinned host -> device copy of one step's frames on every rank at once, max over ranks: the "
+                                      "platform bound of e2e (uploads of different steps cannot overlap each other on one PCIe link)",
                     "how": "pinned host frames -> orbx_upload_frames/extract_staged/orbm_knn2_batched/download, 3 buffers in flight"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mapfusion": mapf, "bow_transform": bow, "other_configs": other,
             "comm": comm,
