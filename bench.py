@@ -121,14 +121,17 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def measured_int8_peak():
+def measured_int8_peak(device=0):
     """Dense int8 tensor-core peak of this GPU: a bare tcgen05.mma kind::i8 issue loop with both operands in shared memory
     (tools/microbench/utcimma_peak.cu) run live when its binary is there, else the value recorded under profiles/, else
     2 x the measured bf16 cuBLAS figure."""
     exe = os.path.join(ROOT, "tools", "microbench", "utcimma_peak")
     try:
         if os.path.exists(exe):
-            for line in subprocess.check_output([exe], text=True, timeout=120).splitlines():
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            ids = vis.split(",") if vis else None
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=(ids[device] if ids and device < len(ids) else str(device)))
+            for line in subprocess.check_output([exe], text=True, timeout=120, env=env).splitlines():
                 if "int8_tops_measured" in line:
                     return json.loads(line)["int8_tops_measured"], "measured live: bare tcgen05.mma kind::i8 issue loop (tools/microbench/utcimma_peak.cu)"
     except Exception:
@@ -382,6 +385,15 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    # NCCL reads its logging environment once, when the library initialises - which may be at `import torch`: set it first.
+    # Its own log (communicator size, transport) is evidence of the N-rank run: INIT lines at INFO level, kept off stdout
+    # (the contract is ONE JSON line there); every rank logs to a file, rank 0 echoes its file to stderr at the end.
+    nccl_log = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        nccl_log = os.path.join(tempfile.gettempdir(), "orb_bench_nccl_%d_rank%s.log" % (os.getppid(), os.environ.get("RANK", "0")))
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
     import torch
     import torch.distributed as dist
     from multiagent_orb_slam2_b200 import _lib
@@ -395,14 +407,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
-    nccl_log = None
     if world > 1:
-        # NCCL's own log (communicator size, transport) is evidence of the N-rank run: INIT lines at INFO level, kept off
-        # stdout (the contract is ONE JSON line there): every rank logs to a file, rank 0 echoes its file to stderr
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        nccl_log = os.path.join(tempfile.gettempdir(), "orb_bench_nccl_%d_rank%d.log" % (os.getppid(), rank))
-        os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()   # creates the communicator now, so that its INIT lines are in the log
     comm = None
@@ -554,19 +559,22 @@ def run_b200(args):
         cmp_per_step = float((pin["counts"].numpy()[:B].astype(np.float64) * np.roll(pin["counts"].numpy()[:B], -1)).sum())
         per_stage["hamming_knn2"] = {"ms": match_ms, "gcmp_per_s": cmp_per_step / (match_ms * 1e-3) / 1e9}
         a = per_stage[STAGES[dom]]
-        # DRAM bytes per frame of each kernel from `ncu --set full` (profiles/r01_ncu_full_s3f_summary.md, B=64:
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch / 64; FAST also at B=512: 561 MB / 512), scaled to
-        # this launch's B frames
-        ncu_traffic_per_frame = {"pyramid_resize": 1.05e6, "gaussian_blur": 1.52e6, "fast_cells": 1.10e6, "quadtree": 0.135e6,
-                                 "orient_describe": 2.06e6}
+        # DRAM bytes per frame of each kernel from this round's `ncu --set full` captures (profiles/r02_ncu_traffic.json names
+        # them), scaled to this launch's B frames; null when the file is missing
+        try:
+            ncu_traffic_per_frame = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))["bytes_per_frame"]
+        except Exception:
+            ncu_traffic_per_frame = {}
         roof = {"kernel": STAGES[dom], "bound": "hbm", "achieved": a["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": a["frac_hbm"], "traffic": ncu_traffic_per_frame.get(STAGES[dom], 0.0) * B,
+                "frac": a["frac_hbm"],
+                "traffic": ncu_traffic_per_frame[STAGES[dom]] * B if STAGES[dom] in ncu_traffic_per_frame else None,
                 "algorithmic_bytes_per_launch": a["alg_bytes_per_frame"] * B,
                 "peak_source": pk_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                "note": "the dominant kernel (FAST) is bound by instruction issue and the shared-memory pipe, not by HBM (ncu at "
-                        "B=512: 80 % of issue slots, 78 % of shared-memory wavefront peak, 46 thread instructions per pixel, DRAM "
-                        "9 %); its DRAM traffic equals its algorithmic bytes. The HBM-streaming stages are pyramid_resize and "
-                        "gaussian_blur (see stages)",
+                "note": "bound is stated against HBM because the contract offers hbm | tensor; the dominant kernel (FAST) is in fact bound "
+                        "by instruction issue and the shared-memory pipe (ncu at B=512, profiles/r02_ncu_fast_b512_summary.md: 78 % of "
+                        "issue slots, 72 % of the shared-memory wavefront peak, 1.33 warp instructions per pixel, DRAM 9 %); its DRAM "
+                        "traffic (1.16 x) matches its algorithmic bytes. The HBM-streaming stages are pyramid_resize and gaussian_blur "
+                        "(see stages)",
                 "stages": per_stage}
 
     # ---- MapFusion cross-map matching (BASELINE config 5): G Hamming cmp/s over all ranks ------------------
@@ -652,7 +660,8 @@ def run_b200(args):
         if world > 2:
             split, _ = xmap_leg(2, 5)   # fewer maps than GPUs: query rows of the 2 maps split over all ranks
             split["what"] = "2 maps on %d GPUs: the 128-row query tiles of both pairs dealt evenly to all ranks" % world
-        int8_peak, int8_src = measured_int8_peak()
+        int8_peak, int8_src = measured_int8_peak(local_rank) if rank == 0 else (1.0, "")
+        barrier()   # the other ranks keep their GPUs idle meanwhile (shared power / clocks are not an issue, but keep the step clean)
         mapf = dict(leg)
         mapf.update({"metric": "G Hamming cmp/s, cross-map brute force + ratio test",
                      "exchange": "fused: peer loads over NVLink inside the operand-expansion kernel (orbm_knn2_allgather), no collective call",

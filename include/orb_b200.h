@@ -107,6 +107,10 @@ int orbx_download_results(orbx_handle h, int n, orbx_keypoint* kps, uint8_t* des
  * (pointer + pitch) or a copy to host (dst_stride >= width). */
 int orbx_pyramid_level_device(orbx_handle h, int frame, int level, const uint8_t** d_ptr, size_t* pitch);
 int orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_stride);
+/* Levels [first, first + count) at once: dst[k] / dst_stride[k] for level first + k. One synchronisation for all of them
+ * (pinned staging inside the handle) instead of one synchronous pageable copy per level; level 0 is the caller's own image
+ * (ComputePyramid copies it, src/ORBextractor.cc:1107-1132), so a host caller only needs levels 1 .. nlevels-1. */
+int orbx_pyramid_levels(orbx_handle h, int frame, int first, int count, uint8_t* const* dst, const size_t* dst_stride);
 
 /* ------------------------------------------------------------------------------------------
  * Matcher primitives. Replace the DescriptorDistance loops of ORBmatcher (src/ORBmatcher.cc:1649-1665

@@ -13,6 +13,7 @@
 #define ORBSLAM2_B200_ORBEXTRACTOR_H
 
 #include <cassert>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -75,12 +76,21 @@ public:
             keypoints.push_back(k);
         }
         if (download_pyramid_) {
+            // level 0 is the input itself (ComputePyramid copies it, 1107-1132): host copy; levels 1.. in one download
+            std::vector<uint8_t*> dst(nlevels > 1 ? nlevels - 1 : 0);
+            std::vector<size_t> strides(dst.size());
             for (int l = 0; l < nlevels; ++l) {
                 int w = 0, h = 0;
                 check(orbx_level_size(handle_, l, &w, &h));
                 mvImagePyramid[l].create(h, w, CV_8UC1);
-                check(orbx_pyramid_level(handle_, 0, l, mvImagePyramid[l].data, (size_t)mvImagePyramid[l].step));
+                if (l == 0) {
+                    for (int y = 0; y < h; ++y) std::memcpy(mvImagePyramid[0].ptr(y), image.ptr(y), (size_t)w);
+                } else {
+                    dst[l - 1] = mvImagePyramid[l].data;
+                    strides[l - 1] = (size_t)mvImagePyramid[l].step;
+                }
             }
+            if (nlevels > 1) check(orbx_pyramid_levels(handle_, 0, 1, nlevels - 1, dst.data(), strides.data()));
         }
     }
 

@@ -52,6 +52,7 @@ def lib():
         "orbx_device_results": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)],
         "orbx_pyramid_level_device": [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)],
         "orbx_pyramid_level": [vp, i32, i32, vp, sz],
+        "orbx_pyramid_levels": [vp, i32, i32, i32, vp, vp],
         "orbx_debug_blurred_level": [vp, i32, i32, vp, sz],
         "orbx_debug_candidates": [vp, i32, i32, vp, i32, C.POINTER(i32)],
         "orbx_debug_quadtree": [i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32)],

@@ -80,6 +80,7 @@ struct orbx_extractor {
     void* d_geom = nullptr; void* d_cells = nullptr; void* d_taps = nullptr; void* d_tiles = nullptr; void* d_pattern = nullptr;
     uint8_t* d_input = nullptr;  // staging for host frames: [max_batch][height][pitch0]
     float* d_stereo = nullptr;   // outputs of the host-buffer stereo call (uRight, depth, sad, kept), allocated on first use
+    uint8_t* h_pyr = nullptr;    // pinned staging of orbx_pyramid_levels (all levels of one frame, tightly packed), on first use
     size_t in_pitch = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
@@ -89,11 +90,15 @@ struct orbx_extractor {
     // Levels >= 1 are encoded once; level 0 follows the frames of the call (cached on the FrameSet).
     TmaMaps maps_resize, maps_blur, maps_fast;
     FrameSet maps_l0{};
-    // CUDA graph of the kernel sequence for small batches (the per-frame operator() path is launch bound:
-    // 11 launches + fork/join). Keyed on (frames, n): state 0 = nothing, 1 = ran eagerly once, 2 = captured.
-    cudaGraphExec_t graph_exec = nullptr;
-    FrameSet graph_fs{};
-    int graph_n = 0, graph_state = 0, graph_kernels = 0;
+    // CUDA graphs of the kernel sequence for small batches (the per-frame operator() path is launch bound: 11 launches +
+    // fork/join). A small LRU keyed on (frames, n) - a caller alternating two input buffers keeps both graphs; state
+    // 0 = free, 1 = ran eagerly once, 2 = captured. Capture failures are tolerated a few times (e.g. the caller's stream
+    // is itself being captured) before graphs are given up for the handle.
+    struct GraphEntry { FrameSet fs{}; int n = 0, state = 0, kernels = 0; cudaGraphExec_t exec = nullptr; unsigned long long stamp = 0; };
+    static constexpr int kGraphEntries = 4;
+    GraphEntry graphs[kGraphEntries];
+    unsigned long long graph_clock = 0;
+    int graph_failures = 0;
     bool use_graphs = true;
     // optional per-stage device timing (bench roofline): events around each stage of the pipeline
     bool stage_timing = false;
@@ -326,14 +331,20 @@ int enqueue_pipeline(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t 
     constexpr int kGraphMaxBatch = 16;
     const bool capturable = h->use_graphs && n <= kGraphMaxBatch && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
     if (capturable) {
-        const bool same = h->graph_n == n && h->graph_fs.base == fs.base && h->graph_fs.pitch == fs.pitch && h->graph_fs.frame_stride == fs.frame_stride;
-        if (same && h->graph_state == 2) {
-            ORB_CUDA_TRY(cudaGraphLaunch(h->graph_exec, st));
-            count_launch(h->graph_kernels);
+        orbx_extractor::GraphEntry* ge = nullptr;
+        orbx_extractor::GraphEntry* lru = &h->graphs[0];
+        for (auto& e : h->graphs) {
+            if (e.state && e.n == n && e.fs.base == fs.base && e.fs.pitch == fs.pitch && e.fs.frame_stride == fs.frame_stride) ge = &e;
+            if (e.stamp < lru->stamp) lru = &e;
+        }
+        if (ge) ge->stamp = ++h->graph_clock;
+        if (ge && ge->state == 2) {
+            ORB_CUDA_TRY(cudaGraphLaunch(ge->exec, st));
+            count_launch(ge->kernels);
             h->last = fs; h->last_n = n;
             return ORB_OK;
         }
-        if (same && h->graph_state == 1) {  // second identical call: capture
+        if (ge && ge->state == 1) {  // second identical call: capture
             const long long before = orb_launch_count();
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
@@ -343,24 +354,27 @@ int enqueue_pipeline(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t 
                 const int captured = (int)(orb_launch_count() - before);
                 count_launch(-captured);  // nothing ran during capture
                 if (rc == ORB_OK && e == cudaSuccess && graph) {
-                    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-                    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+                    e = cudaGraphInstantiate(&ge->exec, graph, 0);
                     cudaGraphDestroy(graph);
                     if (e == cudaSuccess) {
-                        h->graph_state = 2; h->graph_kernels = captured;
-                        ORB_CUDA_TRY(cudaGraphLaunch(h->graph_exec, st));
+                        ge->state = 2; ge->kernels = captured;
+                        h->graph_failures = 0;
+                        ORB_CUDA_TRY(cudaGraphLaunch(ge->exec, st));
                         count_launch(captured);
                         h->last = fs; h->last_n = n;
                         return ORB_OK;
                     }
+                    ge->exec = nullptr;
                 } else if (graph) {
                     cudaGraphDestroy(graph);
                 }
             }
-            cudaGetLastError();      // capture not possible here (e.g. the caller's stream is already capturing):
-            h->use_graphs = false;   // stay on plain launches
-        } else {
-            h->graph_fs = fs; h->graph_n = n; h->graph_state = 1;
+            cudaGetLastError();      // capture not possible right now (e.g. the caller's stream is already capturing):
+            ge->state = 0;           // this call runs as plain launches; only repeated failures switch graphs off
+            if (++h->graph_failures >= 3) h->use_graphs = false;
+        } else if (!ge) {
+            if (lru->exec) { cudaGraphExecDestroy(lru->exec); lru->exec = nullptr; }
+            lru->fs = fs; lru->n = n; lru->state = 1; lru->kernels = 0; lru->stamp = ++h->graph_clock;
         }
     }
     if ((rc = launch_sequence(h, fs, n, st))) return rc;
@@ -397,7 +411,8 @@ void orbx_destroy(orbx_handle h) {
     void* ptrs[] = {h->d_geom, h->d_cells, h->d_taps, h->d_tiles, h->d_pattern, h->db.pyr, h->db.blur, h->db.slots, h->db.cell_counts,
                     h->db.sortbuf, h->db.selected, h->db.sel_counts, h->db.kps, h->db.desc, h->db.counts, h->d_input, h->d_stereo};
     for (void* p : ptrs) if (p) cudaFree(p);
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->h_pyr) cudaFreeHost(h->h_pyr);
+    for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
     for (cudaEvent_t e : h->ev_stage) if (e) cudaEventDestroy(e);
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
@@ -578,6 +593,38 @@ int orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t
     ORB_REQUIRE(dst && dst_stride >= (size_t)L.w, "bad destination");
     ORB_CUDA_TRY(cudaSetDevice(h->device));
     ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, p, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+// mvImagePyramid in one go: levels [first, first + count) of `frame` -> dst[k] (row stride dst_stride[k] >= width of the
+// level). The levels are copied into a pinned staging area by `count` asynchronous 2-D copies on the handle's stream, one
+// synchronisation, then host memcpys - instead of one synchronous pageable copy per level.
+int orbx_pyramid_levels(orbx_handle h, int frame, int first, int count, uint8_t* const* dst, const size_t* dst_stride) {
+    ORB_REQUIRE(h && dst && dst_stride && frame >= 0 && frame < h->last_n, "bad handle / frame");
+    ORB_REQUIRE(first >= 0 && count >= 0 && first + count <= h->cfg.nlevels, "bad level range");
+    if (count == 0) return ORB_OK;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->h_pyr) {
+        size_t total = 0;
+        for (int l = 0; l < h->cfg.nlevels; ++l) total += (size_t)h->hg.lv[l].w * h->hg.lv[l].h;
+        ORB_CUDA_TRY(cudaMallocHost(&h->h_pyr, total));
+    }
+    size_t off = 0;
+    for (int k = 0; k < count; ++k) {
+        const LevelGeom& L = h->hg.lv[first + k];
+        ORB_REQUIRE(dst[k] && dst_stride[k] >= (size_t)L.w, "bad destination");
+        int pitch;
+        const uint8_t* src = level_ptr(h->hg, h->last, h->db.pyr, frame, first + k, &pitch);
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(h->h_pyr + off, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+        off += (size_t)L.w * L.h;
+    }
+    ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    off = 0;
+    for (int k = 0; k < count; ++k) {
+        const LevelGeom& L = h->hg.lv[first + k];
+        for (int y = 0; y < L.h; ++y) memcpy(dst[k] + (size_t)y * dst_stride[k], h->h_pyr + off + (size_t)y * L.w, L.w);
+        off += (size_t)L.w * L.h;
+    }
     return ORB_OK;
 }
 

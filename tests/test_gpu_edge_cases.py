@@ -172,3 +172,31 @@ def test_single_large_cell_levels(w, h, nl):
     assert len(gk) == len(ok)
     if len(ok):
         assert np.array_equal(got.view(np.uint32), ok.view(np.uint32)) and np.array_equal(gd, od)
+
+
+def test_alternating_device_input_buffers_keep_their_graphs():
+    """A caller that double-buffers its device frames alternates two FrameSets on one handle: both get their own captured
+    graph (small LRU), results stay those of the frame actually given - also for a third and fifth buffer (LRU eviction)."""
+    import torch
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=2)
+    imgs = [synth.image("blocks", 640, 480, 70 + i) for i in range(5)]
+    want = [O.OracleExtractor()(im) for im in imgs]
+    bufs = [torch.from_numpy(im).cuda() for im in imgs]
+    st = torch.cuda.Stream()
+    import ctypes as C
+    from multiagent_orb_slam2_b200 import _lib
+    from multiagent_orb_slam2_b200.extractor import KP_DTYPE
+    L = _lib.lib()
+    order = [0, 1, 0, 1, 0, 1, 2, 0, 3, 4, 1, 2, 2, 2, 0, 1]
+    for i in order:
+        with torch.cuda.stream(st):
+            ex.extract_device(bufs[i].data_ptr(), 640, 640 * 480, 1, st.cuda_stream)
+        st.synchronize()
+        kps = np.empty(ex.cap, KP_DTYPE); desc = np.empty((ex.cap, 32), np.uint8); cnt = np.zeros(1, np.int32)
+        _lib.check(L.orbx_download_results(ex._h, 1, kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), ex.cap,
+                                           cnt.ctypes.data_as(C.c_void_p), C.c_void_p(st.cuda_stream)))
+        st.synchronize()
+        n = int(cnt[0])
+        ok, od = want[i]
+        assert n == len(ok) and np.array_equal(desc[:n], od), (i, n, len(ok))
+        assert np.array_equal(kps["x"][:n].view(np.uint32), ok[:, 0].view(np.uint32))
