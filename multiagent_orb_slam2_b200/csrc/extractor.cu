@@ -604,26 +604,28 @@ int orbx_pyramid_levels(orbx_handle h, int frame, int first, int count, uint8_t*
     ORB_REQUIRE(first >= 0 && count >= 0 && first + count <= h->cfg.nlevels, "bad level range");
     if (count == 0) return ORB_OK;
     ORB_CUDA_TRY(cudaSetDevice(h->device));
-    if (!h->h_pyr) {
-        size_t total = 0;
-        for (int l = 0; l < h->cfg.nlevels; ++l) total += (size_t)h->hg.lv[l].w * h->hg.lv[l].h;
-        ORB_CUDA_TRY(cudaMallocHost(&h->h_pyr, total));
-    }
-    size_t off = 0;
+    // levels >= 1 of a frame are one contiguous slab on the device: ONE linear copy into pinned memory (narrow 2-D copies
+    // run far below the link rate), then the rows are unpacked on the host; level 0 lives in the caller's frames
+    if (!h->h_pyr) ORB_CUDA_TRY(cudaMallocHost(&h->h_pyr, h->hg.pyr_bytes + (size_t)h->hg.lv[0].w * h->hg.lv[0].h));
+    uint8_t* h_l0 = h->h_pyr + h->hg.pyr_bytes;
+    bool need_slab = false;
     for (int k = 0; k < count; ++k) {
         const LevelGeom& L = h->hg.lv[first + k];
         ORB_REQUIRE(dst[k] && dst_stride[k] >= (size_t)L.w, "bad destination");
-        int pitch;
-        const uint8_t* src = level_ptr(h->hg, h->last, h->db.pyr, frame, first + k, &pitch);
-        ORB_CUDA_TRY(cudaMemcpy2DAsync(h->h_pyr + off, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
-        off += (size_t)L.w * L.h;
+        if (first + k == 0) {
+            int pitch;
+            const uint8_t* src = level_ptr(h->hg, h->last, h->db.pyr, frame, 0, &pitch);
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(h_l0, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+        } else need_slab = true;
     }
+    if (need_slab)
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->h_pyr, h->db.pyr + (size_t)frame * h->hg.pyr_bytes, h->hg.pyr_bytes, cudaMemcpyDeviceToHost, h->stream));
     ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    off = 0;
     for (int k = 0; k < count; ++k) {
         const LevelGeom& L = h->hg.lv[first + k];
-        for (int y = 0; y < L.h; ++y) memcpy(dst[k] + (size_t)y * dst_stride[k], h->h_pyr + off + (size_t)y * L.w, L.w);
-        off += (size_t)L.w * L.h;
+        const uint8_t* src = first + k == 0 ? h_l0 : h->h_pyr + L.img_off;
+        const size_t sp = first + k == 0 ? (size_t)L.w : (size_t)L.pitch;
+        for (int y = 0; y < L.h; ++y) memcpy(dst[k] + (size_t)y * dst_stride[k], src + (size_t)y * sp, L.w);
     }
     return ORB_OK;
 }
