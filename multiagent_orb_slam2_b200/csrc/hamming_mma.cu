@@ -168,6 +168,7 @@ constexpr int kMmaStages = 2;                 // B tiles in flight in shared mem
 constexpr int kMmaThreads = 320;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
 constexpr int kMmaSmemBytes = kATileBytes + kMmaStages * kBStageBytes + 1024;  // 97 KB: two CTAs per SM
 constexpr int kTmemCols = 2 * kTileN;         // double-buffered accumulator; two CTAs per SM share the 512 columns
+constexpr int kPruneFromTile = 16;            // candidate tiles after which the epilogue first tests groups against the second best
 
 __device__ __forceinline__ void issue_tile_mmas_n128(uint32_t a_smem, uint32_t b_smem, uint32_t tmem_d) {
     constexpr uint32_t idesc = idesc_i8(kMmaM, kTileN);
@@ -308,7 +309,25 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             Top2Packed acc;
             acc.reset();
             auto bias = [](int i) { return (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16; };
-            if (valid >= 64) {
+            if (valid >= 64 && t >= kPruneFromTile) {
+                // Steady state of a long database scan: almost no candidate beats a row's running SECOND best any more, and
+                // one that does not cannot change (best, second, index) - an equal distance leaves all three as they are.
+                // So 16 candidates at a time are first only compared, as raw accumulator halves (64 * dot = 128 * (128 -
+                // distance), signed 16 bit), against the row's second best: 4 three-input packed maxima and one vote per
+                // group instead of 28 key-building and selection instructions; the exact path below runs only for a group
+                // in which some row of the warp has a contender. Rows are independent, so skipping is exact.
+                const uint32_t thr2 = (uint32_t)((R2 * 128 - 16384) & 0xffff) * 0x10001u;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    const int b = 8 * gq;
+                    const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(r[b], r[b + 1], r[b + 2]), __vimax3_s16x2(r[b + 3], r[b + 4], r[b + 5]),
+                                                       __vimax3_s16x2(r[b + 6], r[b + 7], thr2));
+                    if (__any_sync(0xffffffffu, mx != thr2)) {
+#pragma unroll
+                        for (int i = b; i < b + 8; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
+                    }
+                }
+            } else if (valid >= 64) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
             } else {
