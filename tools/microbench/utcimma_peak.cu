@@ -23,21 +23,24 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int N>
+// COMMITS: extra tcgen05.commit instructions (to a barrier nobody waits on) after every 8 MMAs - what a real pipeline does to
+// hand shared-memory slots and accumulators over; ACCS: accumulators used in rotation (1 = always the same TMEM columns)
+template <int N, int COMMITS = 0, int ACCS = 1>
 __global__ void __launch_bounds__(128) peak_kernel(int iters) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar, bar_dummy;
     __shared__ uint32_t tmem_base_s;
     uint8_t* sa = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sb = sa + 128 * 128;
     for (int i = threadIdx.x; i < (128 + N) * 128 / 4; i += blockDim.x) ((uint32_t*)sa)[i] = 0x01FF01FFu * (i | 1);
     const int warp = threadIdx.x >> 5;
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)N) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(N * ACCS)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_dummy)), "r"(1u << 20));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -55,9 +58,14 @@ __global__ void __launch_bounds__(128) peak_kernel(int iters) {
                 asm volatile(
                     "{\n\t.reg .pred p;\n\t"
                     "setp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem),
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem + (uint32_t)(((it >> 1) % ACCS) * N)),
                     "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(it | k)), "r"(0u)
                     : "memory");
+            }
+            if (COMMITS && (it & 1)) {
+#pragma unroll
+                for (int c = 0; c < COMMITS; ++c)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_dummy)) : "memory");
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -75,22 +83,22 @@ __global__ void __launch_bounds__(128) peak_kernel(int iters) {
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)N) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(N * ACCS)) : "memory");
 }
 
-template <int N>
+template <int N, int COMMITS = 0, int ACCS = 1>
 static double run(int ctas_per_sm, int iters, int sms) {
     const size_t smem = (128 + N) * 128 + 1024;
-    cudaFuncSetAttribute(peak_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(peak_kernel<N, COMMITS, ACCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = sms * ctas_per_sm;
-    peak_kernel<N><<<grid, 128, smem>>>(64);
+    peak_kernel<N, COMMITS, ACCS><<<grid, 128, smem>>>(64);
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 1e30;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0);
-        peak_kernel<N><<<grid, 128, smem>>>(iters);
+        peak_kernel<N, COMMITS, ACCS><<<grid, 128, smem>>>(iters);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;
@@ -101,8 +109,8 @@ static double run(int ctas_per_sm, int iters, int sms) {
     if (e != cudaSuccess) { fprintf(stderr, "kernel failed: %s\n", cudaGetErrorString(e)); return -1; }
     const double ops = (double)grid * iters * 4 * 2.0 * 128 * N * 32;
     const double tops = ops / (best * 1e-3) / 1e12;
-    printf("{\"kernel\": \"tcgen05.mma kind::i8 128x%dx32 issue loop\", \"ctas_per_sm\": %d, \"iters\": %d, \"ms\": %.4f, \"int8_tops\": %.1f}\n", N, ctas_per_sm,
-           iters, best, tops);
+    printf("{\"kernel\": \"tcgen05.mma kind::i8 128x%dx32 issue loop\", \"commits_per_8_mma\": %d, \"accumulators\": %d, \"ctas_per_sm\": %d, \"iters\": %d, "
+           "\"ms\": %.4f, \"int8_tops\": %.1f}\n", N, COMMITS, ACCS, ctas_per_sm, iters, best, tops);
     return tops;
 }
 
@@ -115,6 +123,8 @@ int main() {
         double t = run<128>(c, 20000, sms); if (t > best) best = t;
         t = run<256>(c, 10000, sms); if (t > best) best = t;
     }
+    // what the hand-over points of a real pipeline cost: commits after every 8 MMAs, rotating accumulators
+    run<128, 1, 1>(1, 20000, sms); run<128, 2, 1>(1, 20000, sms); run<128, 2, 2>(1, 20000, sms); run<128, 2, 2>(2, 20000, sms);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"int8_tops_measured\": %.1f}\n", p.name, sms, best);
     return best > 0 ? 0 : 1;
 }
