@@ -84,3 +84,73 @@ class KeyFrameDatabase:
             if a > retain and kf not in seen:
                 out.append(kf); seen.add(kf)
         return out
+
+    # ---- the two other place-recognition queries of the reference, same device scoring ------------------------------------
+    def _sharing(self, word_ids, weights, skip=()):
+        common, first, score = self.score_all(word_ids, weights)
+        skip = set(int(c) for c in skip)
+        share = [int(s) for s in np.flatnonzero(common > 0) if int(s) not in skip]
+        share.sort(key=lambda s: (first[s], s))   # ascending word, then insertion order of the word's list
+        return share, common, score.astype(np.float32)
+
+    @staticmethod
+    def _accumulate(matches, in_list, gate, stale, neighbours, best_acc):
+        f32 = np.float32
+        acc = []
+        for s0, slot in matches:
+            best_score, acc_score, best_kf = s0, s0, slot
+            for nb in neighbours(slot):
+                nb = int(nb)
+                if nb in in_list and gate(nb):
+                    acc_score = f32(acc_score + f32(stale[nb]))
+                    if f32(stale[nb]) > best_score:
+                        best_kf, best_score = nb, f32(stale[nb])
+            acc.append((acc_score, best_kf))
+            if acc_score > best_acc:
+                best_acc = acc_score
+        retain = f32(f32(0.75) * best_acc)
+        out, seen = [], set()
+        for a, kf in acc:
+            if a > retain and kf not in seen:
+                out.append(kf); seen.add(kf)
+        return out
+
+    def DetectCovisibilityCandidates(self, word_ids, weights, min_score, ignore=(), neighbours=lambda slot: (), covis_score=None):
+        """KeyFrameDatabase::DetectCovisibilityCandidates (199-308), the fork's query behind MapFusion::CovisibilityDiscovery.
+        The reference never stores the similarity in the keyframe there (mCovisScore is only read, 270-276): the covisibility
+        accumulation adds what the keyframes held before - covis_score[slot], zeros by default."""
+        f32 = np.float32
+        share, common, si = self._sharing(word_ids, weights, ignore)
+        if not share:
+            return []
+        stale = np.zeros(len(self), f32) if covis_score is None else np.asarray(covis_score, f32)
+        min_common = int(f32(max(int(common[s]) for s in share)) * f32(0.8))
+        matches = [(si[s], s) for s in share if common[s] > min_common and si[s] >= f32(min_score)]
+        if not matches:
+            return []
+        return self._accumulate(matches, set(share), lambda nb: common[nb] > min_common, stale, neighbours, f32(min_score))
+
+    def DetectRelocalizationCandidates(self, word_ids, weights, neighbours=lambda slot: (), reloc_score=None):
+        """KeyFrameDatabase::DetectRelocalizationCandidates (310-420). reloc_score: per-slot mRelocScore, updated in place
+        (a neighbour below the common-word floor contributes the score of an earlier query, 378-387); kept on the object
+        when not given."""
+        f32 = np.float32
+        if reloc_score is None:
+            if getattr(self, "_reloc", None) is None or len(self._reloc) < len(self):
+                old = getattr(self, "_reloc", None)
+                self._reloc = np.zeros(len(self), f32)
+                if old is not None:
+                    self._reloc[:len(old)] = old
+            reloc_score = self._reloc
+        share, common, si = self._sharing(word_ids, weights)
+        if not share:
+            return []
+        min_common = int(f32(max(int(common[s]) for s in share)) * f32(0.8))
+        matches = []
+        for s in share:
+            if common[s] > min_common:
+                reloc_score[s] = si[s]
+                matches.append((si[s], s))
+        if not matches:
+            return []
+        return self._accumulate(matches, set(share), lambda nb: True, reloc_score, neighbours, f32(0))

@@ -1178,3 +1178,97 @@ def detect_loop_candidates(db, alive, q_ids, q_w, min_score, connected, neighbou
         if a > retain and kf not in seen:
             out.append(kf); seen.add(kf)
     return out
+
+
+def _sharing(db, alive, q_ids, skip=()):
+    """Keyframes sharing a word with the query in the order the reference meets them (ascending word, then insertion order of
+    the word's list), with their common-word counts. skip: slots left out entirely."""
+    inverted = {}
+    for slot, (ids, _) in enumerate(db):
+        if alive[slot]:
+            for w in ids:
+                inverted.setdefault(int(w), []).append(slot)
+    order, words = [], {}
+    for w in q_ids:
+        for slot in inverted.get(int(w), []):
+            if slot in skip:
+                continue
+            if slot not in words:
+                words[slot] = 0
+                order.append(slot)
+            words[slot] += 1
+    return order, words
+
+
+def detect_covisibility_candidates(db, alive, q_ids, q_w, min_score, ignore, neighbours, covis_score):
+    """KeyFrameDatabase::DetectCovisibilityCandidates, src/KeyFrameDatabase.cc:199-308 (the fork's place recognition for
+    MapFusion::CovisibilityDiscovery). Unlike DetectLoopCandidates it never stores the similarity in the keyframe
+    (mCovisScore is only READ, 270-276), so the covisibility accumulation adds whatever the keyframes held before:
+    covis_score[slot] is that state, an explicit input here."""
+    f = np.float32
+    order, words = _sharing(db, alive, q_ids, set(ignore))
+    if not order:
+        return []
+    min_common = int(f(max(words[s] for s in order)) * f(0.8))
+    matches = []
+    for slot in order:
+        if words[slot] > min_common:
+            si = f(l1_score(q_ids, q_w, db[slot][0], db[slot][1]))
+            if si >= f(min_score):
+                matches.append((si, slot))
+    if not matches:
+        return []
+    acc, best_acc = [], f(min_score)
+    for si, slot in matches:
+        best_score, acc_score, best_kf = si, si, slot
+        for nb in neighbours(slot):
+            if nb in words and words[nb] > min_common:
+                acc_score = f(acc_score + f(covis_score[nb]))
+                if f(covis_score[nb]) > best_score:
+                    best_kf, best_score = nb, f(covis_score[nb])
+        acc.append((acc_score, best_kf))
+        if acc_score > best_acc:
+            best_acc = acc_score
+    retain = f(f(0.75) * best_acc)
+    out, seen = [], set()
+    for a, kf in acc:
+        if a > retain and kf not in seen:
+            out.append(kf); seen.add(kf)
+    return out
+
+
+def detect_relocalization_candidates(db, alive, q_ids, q_w, neighbours, reloc_score):
+    """KeyFrameDatabase::DetectRelocalizationCandidates, src/KeyFrameDatabase.cc:310-420. reloc_score[slot] = the keyframes'
+    mRelocScore, updated in place: a neighbour that shares a word but stays below the common-word floor contributes the score
+    of an EARLIER query (378-387 test only mnRelocQuery)."""
+    f = np.float32
+    order, words = _sharing(db, alive, q_ids)
+    if not order:
+        return []
+    min_common = int(f(max(words[s] for s in order)) * f(0.8))
+    matches = []
+    for slot in order:
+        if words[slot] > min_common:
+            si = f(l1_score(q_ids, q_w, db[slot][0], db[slot][1]))
+            reloc_score[slot] = si
+            matches.append((si, slot))
+    if not matches:
+        return []
+    acc, best_acc = [], f(0)
+    for si, slot in matches:
+        best_score, acc_score, best_kf = si, si, slot
+        for nb in neighbours(slot):
+            if nb not in words:
+                continue
+            acc_score = f(acc_score + f(reloc_score[nb]))
+            if f(reloc_score[nb]) > best_score:
+                best_kf, best_score = nb, f(reloc_score[nb])
+        acc.append((acc_score, best_kf))
+        if acc_score > best_acc:
+            best_acc = acc_score
+    retain = f(f(0.75) * best_acc)
+    out, seen = [], set()
+    for a, kf in acc:
+        if a > retain and kf not in seen:
+            out.append(kf); seen.add(kf)
+    return out

@@ -146,6 +146,17 @@ class World:
         ids, off, feat = self._fv_arrays(fv)
         self.L.rs_kf_set_featvec(self.h, k, len(fv), _p(ids), _p(off), _p(feat))
 
+    def frame_set_bowvec(self, f, ids, wt):
+        ids = _i(ids); wt = np.ascontiguousarray(wt, np.float64)
+        self.L.rs_frame_set_bowvec(self.h, f, len(ids), _p(ids), _p(wt))
+
+    def kf_set_scores(self, k, covis=0.0, reloc=0.0):
+        self.L.rs_kf_set_scores(self.h, k, C.c_float(covis), C.c_float(reloc))
+
+    def kf_reloc_score(self, k):
+        self.L.rs_kf_reloc_score.restype = C.c_float
+        return float(self.L.rs_kf_reloc_score(self.h, k))
+
     def kf_set_bowvec(self, k, ids, wt):
         ids = _i(ids); wt = np.ascontiguousarray(wt, np.float64)
         self.L.rs_kf_set_bowvec(self.h, k, len(ids), _p(ids), _p(wt))

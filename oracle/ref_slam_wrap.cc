@@ -270,6 +270,16 @@ void rs_frame_set_featvec(void* h, int f, int n_nodes, const int* node_ids, cons
 void rs_kf_set_featvec(void* h, int k, int n_nodes, const int* node_ids, const int* node_off, const int* feat) {
     fill_featvec(((World*)h)->kfs[k]->mFeatVec, n_nodes, node_ids, node_off, feat);
 }
+void rs_frame_set_bowvec(void* h, int f, int n, const int* ids, const double* wt) {
+    DBoW2::BowVector& bv = ((World*)h)->frames[f]->mBowVec;
+    bv.clear();
+    for (int i = 0; i < n; ++i) bv.addWeight((DBoW2::WordId)ids[i], wt[i]);
+}
+// mCovisScore is read but never written by DetectCovisibilityCandidates (src/KeyFrameDatabase.cc:270-276) and mRelocScore of a
+// keyframe below the common-word floor is read stale (378-387); neither is initialised by the KeyFrame constructor. The
+// tests make both explicit inputs / outputs.
+void rs_kf_set_scores(void* h, int k, float covis, float reloc) { KeyFrame& K = *((World*)h)->kfs[k]; K.mCovisScore = covis; K.mRelocScore = reloc; }
+float rs_kf_reloc_score(void* h, int k) { return ((World*)h)->kfs[k]->mRelocScore; }
 void rs_kf_set_bowvec(void* h, int k, int n, const int* ids, const double* wt) {
     DBoW2::BowVector& bv = ((World*)h)->kfs[k]->mBowVec;
     bv.clear();

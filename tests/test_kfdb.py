@@ -45,6 +45,9 @@ def test_database_scores_and_loop_candidates_match_oracle(seed, n_kf):
     for slot in rng.choice(n_kf, n_kf // 20, replace=False):  # KeyFrameDatabase::erase
         db.erase(int(slot)); alive[slot] = False
     neigh = {s: [int(x) for x in rng.choice(n_kf, 10, replace=False)] for s in range(n_kf)}
+    covis_state = rng.uniform(0.0, 0.05, n_kf).astype(np.float32)
+    reloc_oracle = rng.uniform(0.0, 0.05, n_kf).astype(np.float32)
+    reloc_device = reloc_oracle.copy()
     for qi in range(n_kf, n_kf + 8):
         q_ids, q_w = vecs[qi]
         common, first, score = db.score_all(q_ids, q_w)
@@ -63,6 +66,14 @@ def test_database_scores_and_loop_candidates_match_oracle(seed, n_kf):
         got = db.DetectLoopCandidates(q_ids, q_w, min_score, connected, lambda s: neigh[s])
         assert got == want
         assert len(want) >= 1
+        # the fork's covisibility query and the relocalisation query (restatements pinned to the reference in
+        # tests/test_oracle_vs_reference_matcher.py), with their stale per-keyframe scores as explicit state
+        ignore = [int(x) for x in rng.choice(n_kf, 12, replace=False)]
+        want_c = O.detect_covisibility_candidates(vecs[:n_kf], alive, q_ids, q_w, min_score, ignore, lambda s: neigh[s], covis_state)
+        assert db.DetectCovisibilityCandidates(q_ids, q_w, min_score, ignore, lambda s: neigh[s], covis_state) == want_c and len(want_c) >= 1
+        want_r = O.detect_relocalization_candidates(vecs[:n_kf], alive, q_ids, q_w, lambda s: neigh[s], reloc_oracle)
+        assert db.DetectRelocalizationCandidates(q_ids, q_w, lambda s: neigh[s], reloc_device) == want_r and len(want_r) >= 1
+        assert np.array_equal(reloc_oracle, reloc_device)
     # a query that shares no word with anything
     none_ids = np.array([n_words - 1], np.int32)
     if not any(n_words - 1 in v[0] for v in vecs[:n_kf]):

@@ -272,6 +272,12 @@ def test_oracle_equals_reference_keyframe_database(tmp_path, seed, n_kf):
         neigh[s] = nb
         for rank, b in enumerate(nb):
             w.kf_add_connection(s, b, 100 - rank)          # distinct weights: GetBestCovisibilityKeyFrames order = nb
+    # the fork's covisibility query and the relocalisation query read per-keyframe scores that they do not (always) write:
+    # start every keyframe from a known value, as an explicit input of both sides
+    covis_state = rng.uniform(0.0, 0.05, n_kf).astype(f32)
+    reloc_state = rng.uniform(0.0, 0.05, n_kf).astype(f32)
+    for s in range(n_kf):
+        w.kf_set_scores(s, float(covis_state[s]), float(reloc_state[s]))
     hits = 0
     for qi in range(n_kf, n_kf + 6):
         q_ids, q_w = vecs[qi]
@@ -284,4 +290,17 @@ def test_oracle_equals_reference_keyframe_database(tmp_path, seed, n_kf):
         got = w.db_detect_loop_candidates(qi, min_score)
         assert got == want
         hits += len(want) > 0
+        # DetectCovisibilityCandidates (199-308): ignore list, stale mCovisScore
+        ignore = [int(x) for x in rng.choice(n_kf, 12, replace=False)]
+        want_c = O.detect_covisibility_candidates(vecs[:n_kf], alive, q_ids, q_w, min_score, ignore, lambda s: neigh[s], covis_state)
+        got_c = w.db_detect_covisibility_candidates(qi, min_score, ignore)
+        assert got_c == want_c and len(want_c) >= 1
+        # DetectRelocalizationCandidates (310-420): a Frame with the query's BowVector; mRelocScore carries over between queries
+        fq = w.frame_arrays(k1, d1, TUM1["K"], W, H)
+        w.frame_set_bowvec(fq, q_ids, q_w)
+        want_r = O.detect_relocalization_candidates(vecs[:n_kf], alive, q_ids, q_w, lambda s: neigh[s], reloc_state)
+        got_r = w.db_detect_relocalization_candidates(fq)
+        assert got_r == want_r and len(want_r) >= 1
+        for s in range(0, n_kf, 9):
+            assert np.float32(w.kf_reloc_score(s)) == reloc_state[s]
     assert hits >= 4
