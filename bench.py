@@ -390,7 +390,8 @@ def run_b200(args):
     # (the contract is ONE JSON line there); every rank logs to a file, rank 0 echoes its file to stderr at the end.
     nccl_log = None
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         nccl_log = os.path.join(tempfile.gettempdir(), "orb_bench_nccl_%d_rank%s.log" % (os.getppid(), os.environ.get("RANK", "0")))
         os.environ["NCCL_DEBUG_FILE"] = nccl_log
@@ -415,10 +416,14 @@ def run_b200(args):
         nr = None
         try:
             import re
-            for line in open(nccl_log, errors="replace"):
-                m = re.search(r"nranks (\d+)", line)
-                if m:
-                    nr = int(m.group(1))
+            import glob
+            for f in sorted(glob.glob(nccl_log + "*")):
+                for line in open(f, errors="replace"):
+                    m = re.search(r"nranks (\d+)", line)
+                    if m:
+                        nr = int(m.group(1))
+                        break
+                if nr is not None:
                     break
         except Exception:
             pass
@@ -736,10 +741,14 @@ def run_b200(args):
         }))
     if world > 1:
         dist.destroy_process_group()
-        if rank == 0 and nccl_log and os.path.exists(nccl_log):
-            lines = [l.rstrip() for l in open(nccl_log, errors="replace")]
-            keep = [l for l in lines if "nranks" in l or "NCCL version" in l or "comm 0x" in l][:12]
-            sys.stderr.write("NCCL log (rank 0, %s):\n" % nccl_log + "\n".join(keep or lines[:12]) + "\n")
+        if rank == 0 and nccl_log:
+            import glob
+            found = sorted(glob.glob(nccl_log + "*"))
+            sys.stderr.write("NCCL log files: %r\n" % [(f, os.path.getsize(f)) for f in found])
+            for f in found[:1]:
+                lines = [l.rstrip() for l in open(f, errors="replace")]
+                keep = [l for l in lines if "nranks" in l or "NCCL version" in l or "comm 0x" in l][:16]
+                sys.stderr.write("NCCL log (rank 0, %s):\n" % f + "\n".join(keep or lines[:16]) + "\n")
 
 
 def main():
