@@ -510,7 +510,10 @@ int orbx_upload_frames(orbx_handle h, const uint8_t* images, size_t stride, size
     ORB_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t dev_frame = h->in_pitch * h->height;
-    if (frame_stride == stride * (size_t)h->height || n == 1) {
+    if ((frame_stride == stride * (size_t)h->height || n == 1) && stride == h->in_pitch && stride == (size_t)h->width) {
+        // tightly packed on both sides: one linear copy (a 2-D descriptor with pitch == width is not guaranteed to be collapsed)
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->d_input, images, dev_frame * n, cudaMemcpyHostToDevice, st));
+    } else if (frame_stride == stride * (size_t)h->height || n == 1) {
         ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_input, h->in_pitch, images, stride, h->width, (size_t)h->height * n, cudaMemcpyHostToDevice, st));
     } else {
         for (int i = 0; i < n; ++i)
