@@ -129,6 +129,11 @@ int orbm_knn2_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32
 int orbm_knn2(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, int32_t* idx, int32_t* best,
               int32_t* second);
 
+/* The tensor-core implementation keeps its expanded operands (256 bytes per descriptor row of the largest call so far) in
+ * scratch memory per (device, stream). A device-call user releases it for a stream it is about to destroy, or to return
+ * the memory; stream-ordered, no synchronisation. The host-buffer entry points do this for their own stream. */
+int orbm_release_scratch(void* stream);
+
 /* Batched brute force: pair p matches A[p] (nA[p] rows at dA + p*strideA_rows*32) against B[p].
  * d_nA / d_nB are device int arrays (e.g. the d_counts of two extractor runs). Outputs [pairs][strideA_rows]. */
 int orbm_knn2_batched_device(const uint8_t* dA, const int32_t* d_nA, int strideA_rows, const uint8_t* dB,

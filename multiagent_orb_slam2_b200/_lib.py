@@ -58,6 +58,7 @@ def lib():
         "orbx_debug_quadtree": [i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(i32)],
         "orbm_knn2_device": [vp, i32, vp, i32, vp, vp, vp, vp],
         "orbm_knn2": [i32, vp, i32, vp, i32, vp, vp, vp],
+        "orbm_release_scratch": [vp],
         "orbm_knn2_batched_device": [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp],
         "orbm_knn2_pairs_device": [vp, vp, i32, vp, i32, vp, vp, vp, vp],
         "orbm_knn2_lists_device": [vp, i32, vp, vp, vp, vp, vp, vp, vp],

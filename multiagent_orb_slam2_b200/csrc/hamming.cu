@@ -235,6 +235,7 @@ __global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, cons
 // ---- host launcher ----------------------------------------------------------------------------
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
                     int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st);
+int release_mma_scratch(int device, cudaStream_t st);
 static thread_local int t_knn2_backend = 0;        // per calling thread: 0 = by problem size, 1 = POPC kernel, 2 = tensor-core kernel
 constexpr long long kMmaMinWork = 1ll << 19;      // comparisons per call from which the tensor-core path is used (measured break-even: ~700 x 700)
 
@@ -367,6 +368,7 @@ struct HostCallWorkspace {
     void release() {
         if (device >= 0) {
             cudaSetDevice(device);
+            if (st) release_mma_scratch(device, st);  // the tensor-core matcher's operand scratch is keyed by this stream
             if (base) cudaFree(base);
             if (st) cudaStreamDestroy(st);
         }

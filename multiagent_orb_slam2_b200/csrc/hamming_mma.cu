@@ -15,6 +15,7 @@
 
 #include <atomic>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <utility>
 
@@ -439,11 +440,51 @@ static int encode_expanded_map(CUtensorMap* out, const void* base, long long row
 
 namespace orb {
 
-// Scratch for the expanded operands: one pair of buffers per (device, stream), grown on demand and kept. Calls on the same
-// stream are ordered, so they can share buffers; calls on different streams (two agents' frontends on one GPU) must not.
-struct MmaScratch { uint8_t* a = nullptr; uint8_t* b = nullptr; size_t cap_a = 0, cap_b = 0; };
+// Scratch for the expanded operands: one pair of buffers per (device, stream), grown on demand and kept until the owner of
+// the stream calls orbm_release_scratch. Calls on the same stream are ordered, so they share buffers; calls on different
+// streams (two agents' frontends on one GPU) must not. The table lock covers the lookup only; growth (stream-ordered
+// allocation, so no host or device-wide synchronisation) and tensor-map encoding happen under the entry's own lock.
+struct MmaScratch {
+    std::mutex mu;
+    uint8_t* a = nullptr;
+    uint8_t* b = nullptr;
+    size_t cap_a = 0, cap_b = 0;
+    CUtensorMap map_a, map_b;          // cached: valid for (a, rows_a) / (b, rows_b)
+    size_t map_rows_a = 0, map_rows_b = 0;
+};
+using MmaScratchTable = std::map<std::pair<int, cudaStream_t>, std::shared_ptr<MmaScratch>>;
 static std::mutex g_mma_mutex;
-static std::map<std::pair<int, cudaStream_t>, MmaScratch> g_mma_scratch;
+static MmaScratchTable& mma_scratch_table() {
+    static MmaScratchTable* t = new MmaScratchTable;  // never destroyed: thread-exit hooks may run after static destructors
+    return *t;
+}
+
+static int grow_stream_buffer(uint8_t** buf, size_t* cap, size_t bytes, cudaStream_t st) {
+    if (bytes <= *cap) return ORB_OK;
+    if (*buf) ORB_CUDA_TRY(cudaFreeAsync(*buf, st));  // ordered after the earlier calls on this stream that still read it
+    *buf = nullptr; *cap = 0;
+    const size_t want = bytes + bytes / 4;
+    ORB_CUDA_TRY(cudaMallocAsync((void**)buf, want, st));
+    *cap = want;
+    return ORB_OK;
+}
+
+int release_mma_scratch(int device, cudaStream_t st) {
+    std::shared_ptr<MmaScratch> sc;
+    {
+        std::lock_guard<std::mutex> lock(g_mma_mutex);
+        MmaScratchTable& t = mma_scratch_table();
+        auto it = t.find(std::make_pair(device, st));
+        if (it == t.end()) return ORB_OK;
+        sc = it->second;
+        t.erase(it);
+    }
+    std::lock_guard<std::mutex> lock(sc->mu);
+    if (sc->a) ORB_CUDA_TRY(cudaFreeAsync(sc->a, st));
+    if (sc->b) ORB_CUDA_TRY(cudaFreeAsync(sc->b, st));
+    sc->a = sc->b = nullptr;
+    return ORB_OK;
+}
 
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
                     int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st) {
@@ -453,30 +494,30 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
     ORB_CUDA_TRY(cudaGetDevice(&device));
     const size_t rows_a = (size_t)pairs * strideA_rows, rows_b = (size_t)pairs * strideB_rows;
     ORB_REQUIRE(rows_a < (1ull << 31) && rows_b < (1ull << 31), "too many descriptor rows for the tensor-core matcher");
-    MmaScratch sc;
+    std::shared_ptr<MmaScratch> entry;
     {
         std::lock_guard<std::mutex> lock(g_mma_mutex);
-        MmaScratch& slot = g_mma_scratch[std::make_pair(device, st)];
-        if (rows_a * 256 > slot.cap_a) {
-            ORB_CUDA_TRY(cudaStreamSynchronize(st));  // earlier calls on this stream may still read the old buffer
-            cudaFree(slot.a);
-            slot.a = nullptr; slot.cap_a = 0;
-            ORB_CUDA_TRY(cudaMalloc(&slot.a, rows_a * 256));
-            slot.cap_a = rows_a * 256;
-        }
-        if (rows_b * 256 > slot.cap_b) {
-            ORB_CUDA_TRY(cudaStreamSynchronize(st));
-            cudaFree(slot.b);
-            slot.b = nullptr; slot.cap_b = 0;
-            ORB_CUDA_TRY(cudaMalloc(&slot.b, rows_b * 256));
-            slot.cap_b = rows_b * 256;
-        }
-        sc = slot;
+        std::shared_ptr<MmaScratch>& slot = mma_scratch_table()[std::make_pair(device, st)];
+        if (!slot) slot = std::make_shared<MmaScratch>();
+        entry = slot;
     }
-    CUtensorMap ma, mb;
-    int rc = encode_expanded_map(&ma, sc.a, (long long)rows_a, kMmaM);
-    if (rc == ORB_OK) rc = encode_expanded_map(&mb, sc.b, (long long)rows_b, kTileN);
-    if (rc != ORB_OK) return rc;
+    std::lock_guard<std::mutex> entry_lock(entry->mu);
+    MmaScratch& sc = *entry;
+    int rc;
+    const uint8_t *old_a = sc.a, *old_b = sc.b;
+    if ((rc = grow_stream_buffer(&sc.a, &sc.cap_a, rows_a * 256, st)) != ORB_OK) return rc;
+    if ((rc = grow_stream_buffer(&sc.b, &sc.cap_b, rows_b * 256, st)) != ORB_OK) return rc;
+    if (sc.a != old_a || sc.map_rows_a != rows_a) {
+        sc.map_rows_a = 0;
+        if ((rc = encode_expanded_map(&sc.map_a, sc.a, (long long)rows_a, kMmaM)) != ORB_OK) return rc;
+        sc.map_rows_a = rows_a;
+    }
+    if (sc.b != old_b || sc.map_rows_b != rows_b) {
+        sc.map_rows_b = 0;
+        if ((rc = encode_expanded_map(&sc.map_b, sc.b, (long long)rows_b, kTileN)) != ORB_OK) return rc;
+        sc.map_rows_b = rows_b;
+    }
+    const CUtensorMap ma = sc.map_a, mb = sc.map_b;
     const int words = 8 * (nA_max > nB_max ? nA_max : nB_max);
     expand_pairs_kernel<<<dim3(ceil_div(words, 256), pairs, 2), 256, 0, st>>>((const uint32_t*)dA, d_nA, nA_max, strideA_rows, (const uint32_t*)dB,
                                                                              d_nB, nB_max, strideB_rows, d_pairs, (uint4*)sc.a, (uint4*)sc.b);
@@ -552,6 +593,15 @@ int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, i
     return ORB_OK;
 }
 }  // namespace orb
+
+// Device-call users own their streams: before destroying one (or to give the memory back) they release the expanded-operand
+// scratch the brute-force matcher keeps for it. Stream-ordered, no synchronisation.
+extern "C" int orbm_release_scratch(void* stream) {
+    using namespace orb;
+    int device = 0;
+    ORB_CUDA_TRY(cudaGetDevice(&device));
+    return release_mma_scratch(device, (cudaStream_t)stream);
+}
 
 // Debug / experiment entry: the tensor-core matcher on one pair of device arrays.
 extern "C" int orbm_knn2_mma_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best, int32_t* d_second,

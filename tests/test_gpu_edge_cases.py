@@ -200,3 +200,64 @@ def test_alternating_device_input_buffers_keep_their_graphs():
         ok, od = want[i]
         assert n == len(ok) and np.array_equal(desc[:n], od), (i, n, len(ok))
         assert np.array_equal(kps["x"][:n].view(np.uint32), ok[:, 0].view(np.uint32))
+
+
+def test_matcher_scratch_grows_is_released_and_survives_thread_exit():
+    """The tensor-core matcher keeps its expanded operands per (device, stream). Growing it between calls queued on the same
+    stream (no synchronisation in between) must not disturb the earlier call; orbm_release_scratch hands the memory back
+    stream-ordered and the next call allocates again; a host-call thread that exits takes its stream's scratch with it."""
+    import torch
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(dev)
+    sizes = [1500, 4000, 2500, 9000]
+    sets = []
+    for k, n in enumerate(sizes):
+        B = synth.descriptors(n, 300 + k)
+        A = synth.descriptors_fast(n, 400 + k, B, 45)
+        sets.append((A, B, torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)))
+    want = []
+    _lib.check(L.orbm_set_knn2_backend(1))
+    for A, B, dA, dB in sets:
+        o = [torch.empty(len(A), dtype=torch.int32, device=dev) for _ in range(3)]
+        _lib.check(L.orbm_knn2_device(C.c_void_p(dA.data_ptr()), len(A), C.c_void_p(dB.data_ptr()), len(B), *[C.c_void_p(x.data_ptr()) for x in o], None))
+        torch.cuda.synchronize()
+        want.append([x.cpu().numpy() for x in o])
+    _lib.check(L.orbm_set_knn2_backend(2))
+    try:
+        for rnd in range(2):
+            outs = []
+            for A, B, dA, dB in sets:      # queued back to back: every second call outgrows the scratch of the one before
+                o = [torch.empty(len(A), dtype=torch.int32, device=dev) for _ in range(3)]
+                _lib.check(L.orbm_knn2_device(C.c_void_p(dA.data_ptr()), len(A), C.c_void_p(dB.data_ptr()), len(B), *[C.c_void_p(x.data_ptr()) for x in o],
+                                              C.c_void_p(st.cuda_stream)))
+                outs.append(o)
+            _lib.check(L.orbm_release_scratch(C.c_void_p(st.cuda_stream)))   # ordered after the queued calls
+            st.synchronize()
+            for o, w in zip(outs, want):
+                for g, ww in zip(o, w):
+                    assert np.array_equal(g.cpu().numpy(), ww)
+        _lib.check(L.orbm_release_scratch(C.c_void_p(st.cuda_stream)))       # nothing left: still fine
+        free_before = torch.cuda.mem_get_info(0)[0]
+        errs = []
+
+        def host_call(k):
+            try:
+                _lib.check(L.orbm_set_knn2_backend(2))
+                A, B = sets[k][0], sets[k][1]
+                idx, b1, b2 = ORBmatcher().knn2(A, B)
+                if not (np.array_equal(idx, want[k][0]) and np.array_equal(b1, want[k][1]) and np.array_equal(b2, want[k][2])):
+                    errs.append(k)
+            except Exception as e:  # noqa: BLE001
+                errs.append(repr(e))
+        for rnd in range(3):
+            ts = [threading.Thread(target=host_call, args=(k,)) for k in range(4)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+        assert not errs, errs
+        torch.cuda.synchronize()
+        free_after = torch.cuda.mem_get_info(0)[0]
+        # 12 exited threads, each with up to 2 x 9000 x 256 B of scratch plus a workspace: none of it may stay behind
+        assert free_before - free_after < (8 << 20), (free_before, free_after)
+    finally:
+        _lib.check(L.orbm_set_knn2_backend(0))
