@@ -34,8 +34,13 @@ int orbx_debug_quadtree(int device, const int32_t* xs, const int32_t* ys, const 
 /* The brute-force searches (orbm_knn2*, orbm_knn2_pairs_device ...) have two implementations with identical results: the
  * POPC kernel (csrc/hamming.cu) and the tensor-core kernel (csrc/hamming_mma.cu), chosen by problem size. This pins the
  * choice FOR THE CALLING THREAD ONLY (thread-local; other matcher threads keep the automatic choice):
- * 0 = automatic (default), 1 = POPC only, 2 = tensor cores only. */
+ * 0 = automatic (default), 1 = POPC only, 2 = tensor cores with one CTA per 128 query rows (tcgen05 cta_group::1),
+ * 3 = tensor cores with a CTA pair per 256 query rows (cta_group::2; automatic choice for long databases). */
 int orbm_set_knn2_backend(int backend);
+
+/* Occupancy of the two tensor-core matcher kernels on the current device: resident CTA pairs (clusters) on the whole GPU and
+ * resident blocks per SM. */
+int orbm_debug_mma_occupancy(int* pair_clusters, int* single_blocks_per_sm);
 /* The tensor-core implementation called directly (one query set against one database set), whatever the size. */
 int orbm_knn2_mma_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best,
                          int32_t* d_second, void* stream);

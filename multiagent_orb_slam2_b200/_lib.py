@@ -79,6 +79,7 @@ def lib():
         "orbm_distance_matrix_device": [vp, i32, vp, i32, vp, vp],
         "orbm_distance_matrix": [i32, vp, i32, vp, i32, vp],
         "orbm_set_knn2_backend": [i32],
+        "orbm_debug_mma_occupancy": [C.POINTER(i32), C.POINTER(i32)],
         "orbm_knn2_mma_device": [vp, i32, vp, i32, vp, vp, vp, vp],
         "orbm_debug_mma_dot": [i32, vp, vp, vp],
         "orbdb_create": [i32, i32, C.POINTER(vp)],

@@ -234,9 +234,10 @@ __global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, cons
 
 // ---- host launcher ----------------------------------------------------------------------------
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
-                    int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st);
+                    int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st,
+                    int variant);
 int release_mma_scratch(int device, cudaStream_t st);
-static thread_local int t_knn2_backend = 0;        // per calling thread: 0 = by problem size, 1 = POPC kernel, 2 = tensor-core kernel
+static thread_local int t_knn2_backend = 0;        // per calling thread: 0 = by problem size, 1 = POPC kernel, 2 / 3 = tensor-core kernel, one CTA / a CTA pair per query tile
 constexpr long long kMmaMinWork = 1ll << 19;      // comparisons per call from which the tensor-core path is used (measured break-even: ~700 x 700)
 
 static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB,
@@ -246,8 +247,9 @@ static int launch_knn2(const uint8_t* dA, const int* d_nA, int nA_max, int strid
     // large problems go to the tensor cores (hamming_mma.cu): same results, several times the POPC pipe's throughput
     const long long work = (long long)pairs * nA_max * nB_max;
     const int backend = t_knn2_backend;
-    if (nB_max > 0 && (backend == 2 || (backend == 0 && work >= kMmaMinWork && nB_max >= 64)))
-        return launch_knn2_mma(dA, d_nA, nA_max, strideA_rows, dB, d_nB, nB_max, strideB_rows, d_pairs, pairs, strideA_rows, d_idx, d_b1, d_b2, st);
+    if (nB_max > 0 && (backend >= 2 || (backend == 0 && work >= kMmaMinWork && nB_max >= 64)))
+        return launch_knn2_mma(dA, d_nA, nA_max, strideA_rows, dB, d_nB, nB_max, strideB_rows, d_pairs, pairs, strideA_rows, d_idx, d_b1, d_b2, st,
+                               backend == 0 ? 0 : backend - 1);
     ORB_REQUIRE(pairs <= 65535, "more than 65535 set pairs in one call");   // grid.z
     // pick the slice count so that the grid covers the machine about twice
     int S = 1;
@@ -275,7 +277,7 @@ using namespace orb;
 extern "C" {
 
 int orbm_set_knn2_backend(int backend) {
-    ORB_REQUIRE(backend >= 0 && backend <= 2, "backend must be 0 (auto), 1 (POPC) or 2 (tensor cores)");
+    ORB_REQUIRE(backend >= 0 && backend <= 3, "backend must be 0 (auto), 1 (POPC), 2 (tensor cores, one CTA per query tile) or 3 (tensor cores, CTA pairs)");
     t_knn2_backend = backend;
     return ORB_OK;
 }

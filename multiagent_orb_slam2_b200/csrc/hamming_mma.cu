@@ -220,10 +220,74 @@ struct Top2Packed {
     }
 };
 
+// One epilogue warp's update of its rows' running (best, second, index) with the 64 candidates (two per register, raw
+// accumulator halves) of tile t that start at candidate col0; `valid` of them are real.
+__device__ __forceinline__ void top2_tile_update(const uint32_t (&r)[32], int t, int col0, int valid, int& R1, int& R2, int& Ridx) {
+    Top2Packed acc;
+    acc.reset();
+    auto bias = [](int i) { return (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16; };
+    if (valid >= 64 && t >= kPruneFromTile) {
+        // Steady state of a long database scan: almost no candidate beats a row's running SECOND best any more, and
+        // one that does not cannot change (best, second, index) - an equal distance leaves all three as they are.
+        // So 16 candidates at a time are first only compared, as raw accumulator halves (64 * dot = 128 * (128 -
+        // distance), signed 16 bit), against the row's second best: 4 three-input packed maxima and one vote per
+        // group instead of 28 key-building and selection instructions; the exact path below runs only for a group
+        // in which some row of the warp has a contender. Rows are independent, so skipping is exact.
+        const uint32_t thr2 = (uint32_t)((R2 * 128 - 16384) & 0xffff) * 0x10001u;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+            const int b = 8 * gq;
+            const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(r[b], r[b + 1], r[b + 2]), __vimax3_s16x2(r[b + 3], r[b + 4], r[b + 5]),
+                                               __vimax3_s16x2(r[b + 6], r[b + 7], thr2));
+            if (__any_sync(0xffffffffu, mx != thr2)) {
+#pragma unroll
+                for (int i = b; i < b + 8; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
+            }
+        }
+    } else if (valid >= 64) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
+    } else {
+        auto mask = [valid](int i) { return (2 * i < valid ? 0xFFFFu : 0u) | (2 * i + 1 < valid ? 0xFFFF0000u : 0u); };
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+            acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)) & mask(i), __vadd2(r[i + 1], bias(i + 1)) & mask(i + 1));
+    }
+    int k1, k2;
+    acc.reduce(k1, k2);
+    const int d1 = k1 >> 7, d2 = k2 >> 7;
+    if (d1 > R1) {
+        R2 = max(R1, d2);
+        R1 = d1;
+        Ridx = col0 + 127 - (k1 & 127);
+    } else {
+        R2 = max(R2, d1);
+    }
+}
+
+// the two column halves of a row meet in shared memory (epilogue warps only: named barrier 1, 256 threads), half 0 writes
+__device__ __forceinline__ void top2_merge_halves_and_store(int h, int row, bool row_valid, int R1, int R2, int Ridx, int* s_r1, int* s_r2, int* s_ri,
+                                                            int* o_idx, int* o_b1, int* o_b2) {
+    if (h == 1) { s_r1[row] = R1; s_r2[row] = R2; s_ri[row] = Ridx; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (h == 0 && row_valid) {
+        const int B1 = s_r1[row], B2 = s_r2[row], Bi = s_ri[row];
+        const int m1 = max(R1, B1);
+        const int m2 = max(min(R1, B1), max(R2, B2));
+        int idx;
+        if (B1 > R1) idx = Bi;
+        else if (B1 < R1) idx = Ridx;
+        else idx = (Ridx < 0 || Bi < 0) ? max(Ridx, Bi) : min(Ridx, Bi);
+        *o_idx = idx;
+        *o_b1 = 256 - m1;
+        *o_b2 = 256 - m2;
+    }
+}
+
 __global__ void __launch_bounds__(kMmaThreads, 2)
 knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const int* __restrict__ d_nA, int nA_max,
                 int strideA, const int* __restrict__ d_nB, int nB_max, int strideB, const int* __restrict__ d_pairs, int out_stride,
-                int* __restrict__ out_idx, int* __restrict__ out_b1, int* __restrict__ out_b2) {
+                int* __restrict__ out_idx, int* __restrict__ out_b1, int* __restrict__ out_b2, long long split_stride) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_a, bar_full[kMmaStages], bar_empty[kMmaStages], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -236,15 +300,18 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int row0 = mtile * kMmaM;
     if (row0 >= na) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* o_idx = out_idx + (size_t)p * out_stride;
-    int* o_b1 = out_b1 + (size_t)p * out_stride;
-    int* o_b2 = out_b2 + (size_t)p * out_stride;
+    // gridDim.z > 1: this CTA scans only its share of the candidate tiles and writes a partial result (split_stride apart)
+    int* o_idx = out_idx + (size_t)blockIdx.z * split_stride + (size_t)p * out_stride;
+    int* o_b1 = out_b1 + (size_t)blockIdx.z * split_stride + (size_t)p * out_stride;
+    int* o_b2 = out_b2 + (size_t)blockIdx.z * split_stride + (size_t)p * out_stride;
     if (nb <= 0) {  // no candidates: the initial state of the reference loop
         for (int r = threadIdx.x; r < kMmaM; r += kMmaThreads)
             if (row0 + r < na) { o_idx[row0 + r] = -1; o_b1[row0 + r] = 256; o_b2[row0 + r] = 256; }
         return;
     }
-    const int ntiles = (nb + kTileN - 1) / kTileN;
+    const int all_tiles = (nb + kTileN - 1) / kTileN;
+    const int tile0 = (int)((long long)blockIdx.z * all_tiles / gridDim.z);                       // first candidate tile of this CTA
+    const int ntiles = (int)((long long)(blockIdx.z + 1) * all_tiles / gridDim.z) - tile0;       // and how many (t below is local)
     uint8_t* sa = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B blocks: 1024-byte aligned
     uint8_t* sb = sa + kATileBytes;
 
@@ -272,8 +339,8 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (t >= kMmaStages) mbar_wait_or_trap(&bar_empty[s], ((t / kMmaStages) & 1) ^ 1);
                 uint8_t* dst = sb + s * kBStageBytes;
                 mbar_expect_tx(&bar_full[s], kBStageBytes);
-                tma_load_2d(dst, &map_b, 0, brow + t * kTileN, &bar_full[s]);
-                tma_load_2d(dst + kTileN * 128, &map_b, 128, brow + t * kTileN, &bar_full[s]);
+                tma_load_2d(dst, &map_b, 0, brow + (tile0 + t) * kTileN, &bar_full[s]);
+                tma_load_2d(dst + kTileN * 128, &map_b, 128, brow + (tile0 + t) * kTileN, &bar_full[s]);
             }
         }
     } else if (warp == 1) {
@@ -299,7 +366,7 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int a = t & 1;
             mbar_wait_or_trap(&bar_tfull[a], (t >> 1) & 1);
             tc_fence_after();
-            const int col0 = t * kTileN + h * 64;      // candidate index of this half's first column
+            const int col0 = (tile0 + t) * kTileN + h * 64;      // candidate index of this half's first column
             const int valid = nb - col0;               // columns of this half that are real candidates
             uint32_t r[32];
             tmem_ld64_pack16(tmem_base + ((uint32_t)(q * 32) << 16) + a * kTileN + h * 64, r);
@@ -307,66 +374,197 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);  // values are in registers: the accumulator can be overwritten
-            Top2Packed acc;
-            acc.reset();
-            auto bias = [](int i) { return (uint32_t)(16384 + 127 - 2 * i) | (uint32_t)(16384 + 127 - (2 * i + 1)) << 16; };
-            if (valid >= 64 && t >= kPruneFromTile) {
-                // Steady state of a long database scan: almost no candidate beats a row's running SECOND best any more, and
-                // one that does not cannot change (best, second, index) - an equal distance leaves all three as they are.
-                // So 16 candidates at a time are first only compared, as raw accumulator halves (64 * dot = 128 * (128 -
-                // distance), signed 16 bit), against the row's second best: 4 three-input packed maxima and one vote per
-                // group instead of 28 key-building and selection instructions; the exact path below runs only for a group
-                // in which some row of the warp has a contender. Rows are independent, so skipping is exact.
-                const uint32_t thr2 = (uint32_t)((R2 * 128 - 16384) & 0xffff) * 0x10001u;
-#pragma unroll
-                for (int gq = 0; gq < 4; ++gq) {
-                    const int b = 8 * gq;
-                    const uint32_t mx = __vimax3_s16x2(__vimax3_s16x2(r[b], r[b + 1], r[b + 2]), __vimax3_s16x2(r[b + 3], r[b + 4], r[b + 5]),
-                                                       __vimax3_s16x2(r[b + 6], r[b + 7], thr2));
-                    if (__any_sync(0xffffffffu, mx != thr2)) {
-#pragma unroll
-                        for (int i = b; i < b + 8; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
-                    }
-                }
-            } else if (valid >= 64) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)), __vadd2(r[i + 1], bias(i + 1)));
-            } else {
-                auto mask = [valid](int i) { return (2 * i < valid ? 0xFFFFu : 0u) | (2 * i + 1 < valid ? 0xFFFF0000u : 0u); };
-#pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    acc.push2((i >> 1) & 1, __vadd2(r[i], bias(i)) & mask(i), __vadd2(r[i + 1], bias(i + 1)) & mask(i + 1));
-            }
-            int k1, k2;
-            acc.reduce(k1, k2);
-            const int d1 = k1 >> 7, d2 = k2 >> 7;
-            if (d1 > R1) {
-                R2 = max(R1, d2);
-                R1 = d1;
-                Ridx = col0 + 127 - (k1 & 127);
-            } else {
-                R2 = max(R2, d1);
-            }
+            top2_tile_update(r, t, col0, valid, R1, R2, Ridx);
         }
-        if (h == 1) { s_r1[row] = R1; s_r2[row] = R2; s_ri[row] = Ridx; }
-        // the two column halves of a row meet here (epilogue warps only: named barrier 1, 256 threads)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (h == 0 && row0 + row < na) {
-            const int B1 = s_r1[row], B2 = s_r2[row], Bi = s_ri[row];
-            const int m1 = max(R1, B1);
-            const int m2 = max(min(R1, B1), max(R2, B2));
-            int idx;
-            if (B1 > R1) idx = Bi;
-            else if (B1 < R1) idx = Ridx;
-            else idx = (Ridx < 0 || Bi < 0) ? max(Ridx, Bi) : min(Ridx, Bi);
-            o_idx[row0 + row] = idx;
-            o_b1[row0 + row] = 256 - m1;
-            o_b2[row0 + row] = 256 - m2;
-        }
+        top2_merge_halves_and_store(h, row, row0 + row < na, R1, R2, Ridx, s_r1, s_r2, s_ri, o_idx + row0 + row, o_b1 + row0 + row, o_b2 + row0 + row);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- the matcher on CTA pairs (cta_group::2) ---------------------------------------------------------------------
+// Two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma of M = 256: each CTA holds its own 128 query rows and
+// its own 128 x 128 accumulator in its TMEM, and stages only HALF of every candidate tile (64 rows) in its shared memory -
+// the tensor cores exchange the halves. Per comparison that is 3/4 of the shared-memory operand reads and half of the TMA
+// writes of the one-CTA kernel, whose steady state is bound by exactly that (182 B/clk wanted of 128: DESIGN.md section 4).
+// Roles per CTA as above; only the leader (cluster rank 0) issues MMAs. Barriers: every TMA of either CTA reports to the
+// LEADER's full barrier; the leader's commits are multicast to both CTAs' empty / accumulator-full barriers; both CTAs'
+// epilogue warps arrive on the leader's accumulator-empty barrier.
+constexpr int kPairHalfN = kTileN / 2;                                // candidates a CTA stages per tile
+constexpr int kPairStageBytes = kPairHalfN * kMmaKBytes;              // 16 KB
+constexpr int kPairStages = 4;                                        // 4 half tiles per CTA = 4 tiles in flight per pair
+constexpr int kPairSmemBytes = kATileBytes + kPairStages * kPairStageBytes + 1024;  // 97 KB: two CTAs (of two pairs) per SM
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA box load into THIS CTA's shared memory that reports its bytes to the barrier at the same offset in the pair's even CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar) & 0xFEFFFFFFu)
+                 : "memory");
+}
+// arrive on `bar` of CTA `cta` of the cluster. Default (CTA-scope) semantics on purpose: what the barrier orders here are TMEM
+// reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already retired - the .release.cluster form costs a
+// MEMBAR.ALL.GPU + ERRBAR per arrival (20 % of this kernel's stall samples when it was tried)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_or_trap(uint64_t* bar, uint32_t parity) {  // arrivals come from both CTAs
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t cols) {  // the same warp of both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrives on `bar` of BOTH CTAs when the MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 2)
+knn2_mma_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh, const int* __restrict__ d_nA,
+                     int nA_max, int strideA, const int* __restrict__ d_nB, int nB_max, int strideB, const int* __restrict__ d_pairs,
+                     int out_stride, int* __restrict__ out_idx, int* __restrict__ out_b1, int* __restrict__ out_b2, long long split_stride) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a, bar_full[kPairStages], bar_empty[kPairStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_r1[kMmaM], s_r2[kMmaM], s_ri[kMmaM];
+
+    const uint32_t rank = cluster_ctarank();     // == blockIdx.x & 1
+    const bool leader = rank == 0;
+    const int p = blockIdx.y;
+    const int setA = d_pairs ? d_pairs[2 * p] : p, setB = d_pairs ? d_pairs[2 * p + 1] : p;
+    const int na = d_nA ? min(d_nA[setA], nA_max) : nA_max;
+    const int nb = d_nB ? min(d_nB[setB], nB_max) : nB_max;
+    const int pair_row0 = (int)(blockIdx.x >> 1) * (2 * kMmaM);
+    if (pair_row0 >= na) return;                 // both CTAs of the pair leave together
+    const int row0 = pair_row0 + (int)rank * kMmaM;   // may lie beyond na for the odd CTA of the last pair: computes, writes nothing
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // gridDim.z > 1: this CTA scans only its share of the candidate tiles and writes a partial result (split_stride apart)
+    int* o_idx = out_idx + (size_t)blockIdx.z * split_stride + (size_t)p * out_stride;
+    int* o_b1 = out_b1 + (size_t)blockIdx.z * split_stride + (size_t)p * out_stride;
+    int* o_b2 = out_b2 + (size_t)blockIdx.z * split_stride + (size_t)p * out_stride;
+    if (nb <= 0) {
+        for (int r = threadIdx.x; r < kMmaM; r += kMmaThreads)
+            if (row0 + r < na) { o_idx[row0 + r] = -1; o_b1[row0 + r] = 256; o_b2[row0 + r] = 256; }
+        return;
+    }
+    const int all_tiles = (nb + kTileN - 1) / kTileN;
+    const int tile0 = (int)((long long)blockIdx.z * all_tiles / gridDim.z);                       // first candidate tile of this CTA
+    const int ntiles = (int)((long long)(blockIdx.z + 1) * all_tiles / gridDim.z) - tile0;       // and how many (t below is local)
+    uint8_t* sa = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // same offset in both CTAs
+    uint8_t* sb = sa + kATileBytes;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_a, 1);
+        for (int s = 0; s < kPairStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 16); }  // 8 epilogue warps of each CTA
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_pair(&tmem_base_s, kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();   // barriers of both CTAs initialised before either CTA's TMA or commit can reach them
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own query rows, own half of every candidate tile =====
+        if (lane == 0) {
+            const int arow = p * strideA + row0, brow = p * strideB + (int)rank * kPairHalfN;
+            if (leader) mbar_expect_tx(&bar_a, 2 * kATileBytes);
+            tma_load_2d_pair(sa, &map_a, 0, arow, &bar_a);
+            tma_load_2d_pair(sa + kMmaM * 128, &map_a, 128, arow, &bar_a);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kPairStages;
+                if (t >= kPairStages) mbar_wait_or_trap(&bar_empty[s], ((t / kPairStages) & 1) ^ 1);
+                uint8_t* dst = sb + s * kPairStageBytes;
+                if (leader) mbar_expect_tx(&bar_full[s], 2 * kPairStageBytes);
+                tma_load_2d_pair(dst, &map_bh, 0, brow + (tile0 + t) * kTileN, &bar_full[s]);
+                tma_load_2d_pair(dst + kPairHalfN * 128, &map_bh, 128, brow + (tile0 + t) * kTileN, &bar_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA for the pair =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = idesc_i8(2 * kMmaM, kTileN);
+            mbar_wait_or_trap(&bar_a, 0);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kPairStages, a = t & 1;
+                if (t >= 2) mbar_wait_cluster_or_trap(&bar_tempty[a], ((t >> 1) & 1) ^ 1);  // both CTAs' epilogues drained accumulator a
+                mbar_wait_or_trap(&bar_full[s], (t / kPairStages) & 1);                     // both halves of the tile have landed
+                tc_fence_after();
+                const uint32_t a_smem = smem_u32(sa), b_smem = smem_u32(sb + s * kPairStageBytes), tmem_d = tmem_base + a * kTileN;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_i8_pair(tmem_d, smem_desc_k_sw128(a_smem + c * (kMmaM * 128) + k * 32),
+                                    smem_desc_k_sw128(b_smem + c * (kPairHalfN * 128) + k * 32), idesc, (c | k) ? 1u : 0u);
+                }
+                tc_commit_pair(&bar_empty[s]);
+                tc_commit_pair(&bar_tfull[a]);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own rows): 8 warps = 4 TMEM lane quarters x 2 column halves of 64 =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int R1 = 0, R2 = 0, Ridx = -1;
+        for (int t = 0; t < ntiles; ++t) {
+            const int a = t & 1;
+            mbar_wait_or_trap(&bar_tfull[a], (t >> 1) & 1);
+            tc_fence_after();
+            const int col0 = (tile0 + t) * kTileN + h * 64;
+            const int valid = nb - col0;
+            uint32_t r[32];
+            tmem_ld64_pack16(tmem_base + ((uint32_t)(q * 32) << 16) + a * kTileN + h * 64, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bar_tempty[a], 0u);
+            top2_tile_update(r, t, col0, valid, R1, R2, Ridx);
+        }
+        top2_merge_halves_and_store(h, row, row0 + row < na, R1, R2, Ridx, s_r1, s_r2, s_ri, o_idx + row0 + row, o_b1 + row0 + row, o_b2 + row0 + row);
+    }
+    tc_fence_before();
+    cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still be signalled or read
+    if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
 // ---- debug: one tile, the raw dot products ----------------------------------------------------------------------
@@ -448,8 +646,9 @@ struct MmaScratch {
     std::mutex mu;
     uint8_t* a = nullptr;
     uint8_t* b = nullptr;
-    size_t cap_a = 0, cap_b = 0;
-    CUtensorMap map_a, map_b;          // cached: valid for (a, rows_a) / (b, rows_b)
+    uint8_t* part = nullptr;           // partial results of a split candidate scan
+    size_t cap_a = 0, cap_b = 0, cap_part = 0;
+    CUtensorMap map_a, map_b, map_bh;  // cached: valid for (a, rows_a) / (b, rows_b); map_bh = b in boxes of half a tile (CTA pairs)
     size_t map_rows_a = 0, map_rows_b = 0;
 };
 using MmaScratchTable = std::map<std::pair<int, cudaStream_t>, std::shared_ptr<MmaScratch>>;
@@ -482,12 +681,70 @@ int release_mma_scratch(int device, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(sc->mu);
     if (sc->a) ORB_CUDA_TRY(cudaFreeAsync(sc->a, st));
     if (sc->b) ORB_CUDA_TRY(cudaFreeAsync(sc->b, st));
-    sc->a = sc->b = nullptr;
+    if (sc->part) ORB_CUDA_TRY(cudaFreeAsync(sc->part, st));
+    sc->a = sc->b = sc->part = nullptr;
+    return ORB_OK;
+}
+
+// ---- candidate-range split ---------------------------------------------------------------------------------------
+// Every CTA of a launch does the same amount of work, so a launch runs in waves: 1563 query tiles on 296 CTA slots are 5.28
+// waves that cost 6. When that loses more than a few percent (and the database is long enough to keep every CTA's pipeline
+// and pruning warm) the candidate tiles are dealt to gridDim.z CTAs per query tile, each leaving a partial (index, best,
+// second); this kernel folds the partials in candidate order with the reference's update rule (strict '<' for the best,
+// src/ORBmatcher.cc:589-598), so the result is the one-pass result.
+constexpr int kMaxSplit = 4, kMinTilesPerSplit = 64;
+__global__ void __launch_bounds__(256) top2_merge_splits_kernel(const int* __restrict__ part_idx, const int* __restrict__ part_b1,
+                                                                const int* __restrict__ part_b2, long long split_stride, int nsplit,
+                                                                const int* __restrict__ d_nA, int nA_max, const int* __restrict__ d_pairs,
+                                                                int out_stride, long long total, int* __restrict__ out_idx,
+                                                                int* __restrict__ out_b1, int* __restrict__ out_b2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int p = (int)(i / out_stride), r = (int)(i - (long long)p * out_stride);
+    const int na = d_nA ? min(d_nA[d_pairs ? d_pairs[2 * p] : p], nA_max) : nA_max;
+    if (r >= na) return;
+    int idx = -1, m1 = 256, m2 = 256;
+    for (int z = 0; z < nsplit; ++z) {
+        const int d1 = part_b1[z * split_stride + i], d2 = part_b2[z * split_stride + i];
+        if (d1 < m1) { m2 = min(m1, d2); m1 = d1; idx = part_idx[z * split_stride + i]; }
+        else m2 = min(m2, d1);
+    }
+    out_idx[i] = idx; out_b1[i] = m1; out_b2[i] = m2;
+}
+
+// how many ways to split the candidate scan of `ctas` equal CTAs over `slots` resident ones: the smallest count within 3 %
+// of the best wave efficiency
+static int choose_split(long long ctas, int candidate_tiles, int slots) {
+    int best = 1;
+    double best_eff = 0.0;
+    for (int n = 1; n <= kMaxSplit; ++n) {
+        if (n > 1 && candidate_tiles / n < kMinTilesPerSplit) break;
+        const long long units = ctas * n, waves = (units + slots - 1) / slots;
+        const double eff = (double)units / (double)(waves * slots);
+        if (eff > best_eff + 0.03) { best_eff = eff; best = n; }
+    }
+    return best;
+}
+
+// variant: 0 = automatic, 1 = one CTA per query tile, 2 = CTA pairs (cta_group::2). Measured on B200 with the candidate split in
+// place (tools/exp_knn2_pair.py, profiles/r02_experiments.md): the pair kernel needs 3/4 of the shared-memory operand
+// bandwidth (tc wavefronts 51 % against 68 %) but the tensor pipe is equally busy in both (72 %), and the one-CTA kernel is
+// as fast or faster at every size - so the automatic choice is the one-CTA kernel and pairs run only when asked for.
+static bool use_pair_kernel(int variant, int /*nA_max*/, int /*nB_max*/) { return variant == 2; }
+
+static int set_mma_kernel_attributes(int device) {
+    static std::atomic<bool> attr_set[64];  // per device, once: the attribute calls are not free on the launch path
+    if (device >= 64 || !attr_set[device].load()) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
+        ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+        if (device < 64) attr_set[device].store(true);
+    }
     return ORB_OK;
 }
 
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
-                    int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st) {
+                    int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st,
+                    int variant) {
     if (pairs <= 0 || nA_max <= 0) return ORB_OK;
     ORB_REQUIRE(pairs <= 65535, "more than 65535 set pairs in one call");
     int device = 0;
@@ -515,19 +772,36 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
     if (sc.b != old_b || sc.map_rows_b != rows_b) {
         sc.map_rows_b = 0;
         if ((rc = encode_expanded_map(&sc.map_b, sc.b, (long long)rows_b, kTileN)) != ORB_OK) return rc;
+        if ((rc = encode_expanded_map(&sc.map_bh, sc.b, (long long)rows_b, kPairHalfN)) != ORB_OK) return rc;
         sc.map_rows_b = rows_b;
     }
-    const CUtensorMap ma = sc.map_a, mb = sc.map_b;
+    const bool pair_kernel = use_pair_kernel(variant, nA_max, nB_max);
+    const CUtensorMap ma = sc.map_a, mb = pair_kernel ? sc.map_bh : sc.map_b;
     const int words = 8 * (nA_max > nB_max ? nA_max : nB_max);
     expand_pairs_kernel<<<dim3(ceil_div(words, 256), pairs, 2), 256, 0, st>>>((const uint32_t*)dA, d_nA, nA_max, strideA_rows, (const uint32_t*)dB,
                                                                              d_nB, nB_max, strideB_rows, d_pairs, (uint4*)sc.a, (uint4*)sc.b);
-    static std::atomic<bool> attr_set[64];  // per device, once: the attribute call is not free on the launch path
-    if (device >= 64 || !attr_set[device].load()) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
-        if (device < 64) attr_set[device].store(true);
+    if ((rc = set_mma_kernel_attributes(device)) != ORB_OK) return rc;
+    const int qtiles = pair_kernel ? 2 * ceil_div(nA_max, 2 * kMmaM) : ceil_div(nA_max, kMmaM);
+    const int nsplit = choose_split((long long)qtiles * pairs, ceil_div(nB_max, kTileN), 2 * kNumSMs);
+    const long long total = (long long)pairs * out_stride;
+    int *k_idx = d_idx, *k_b1 = d_b1, *k_b2 = d_b2;
+    if (nsplit > 1) {
+        if ((rc = grow_stream_buffer(&sc.part, &sc.cap_part, (size_t)3 * nsplit * total * sizeof(int), st)) != ORB_OK) return rc;
+        k_idx = reinterpret_cast<int*>(sc.part);
+        k_b1 = k_idx + (size_t)nsplit * total;
+        k_b2 = k_b1 + (size_t)nsplit * total;
     }
-    knn2_mma_kernel<<<dim3(ceil_div(nA_max, kMmaM), pairs), kMmaThreads, kMmaSmemBytes, st>>>(ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max,
-                                                                                          strideB_rows, d_pairs, out_stride, d_idx, d_b1, d_b2);
+    if (pair_kernel)
+        knn2_mma_pair_kernel<<<dim3(qtiles, pairs, nsplit), kMmaThreads, kPairSmemBytes, st>>>(
+            ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max, strideB_rows, d_pairs, out_stride, k_idx, k_b1, k_b2, total);
+    else
+        knn2_mma_kernel<<<dim3(qtiles, pairs, nsplit), kMmaThreads, kMmaSmemBytes, st>>>(ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max, strideB_rows,
+                                                                                       d_pairs, out_stride, k_idx, k_b1, k_b2, total);
+    if (nsplit > 1) {
+        top2_merge_splits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(k_idx, k_b1, k_b2, total, nsplit, d_nA, nA_max, d_pairs, out_stride,
+                                                                                 total, d_idx, d_b1, d_b2);
+        count_launch();
+    }
     count_launch(2);
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
@@ -540,6 +814,8 @@ namespace orb {
 int mma_encode_operand_map(CUtensorMap* out, const void* base, long long rows, bool query_side) {
     return encode_expanded_map(out, base, rows, query_side ? kMmaM : kTileN);
 }
+// the database operand in boxes of half a candidate tile: what each CTA of a pair stages (knn2_mma_pair_kernel)
+int mma_encode_operand_map_half(CUtensorMap* out, const void* base, long long rows) { return encode_expanded_map(out, base, rows, kPairHalfN); }
 // rows [0, n_rows) of a packed 32-byte descriptor array (which may live in a PEER GPU's memory: the loads then travel over
 // NVLink) -> 256 int8 per row, +-64 (query operand) or +-1 (database operand), into local memory
 __global__ void __launch_bounds__(256) expand_rows_kernel(const uint32_t* __restrict__ src, int n_words, uint32_t neg, uint32_t flip,
@@ -572,23 +848,39 @@ int mma_preload_kernels() {
     cudaFuncAttributes fa;
     ORB_CUDA_TRY(cudaFuncGetAttributes(&fa, expand_rows_kernel));
     ORB_CUDA_TRY(cudaFuncGetAttributes(&fa, knn2_mma_kernel));
-    ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
-    return ORB_OK;
+    ORB_CUDA_TRY(cudaFuncGetAttributes(&fa, knn2_mma_pair_kernel));
+    ORB_CUDA_TRY(cudaFuncGetAttributes(&fa, top2_merge_splits_kernel));
+    int device = 0;
+    ORB_CUDA_TRY(cudaGetDevice(&device));
+    return set_mma_kernel_attributes(device);
 }
 // one query block (na rows, expanded, starting at row 0 of map_a) against one database (nb rows of map_b); the three
 // output arrays may point into a peer GPU's memory
-int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, int na, int nb, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st) {
+// `part`: scratch of mma_partial_ints(rows) ints for the partial results of a split candidate scan
+size_t mma_partial_ints(size_t rows) { return (size_t)3 * kMaxSplit * rows; }
+int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_bh, int na, int nb, int* d_idx, int* d_b1,
+                           int* d_b2, int* part, cudaStream_t st) {
     if (na <= 0) return ORB_OK;
-    int device = 0;
+    int device = 0, rc;
     ORB_CUDA_TRY(cudaGetDevice(&device));
-    static std::atomic<bool> attr_set[64];
-    if (device >= 64 || !attr_set[device].load()) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
-        if (device < 64) attr_set[device].store(true);
-    }
-    knn2_mma_kernel<<<dim3(ceil_div(na, kMmaM), 1), kMmaThreads, kMmaSmemBytes, st>>>(map_a, map_b, nullptr, na, na, nullptr, nb, nb, nullptr, na,
-                                                                                    d_idx, d_b1, d_b2);
+    if ((rc = set_mma_kernel_attributes(device)) != ORB_OK) return rc;
+    const bool pair_kernel = use_pair_kernel(0, na, nb);
+    const int qtiles = pair_kernel ? 2 * ceil_div(na, 2 * kMmaM) : ceil_div(na, kMmaM);
+    const int nsplit = part ? choose_split(qtiles, ceil_div(nb, kTileN), 2 * kNumSMs) : 1;
+    int *k_idx = d_idx, *k_b1 = d_b1, *k_b2 = d_b2;
+    if (nsplit > 1) { k_idx = part; k_b1 = part + (size_t)nsplit * na; k_b2 = k_b1 + (size_t)nsplit * na; }
+    if (pair_kernel)
+        knn2_mma_pair_kernel<<<dim3(qtiles, 1, nsplit), kMmaThreads, kPairSmemBytes, st>>>(map_a, map_bh, nullptr, na, na, nullptr, nb, nb, nullptr, na,
+                                                                                         k_idx, k_b1, k_b2, (long long)na);
+    else
+        knn2_mma_kernel<<<dim3(qtiles, 1, nsplit), kMmaThreads, kMmaSmemBytes, st>>>(map_a, map_b, nullptr, na, na, nullptr, nb, nb, nullptr, na, k_idx,
+                                                                                   k_b1, k_b2, (long long)na);
     count_launch();
+    if (nsplit > 1) {
+        top2_merge_splits_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(k_idx, k_b1, k_b2, (long long)na, nsplit, nullptr, na, nullptr, na,
+                                                                              (long long)na, d_idx, d_b1, d_b2);
+        count_launch();
+    }
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }
@@ -603,13 +895,34 @@ extern "C" int orbm_release_scratch(void* stream) {
     return release_mma_scratch(device, (cudaStream_t)stream);
 }
 
+// Debug: how many CTA pairs of knn2_mma_pair_kernel the current device holds at once, and one-CTA blocks per SM of knn2_mma_kernel.
+extern "C" int orbm_debug_mma_occupancy(int* pair_clusters, int* single_blocks_per_sm) {
+    using namespace orb;
+    ORB_REQUIRE(pair_clusters && single_blocks_per_sm, "null pointer");
+    int device = 0, rc;
+    ORB_CUDA_TRY(cudaGetDevice(&device));
+    if ((rc = set_mma_kernel_attributes(device)) != ORB_OK) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * kNumSMs, 1, 1);
+    cfg.blockDim = dim3(kMmaThreads, 1, 1);
+    cfg.dynamicSmemBytes = kPairSmemBytes;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    ORB_CUDA_TRY(cudaOccupancyMaxActiveClusters(pair_clusters, knn2_mma_pair_kernel, &cfg));
+    ORB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(single_blocks_per_sm, knn2_mma_kernel, kMmaThreads, kMmaSmemBytes));
+    return ORB_OK;
+}
+
 // Debug / experiment entry: the tensor-core matcher on one pair of device arrays.
 extern "C" int orbm_knn2_mma_device(const uint8_t* dA, int nA, const uint8_t* dB, int nB, int32_t* d_idx, int32_t* d_best, int32_t* d_second,
                                     void* stream) {
     using namespace orb;
     ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
     ORB_REQUIRE(nA == 0 || (dA && d_idx && d_best && d_second), "null pointer");
-    return launch_knn2_mma(dA, nullptr, nA, nA, dB, nullptr, nB, nB, nullptr, 1, nA, d_idx, d_best, d_second, (cudaStream_t)stream);
+    return launch_knn2_mma(dA, nullptr, nA, nA, dB, nullptr, nB, nB, nullptr, 1, nA, d_idx, d_best, d_second, (cudaStream_t)stream, 0);
 }
 
 // Debug tap: dot products (+-1 encoding) of 128 x 256 descriptors through expand + TMA + tcgen05.mma + tcgen05.ld.

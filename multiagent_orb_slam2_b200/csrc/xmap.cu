@@ -34,7 +34,10 @@
 namespace orb {
 int mma_encode_operand_map(CUtensorMap* out, const void* base, long long rows, bool query_side);
 int mma_expand_rows(const uint8_t* packed, int n_rows, bool query_side, uint8_t* out, cudaStream_t st);
-int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, int na, int nb, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st);
+int mma_encode_operand_map_half(CUtensorMap* out, const void* base, long long rows);
+size_t mma_partial_ints(size_t rows);
+int mma_launch_preexpanded(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_bh, int na, int nb, int* d_idx, int* d_b1,
+                           int* d_b2, int* part, cudaStream_t st);
 int mma_preload_kernels();
 
 constexpr int kXmapMaxWorld = 16, kXmapMaxSlots = 8, kXmapCtrlBytes = 4096, kXmapTile = 128;
@@ -103,7 +106,8 @@ struct orbm_xmap {
     bool attached = false;
     uint32_t step = 0;
     uint8_t *scr_a = nullptr, *scr_b = nullptr;   // local expanded operands (rows_cap x 256 B each)
-    CUtensorMap map_a, map_b;
+    int* scr_part = nullptr;                      // partial results of a split candidate scan (hamming_mma.cu)
+    CUtensorMap map_a, map_b, map_bh;
     void** d_ptrs = nullptr;                      // device array of flag pointers for the wait / signal kernels
     void** h_ptrs = nullptr;                      // pinned staging for it
     int ptr_cursor = 0;
@@ -179,7 +183,7 @@ int orbm_xmap_create(int device, int rank, int world, int n_maps, int rows_cap, 
     x->window_bytes = x->off_results + (size_t)x->slots * (n_maps - 1) * 3 * x->res_rows * sizeof(int);
     auto fail = [&](const char* what, cudaError_t e) {
         set_error("%s failed: %s", what, cudaGetErrorString(e));
-        cudaFree(x->window); cudaFree(x->scr_a); cudaFree(x->scr_b); cudaFree(x->d_ptrs); cudaFreeHost(x->h_ptrs);
+        cudaFree(x->window); cudaFree(x->scr_a); cudaFree(x->scr_b); cudaFree(x->scr_part); cudaFree(x->d_ptrs); cudaFreeHost(x->h_ptrs);
         delete x;
         return ORB_ECUDA;
     };
@@ -188,6 +192,7 @@ int orbm_xmap_create(int device, int rank, int world, int n_maps, int rows_cap, 
     if ((e = cudaMemset(x->window, 0, x->window_bytes)) != cudaSuccess) return fail("cudaMemset(window)", e);
     if ((e = cudaMalloc(&x->scr_a, x->res_rows * 256)) != cudaSuccess) return fail("cudaMalloc(operand A)", e);
     if ((e = cudaMalloc(&x->scr_b, x->res_rows * 256)) != cudaSuccess) return fail("cudaMalloc(operand B)", e);
+    if ((e = cudaMalloc(&x->scr_part, mma_partial_ints(x->res_rows) * sizeof(int))) != cudaSuccess) return fail("cudaMalloc(partial results)", e);
     if ((e = cudaMemset(x->scr_a, 0, x->res_rows * 256)) != cudaSuccess) return fail("cudaMemset", e);
     if ((e = cudaMemset(x->scr_b, 0, x->res_rows * 256)) != cudaSuccess) return fail("cudaMemset", e);
     if ((e = cudaMalloc(&x->d_ptrs, orbm_xmap::kPtrSlots * sizeof(void*))) != cudaSuccess) return fail("cudaMalloc(flags)", e);
@@ -198,9 +203,10 @@ int orbm_xmap_create(int device, int rank, int world, int n_maps, int rows_cap, 
     if ((e = cudaFuncGetAttributes(&fa, xmap_wait_kernel)) != cudaSuccess) return fail("cudaFuncGetAttributes", e);
     if ((e = cudaFuncGetAttributes(&fa, xmap_signal_kernel)) != cudaSuccess) return fail("cudaFuncGetAttributes", e);
     int rc = mma_preload_kernels();
-    if (rc != ORB_OK) { cudaFree(x->window); cudaFree(x->scr_a); cudaFree(x->scr_b); cudaFree(x->d_ptrs); cudaFreeHost(x->h_ptrs); delete x; return rc; }
+    if (rc != ORB_OK) { cudaFree(x->window); cudaFree(x->scr_a); cudaFree(x->scr_b); cudaFree(x->scr_part); cudaFree(x->d_ptrs); cudaFreeHost(x->h_ptrs); delete x; return rc; }
     rc = mma_encode_operand_map(&x->map_a, x->scr_a, (long long)x->res_rows, true);
     if (rc == ORB_OK) rc = mma_encode_operand_map(&x->map_b, x->scr_b, (long long)x->res_rows, false);
+    if (rc == ORB_OK) rc = mma_encode_operand_map_half(&x->map_bh, x->scr_b, (long long)x->res_rows);
     if (rc != ORB_OK) { fail("tensor map", cudaSuccess); return rc; }
     x->peer[rank] = x->window;
     x->attached = world == 1;
@@ -214,7 +220,7 @@ void orbm_xmap_destroy(orbm_xmap_t x) {
     cudaDeviceSynchronize();
     for (int r = 0; r < x->world; ++r)
         if (x->ipc_opened[r]) cudaIpcCloseMemHandle(x->peer[r]);
-    cudaFree(x->window); cudaFree(x->scr_a); cudaFree(x->scr_b); cudaFree(x->d_ptrs); cudaFreeHost(x->h_ptrs);
+    cudaFree(x->window); cudaFree(x->scr_a); cudaFree(x->scr_b); cudaFree(x->scr_part); cudaFree(x->d_ptrs); cudaFreeHost(x->h_ptrs);
     delete x;
 }
 
@@ -325,8 +331,8 @@ int orbm_knn2_allgather(orbm_xmap_t x, const uint8_t* const* d_sets, const int32
             cur_b = c.b;
         }
         const int ps = c.b < c.a ? c.b : c.b - 1;
-        if ((rc = mma_launch_preexpanded(x->map_a, x->map_b, na, nb, x->result(oa, sa, ps, 0) + row0, x->result(oa, sa, ps, 1) + row0,
-                                         x->result(oa, sa, ps, 2) + row0, st)) != ORB_OK)
+        if ((rc = mma_launch_preexpanded(x->map_a, x->map_b, x->map_bh, na, nb, x->result(oa, sa, ps, 0) + row0, x->result(oa, sa, ps, 1) + row0,
+                                         x->result(oa, sa, ps, 2) + row0, x->scr_part, st)) != ORB_OK)
             return rc;
     }
     // ---- done with every window for this step; owners then wait for their contributors -------------------------------------

@@ -38,8 +38,8 @@ def test_argument_validation_needs_no_gpu():
     cfg = _lib.Config(1000, 1.2, 8, 5, 7)
     assert L.orbx_create(C.byref(cfg), 0, 640, 480, 1, C.byref(h)) == _lib.ORB_EINVAL
     assert L.orbm_knn2_device(None, -1, None, 0, None, None, None, None) == _lib.ORB_EINVAL
-    assert L.orbm_set_knn2_backend(3) == _lib.ORB_EINVAL and L.orbm_set_knn2_backend(-1) == _lib.ORB_EINVAL
-    assert L.orbm_set_knn2_backend(2) == _lib.ORB_OK and L.orbm_set_knn2_backend(0) == _lib.ORB_OK
+    assert L.orbm_set_knn2_backend(4) == _lib.ORB_EINVAL and L.orbm_set_knn2_backend(-1) == _lib.ORB_EINVAL
+    assert L.orbm_set_knn2_backend(3) == _lib.ORB_OK and L.orbm_set_knn2_backend(2) == _lib.ORB_OK and L.orbm_set_knn2_backend(0) == _lib.ORB_OK
     assert L.orbm_knn2_mma_device(None, -1, None, 0, None, None, None, None) == _lib.ORB_EINVAL
     db = C.c_void_p()
     assert L.orbdb_create(0, 0, C.byref(db)) == _lib.ORB_EINVAL

@@ -105,9 +105,10 @@ def test_quadtree_kernel_on_random_candidate_sets(seed):
 
 
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(params=[1, 2], ids=["popc", "tensorcore"])
+@pytest.fixture(params=[1, 2, 3], ids=["popc", "tensorcore", "tensorcore-cta-pairs"])
 def knn2_backend(request):
-    """Run a test once per brute-force implementation (csrc/hamming.cu POPC kernel, csrc/hamming_mma.cu tcgen05 kernel)."""
+    """Run a test once per brute-force implementation (csrc/hamming.cu POPC kernel, csrc/hamming_mma.cu tcgen05 kernel with one
+    CTA per query tile, the same with cta_group::2 CTA pairs)."""
     from multiagent_orb_slam2_b200 import _lib
     _lib.check(_lib.lib().orbm_set_knn2_backend(request.param))
     yield request.param
@@ -135,6 +136,27 @@ def test_knn2_large_split_database(knn2_backend):
     assert np.array_equal(gi, oi) and np.array_equal(g1, o1) and np.array_equal(g2, o2)
     acc = m.accept(gi, g1, g2)
     assert (acc >= 0).sum() > 1000
+
+
+def test_knn2_split_scan_keeps_first_minimum_across_segments(knn2_backend):
+    """Long databases are scanned by several CTAs per query tile (candidate-range split, csrc/hamming_mma.cu) and the partial
+    results folded afterwards: exact duplicates of a query's best row that fall into different segments must still resolve to
+    the FIRST one, with second best == best (the reference's strict '<', src/ORBmatcher.cc:589-598)."""
+    nB, nA = 40000, 300
+    B = synth.descriptors(nB, 11)
+    src = np.array([5, 9000, 13000, 21000, 33000, 39999])
+    A = synth.descriptors_fast(nA, 12, B, 40)
+    A[:6] = B[src]                                  # exact hits, one per region of the database
+    for k, j in enumerate(src):                     # and later copies of each of them in other segments
+        for off in (7001, 15003, 26007):
+            if j + off < nB:
+                B[j + off] = B[j]
+    A[6] = B[39999]
+    m = ORBmatcher(0.75)
+    gi, g1, g2 = m.knn2(A, B)
+    oi, o1, o2 = O.knn2(A, B, threads=8)
+    assert np.array_equal(gi, oi) and np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    assert g1[0] == 0 and g2[0] == 0 and gi[0] == 5 and gi[1] == 9000
 
 
 def test_knn2_lists_and_distance_matrix():
