@@ -84,6 +84,10 @@ struct orbx_extractor {
     size_t in_pitch = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    uint8_t* h_out = nullptr;                          // pinned staging of the results for small synchronous host calls
+    size_t h_out_bytes = 0;
+    cudaStream_t lvl_stream[kMaxLevels] = {};          // small batches: one branch per pyramid level (launch_sequence)
+    cudaEvent_t ev_lvl_ready[kMaxLevels] = {}, ev_lvl_done[kMaxLevels] = {};
     FrameSet last{};  // frames of the last call (for mvImagePyramid level 0)
     int last_n = 0;
     // TMA tensor maps per level: source windows of the resize, blur tiles, FAST cell tiles.
@@ -277,14 +281,47 @@ int build_geometry(orbx_extractor* h) {
     ORB_CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     ORB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming));
     ORB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming));
+    for (int l = 0; l < nl; ++l) {
+        ORB_CUDA_TRY(cudaStreamCreateWithFlags(&h->lvl_stream[l], cudaStreamNonBlocking));
+        ORB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_lvl_ready[l], cudaEventDisableTiming));
+        ORB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_lvl_done[l], cudaEventDisableTiming));
+    }
     return ORB_OK;
 }
 
 // the kernel sequence of operator(): resize chain, then blur on the side stream next to FAST + quadtree, joined
 // before orientation + description
+// Up to this many frames per call the GPU is far from full (one frame: 1300 FAST warps, 8 quadtree blocks) and the call's
+// latency is the dependency chain resize 1..7 -> FAST -> quadtree -> describe (37 + 15 + 41 + 16 us at batch 1). Level l's
+// detection and distribution only need pyramid level l, so they run as one branch per level next to the resize chain:
+// the critical path becomes FAST + quadtree of level 0 (the input image itself) -> describe.
+constexpr int kLevelParallelMaxBatch = 2;
+
+static int launch_sequence_level_parallel(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t st) {
+    const Geometry& g = h->hg;
+    int rc;
+    for (int l = 0; l < g.nlevels; ++l) {
+        if (l > 0 && (rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
+        cudaStream_t s = h->lvl_stream[l];
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_lvl_ready[l], st));
+        ORB_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_lvl_ready[l], 0));
+        if ((rc = launch_fast(g, h->db, h->maps_fast, n, s, l))) return rc;
+        if ((rc = launch_quadtree(g, h->db, n, s, l))) return rc;
+        ORB_CUDA_TRY(cudaEventRecord(h->ev_lvl_done[l], s));
+    }
+    ORB_CUDA_TRY(cudaEventRecord(h->ev_pyr, st));
+    ORB_CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_pyr, 0));
+    if ((rc = launch_blur(g, h->db, h->maps_blur, n, h->stream2))) return rc;
+    ORB_CUDA_TRY(cudaEventRecord(h->ev_blur, h->stream2));
+    for (int l = 0; l < g.nlevels; ++l) ORB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_lvl_done[l], 0));
+    ORB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_blur, 0));
+    return launch_describe(g, h->db, fs, n, st);
+}
+
 int launch_sequence(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t st) {
     const Geometry& g = h->hg;
     int rc;
+    if (n <= kLevelParallelMaxBatch) return launch_sequence_level_parallel(h, fs, n, st);
     for (int l = 1; l < g.nlevels; ++l)
         if ((rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
     // fork: the Gaussian blur (1085-1086) only depends on the pyramid
@@ -412,10 +449,16 @@ void orbx_destroy(orbx_handle h) {
                     h->db.sortbuf, h->db.selected, h->db.sel_counts, h->db.kps, h->db.desc, h->db.counts, h->d_input, h->d_stereo};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_pyr) cudaFreeHost(h->h_pyr);
+    if (h->h_out) cudaFreeHost(h->h_out);
     for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
     for (cudaEvent_t e : h->ev_stage) if (e) cudaEventDestroy(e);
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
+    for (int l = 0; l < kMaxLevels; ++l) {
+        if (h->lvl_stream[l]) { cudaStreamSynchronize(h->lvl_stream[l]); cudaStreamDestroy(h->lvl_stream[l]); }
+        if (h->ev_lvl_ready[l]) cudaEventDestroy(h->ev_lvl_ready[l]);
+        if (h->ev_lvl_done[l]) cudaEventDestroy(h->ev_lvl_done[l]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
@@ -562,10 +605,36 @@ int orbx_extract_batch(orbx_handle h, const uint8_t* images, size_t stride, size
     ORB_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     int rc;
-    if ((rc = orbx_upload_frames(h, images, stride, frame_stride, n, st)) || (rc = orbx_extract_staged(h, n, st)) ||
-        (rc = orbx_download_results(h, n, kps, desc, cap, counts, st)))
-        return rc;
-    ORB_CUDA_TRY(cudaStreamSynchronize(st));
+    if ((rc = orbx_upload_frames(h, images, stride, frame_stride, n, st)) || (rc = orbx_extract_staged(h, n, st))) return rc;
+    // Results of a small call come back through pinned staging: a copy into the caller's pageable buffers blocks the host
+    // and costs ~15 us each (3 of them: 47 us behind the 75 us of kernels of one frame, measured); three asynchronous copies
+    // into pinned memory, one synchronisation and a host memcpy of the used entries cost ~12 us.
+    const int oc = h->hg.out_cap, take = std::min(cap, oc);
+    const size_t kp_row = (size_t)take * sizeof(orbx_keypoint), de_row = (size_t)take * 32;
+    const size_t staged_bytes = align_up((size_t)n * 4, 256) + (size_t)n * (kp_row + de_row);
+    if (take > 0 && staged_bytes <= ((size_t)4 << 20)) {
+        if (h->h_out_bytes < staged_bytes) {
+            if (h->h_out) { cudaStreamSynchronize(st); cudaFreeHost(h->h_out); h->h_out = nullptr; h->h_out_bytes = 0; }
+            ORB_CUDA_TRY(cudaMallocHost(&h->h_out, staged_bytes));
+            h->h_out_bytes = staged_bytes;
+        }
+        int32_t* s_cnt = reinterpret_cast<int32_t*>(h->h_out);
+        uint8_t* s_kps = h->h_out + align_up((size_t)n * 4, 256);
+        uint8_t* s_desc = s_kps + (size_t)n * kp_row;
+        ORB_CUDA_TRY(cudaMemcpyAsync(s_cnt, h->db.counts, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(s_kps, kp_row, h->db.kps, (size_t)oc * sizeof(orbx_keypoint), kp_row, n, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(s_desc, de_row, h->db.desc, (size_t)oc * 32, de_row, n, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int i = 0; i < n; ++i) {
+            counts[i] = s_cnt[i];
+            const size_t c = (size_t)std::max(0, std::min(s_cnt[i], take));
+            memcpy(kps + (size_t)i * cap, s_kps + (size_t)i * kp_row, c * sizeof(orbx_keypoint));
+            memcpy(desc + (size_t)i * cap * 32, s_desc + (size_t)i * de_row, c * 32);
+        }
+    } else {
+        if ((rc = orbx_download_results(h, n, kps, desc, cap, counts, st))) return rc;
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     for (int i = 0; i < n; ++i)
         if (counts[i] > cap) { set_error("frame %d has %d keypoints, buffer holds %d", i, counts[i], cap); rc = ORB_ECAPACITY; }
     return rc;

@@ -95,7 +95,7 @@ __device__ __forceinline__ int fast_side_margin(const int (&r)[16], int v, int s
 template <int TP>
 __global__ void __launch_bounds__(kFastThreads, 32 / kFastWarps)
 fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ cells, const __grid_constant__ TmaMaps maps,
-                  uint32_t* __restrict__ slots, int* __restrict__ cell_counts) {
+                  uint32_t* __restrict__ slots, int* __restrict__ cell_counts, int cell_first, int cell_end) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kFastWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,14 +111,14 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     uint64_t* bar = &bars[warp];
     const int frame = blockIdx.y, ncells = g->ncells;
     const int stride = gridDim.x * kFastWarps;       // cells gw, gw + stride, ... belong to this warp
-    const int gw = blockIdx.x * kFastWarps + warp;
+    const int gw = cell_first + blockIdx.x * kFastWarps + warp;   // this launch covers cells [cell_first, cell_end): all, or one level
     const int minTh = g->minTh, iniTh = g->iniTh;
-    if (gw >= ncells) return;
+    if (gw >= cell_end) return;
 
     // one elected lane per warp owns the mbarrier and issues the tile loads. The tile is dead once a
     // cell's scores are known, so the next cell's load is issued there and lands during phases 3-4.
     auto issue = [&](int ci) {
-        if (ci >= ncells) return;
+        if (ci >= cell_end) return;
         const CellDesc c = cells[ci];
         if (c.tw > 6 && c.th > 6) {
             mbar_expect_tx(bar, (uint32_t)T);
@@ -132,7 +132,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     }
     uint32_t parity = 0;
 
-    for (int ci = gw; ci < ncells; ci += stride) {
+    for (int ci = gw; ci < cell_end; ci += stride) {
         __syncwarp();  // every lane is done with the previous cell
         const CellDesc c = cells[ci];
         const LevelGeom& L = g->lv[c.level];
@@ -314,7 +314,8 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     }
 }
 
-int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st) {
+// level < 0: the cells of all levels in one launch; otherwise only that level's (small batches run the levels as parallel branches)
+int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st, int level) {
     // list entries hold the byte column in 7 bits and the row in 7 bits
     ORB_REQUIRE(hg.fast_bw <= 128 && hg.max_th <= 128 && hg.max_tw - 6 <= 64, "FAST cell larger than 64 x 122 pixels");
     const FastLayout lay = fast_layout(hg.max_tw, hg.max_th, hg.fast_bw);
@@ -329,10 +330,13 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps
         if (dev < 64) attr_bytes[dev] = (int)smem;
     }
     // cells per warp: as many as keeps every SM's warp slots (about 30 one-warp blocks) busy, at most 8
+    const int cell_first = level < 0 ? 0 : hg.lv[level].cell_begin;
+    const int cell_count = level < 0 ? hg.ncells : hg.lv[level].cell_count;
+    if (cell_count <= 0) return ORB_OK;
     const long long warps_wanted = (long long)kNumSMs * 32;
-    int cpw = (int)std::min<long long>(kFastMaxCellsPerWarp, std::max<long long>(1, (long long)hg.ncells * n / warps_wanted));
-    const int blocks_x = ceil_div(ceil_div(hg.ncells, cpw), kFastWarps);
-    kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts);
+    int cpw = (int)std::min<long long>(kFastMaxCellsPerWarp, std::max<long long>(1, (long long)cell_count * n / warps_wanted));
+    const int blocks_x = ceil_div(ceil_div(cell_count, cpw), kFastWarps);
+    kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts, cell_first, cell_first + cell_count);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

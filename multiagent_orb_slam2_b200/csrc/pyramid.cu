@@ -21,6 +21,13 @@ namespace orb {
 // (except in the narrow tiles of a level's last column, see below).
 constexpr int kRsTW = 128, kRsTH = 32, kRsRowsPerWarp = 8, kRsThreads = 32 * kRsTH / kRsRowsPerWarp;
 
+// PRMT with a run-time selector whose nibbles are all < 8 (__byte_perm masks the selector with 0x7777 first: one LOP3 per use)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 __global__ void __launch_bounds__(kRsThreads)
 resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, const __grid_constant__ TmaMaps maps,
               uint8_t* __restrict__ pyr, int level) {
@@ -84,7 +91,7 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
         const uint32_t a0 = r[0], a1 = r[1], a2 = r[2];
         const uint32_t u0 = __funnelshift_r(a0, a1, shbits), u1 = __funnelshift_r(a1, a2, shbits);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = __dp2a_lo(coef[k], __byte_perm(u0, u1, sel[k]), 0u) >> 4;
+        for (int k = 0; k < 4; ++k) h[k] = __dp2a_lo(coef[k], prmt(u0, u1, sel[k]), 0u) >> 4;
     };
     int crow = -1;
     uint32_t hc[4] = {0, 0, 0, 0};  // cached horizontal pass: source row and values
@@ -110,13 +117,14 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
         crow = s1;
         // (b * h) >> 16 as the high word of (b << 16) * h: weights are 0..2048, h < 2^15
         const uint32_t b0 = trow[rr].y << 16, b1 = trow[rr].y & 0xffff0000u;
-        uint32_t packed = 0;
+        uint32_t v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             hc[k] = h1[k];
-            const uint32_t v = (__umulhi(b0, h0[k]) + __umulhi(b1, h1[k]) + 2u) >> 2;
-            packed |= (v & 0xffu) << (8 * k);
+            v[k] = (__umulhi(b0, h0[k]) + __umulhi(b1, h1[k]) + 2u) >> 2;  // <= 255: the weights of each pass sum to 2048
         }
+        // four results, each in the low byte of its register -> one word: 3 byte permutes
+        const uint32_t packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
         // rows are 128-byte pitched and x0 is a multiple of 4: aligned 32-bit store (pitch slack absorbs the tail)
         *reinterpret_cast<uint32_t*>(drow) = packed;
         drow += dpitch;
@@ -242,14 +250,15 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
             const uint4 p3 = *reinterpret_cast<const uint4*>(&hsv[m + 3][4 * quad]);
             const uint32_t c0[4] = {p0.x, p0.y, p0.z, p0.w}, c1[4] = {p1.x, p1.y, p1.z, p1.w};
             const uint32_t c2[4] = {p2.x, p2.y, p2.z, p2.w}, c3[4] = {p3.x, p3.y, p3.z, p3.w};
-            uint32_t ev = 0, od = 0;
+            uint32_t se[4], so[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t se = __dp2a_lo(c0[j], e0, __dp2a_lo(c1[j], e1, __dp2a_lo(c2[j], e2, __dp2a_lo(c3[j], e3, 32768u))));
-                const uint32_t so = __dp2a_lo(c0[j], o0, __dp2a_lo(c1[j], o1, __dp2a_lo(c2[j], o2, __dp2a_lo(c3[j], o3, 32768u))));
-                ev |= (se >> 16) << (8 * j);
-                od |= (so >> 16) << (8 * j);
+                se[j] = __dp2a_lo(c0[j], e0, __dp2a_lo(c1[j], e1, __dp2a_lo(c2[j], e2, __dp2a_lo(c3[j], e3, 32768u))));
+                so[j] = __dp2a_lo(c0[j], o0, __dp2a_lo(c1[j], o1, __dp2a_lo(c2[j], o2, __dp2a_lo(c3[j], o3, 32768u))));
             }
+            // the result is (sum + 2^15) >> 16 <= 255, i.e. byte 2 of the accumulator: four of them -> one word by 3 byte permutes
+            const uint32_t ev = __byte_perm(__byte_perm(se[0], se[1], 0x0062), __byte_perm(se[2], se[3], 0x0062), 0x5410);
+            const uint32_t od = __byte_perm(__byte_perm(so[0], so[1], 0x0062), __byte_perm(so[2], so[3], 0x0062), 0x5410);
             const int y = Y0 + 2 * m;
             if (y < L.h) *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x) = ev;
             if (y + 1 < L.h) *reinterpret_cast<uint32_t*>(dst + (size_t)(y + 1) * L.pitch + x) = od;

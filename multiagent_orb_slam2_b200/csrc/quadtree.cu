@@ -386,10 +386,10 @@ static size_t qt_smem_bytes(int sel_cap) { return (size_t)sel_cap * 14 * sizeof(
 // grid (levels, frames)
 __global__ void __launch_bounds__(kQtThreads)
 quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slots, const int* __restrict__ cell_counts,
-                uint32_t* sortbuf, uint32_t* selected, int* sel_counts) {
+                uint32_t* sortbuf, uint32_t* selected, int* sel_counts, int level0) {
     extern __shared__ __align__(16) int nodemem[];
     __shared__ QtShared sh;
-    const int level = blockIdx.x, frame = blockIdx.y;
+    const int level = level0 + blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g->lv[level];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* fb = sortbuf + (size_t)frame * 5 * g->cand_words;
@@ -443,13 +443,15 @@ static int qt_configure(size_t need) {
     return ORB_OK;
 }
 
-int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStream_t st) {
+// level < 0: all levels (grid.x = levels); otherwise that level only
+int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStream_t st, int level) {
     int max_cap = 0;
     for (int l = 0; l < hg.nlevels; ++l) max_cap = max(max_cap, max(hg.lv[l].sel_cap, ceil_div(2 * hg.lv[l].cell_count, 14) + 1));
     const size_t smem = qt_smem_bytes(max_cap);
     int rc = qt_configure(smem);
     if (rc) return rc;
-    quadtree_kernel<<<dim3(hg.nlevels, n), kQtThreads, smem, st>>>(db.geom, db.slots, db.cell_counts, db.sortbuf, db.selected, db.sel_counts);
+    quadtree_kernel<<<dim3(level < 0 ? hg.nlevels : 1, n), kQtThreads, smem, st>>>(db.geom, db.slots, db.cell_counts, db.sortbuf, db.selected,
+                                                                                    db.sel_counts, level < 0 ? 0 : level);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
