@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
             continue
         o = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", o]
+        extra = os.environ.get("ORB_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DORB_QT_PROFILE)
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -20,6 +20,17 @@
 
 namespace orb {
 
+// -DORB_QT_PROFILE (experiments only, ORB_EXTRA_NVCC_FLAGS): block (0, 0) prints clock64 marks of its phases
+#ifdef ORB_QT_PROFILE
+#include <cstdio>
+__device__ long long g_qt_marks[64];
+__device__ int g_qt_nmarks;
+#define QT_MARK(tag) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && g_qt_nmarks < 62) { g_qt_marks[g_qt_nmarks] = clock64(); g_qt_tags[g_qt_nmarks++] = (tag); } } while (0)
+__device__ int g_qt_tags[64];
+#else
+#define QT_MARK(tag) do { } while (0)
+#endif
+
 constexpr int kQtThreads = 256;  // several blocks per SM hide each other's barrier stalls
 constexpr int kQtWarps = kQtThreads / 32;
 constexpr int kQtSmemKeys = 4096;  // candidates per (level, frame) served from shared memory; more fall back to global
@@ -178,6 +189,82 @@ __device__ int block_radix_sort(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32
     return flip;
 }
 
+// The same stable LSD sort for sets that fit BOTH buffer pairs into shared memory (n <= kQtSmemKeys / 2: every level of a
+// 1000-feature extraction). A warp's chunk (at most 8 x 32 elements) is read into registers once per pass and serves the
+// counting and the scatter sweep; the match masks are kept too. No global memory, no load latency inside the sweeps.
+constexpr int kQtRegSteps = 8;
+__device__ int block_radix_sort_small(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32_t* vB, int n, int key_bits, QtShared& sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = ((n + kQtThreads - 1) / kQtThreads) * 32;  // elements per warp, a multiple of 32, <= 32 * kQtRegSteps
+    const int lo = min(warp * per, n), hi = min(lo + per, n);
+    const uint32_t lt = (1u << lane) - 1u;
+    int flip = 0;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        const uint32_t* ki = flip ? kB : kA; const uint32_t* vi = flip ? vB : vA;
+        uint32_t* ko = flip ? kA : kB;       uint32_t* vo = flip ? vA : vB;
+        for (int i = threadIdx.x; i < kQtWarps * 256; i += kQtThreads) (&sh.wcount[0][0])[i] = 0;
+        uint32_t k[kQtRegSteps], peers[kQtRegSteps];   // (the values are re-read in the scatter sweep: registers are what caps the blocks per SM)
+#pragma unroll
+        for (int j = 0; j < kQtRegSteps; ++j) {
+            const int i = lo + 32 * j + lane;
+            k[j] = i < hi ? ki[i] : 0u;
+            peers[j] = 0u;
+        }
+        __syncthreads();
+        // lanes of a step with the same digit; the matches of all steps are independent, the counter updates behind them are not
+#pragma unroll
+        for (int j = 0; j < kQtRegSteps; ++j) {
+            if (lo + 32 * j < hi) {  // warp-uniform
+                const bool valid = lo + 32 * j + lane < hi;
+                peers[j] = __match_any_sync(0xffffffffu, valid ? (k[j] >> shift) & 255u : 0x100u + lane);  // invalid lanes never group
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kQtRegSteps; ++j) {
+            if (lo + 32 * j < hi) {
+                const bool valid = lo + 32 * j + lane < hi;
+                const uint32_t digit = (k[j] >> shift) & 255u;
+                if (valid && (peers[j] & lt) == 0) sh.wcount[warp][digit] += __popc(peers[j]);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        {
+            int c[kQtWarps], t = 0;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) { c[w] = sh.wcount[w][threadIdx.x]; t += c[w]; }
+            int inc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            if (lane == 31) sh.warp_tmp[warp] = inc;
+            __syncthreads();
+            int run = inc - t;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) run += w < warp ? sh.warp_tmp[w] : 0;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) { sh.wcount[w][threadIdx.x] = run; run += c[w]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kQtRegSteps; ++j) {
+            if (lo + 32 * j < hi) {
+                const bool valid = lo + 32 * j + lane < hi;
+                const uint32_t digit = (k[j] >> shift) & 255u;
+                const int rank = __popc(peers[j] & lt);
+                int pos = 0;
+                if (valid) pos = sh.wcount[warp][digit] + rank;
+                __syncwarp();
+                if (valid && rank == 0) sh.wcount[warp][digit] += __popc(peers[j]);
+                if (valid) { ko[pos] = k[j]; vo[pos] = vi[lo + 32 * j + lane]; }
+                __syncwarp();
+            }
+        }
+        flip ^= 1;
+        __syncthreads();
+    }
+    return flip;
+}
+
 // The node list simulation. Node arrays live in shared memory (cap entries each).
 struct QtNodes {
     int* lo[2]; int* hi[2]; int* dep[2];  // double-buffered list
@@ -191,18 +278,37 @@ struct QtNodes {
 // core: candidates packed (x | y<<12 | score<<24) in cand[0..n); scratch = 4 arrays of n words.
 // Writes the survivors (packed) in list order to sel[] and their number to *count_out.
 // (no __restrict__ / read-only-cache hints: cand and scratch are written earlier in the same kernel)
+// layout_cap >= sel_cap sizes the node arrays (the key area starts behind 14 * layout_cap ints of nodemem);
+// keys_ready: the caller has already written path keys and candidate indices where qt_sort_input() points.
+struct QtSortInput { uint32_t* keys; uint32_t* vals; bool small; };
+__device__ __forceinline__ QtSortInput qt_sort_input(int n, uint32_t* scratch, int* nodemem, int layout_cap) {
+    QtSortInput in;
+    in.small = n <= kQtSmemKeys / 2;   // both buffer pairs of the sort are quarters of the shared-memory key area
+    uint32_t* const sarea = reinterpret_cast<uint32_t*>(nodemem + 14 * layout_cap);
+    in.keys = in.small ? sarea : scratch;
+    in.vals = in.small ? sarea + kQtSmemKeys / 2 : scratch + n;
+    return in;
+}
+
 __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, float rootW, int H, int depth,
                                 uint32_t* scratch, uint32_t* sel, int sel_cap, int* count_out,
-                                QtShared& sh, int* nodemem) {
+                                QtShared& sh, int* nodemem, int layout_cap, bool keys_ready) {
     if (n <= 0 || nRoots <= 0) {
         if (threadIdx.x == 0) *count_out = 0;
         return;
     }
     uint32_t *kA = scratch, *vA = scratch + n, *kB = scratch + 2 * (size_t)n, *vB = scratch + 3 * (size_t)n;
-    for (int i = threadIdx.x; i < n; i += kQtThreads) {
-        const uint32_t p = cand[i];
-        kA[i] = qt_path_key(p & 0xfff, (p >> 12) & 0xfff, H, rootW, depth);
-        vA[i] = i;
+    QT_MARK(1);
+    const QtSortInput in = qt_sort_input(n, scratch, nodemem, layout_cap);
+    const bool small = in.small;
+    uint32_t* const sarea = reinterpret_cast<uint32_t*>(nodemem + 14 * layout_cap);
+    if (small) { kA = in.keys; vA = in.vals; kB = sarea + kQtSmemKeys; vB = sarea + kQtSmemKeys + kQtSmemKeys / 2; }
+    if (!keys_ready) {
+        for (int i = threadIdx.x; i < n; i += kQtThreads) {
+            const uint32_t p = cand[i];
+            kA[i] = qt_path_key(p & 0xfff, (p >> 12) & 0xfff, H, rootW, depth);
+            vA[i] = i;
+        }
     }
     __syncthreads();
     int root_bits = 0;
@@ -212,13 +318,27 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
     // buffer pair of the sort IS that shared memory: with the usual three 8-bit passes the sorted set ends
     // there (global -> shared -> global -> shared) and only every other pass touches L2.
     const bool fast = n <= kQtSmemKeys;
-    uint32_t* skey = reinterpret_cast<uint32_t*>(nodemem + 14 * sel_cap);
+    uint32_t* skey = sarea;
     uint32_t* comb = skey + kQtSmemKeys;  // response << 24 | (0xffffff - candidate index): max = best, earliest on ties
-    if (fast) { kB = skey; vB = comb; }
-    const int flip = block_radix_sort(kA, vA, kB, vB, n, 2 * depth + root_bits, sh);
+    if (fast && !small) { kB = skey; vB = comb; }
+    QT_MARK(2);
+    const int flip = small ? block_radix_sort_small(kA, vA, kB, vB, n, 2 * depth + root_bits, sh)
+                           : block_radix_sort(kA, vA, kB, vB, n, 2 * depth + root_bits, sh);
+    QT_MARK(3);
     const uint32_t* sk = flip ? kB : kA;
     const uint32_t* sv = flip ? vB : vA;
-    if (fast) {
+    if (small) {
+        // sorted keys -> skey[0, n), selection words -> comb[0, n). Either buffer pair overlaps one of the two targets, but
+        // element i of a source only ever shares its address with element i of a target, and each thread reads both of its
+        // sources before it writes: no barrier needed in between.
+        for (int i = threadIdx.x; i < n; i += kQtThreads) {
+            const uint32_t kk = sk[i], c = sv[i];
+            skey[i] = kk;
+            comb[i] = (cand[c] >> 24) << 24 | (0xffffffu - c);
+        }
+        __syncthreads();
+        sk = skey;
+    } else if (fast) {
         if (flip) {  // already in shared memory: turn the candidate indices into selection words in place
             for (int i = threadIdx.x; i < n; i += kQtThreads) {
                 const uint32_t c = comb[i];
@@ -235,7 +355,7 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
         sk = skey;
     }
 
-    const int cap = sel_cap;
+    const int cap = layout_cap;
     QtNodes q;
     {
         int* p = nodemem;
@@ -263,6 +383,7 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
     __syncthreads();
 
     bool final_phase = false;
+    QT_MARK(4);
     for (;;) {
         const int before = count;
         int *lo = q.lo[cur], *hi = q.hi[cur], *dep = q.dep[cur];
@@ -279,6 +400,52 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
             }
         }
         __syncthreads();
+        if (!final_phase && before <= kQtThreads) {
+            // A full pass over a list that fits one node per thread (the usual case): every expandable node is processed
+            // in list order, so the place of its children (pushed to the front, later nodes first) and of every untouched
+            // node follows from ONE scan over (children | expandable | expandable children) packed in a word - three block
+            // barriers per pass instead of ~25 (the general form below also serves the final, size-ordered phase).
+            const int i = threadIdx.x, lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+            int l = 0, h = 0, d = 0, c = 0, ex = 0, me = 0, bb[5] = {0, 0, 0, 0, 0};
+            if (i < before) {
+                l = lo[i]; h = hi[i]; d = dep[i];
+                if (h - l >= 2 && d < depth) {
+                    bb[0] = l; bb[1] = q.b1[i]; bb[2] = q.b2[i]; bb[3] = q.b3[i]; bb[4] = h;
+                    ex = 1;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { c += bb[t + 1] > bb[t]; me += bb[t + 1] - bb[t] >= 2; }
+                }
+            }
+            const int v = c | ex << 11 | me << 20;   // sums stay below 2^11, 2^9, 2^11
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane_ >= o) inc += t; }
+            if (lane_ == 31) sh.warp_tmp[warp_] = inc;
+            __syncthreads();
+            int off = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) { const int t = sh.warp_tmp[w]; total += t; off += w < warp_ ? t : 0; }
+            const int excl = off + inc - v;
+            const int children = total & 0x7ff, m = (total >> 11) & 0x1ff, n_expand = total >> 20;
+            if (i < before) {
+                if (ex) {
+                    int pos = children - (excl & 0x7ff) - c;
+#pragma unroll
+                    for (int t = 3; t >= 0; --t)
+                        if (bb[t + 1] > bb[t]) { nlo[pos] = bb[t]; nhi[pos] = bb[t + 1]; ndep[pos] = d + 1; ++pos; }
+                } else {
+                    const int p = children + i - ((excl >> 11) & 0x1ff);
+                    nlo[p] = l; nhi[p] = h; ndep[p] = d;
+                }
+            }
+            __syncthreads();  // the new list is complete; warp_tmp may be reused
+            count = children + (before - m);
+            cur ^= 1;
+            QT_MARK(10000 + before);
+            if (count >= N || count == before) break;
+            if (count + 3 * n_expand > N) final_phase = true;
+            continue;
+        }
         for (int i = threadIdx.x; i < before; i += kQtThreads) {
             const int l = lo[i], h = hi[i];
             int c = 0;
@@ -352,6 +519,7 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
         const int n_expand = sh.bcast[2];
         count = children + (before - processed);
         cur ^= 1;
+        QT_MARK(final_phase ? 100000 + before : 10000 + before);
         if (count >= N || count == before) break;
         if (!final_phase && count + 3 * n_expand > N) final_phase = true;
         __syncthreads();
@@ -378,13 +546,22 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
             if (lane == 0 && p < sel_cap) sel[p] = cand[0xffffffu - (best & 0xffffffu)];
         }
     }
+    QT_MARK(5);
     if (threadIdx.x == 0) *count_out = min(count, sel_cap);
+#ifdef ORB_QT_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        printf("qt n=%d N=%d depth=%d:", n, N, depth);
+        for (int i = 1; i < g_qt_nmarks; ++i) printf(" [%d]%lld", g_qt_tags[i], g_qt_marks[i] - g_qt_marks[i - 1]);
+        printf("\n");
+        g_qt_nmarks = 0;
+    }
+#endif
 }
 
 static size_t qt_smem_bytes(int sel_cap) { return (size_t)sel_cap * 14 * sizeof(int) + 2 * (size_t)kQtSmemKeys * sizeof(uint32_t); }
 
 // grid (levels, frames)
-__global__ void __launch_bounds__(kQtThreads)
+__global__ void __launch_bounds__(kQtThreads, 4)
 quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slots, const int* __restrict__ cell_counts,
                 uint32_t* sortbuf, uint32_t* selected, int* sel_counts, int level0) {
     extern __shared__ __align__(16) int nodemem[];
@@ -392,6 +569,7 @@ quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slo
     const int level = level0 + blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g->lv[level];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    QT_MARK(0);
     uint32_t* fb = sortbuf + (size_t)frame * 5 * g->cand_words;
     uint32_t* cand = fb + L.cand_off;
     uint32_t* scratch = fb + g->cand_words + 4 * L.cand_off;
@@ -400,7 +578,8 @@ quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slo
 
     // stitch the cells' lists in row-major cell order (789-829): offsets = scan of counts.
     // nodemem is free until quadtree_select: cell counts (one coalesced pass) and their offsets live there
-    // (14 * max_cap ints >= 2 * cell_count, sized on the host)
+    // (14 * layout_cap ints >= 2 * cell_count)
+    const int layout_cap = max(L.sel_cap, (2 * L.cell_count + 13) / 14 + 1);
     int* offs = nodemem;
     int* cnt_s = nodemem + L.cell_count;
     for (int c = threadIdx.x; c < L.cell_count; c += kQtThreads) cnt_s[c] = counts[c];
@@ -416,9 +595,10 @@ quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slo
         }
     }
     __syncthreads();
-    quadtree_select(cand, total, L.quota, L.nRoots, L.rootW, L.h - 2 * kMinBorder, L.key_depth, scratch,
+    const int H = L.h - 2 * kMinBorder;
+    quadtree_select(cand, total, L.quota, L.nRoots, L.rootW, H, L.key_depth, scratch,
                     selected + (size_t)frame * g->sel_words + L.sel_off, L.sel_cap,
-                    sel_counts + (size_t)frame * g->nlevels + level, sh, nodemem);
+                    sel_counts + (size_t)frame * g->nlevels + level, sh, nodemem, layout_cap, false);
 }
 
 __global__ void __launch_bounds__(kQtThreads)
@@ -426,7 +606,7 @@ quadtree_standalone_kernel(const uint32_t* cand, int n, int N, int nRoots, float
                            uint32_t* scratch, uint32_t* sel, int sel_cap, int* count) {
     extern __shared__ __align__(16) int nodemem[];
     __shared__ QtShared sh;
-    quadtree_select(cand, n, N, nRoots, rootW, H, depth, scratch, sel, sel_cap, count, sh, nodemem);
+    quadtree_select(cand, n, N, nRoots, rootW, H, depth, scratch, sel, sel_cap, count, sh, nodemem, sel_cap, false);
 }
 
 // opt in once per device to the large dynamic shared memory carve-out
