@@ -749,12 +749,26 @@ int orbm_stereo_match(orbx_handle left, orbx_handle right, int frame, float mbf,
     cudaStream_t st = left->stream;
     int rc = orbm_stereo_match_device(left, right, frame, mbf, mb, d_u, d_d, d_s, d_k, st);
     if (rc == ORB_OK) {
-        const int take = std::min(cap, oc);
-        cudaError_t e = cudaMemcpyAsync(uRight, d_u, (size_t)take * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(depth, d_d, (size_t)take * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(kept, d_k, 4, cudaMemcpyDeviceToHost, st);
+        // uRight | depth are adjacent on the device: one copy into pinned staging + the counter, one synchronisation, then
+        // host memcpys (copies straight into the caller's pageable arrays block the host one by one, see orbx_extract_batch)
+        const int take = std::max(0, std::min(cap, oc));
+        const size_t need = (size_t)oc * 8 + 16;
+        if (left->h_out_bytes < need) {
+            if (left->h_out) { cudaStreamSynchronize(st); cudaFreeHost(left->h_out); left->h_out = nullptr; left->h_out_bytes = 0; }
+            ORB_CUDA_TRY(cudaMallocHost(&left->h_out, need));
+            left->h_out_bytes = need;
+        }
+        float* s_u = reinterpret_cast<float*>(left->h_out);
+        int* s_k = reinterpret_cast<int*>(left->h_out + (size_t)oc * 8);
+        cudaError_t e = cudaMemcpyAsync(s_u, d_u, (size_t)oc * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s_k, d_k, 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { set_error("stereo copy failed: %s", cudaGetErrorString(e)); rc = ORB_ECUDA; }
+        else {
+            memcpy(uRight, s_u, (size_t)take * 4);
+            memcpy(depth, s_u + oc, (size_t)take * 4);
+            *kept = *s_k;
+        }
     }
     return rc;
 }

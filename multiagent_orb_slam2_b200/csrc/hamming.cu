@@ -17,6 +17,8 @@
 // L2-resident tile re-reads, i.e. irrelevant next to the bit counting.
 #include <atomic>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace orb {
@@ -366,8 +368,20 @@ struct HostCallWorkspace {
     cudaStream_t st = nullptr;
     uint8_t* base = nullptr;
     size_t cap = 0, used = 0;
+    uint8_t* pin = nullptr;   // pinned staging for the results: ONE device -> host copy per call instead of one blocking
+    size_t pin_cap = 0;       // copy into pageable memory per output array (~15 us each)
     ~HostCallWorkspace() { release(); }
+    int pinned(size_t bytes, uint8_t** out) {
+        if (bytes > pin_cap) {
+            if (pin) { cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
+            ORB_CUDA_TRY(cudaMallocHost(&pin, bytes + bytes / 2 + 4096));
+            pin_cap = bytes + bytes / 2 + 4096;
+        }
+        *out = pin;
+        return ORB_OK;
+    }
     void release() {
+        if (pin) { cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
         if (device >= 0) {
             cudaSetDevice(device);
             if (st) release_mma_scratch(device, st);  // the tensor-core matcher's operand scratch is keyed by this stream
@@ -403,6 +417,19 @@ struct HostCallWorkspace {
     static size_t need(size_t bytes) { return align_up(bytes + 1, 256); }
 };
 thread_local HostCallWorkspace tls_ws;
+
+// the three result arrays of a search lie back to back on the device: one copy into pinned staging, one synchronisation
+static int download_three(HostCallWorkspace& ws, const int* d_o, size_t n, int32_t* idx, int32_t* best, int32_t* second) {
+    uint8_t* p = nullptr;
+    int rc;
+    if ((rc = ws.pinned(n * 12, &p))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(p, d_o, n * 12, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
+    memcpy(idx, p, n * 4);
+    memcpy(best, p + n * 4, n * 4);
+    memcpy(second, p + n * 8, n * 4);
+    return ORB_OK;
+}
 }  // namespace
 }  // extern "C++"
 
@@ -419,11 +446,7 @@ int orbm_knn2(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, in
     ORB_CUDA_TRY(cudaMemcpyAsync(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice, ws.st));
     if (nB) ORB_CUDA_TRY(cudaMemcpyAsync(dB, B, (size_t)nB * 32, cudaMemcpyHostToDevice, ws.st));
     if ((rc = orbm_knn2_device(dA, nA, dB, nB, o, o + nA, o + 2 * (size_t)nA, ws.st))) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
-    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
-    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
-    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
-    return ORB_OK;
+    return download_three(ws, o, (size_t)nA, idx, best, second);
 }
 
 int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* offsets,
@@ -448,11 +471,7 @@ int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int 
     ORB_CUDA_TRY(cudaMemcpyAsync(dOf, offsets, (size_t)(nA + 1) * 4, cudaMemcpyHostToDevice, ws.st));
     if (total) ORB_CUDA_TRY(cudaMemcpyAsync(dC, cands, (size_t)total * 4, cudaMemcpyHostToDevice, ws.st));
     if ((rc = orbm_knn2_lists_device(dA, nA, dB, dOf, dC, o, o + nA, o + 2 * (size_t)nA, ws.st))) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(idx, o, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
-    ORB_CUDA_TRY(cudaMemcpyAsync(best, o + nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
-    ORB_CUDA_TRY(cudaMemcpyAsync(second, o + 2 * (size_t)nA, (size_t)nA * 4, cudaMemcpyDeviceToHost, ws.st));
-    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
-    return ORB_OK;
+    return download_three(ws, o, (size_t)nA, idx, best, second);
 }
 
 int orbm_list_distances(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* offsets, const int32_t* cands,
