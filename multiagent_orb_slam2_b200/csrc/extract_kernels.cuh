@@ -108,7 +108,7 @@ int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, int n_fram
                   float* d_depth, int* d_sad, int* d_kept, cudaStream_t st);
 
 // launchers (each enqueues on `st`; n = frames in this call)
-int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int level, int n, cudaStream_t st);
+int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int level, int n, cudaStream_t st, bool pdl = false);
 int launch_blur(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st);
 int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st, int level = -1);
 int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStream_t st, int level = -1);

@@ -301,7 +301,7 @@ static int launch_sequence_level_parallel(orbx_extractor* h, const FrameSet& fs,
     const Geometry& g = h->hg;
     int rc;
     for (int l = 0; l < g.nlevels; ++l) {
-        if (l > 0 && (rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
+        if (l > 0 && (rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st, l > 1))) return rc;
         cudaStream_t s = h->lvl_stream[l];
         ORB_CUDA_TRY(cudaEventRecord(h->ev_lvl_ready[l], st));
         ORB_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_lvl_ready[l], 0));

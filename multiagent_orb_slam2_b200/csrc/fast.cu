@@ -98,6 +98,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
                   uint32_t* __restrict__ slots, int* __restrict__ cell_counts, int cell_first, int cell_end) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kFastWarps];
+    asm volatile("griddepcontrol.launch_dependents;");  // small batches: the level's quadtree grid may be set up meanwhile (no-op otherwise)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int max_th = g->max_th, tp = TP ? TP : g->fast_bw, tpw = tp >> 2;
