@@ -62,4 +62,19 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
+// Launch `kernel` as a programmatic dependent of the previous kernel in `st`: it may be scheduled while that kernel's last
+// blocks still run and must execute griddepcontrol.wait before it touches anything the predecessor writes.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }            // no-ops in an ordinary launch
+__device__ __forceinline__ void pdl_release_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 }  // namespace orb

@@ -67,6 +67,7 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     __shared__ uint32_t ictab[kIcTableWords];  // [phase][u | v][item]
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) patf[i] = pattern[i];
     for (int i = threadIdx.x; i < kIcTableWords; i += blockDim.x) ictab[i] = ic_table[i];
+    pdl_wait();   // programmatic dependent of the quadtree launch: the tables above are filled while the trees are still built
 
     const int frame = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -235,9 +236,14 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     }
 }
 
-int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st) {
-    orient_describe_kernel<<<dim3(ceil_div(hg.sel_words, kDescSlots), n), kDescWarps * 32, 0, st>>>(
-        db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.ic_table, db.kps, db.desc, db.counts);
+int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st, bool pdl) {
+    const dim3 grid(ceil_div(hg.sel_words, kDescSlots), n);
+    if (pdl)
+        ORB_CUDA_TRY(launch_pdl(orient_describe_kernel, grid, dim3(kDescWarps * 32), 0, st, db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts,
+                                db.pattern, db.ic_table, db.kps, db.desc, db.counts));
+    else
+        orient_describe_kernel<<<grid, kDescWarps * 32, 0, st>>>(db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.ic_table,
+                                                                 db.kps, db.desc, db.counts);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

@@ -110,9 +110,10 @@ int launch_stereo(const StereoSide& L, const StereoSide& R, int capL, int n_fram
 // launchers (each enqueues on `st`; n = frames in this call)
 int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int level, int n, cudaStream_t st, bool pdl = false);
 int launch_blur(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st);
-int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st, int level = -1);
+// pdl: launched as a programmatic dependent of the previous kernel in the stream (common.cuh)
+int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st, int level = -1, bool pdl = false);
 int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStream_t st, int level = -1);
-int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st);
+int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st, bool pdl = false);
 int launch_quadtree_standalone(const uint32_t* d_cand, int n, int N, int nRoots, float rootW, int H, int key_depth,
                                uint32_t* d_scratch4n, uint32_t* d_sel, int sel_cap, int* d_count, cudaStream_t st);
 

@@ -322,17 +322,19 @@ int launch_sequence(orbx_extractor* h, const FrameSet& fs, int n, cudaStream_t s
     const Geometry& g = h->hg;
     int rc;
     if (n <= kLevelParallelMaxBatch) return launch_sequence_level_parallel(h, fs, n, st);
+    // the kernels of the main chain are programmatic dependents of each other: the next grid is scheduled while the last
+    // blocks of the one before it still run and waits (griddepcontrol.wait) before it reads what that one writes
     for (int l = 1; l < g.nlevels; ++l)
-        if ((rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st))) return rc;
+        if ((rc = launch_resize_level(g, h->db, h->maps_resize, l, n, st, l > 1))) return rc;
     // fork: the Gaussian blur (1085-1086) only depends on the pyramid
     ORB_CUDA_TRY(cudaEventRecord(h->ev_pyr, st));
     ORB_CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_pyr, 0));
     if ((rc = launch_blur(g, h->db, h->maps_blur, n, h->stream2))) return rc;
     ORB_CUDA_TRY(cudaEventRecord(h->ev_blur, h->stream2));
-    if ((rc = launch_fast(g, h->db, h->maps_fast, n, st))) return rc;
+    if ((rc = launch_fast(g, h->db, h->maps_fast, n, st, -1, g.nlevels > 1))) return rc;
     if ((rc = launch_quadtree(g, h->db, n, st))) return rc;
     ORB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_blur, 0));
-    return launch_describe(g, h->db, fs, n, st);
+    return launch_describe(g, h->db, fs, n, st, true);
 }
 
 // the whole of operator() for n frames, enqueued on st

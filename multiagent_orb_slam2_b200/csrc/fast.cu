@@ -98,7 +98,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
                   uint32_t* __restrict__ slots, int* __restrict__ cell_counts, int cell_first, int cell_end) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kFastWarps];
-    asm volatile("griddepcontrol.launch_dependents;");  // small batches: the level's quadtree grid may be set up meanwhile (no-op otherwise)
+    pdl_release_dependents();   // the quadtree grid behind this launch may be scheduled as soon as every FAST block has started
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int max_th = g->max_th, tp = TP ? TP : g->fast_bw, tpw = tp >> 2;
@@ -129,6 +129,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
+        pdl_wait();   // behind the last resize launch: the pyramid is complete from here on
         issue(gw);
     }
     uint32_t parity = 0;
@@ -316,7 +317,7 @@ fast_cells_kernel(const Geometry* __restrict__ g, const CellDesc* __restrict__ c
 }
 
 // level < 0: the cells of all levels in one launch; otherwise only that level's (small batches run the levels as parallel branches)
-int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st, int level) {
+int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int n, cudaStream_t st, int level, bool pdl) {
     // list entries hold the byte column in 7 bits and the row in 7 bits
     ORB_REQUIRE(hg.fast_bw <= 128 && hg.max_th <= 128 && hg.max_tw - 6 <= 64, "FAST cell larger than 64 x 122 pixels");
     const FastLayout lay = fast_layout(hg.max_tw, hg.max_th, hg.fast_bw);
@@ -337,7 +338,11 @@ int launch_fast(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps
     const long long warps_wanted = (long long)kNumSMs * 32;
     int cpw = (int)std::min<long long>(kFastMaxCellsPerWarp, std::max<long long>(1, (long long)cell_count * n / warps_wanted));
     const int blocks_x = ceil_div(ceil_div(cell_count, cpw), kFastWarps);
-    kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts, cell_first, cell_first + cell_count);
+    if (pdl)
+        ORB_CUDA_TRY(launch_pdl(kernel, dim3(blocks_x, n), dim3(kFastThreads), smem, st, db.geom, db.cells, maps, db.slots, db.cell_counts, cell_first,
+                                cell_first + cell_count));
+    else
+        kernel<<<dim3(blocks_x, n), kFastThreads, smem, st>>>(db.geom, db.cells, maps, db.slots, db.cell_counts, cell_first, cell_first + cell_count);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

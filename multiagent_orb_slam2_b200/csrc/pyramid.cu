@@ -44,14 +44,14 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
 
     // source window origin (taps are monotone); the box covers the whole tile at any supported scale
     const int sx_lo = tx[X0].ofs & ~15, sy_lo = ty[Y0].ofs;  // innermost TMA coordinate: 16-byte granular
-    // Programmatic dependent launch (small batches, launch_resize_level(..., pdl)): the next level's grid may be scheduled
+    // Programmatic dependent launch (launch_resize_level(..., pdl)): the next level's grid may be scheduled
     // while this one runs - its blocks get as far as the wait below (set-up, table reads) - and this grid's own source level
     // is only touched after the previous grid has completed. Both instructions are no-ops in an ordinary launch.
-    asm volatile("griddepcontrol.launch_dependents;");
+    pdl_release_dependents();
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        pdl_wait();
         mbar_expect_tx(&bar, (uint32_t)(bw * g->rs_bh));
         tma_load_3d(win, &maps.m[level - 1], sx_lo, sy_lo, frame, &bar);
     }
@@ -139,17 +139,10 @@ resize_kernel(const Geometry* __restrict__ g, const LinTap* __restrict__ taps, c
 int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMaps& maps, int level, int n, cudaStream_t st, bool pdl) {
     const LevelGeom& L = hg.lv[level];
     dim3 grid(ceil_div(L.w, kRsTW), ceil_div(L.h, kRsTH), n);
-    if (pdl) {  // overlap this level's launch and set-up with the tail of the level before it (same stream)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid; cfg.blockDim = dim3(kRsThreads, 1, 1); cfg.dynamicSmemBytes = (size_t)hg.rs_bw * hg.rs_bh; cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        ORB_CUDA_TRY(cudaLaunchKernelEx(&cfg, resize_kernel, db.geom, db.taps, maps, db.pyr, level));
-    } else {
+    if (pdl)  // overlap this level's launch and set-up with the tail of the level before it (same stream)
+        ORB_CUDA_TRY(launch_pdl(resize_kernel, grid, dim3(kRsThreads), (size_t)hg.rs_bw * hg.rs_bh, st, db.geom, db.taps, maps, db.pyr, level));
+    else
         resize_kernel<<<grid, kRsThreads, (size_t)hg.rs_bw * hg.rs_bh, st>>>(db.geom, db.taps, maps, db.pyr, level);
-    }
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

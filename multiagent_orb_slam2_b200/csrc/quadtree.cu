@@ -570,7 +570,8 @@ quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slo
     const LevelGeom& L = g->lv[level];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     QT_MARK(0);
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch behind FAST (small batches); no-op otherwise
+    pdl_release_dependents();   // the description kernel may be set up (its tables filled) while the trees are built
+    pdl_wait();                 // programmatic dependent of the FAST launch: its candidate lists are complete from here on
     uint32_t* fb = sortbuf + (size_t)frame * 5 * g->cand_words;
     uint32_t* cand = fb + L.cand_off;
     uint32_t* scratch = fb + g->cand_words + 4 * L.cand_off;
@@ -631,18 +632,9 @@ int launch_quadtree(const Geometry& hg, const DeviceBuffers& db, int n, cudaStre
     const size_t smem = qt_smem_bytes(max_cap);
     int rc = qt_configure(smem);
     if (rc) return rc;
-    if (level >= 0) {  // one level of a small batch, directly behind that level's FAST launch on the same stream
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(1, n, 1); cfg.blockDim = dim3(kQtThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        ORB_CUDA_TRY(cudaLaunchKernelEx(&cfg, quadtree_kernel, db.geom, (const uint32_t*)db.slots, (const int*)db.cell_counts, db.sortbuf, db.selected,
-                                        db.sel_counts, level));
-    } else {
-        quadtree_kernel<<<dim3(hg.nlevels, n), kQtThreads, smem, st>>>(db.geom, db.slots, db.cell_counts, db.sortbuf, db.selected, db.sel_counts, 0);
-    }
+    // always a programmatic dependent of the FAST launch before it in the stream (the kernel waits before its first read)
+    ORB_CUDA_TRY(launch_pdl(quadtree_kernel, dim3(level < 0 ? hg.nlevels : 1, n), dim3(kQtThreads), smem, st, db.geom, db.slots, db.cell_counts,
+                            db.sortbuf, db.selected, db.sel_counts, level < 0 ? 0 : level));
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
