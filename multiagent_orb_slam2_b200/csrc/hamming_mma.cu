@@ -142,6 +142,7 @@ __device__ __forceinline__ void issue_tile_mmas(uint32_t a_smem, uint32_t b_smem
 __global__ void __launch_bounds__(256) expand_pairs_kernel(const uint32_t* __restrict__ dA, const int* __restrict__ d_nA, int nA_max, int strideA,
                                                            const uint32_t* __restrict__ dB, const int* __restrict__ d_nB, int nB_max, int strideB,
                                                            const int* __restrict__ d_pairs, uint4* __restrict__ outA, uint4* __restrict__ outB) {
+    pdl_release_dependents();   // the matcher behind this launch sets itself up (TMEM, barriers) meanwhile and waits before its first load
     const int p = blockIdx.y, side = blockIdx.z;
     const int set = d_pairs ? d_pairs[2 * p + side] : p;
     const int n = side ? (d_nB ? min(d_nB[set], nB_max) : nB_max) : (d_nA ? min(d_nA[set], nA_max) : nA_max);
@@ -331,6 +332,7 @@ knn2_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ===== TMA producer =====
         if (lane == 0) {
             const int arow = p * strideA + row0, brow = p * strideB;
+            pdl_wait();   // programmatic dependent of the expansion kernel: the operands are complete from here on
             mbar_expect_tx(&bar_a, kATileBytes);
             tma_load_2d(sa, &map_a, 0, arow, &bar_a);
             tma_load_2d(sa + kMmaM * 128, &map_a, 128, arow, &bar_a);
@@ -507,6 +509,7 @@ knn2_mma_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ===== TMA producer (both CTAs): own query rows, own half of every candidate tile =====
         if (lane == 0) {
             const int arow = p * strideA + row0, brow = p * strideB + (int)rank * kPairHalfN;
+            pdl_wait();
             if (leader) mbar_expect_tx(&bar_a, 2 * kATileBytes);
             tma_load_2d_pair(sa, &map_a, 0, arow, &bar_a);
             tma_load_2d_pair(sa + kMmaM * 128, &map_a, 128, arow, &bar_a);
@@ -777,9 +780,6 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
     }
     const bool pair_kernel = use_pair_kernel(variant, nA_max, nB_max);
     const CUtensorMap ma = sc.map_a, mb = pair_kernel ? sc.map_bh : sc.map_b;
-    const int words = 8 * (nA_max > nB_max ? nA_max : nB_max);
-    expand_pairs_kernel<<<dim3(ceil_div(words, 256), pairs, 2), 256, 0, st>>>((const uint32_t*)dA, d_nA, nA_max, strideA_rows, (const uint32_t*)dB,
-                                                                             d_nB, nB_max, strideB_rows, d_pairs, (uint4*)sc.a, (uint4*)sc.b);
     if ((rc = set_mma_kernel_attributes(device)) != ORB_OK) return rc;
     const int qtiles = pair_kernel ? 2 * ceil_div(nA_max, 2 * kMmaM) : ceil_div(nA_max, kMmaM);
     const int nsplit = choose_split((long long)qtiles * pairs, ceil_div(nB_max, kTileN), 2 * kNumSMs);
@@ -791,12 +791,16 @@ int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_
         k_b1 = k_idx + (size_t)nsplit * total;
         k_b2 = k_b1 + (size_t)nsplit * total;
     }
+    // expansion and matcher back to back in the stream (nothing in between: the matcher is a programmatic dependent)
+    const int words = 8 * (nA_max > nB_max ? nA_max : nB_max);
+    expand_pairs_kernel<<<dim3(ceil_div(words, 256), pairs, 2), 256, 0, st>>>((const uint32_t*)dA, d_nA, nA_max, strideA_rows, (const uint32_t*)dB,
+                                                                             d_nB, nB_max, strideB_rows, d_pairs, (uint4*)sc.a, (uint4*)sc.b);
     if (pair_kernel)
         knn2_mma_pair_kernel<<<dim3(qtiles, pairs, nsplit), kMmaThreads, kPairSmemBytes, st>>>(
             ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max, strideB_rows, d_pairs, out_stride, k_idx, k_b1, k_b2, total);
-    else
-        knn2_mma_kernel<<<dim3(qtiles, pairs, nsplit), kMmaThreads, kMmaSmemBytes, st>>>(ma, mb, d_nA, nA_max, strideA_rows, d_nB, nB_max, strideB_rows,
-                                                                                       d_pairs, out_stride, k_idx, k_b1, k_b2, total);
+    else  // directly behind the expansion kernel in the stream: programmatic dependent launch
+        ORB_CUDA_TRY(launch_pdl(knn2_mma_kernel, dim3(qtiles, pairs, nsplit), dim3(kMmaThreads), (size_t)kMmaSmemBytes, st, ma, mb, d_nA, nA_max,
+                                strideA_rows, d_nB, nB_max, strideB_rows, d_pairs, out_stride, k_idx, k_b1, k_b2, total));
     if (nsplit > 1) {
         top2_merge_splits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(k_idx, k_b1, k_b2, total, nsplit, d_nA, nA_max, d_pairs, out_stride,
                                                                                  total, d_idx, d_b1, d_b2);
