@@ -57,15 +57,17 @@ struct SlotInfo { int valid, level, x, y, response, dst; };
 __global__ void __launch_bounds__(kDescWarps * 32, 5)
 orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_t* __restrict__ pyr,
                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ selected,
-                       const int* __restrict__ sel_counts, const float* __restrict__ pattern, const uint32_t* __restrict__ ic_table,
+                       const int* __restrict__ sel_counts, const uint32_t* __restrict__ pattern, const uint32_t* __restrict__ ic_table,
                        orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int* __restrict__ counts) {
-    __shared__ float patf[1024];  // transposed: value (test t, component c) of byte `lane` at [(4t+c)*32 + lane]
+    // Shared memory is kept below 31.8 KB per block on purpose: five blocks then fit the 164 KB carve-out and leave 92 KB of L1
+    // to the window gathers (37.7 KB per block = 196 KB carve-out measured 0.469 ms, this layout 0.36 ms at B=512).
+    __shared__ uint32_t pat8[kPatternWords];  // x0 | y0 << 8 | x1 << 16 | y1 << 24 (int8) of test t of byte `lane` at [t * 32 + lane]
     __shared__ SlotInfo info[kDescSlots];
     __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
     __shared__ __align__(16) uint32_t patch[kDescWarps * 2 * kPatchWords];  // per warp: blurred windows of two keypoints
     __shared__ int s_m10[kDescSlots], s_m01[kDescSlots];
-    __shared__ uint32_t ictab[kIcTableWords];  // [phase][u | v][item]
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) patf[i] = pattern[i];
+    __shared__ uint32_t ictab[kIcTableWords];  // [phase][item]: u + 16 per byte, 0 outside the patch
+    for (int i = threadIdx.x; i < kPatternWords; i += blockDim.x) pat8[i] = pattern[i];
     for (int i = threadIdx.x; i < kIcTableWords; i += blockDim.x) ictab[i] = ic_table[i];
     pdl_wait();   // programmatic dependent of the quadtree launch: the tables above are filled while the trees are still built
 
@@ -113,8 +115,7 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
         const uint8_t* img = level_ptr(*g, fs, pyr, frame, si.level, &spitch);
         const int xs = si.x - kHalfPatch;
         const uint8_t* base = img + (size_t)(si.y - kHalfPatch) * spitch + (xs & ~3);
-        const uint32_t* tu = ictab + (xs & 3) * 2 * kIcItems + lane;
-        int m10 = 0, m01 = 0;
+        const uint32_t* tu = ictab + (xs & 3) * kIcItems + lane;
         // 3 rows (27 words) per warp step: item 27 s + lane, its word at a fixed per-lane offset + s * 3 rows
         const uint8_t* wp = base + ic_lr * spitch + 4 * ic_lj;
         const int step = 3 * spitch;
@@ -124,13 +125,21 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
         uint32_t w[kSteps];
 #pragma unroll
         for (int s = 0; s < kSteps; ++s) w[s] = *reinterpret_cast<const uint32_t*>(wp + s * step);
+        // per word: a = sum (u + 16) I and n = sum I over its bytes inside the patch ("inside" <=> table byte != 0);
+        // m10 = sum a - 16 sum n, m01 = sum over rows of v * n (v is the word's row: 3 s + ic_lr - 15)
+        uint32_t acc_a = 0, acc_n = 0;
+        int acc_v = 0;
 #pragma unroll
         for (int s = 0; s < kSteps; ++s) {
             const bool on = lane < 27 && 27 * s + lane < kIcRows * kIcWordsPerRow;
-            const uint32_t cu = on ? tu[27 * s] : 0u, cv = on ? tu[kIcItems + 27 * s] : 0u;
-            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w[s]), "r"(cu));
-            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m01) : "r"(w[s]), "r"(cv));
+            const uint32_t cu = on ? tu[27 * s] : 0u;
+            const uint32_t inside = ((cu + 0x7f7f7f7fu) >> 7) & 0x01010101u;   // bytes are <= 31: no carry between them
+            const uint32_t n = __dp4a(w[s], inside, 0u);
+            acc_a = __dp4a(w[s], cu, acc_a);
+            acc_n += n;
+            acc_v += (3 * s + ic_lr - kHalfPatch) * (int)n;
         }
+        int m10 = (int)acc_a - 16 * (int)acc_n, m01 = acc_v;
         m10 = __reduce_add_sync(0xffffffffu, m10);
         m01 = __reduce_add_sync(0xffffffffu, m01);
         if (lane == 0) { s_m10[sidx] = m10; s_m01[sidx] = m01; }
@@ -193,12 +202,14 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
         const uint8_t* p1 = reinterpret_cast<const uint8_t*>(mypatch + kPatchWords) + off[1];
         const float a0 = si0.valid ? s_cos[sidx0] : 0.f, b0 = si0.valid ? s_sin[sidx0] : 0.f;  // s_cos / s_sin are unset for invalid slots
         const float a1 = si1.valid ? s_cos[sidx0 + 1] : 0.f, b1 = si1.valid ? s_sin[sidx0 + 1] : 0.f;
-        const float* pp = patf + lane;
+        const uint32_t* pp = pat8 + lane;
         uint32_t val0 = 0, val1 = 0;  // bits enter at the bottom, test 7 first: sign of I(p0) - I(p1) by one funnel shift
         constexpr int kRow = kPatchRowWords * 4;
 #pragma unroll
         for (int t = 7; t >= 0; --t) {
-            const float x0 = pp[(4 * t) * 32], y0 = pp[(4 * t + 1) * 32], x1 = pp[(4 * t + 2) * 32], y1 = pp[(4 * t + 3) * 32];
+            const uint32_t pw = pp[t * 32];   // small integers: the conversions are exact
+            const float x0 = (float)(int8_t)(pw & 0xff), y0 = (float)(int8_t)((pw >> 8) & 0xff), x1 = (float)(int8_t)((pw >> 16) & 0xff),
+                        y1 = (float)(int8_t)(pw >> 24);
             {
                 const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b0), __fmul_rn(y0, a0)));
                 const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a0), __fmul_rn(y0, b0)));

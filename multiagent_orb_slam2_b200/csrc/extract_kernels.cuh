@@ -24,7 +24,8 @@ constexpr int kMinBorder = kEdgeThreshold - 3;  // 16
 constexpr int kHalfPatch = 15;
 constexpr int kQtMaxDepth = 13;
 // IC_Angle by word loads: 31 rows x 9 words (31 + 3 alignment bytes) = 279 items, padded to 9 warp steps; 4 phases x (u, v)
-constexpr int kIcWordsPerRow = 9, kIcItems = 288, kIcTableWords = 4 * 2 * kIcItems;
+constexpr int kIcWordsPerRow = 9, kIcItems = 288, kIcTableWords = 4 * kIcItems;   // [alignment phase][item]: u + 16 of the word's 4 bytes, 0 outside the patch
+constexpr int kPatternWords = 256;   // [test of the byte][descriptor byte]: x0 | y0 << 8 | x1 << 16 | y1 << 24 as int8
 
 struct LevelGeom {
     int w, h, pitch;
@@ -82,7 +83,7 @@ struct DeviceBuffers {
     const LinTap* taps;
     const BlurTile* tiles;
     const uint32_t* ic_table;  // kIcTableWords
-    const float* pattern;   // 1024 floats, transposed: [4 * test + component][descriptor byte]
+    const uint32_t* pattern;   // kPatternWords
     uint8_t* pyr;
     uint8_t* blur;
     uint32_t* slots;

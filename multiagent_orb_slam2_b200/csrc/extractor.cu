@@ -226,40 +226,44 @@ int build_geometry(orbx_extractor* h) {
     int rc;
     if ((rc = dalloc(&h->d_geom, sizeof(Geometry))) || (rc = dalloc(&h->d_cells, cells.size() * sizeof(CellDesc))) ||
         (rc = dalloc(&h->d_taps, taps.size() * sizeof(LinTap))) || (rc = dalloc(&h->d_tiles, tiles.size() * sizeof(BlurTile))) ||
-        (rc = dalloc(&h->d_pattern, 1024 * sizeof(float) + kIcTableWords * 4)))
+        (rc = dalloc(&h->d_pattern, (kPatternWords + kIcTableWords) * 4)))
         return rc;
-    // sampling pattern as floats, transposed for the describe kernel: value q = 4 * test + component of
-    // descriptor byte b at [q * 32 + b]
-    float patT[1024];
-    for (int i = 0; i < 1024; ++i) patT[(i & 31) * 32 + (i >> 5)] = (float)kPatternInts[i];
+    // sampling pattern for the describe kernel: the four int8 coordinates (x0, y0, x1, y1; |value| <= 13) of test t of
+    // descriptor byte b in one word at [t * 32 + b] (1 KB of shared memory instead of 4 KB of floats)
+    uint32_t patT[kPatternWords];
+    for (int b = 0; b < 32; ++b)
+        for (int t = 0; t < 8; ++t) {
+            uint32_t w = 0;
+            for (int c4 = 0; c4 < 4; ++c4) w |= (uint32_t)(uint8_t)(int8_t)kPatternInts[4 * (8 * b + t) + c4] << (8 * c4);
+            patT[t * 32 + b] = w;
+        }
     ORB_CUDA_TRY(cudaMemcpy(h->d_geom, &g, sizeof(Geometry), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_taps, taps.data(), taps.size() * sizeof(LinTap), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(h->d_pattern, patT, sizeof(patT), cudaMemcpyHostToDevice));
-    {   // IC_Angle coefficient words (describe.cu): for each alignment phase p of the patch's left edge, item
-        // i = row * 9 + word: the int8 u (then v) coordinates of the 4 bytes, 0 outside the circular patch
+    {   // IC_Angle coefficient words (describe.cu): for each alignment phase p of the patch's left edge, item i = row * 9 + word:
+        // u + 16 (1 .. 31) of the word's 4 bytes, 0 outside the circular patch. v is the same for a whole row, so
+        // m01 = sum_rows v * sum_inside I needs no table of its own: "inside" is "byte != 0".
         std::vector<uint32_t> tab(kIcTableWords, 0u);
         for (int p = 0; p < 4; ++p)
             for (int r = 0; r < 2 * kHalfPatch + 1; ++r)
                 for (int j = 0; j < kIcWordsPerRow; ++j) {
-                    uint32_t cu = 0, cv = 0;
+                    uint32_t cu = 0;
                     const int v = r - kHalfPatch;
                     for (int k = 0; k < 4; ++k) {
                         const int u = 4 * j + k - kHalfPatch - p;
                         if (u < -kHalfPatch || u > kHalfPatch || std::abs(u) > g.umax[std::abs(v)]) continue;
-                        cu |= (uint32_t)(uint8_t)(int8_t)u << (8 * k);
-                        cv |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+                        cu |= (uint32_t)(u + 16) << (8 * k);
                     }
-                    tab[(size_t)p * 2 * kIcItems + r * kIcWordsPerRow + j] = cu;
-                    tab[(size_t)p * 2 * kIcItems + kIcItems + r * kIcWordsPerRow + j] = cv;
+                    tab[(size_t)p * kIcItems + r * kIcWordsPerRow + j] = cu;
                 }
         ORB_CUDA_TRY(cudaMemcpy((uint8_t*)h->d_pattern + sizeof(patT), tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     }
     DeviceBuffers& db = h->db;
     db.geom = (const Geometry*)h->d_geom; db.cells = (const CellDesc*)h->d_cells; db.taps = (const LinTap*)h->d_taps;
-    db.tiles = (const BlurTile*)h->d_tiles; db.pattern = (const float*)h->d_pattern;
-    db.ic_table = (const uint32_t*)((const uint8_t*)h->d_pattern + 1024 * sizeof(float));
+    db.tiles = (const BlurTile*)h->d_tiles; db.pattern = (const uint32_t*)h->d_pattern;
+    db.ic_table = (const uint32_t*)h->d_pattern + kPatternWords;
     h->in_pitch = align_up((size_t)h->width, 128);
     if ((rc = dalloc((void**)&db.pyr, (size_t)B * g.pyr_bytes)) || (rc = dalloc((void**)&db.blur, (size_t)B * g.blur_bytes)) ||
         (rc = dalloc((void**)&db.slots, (size_t)B * g.slot_words * 4)) || (rc = dalloc((void**)&db.cell_counts, (size_t)B * g.ncells * 4)) ||
