@@ -261,3 +261,26 @@ def test_matcher_scratch_grows_is_released_and_survives_thread_exit():
         assert free_before - free_after < (8 << 20), (free_before, free_after)
     finally:
         _lib.check(L.orbm_set_knn2_backend(0))
+
+
+def test_small_batches_take_the_level_parallel_path_and_agree_with_large_ones():
+    """Batches of 1 and 2 frames run FAST + quadtree of every pyramid level as its own branch next to the resize chain
+    (programmatic dependent launches, captured into a graph from the second identical call on); larger batches run the plain
+    sequence. The same frames must give the same keypoints and descriptors whichever way they are batched, call after call."""
+    imgs = np.stack([synth.image(kind, 640, 480, 90 + i) for i, kind in enumerate(["blocks", "noise", "blocks", "blurnoise", "blocks", "flat"])])
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, 640, 480, max_batch=6)
+    want_k, want_d, want_c = ex.extract_batch(imgs)            # plain sequence, 6 frames
+    for i, im in enumerate(imgs[:3]):                           # the reference itself for three of them
+        ok, od = O.OracleExtractor()(im)
+        assert want_c[i] == len(ok) and np.array_equal(want_d[i, :want_c[i]], od)
+    for rep in range(3):                                        # plain launches, capture, graph replay
+        for i in range(6):
+            k, d, c = ex.extract_batch(imgs[i:i + 1])
+            assert c[0] == want_c[i] and np.array_equal(d[0, :c[0]], want_d[i, :c[0]]) and np.array_equal(k[0, :c[0]], want_k[i, :c[0]]), (rep, i)
+        for i in range(0, 6, 2):
+            k, d, c = ex.extract_batch(imgs[i:i + 2])
+            for j in range(2):
+                n = want_c[i + j]
+                assert c[j] == n and np.array_equal(d[j, :n], want_d[i + j, :n]) and np.array_equal(k[j, :n], want_k[i + j, :n]), (rep, i, j)
+        k, d, c = ex.extract_batch(imgs[:3])
+        assert np.array_equal(c, want_c[:3]) and all(np.array_equal(d[j, :c[j]], want_d[j, :c[j]]) for j in range(3))
