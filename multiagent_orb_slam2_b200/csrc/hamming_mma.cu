@@ -6,11 +6,16 @@
 // (M = queries, N = candidates, K = 256) followed by a row-wise top-2 - and sm_100a's int8 tensor throughput is an order of
 // magnitude above the POPC pipe (0.58 T comparisons/s/GPU) even at 8 bytes per bit-octet.
 //
-//   expand_pm1_kernel : 32-byte descriptors -> 256 int8 (+1 / -1), row-major, K contiguous (the K-major operand layout)
-//   knn2_mma_kernel   : one CTA = 128 query rows; TMA (SWIZZLE_128B) streams 256-candidate tiles through a shared-memory
-//                       ring, one elected thread issues 8 tcgen05.mma (K = 32 each) per tile into a double-buffered
-//                       128 x 256 int32 accumulator in TMEM, 8 epilogue warps read it back with tcgen05.ld and keep the
-//                       two largest dot products (= two smallest distances, first minimum by candidate order) per row.
+//   expand_pairs_kernel / expand_rows_kernel : 32-byte descriptors -> 256 int8 (queries +-64, database +-1), row-major, K
+//                       contiguous (the K-major operand layout)
+//   knn2_mma_kernel   : one CTA = 128 query rows, two CTAs per SM; TMA (SWIZZLE_128B) streams 128-candidate tiles through a
+//                       shared-memory ring, one elected thread issues 8 tcgen05.mma (128 x 128 x 32) per tile into a
+//                       double-buffered accumulator in TMEM, 8 epilogue warps read it back (tcgen05.ld, 16-bit packed) and
+//                       keep the two largest dot products (= two smallest distances, first minimum by candidate order) per
+//                       row; in a long scan groups of 16 candidates are first tested against the running second best.
+//   knn2_mma_pair_kernel : the same on CTA pairs (cta_group::2, M = 256): selectable, measured, not the default.
+//   top2_merge_splits_kernel : folds the partial results when a long database is scanned by 2 - 4 CTAs per query tile
+//                       (against wave quantisation); the result is the one-pass result.
 #include <cuda.h>
 
 #include <atomic>

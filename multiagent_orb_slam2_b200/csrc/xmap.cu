@@ -18,8 +18,9 @@
 //   * the directed (query map, database map) pairs are cut into 128-row query tiles and the flattened tile list is dealt
 //     evenly to the ranks: with as many maps as GPUs every rank matches its own map against all others, with FEWER maps than
 //     GPUs the query rows of a map are split over several ranks, whose results go straight into the
-//     owner's window by peer stores; a query's (best, second, index) is always computed by one CTA over the whole database in
-//     canonical order, so the result does not depend on the split;
+//     owner's window by peer stores; a query's (best, second, index) is always computed over the whole database in canonical
+//     order (by one CTA, or by 2 - 4 CTAs over consecutive candidate ranges whose partial results are folded in order), so the
+//     result does not depend on the split;
 //   * completion = a release-store of the step number into every owner's done[rank] flag; an owner's call ends with an
 //     acquire-wait for all contributors, and a publish of step e waits until every rank is done with step e-2 (the step that
 //     used the same half of the double buffer).
