@@ -152,8 +152,8 @@ int launch_resize_level(const Geometry& hg, const DeviceBuffers& db, const TmaMa
 // blur: separable {18,34,48,56,48,34,18}, single rounding (sum + 2^15) >> 16, BORDER_REFLECT_101.
 // One block = one 128 x 58 output tile of one level of one frame (input 136 x 64 incl. halo).
 //   load : one TMA box (144 x 64 bytes) into shared memory; border tiles patch the reflected bytes
-//   h    : 4 outputs per thread from 3 words: byte windows by funnel shift, 2 x IDP.4A per output
-//          (4+3 taps, u8 x u8 -> u32, exact); rows are processed in vertical pairs and stored as
+//   h    : 4 outputs per thread from 3 words: the taps laid over the words at each output's byte offset, 10 x IDP.4A per
+//          4 outputs (u8 x u8 -> u32, exact); rows are processed in vertical pairs and stored as
 //          (row 2m | row 2m+1 << 16) so that
 //   v    : one IDP.2A covers two vertical taps: 4 x IDP.2A per output, accumulator preloaded with
 //          the rounding constant; 4 columns per thread, sliding window down the tile.
@@ -218,7 +218,6 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
     const int nrp = min(kBlurInRows / 2, (min(kBlurTH, L.h - Y0) + 6 + 1) >> 1);  // output rows + 6 halo rows, in pairs
     const uint32_t qinv = (65536u + nq - 1) / nq;  // floor(i / nq) == i * qinv >> 16 for i * nq < 65536
     // horizontal pass: item = (row pair, column quad)
-    constexpr uint32_t kLo = 18u | 34u << 8 | 48u << 16 | 56u << 24, kHi = 48u | 34u << 8 | 18u << 16;
     for (int it = tid; it < nrp * nq; it += 256) {
         const int pr = (int)((uint32_t)it * qinv >> 16), k = it - pr * nq;
         uint32_t h[2][4];
@@ -226,13 +225,14 @@ blur_kernel(const Geometry* __restrict__ g, const BlurTile* __restrict__ tiles, 
         for (int rr = 0; rr < 2; ++rr) {
             const uint32_t* wr = &in_w[2 * pr + rr][kBlurLead / 4 - 1 + k];  // word of bytes X0+4k-4 .. X0+4k-1
             const uint32_t w0 = wr[0], w1 = wr[1], w2 = wr[2];
-            // output j (column 4k+j) uses bytes j+1..j+4 and j+5..j+8 of the 12-byte string w0 w1 w2
-            const uint32_t a1 = __funnelshift_r(w0, w1, 8), a2 = __funnelshift_r(w0, w1, 16), a3 = __funnelshift_r(w0, w1, 24);
-            const uint32_t b1 = __funnelshift_r(w1, w2, 8), b2 = __funnelshift_r(w1, w2, 16), b3 = __funnelshift_r(w1, w2, 24);
-            h[rr][0] = __dp4a(a1, kLo, __dp4a(b1, kHi, 0u));
-            h[rr][1] = __dp4a(a2, kLo, __dp4a(b2, kHi, 0u));
-            h[rr][2] = __dp4a(a3, kLo, __dp4a(b3, kHi, 0u));
-            h[rr][3] = __dp4a(w1, kLo, __dp4a(w2, kHi, 0u));
+            // output j (column 4k+j) uses bytes j+1 .. j+7 of the 12-byte string w0 w1 w2. The data words stay where they
+            // are and the seven taps are laid over them at the byte offset of each output: 10 IDP.4A per 4 outputs instead of
+            // 6 funnel shifts + 8 IDP.4A (the shifts ran on the ALU pipe, the busier one of this kernel)
+            constexpr uint32_t T18 = 18u, T34 = 34u, T48 = 48u, T56 = 56u;
+            h[rr][0] = __dp4a(w0, T18 << 8 | T34 << 16 | T48 << 24, __dp4a(w1, T56 | T48 << 8 | T34 << 16 | T18 << 24, 0u));
+            h[rr][1] = __dp4a(w0, T18 << 16 | T34 << 24, __dp4a(w1, T48 | T56 << 8 | T48 << 16 | T34 << 24, __dp4a(w2, T18, 0u)));
+            h[rr][2] = __dp4a(w0, T18 << 24, __dp4a(w1, T34 | T48 << 8 | T56 << 16 | T48 << 24, __dp4a(w2, T34 | T18 << 8, 0u)));
+            h[rr][3] = __dp4a(w1, T18 | T34 << 8 | T48 << 16 | T56 << 24, __dp4a(w2, T48 | T34 << 8 | T18 << 16, 0u));
         }
         uint4 o;
         o.x = h[0][0] | h[1][0] << 16; o.y = h[0][1] | h[1][1] << 16; o.z = h[0][2] | h[1][2] << 16; o.w = h[0][3] | h[1][3] << 16;
