@@ -84,6 +84,9 @@ struct orbx_extractor {
     size_t in_pitch = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    uint8_t* d_results = nullptr;                      // counts | kps | desc (db.counts / db.kps / db.desc point into it)
+    size_t results_kps_off() const { return align_up((size_t)max_batch * 4, 256); }
+    size_t results_bytes() const { return results_kps_off() + (size_t)max_batch * hg.out_cap * (sizeof(orbx_keypoint) + 32); }
     uint8_t* h_out = nullptr;                          // pinned staging of the results for small synchronous host calls
     size_t h_out_bytes = 0;
     cudaStream_t lvl_stream[kMaxLevels] = {};          // small batches: one branch per pyramid level (launch_sequence)
@@ -268,10 +271,14 @@ int build_geometry(orbx_extractor* h) {
     if ((rc = dalloc((void**)&db.pyr, (size_t)B * g.pyr_bytes)) || (rc = dalloc((void**)&db.blur, (size_t)B * g.blur_bytes)) ||
         (rc = dalloc((void**)&db.slots, (size_t)B * g.slot_words * 4)) || (rc = dalloc((void**)&db.cell_counts, (size_t)B * g.ncells * 4)) ||
         (rc = dalloc((void**)&db.sortbuf, (size_t)B * 5 * g.cand_words * 4)) || (rc = dalloc((void**)&db.selected, (size_t)B * g.sel_words * 4)) ||
-        (rc = dalloc((void**)&db.sel_counts, (size_t)B * nl * 4)) || (rc = dalloc((void**)&db.kps, (size_t)B * g.out_cap * sizeof(orbx_keypoint))) ||
-        (rc = dalloc((void**)&db.desc, (size_t)B * g.out_cap * 32)) || (rc = dalloc((void**)&db.counts, (size_t)B * 4)) ||
+        (rc = dalloc((void**)&db.sel_counts, (size_t)B * nl * 4)) || (rc = dalloc((void**)&h->d_results, h->results_bytes())) ||
         (rc = dalloc((void**)&h->d_input, (size_t)B * h->in_pitch * h->height)))
         return rc;
+    // counts | keypoints | descriptors of all frames in ONE allocation: a call that uses the whole handle (always the case
+    // for max_batch = 1, the facade) fetches its results with a single copy
+    db.counts = (int*)h->d_results;
+    db.kps = (orbx_keypoint*)(h->d_results + h->results_kps_off());
+    db.desc = h->d_results + h->results_kps_off() + (size_t)B * g.out_cap * sizeof(orbx_keypoint);
     ORB_CUDA_TRY(cudaMemset(db.counts, 0, (size_t)B * 4));
     for (int l = 1; l < nl; ++l) {
         const LevelGeom& L = g.lv[l];
@@ -452,7 +459,7 @@ void orbx_destroy(orbx_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     void* ptrs[] = {h->d_geom, h->d_cells, h->d_taps, h->d_tiles, h->d_pattern, h->db.pyr, h->db.blur, h->db.slots, h->db.cell_counts,
-                    h->db.sortbuf, h->db.selected, h->db.sel_counts, h->db.kps, h->db.desc, h->db.counts, h->d_input, h->d_stereo};
+                    h->db.sortbuf, h->db.selected, h->db.sel_counts, h->d_results, h->d_input, h->d_stereo};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_pyr) cudaFreeHost(h->h_pyr);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -618,7 +625,26 @@ int orbx_extract_batch(orbx_handle h, const uint8_t* images, size_t stride, size
     const int oc = h->hg.out_cap, take = std::min(cap, oc);
     const size_t kp_row = (size_t)take * sizeof(orbx_keypoint), de_row = (size_t)take * 32;
     const size_t staged_bytes = align_up((size_t)n * 4, 256) + (size_t)n * (kp_row + de_row);
-    if (take > 0 && staged_bytes <= ((size_t)4 << 20)) {
+    if (take == oc && n == h->max_batch && h->results_bytes() <= ((size_t)4 << 20)) {
+        // the whole handle is in use: counts | kps | desc are one contiguous slab on the device -> one copy
+        const size_t bytes = h->results_bytes();
+        if (h->h_out_bytes < bytes) {
+            if (h->h_out) { cudaStreamSynchronize(st); cudaFreeHost(h->h_out); h->h_out = nullptr; h->h_out_bytes = 0; }
+            ORB_CUDA_TRY(cudaMallocHost(&h->h_out, bytes));
+            h->h_out_bytes = bytes;
+        }
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_results, bytes, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+        const int32_t* s_cnt = reinterpret_cast<const int32_t*>(h->h_out);
+        const uint8_t* s_kps = h->h_out + h->results_kps_off();
+        const uint8_t* s_desc = s_kps + (size_t)n * kp_row;
+        for (int i = 0; i < n; ++i) {
+            counts[i] = s_cnt[i];
+            const size_t c = (size_t)std::max(0, std::min(s_cnt[i], take));
+            memcpy(kps + (size_t)i * cap, s_kps + (size_t)i * kp_row, c * sizeof(orbx_keypoint));
+            memcpy(desc + (size_t)i * cap * 32, s_desc + (size_t)i * de_row, c * 32);
+        }
+    } else if (take > 0 && staged_bytes <= ((size_t)4 << 20)) {
         if (h->h_out_bytes < staged_bytes) {
             if (h->h_out) { cudaStreamSynchronize(st); cudaFreeHost(h->h_out); h->h_out = nullptr; h->h_out_bytes = 0; }
             ORB_CUDA_TRY(cudaMallocHost(&h->h_out, staged_bytes));
