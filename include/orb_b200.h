@@ -254,6 +254,14 @@ int orbm_window_lists_device(orbm_grid_handle g, const uint8_t* d_desc_frame, co
                              const float* d_y, const float* d_r, const int32_t* d_min_level, const int32_t* d_max_level,
                              int32_t* d_offsets, int32_t* d_cands, int16_t* d_dist, int cap, int32_t* total_out, void* stream);
 
+/* Host-buffer form for callers whose frames live in host containers (the C++ facade on the reference's Frame): keypoints
+ * (x, y, octave are read) with their descriptors, the image bounds {mnMinX, mnMinY, mnMaxX, mnMaxY} and nq windows go up in one
+ * copy; grid build, window lists and distances run on the device; the lists come back in GetFeaturesInArea order. Per-thread
+ * stream and buffers. ORB_ECAPACITY (with *total_out = needed room) when the lists do not fit `cap` entries. */
+int orbm_window_lists(int device, const orbx_keypoint* kps, int n_kps, const float* bounds4, const uint8_t* desc_frame,
+                      const uint8_t* queries, int nq, const float* x, const float* y, const float* r, const int32_t* min_level,
+                      const int32_t* max_level, int32_t* offsets, int32_t* cands, int16_t* dist, int cap, int32_t* total_out);
+
 /* ------------------------------------------------------------------------------------------
  * Map-point projection: Frame::isInFrustum (src/Frame.cc:269-325; mode 0) and the projection
  * prologue of ORBmatcher::Fuse / SearchByProjection(KF, Scw, ...) / SearchBySim3 (src/ORBmatcher.cc:849-889, 323-363,

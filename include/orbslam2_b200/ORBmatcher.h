@@ -173,6 +173,12 @@ private:
     std::vector<int> votes_[kBins];
 };
 
+// Does the frame type carry the undistorted image bounds as (static) members like the reference's Frame (include/Frame.h:190-193)?
+// Then its grid can be rebuilt on the device and the window gates of a search run there (orbm_window_lists).
+template <class F, class = void> struct has_image_bounds : std::false_type {};
+template <class F>
+struct has_image_bounds<F, decltype((void)(F::mnMinX + F::mnMaxX + F::mnMinY + F::mnMaxY))> : std::true_type {};
+
 }  // namespace b200_detail
 
 class ORBmatcher {
@@ -198,22 +204,25 @@ public:
         std::vector<int> claimed_at(F2.mvKeysUn.size(), INT_MAX);   // distance at which a keypoint of F2 is currently matched
         std::vector<int> owner(F2.mvKeysUn.size(), -1);             // ... and by which keypoint of F1
 
-        // 1. host: gate. Candidate lists in the reference's iteration order, CSR.
+        // 1. + 2. gate and distances. Candidate lists in the reference's iteration order, CSR.
         const size_t n1 = F1.mvKeysUn.size();
         std::vector<int32_t> offsets(n1 + 1, 0), cands;
-        for (size_t i1 = 0; i1 < n1; i1++) {
-            if (F1.mvKeysUn[i1].octave <= 0) {
-                std::vector<size_t> v = F2.GetFeaturesInArea(vbPrevMatched[i1].x, vbPrevMatched[i1].y, windowSize, 0, 0);
-                for (size_t k = 0; k < v.size(); ++k) cands.push_back((int32_t)v[k]);
+        std::vector<int16_t> dist;
+        if (!window_lists_on_device(F1, F2, vbPrevMatched, windowSize, offsets, cands, dist)) {
+            // host gate (frame types without image bounds): the caller's own GetFeaturesInArea, then one launch for all distances
+            for (size_t i1 = 0; i1 < n1; i1++) {
+                if (F1.mvKeysUn[i1].octave <= 0) {
+                    std::vector<size_t> v = F2.GetFeaturesInArea(vbPrevMatched[i1].x, vbPrevMatched[i1].y, windowSize, 0, 0);
+                    for (size_t k = 0; k < v.size(); ++k) cands.push_back((int32_t)v[k]);
+                }
+                offsets[i1 + 1] = (int32_t)cands.size();
             }
-            offsets[i1 + 1] = (int32_t)cands.size();
-        }
-        // 2. device: all distances
-        std::vector<int16_t> dist(cands.size());
-        if (!cands.empty()) {
-            const std::vector<uint8_t> A = pack(F1.mDescriptors), B = pack(F2.mDescriptors);
-            const int rc = orbm_list_distances(device_, A.data(), (int)n1, B.data(), (int)F2.mvKeysUn.size(), offsets.data(), cands.data(), dist.data());
-            if (rc != ORB_OK) throw std::runtime_error(std::string("orb_b200: ") + orb_last_error());
+            dist.resize(cands.size());
+            if (!cands.empty()) {
+                const std::vector<uint8_t> A = pack(F1.mDescriptors), B = pack(F2.mDescriptors);
+                const int rc = orbm_list_distances(device_, A.data(), (int)n1, B.data(), (int)F2.mvKeysUn.size(), offsets.data(), cands.data(), dist.data());
+                if (rc != ORB_OK) throw std::runtime_error(std::string("orb_b200: ") + orb_last_error());
+            }
         }
         // 3. host: the reference's ordered resolve (src/ORBmatcher.cc:434-488)
         for (size_t i1 = 0; i1 < n1; i1++) {
@@ -924,6 +933,46 @@ protected:
         return vnMatch;
     }
 
+    // SearchForInitialization's gate on the device, for frame types that expose the image bounds (the reference's Frame):
+    // F2's keypoints + descriptors and the level-0 windows of F1 go up in one copy, the device rebuilds F2's grid
+    // (AssignFeaturesToGrid, src/Frame.cc:230-245), walks every window in GetFeaturesInArea's order (327-380) and returns
+    // candidates + Hamming distances - instead of ~3 us of host grid walking per 100 px window plus a separate distance launch.
+    template <class FrameT>
+    typename std::enable_if<b200_detail::has_image_bounds<FrameT>::value, bool>::type
+    window_lists_on_device(FrameT& F1, FrameT& F2, const std::vector<cv::Point2f>& centres, int windowSize, std::vector<int32_t>& offsets,
+                           std::vector<int32_t>& cands, std::vector<int16_t>& dist) {
+        const size_t n1 = F1.mvKeysUn.size(), n2 = F2.mvKeysUn.size();
+        if (n1 == 0 || n2 == 0) return true;   // offsets are all zero already
+        std::vector<orbx_keypoint> kp2(n2);
+        for (size_t i = 0; i < n2; ++i) {
+            const cv::KeyPoint& k = F2.mvKeysUn[i];
+            kp2[i].x = k.pt.x; kp2[i].y = k.pt.y; kp2[i].size = k.size; kp2[i].angle = k.angle; kp2[i].response = k.response; kp2[i].octave = k.octave;
+        }
+        std::vector<float> x(n1), y(n1), r(n1);
+        std::vector<int32_t> lo(n1, 0), hi(n1, 0);   // GetFeaturesInArea(..., minLevel 0, maxLevel 0)
+        for (size_t i = 0; i < n1; ++i) {
+            x[i] = centres[i].x; y[i] = centres[i].y;
+            r[i] = F1.mvKeysUn[i].octave <= 0 ? (float)windowSize : 0.f;   // radius 0: an empty window, like the skipped keypoints (431-432)
+        }
+        const float bounds[4] = {(float)FrameT::mnMinX, (float)FrameT::mnMinY, (float)FrameT::mnMaxX, (float)FrameT::mnMaxY};
+        const std::vector<uint8_t> A = pack(F1.mDescriptors), B = pack(F2.mDescriptors);
+        int cap = (int)std::max<size_t>(4096, 32 * n1);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            cands.resize((size_t)cap); dist.resize((size_t)cap);
+            int32_t total = 0;
+            const int rc = orbm_window_lists(device_, kp2.data(), (int)n2, bounds, B.data(), A.data(), (int)n1, x.data(), y.data(), r.data(), lo.data(),
+                                             hi.data(), offsets.data(), cands.data(), dist.data(), cap, &total);
+            if (rc == ORB_OK) { cands.resize((size_t)total); dist.resize((size_t)total); return true; }
+            if (rc != ORB_ECAPACITY) throw std::runtime_error(std::string("orb_b200: ") + orb_last_error());
+            cap = total;   // the lists need this much room: once more
+        }
+        throw std::runtime_error("orb_b200: window lists did not fit their own size");
+    }
+    template <class FrameT>
+    typename std::enable_if<!b200_detail::has_image_bounds<FrameT>::value, bool>::type
+    window_lists_on_device(FrameT&, FrameT&, const std::vector<cv::Point2f>&, int, std::vector<int32_t>&, std::vector<int32_t>&, std::vector<int16_t>&) {
+        return false;
+    }
     static std::vector<uint8_t> pack(const cv::Mat& D) {  // rows contiguous, 32 bytes each
         std::vector<uint8_t> v((size_t)D.rows * 32);
         for (int i = 0; i < D.rows; ++i) std::memcpy(&v[(size_t)i * 32], D.ptr(i), 32);

@@ -73,6 +73,7 @@ def lib():
         "orbm_grid_build_device": [vp, vp, vp, f32, f32, f32, f32, vp],
         "orbm_window_knn2_device": [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "orbm_window_lists_device": [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(i32), vp],
+        "orbm_window_lists": [i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(i32)],
         "orbv_create": [i32, vp, vp, vp, i32, i32, i32, C.POINTER(vp)],
         "orbv_descend_device": [vp, vp, i32, i32, vp, vp, vp, vp],
         "orbv_descend": [vp, vp, i32, i32, vp, vp, vp],

@@ -10,6 +10,9 @@
 // gate depends on earlier matches take the distances (orbm_list_distances) and replay the loop on the host.
 #include <new>
 
+#include <algorithm>
+#include <cstring>
+
 #include "common.cuh"
 
 struct orbm_grid {
@@ -314,6 +317,118 @@ int orbm_window_lists_device(orbm_grid_handle g, const uint8_t* d_desc_frame, co
                                                       g->h_inv, nullptr, d_offsets, d_cands, d_dist);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+// ---- host-buffer form ----------------------------------------------------------------------------------------------
+// The facade's windowed searches on host-resident frames (std::vector<cv::KeyPoint> + cv::Mat): keypoints, descriptors and
+// queries go up in ONE staged copy, grid build + window lists + distances run on the device, offsets / candidates /
+// distances come back through pinned staging. Replaces a host loop of Frame::GetFeaturesInArea calls (src/Frame.cc:327-380;
+// ~3 us each for the 100 px windows of SearchForInitialization) + DescriptorDistance per candidate. Per calling thread:
+// stream, grid, device and pinned arenas (grown on demand, freed at thread exit).
+extern "C++" {
+namespace {
+struct HostWindowContext {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    orbm_grid_handle grid = nullptr;
+    int grid_cap = 0;
+    uint8_t* dev = nullptr; size_t dev_cap = 0;
+    uint8_t* pin = nullptr; size_t pin_cap = 0;
+    ~HostWindowContext() { release(); }
+    void release() {
+        if (device >= 0) {
+            cudaSetDevice(device);
+            if (st) cudaStreamSynchronize(st);
+            if (grid) orbm_grid_destroy(grid);
+            if (dev) cudaFree(dev);
+            if (pin) cudaFreeHost(pin);
+            if (st) cudaStreamDestroy(st);
+        }
+        grid = nullptr; dev = nullptr; pin = nullptr; st = nullptr; dev_cap = pin_cap = 0; grid_cap = 0; device = -1;
+    }
+    int prepare(int d, int n_kps, size_t dev_bytes, size_t pin_bytes) {
+        if (d != device) {
+            release();
+            ORB_CUDA_TRY(cudaSetDevice(d));
+            ORB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            device = d;
+        } else {
+            ORB_CUDA_TRY(cudaSetDevice(d));
+        }
+        if (n_kps > grid_cap) {
+            if (grid) { cudaStreamSynchronize(st); orbm_grid_destroy(grid); grid = nullptr; grid_cap = 0; }
+            const int want = std::max(4096, n_kps + n_kps / 2);
+            int rc = orbm_grid_create(d, std::min(want, (1 << 20) - 1), &grid);
+            if (rc) return rc;
+            grid_cap = std::min(want, (1 << 20) - 1);
+        }
+        if (dev_bytes > dev_cap) {
+            if (dev) { cudaStreamSynchronize(st); cudaFree(dev); dev = nullptr; dev_cap = 0; }
+            ORB_CUDA_TRY(cudaMalloc(&dev, dev_bytes + dev_bytes / 2));
+            dev_cap = dev_bytes + dev_bytes / 2;
+        }
+        if (pin_bytes > pin_cap) {
+            if (pin) { cudaStreamSynchronize(st); cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
+            ORB_CUDA_TRY(cudaMallocHost(&pin, pin_bytes + pin_bytes / 2));
+            pin_cap = pin_bytes + pin_bytes / 2;
+        }
+        return ORB_OK;
+    }
+};
+thread_local HostWindowContext tls_window;
+}  // namespace
+}  // extern "C++"
+
+int orbm_window_lists(int device, const orbx_keypoint* kps, int n_kps, const float* bounds4, const uint8_t* desc_frame, const uint8_t* queries,
+                      int nq, const float* x, const float* y, const float* r, const int32_t* min_level, const int32_t* max_level,
+                      int32_t* offsets, int32_t* cands, int16_t* dist, int cap, int32_t* total_out) {
+    ORB_REQUIRE(total_out && nq >= 0 && n_kps >= 0 && cap >= 0, "bad arguments");
+    *total_out = 0;
+    if (nq == 0) return ORB_OK;
+    ORB_REQUIRE(offsets && bounds4 && queries && x && y && r && min_level && max_level && (n_kps == 0 || (kps && desc_frame)), "null pointer");
+    ORB_REQUIRE(n_kps < (1 << 20), "too many keypoints");
+    if (n_kps == 0) { for (int i = 0; i <= nq; ++i) offsets[i] = 0; return ORB_OK; }
+    ORB_REQUIRE(cap == 0 || (cands && dist), "null output");
+    auto pad = [](size_t b) { return align_up(b, 256); };
+    // input block (one copy): count | kps | frame descriptors | query descriptors | x | y | r | min level | max level
+    const size_t o_cnt = 0, o_kps = pad(4), o_df = o_kps + pad((size_t)n_kps * sizeof(orbx_keypoint)), o_dq = o_df + pad((size_t)n_kps * 32),
+                 o_x = o_dq + pad((size_t)nq * 32), o_y = o_x + pad((size_t)nq * 4), o_r = o_y + pad((size_t)nq * 4), o_lo = o_r + pad((size_t)nq * 4),
+                 o_hi = o_lo + pad((size_t)nq * 4), in_bytes = o_hi + pad((size_t)nq * 4);
+    // output block: offsets | candidates | distances
+    const size_t o_off = in_bytes, o_cd = o_off + pad((size_t)(nq + 1) * 4), o_ds = o_cd + pad((size_t)cap * 4), dev_bytes = o_ds + pad((size_t)cap * 2);
+    HostWindowContext& c = tls_window;
+    int rc;
+    if ((rc = c.prepare(device, n_kps, dev_bytes, std::max(in_bytes, dev_bytes - in_bytes)))) return rc;
+    uint8_t* p = c.pin;
+    *reinterpret_cast<int32_t*>(p + o_cnt) = n_kps;
+    memcpy(p + o_kps, kps, (size_t)n_kps * sizeof(orbx_keypoint));
+    memcpy(p + o_df, desc_frame, (size_t)n_kps * 32);
+    memcpy(p + o_dq, queries, (size_t)nq * 32);
+    memcpy(p + o_x, x, (size_t)nq * 4); memcpy(p + o_y, y, (size_t)nq * 4); memcpy(p + o_r, r, (size_t)nq * 4);
+    memcpy(p + o_lo, min_level, (size_t)nq * 4); memcpy(p + o_hi, max_level, (size_t)nq * 4);
+    ORB_CUDA_TRY(cudaMemcpyAsync(c.dev, p, in_bytes, cudaMemcpyHostToDevice, c.st));
+    uint8_t* d = c.dev;
+    if ((rc = orbm_grid_build_device(c.grid, (const orbx_keypoint*)(d + o_kps), (const int32_t*)(d + o_cnt), bounds4[0], bounds4[1], bounds4[2],
+                                     bounds4[3], c.st)))
+        return rc;
+    int total = 0;
+    rc = orbm_window_lists_device(c.grid, d + o_df, d + o_dq, nq, (const float*)(d + o_x), (const float*)(d + o_y), (const float*)(d + o_r),
+                                  (const int32_t*)(d + o_lo), (const int32_t*)(d + o_hi), (int32_t*)(d + o_off), (int32_t*)(d + o_cd),
+                                  (int16_t*)(d + o_ds), cap, &total, c.st);
+    *total_out = total;
+    if (rc) return rc;   // ORB_ECAPACITY: *total_out tells how much room the lists need
+    // results: offsets | used part of the candidates | used part of the distances -> pinned staging, one synchronisation
+    uint8_t* q = c.pin;
+    const size_t s_off = 0, s_cd = pad((size_t)(nq + 1) * 4), s_ds = s_cd + pad((size_t)total * 4);
+    ORB_CUDA_TRY(cudaMemcpyAsync(q + s_off, d + o_off, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, c.st));
+    if (total) {
+        ORB_CUDA_TRY(cudaMemcpyAsync(q + s_cd, d + o_cd, (size_t)total * 4, cudaMemcpyDeviceToHost, c.st));
+        ORB_CUDA_TRY(cudaMemcpyAsync(q + s_ds, d + o_ds, (size_t)total * 2, cudaMemcpyDeviceToHost, c.st));
+    }
+    ORB_CUDA_TRY(cudaStreamSynchronize(c.st));
+    memcpy(offsets, q + s_off, (size_t)(nq + 1) * 4);
+    if (total) { memcpy(cands, q + s_cd, (size_t)total * 4); memcpy(dist, q + s_ds, (size_t)total * 2); }
     return ORB_OK;
 }
 

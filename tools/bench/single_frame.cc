@@ -13,14 +13,16 @@
 #include "orbslam2_b200/ORBextractor.h"
 #include "orbslam2_b200/ORBmatcher.h"
 
-struct FrameLite {
+struct FrameLite {   // the members ORBmatcher::SearchForInitialization touches on the reference's Frame (include/Frame.h)
     std::vector<cv::KeyPoint> mvKeysUn;
     cv::Mat mDescriptors;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;   // undistorted image bounds, static like Frame's (190-193): the facade gates on the device
     ORB_SLAM2::FrameGrid<cv::KeyPoint> grid;
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, int minLevel, int maxLevel) const {
         return grid.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
     }
 };
+float FrameLite::mnMinX = 0.f, FrameLite::mnMaxX = 0.f, FrameLite::mnMinY = 0.f, FrameLite::mnMaxY = 0.f;
 static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static double median(std::vector<double> v) { std::sort(v.begin(), v.end()); return v[v.size() / 2]; }
 
@@ -52,6 +54,7 @@ int main(int argc, char** argv) {
     ORB_SLAM2::ORBextractor ini(2 * nf, 1.2f, 8, 20, 7);
     ini.SetPyramidDownload(false);
     FrameLite F[2];
+    FrameLite::mnMinX = 0.f; FrameLite::mnMinY = 0.f; FrameLite::mnMaxX = (float)w; FrameLite::mnMaxY = (float)h;
     for (int k = 0; k < 2; ++k) {
         cv::Mat im(h, w, CV_8UC1, buf.data() + (size_t)(k % n) * w * h, (size_t)w);
         ini(im, cv::Mat(), F[k].mvKeysUn, F[k].mDescriptors);
