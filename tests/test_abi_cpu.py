@@ -43,6 +43,11 @@ def test_argument_validation_needs_no_gpu():
     assert L.orbm_knn2_mma_device(None, -1, None, 0, None, None, None, None) == _lib.ORB_EINVAL
     db = C.c_void_p()
     assert L.orbdb_create(0, 0, C.byref(db)) == _lib.ORB_EINVAL
+    total = C.c_int(7)
+    assert L.orbm_window_lists(0, None, 0, None, None, None, 0, None, None, None, None, None, None, None, None, 0, C.byref(total)) == _lib.ORB_OK
+    assert total.value == 0                                                                   # no queries: nothing to do, no GPU needed
+    assert L.orbm_window_lists(0, None, 5, None, None, None, 3, None, None, None, None, None, None, None, None, 0, C.byref(total)) == _lib.ORB_EINVAL
+    assert L.orbm_release_scratch(None) in (_lib.ORB_OK, _lib.ORB_ECUDA)                      # exported; needs a device to do anything
 
 
 def test_no_cpu_fallback_without_device():

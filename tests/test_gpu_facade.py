@@ -261,3 +261,50 @@ def test_device_grid_built_and_queried_on_a_side_stream_right_after_process_asyn
             want = (cand[int(np.argmin(ds))], min(ds)) if cand else (-1, 256)
             assert (gi[i], g1[i]) == want, (rep, i)
         grid.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,radius,levels", [(0, 100.0, (0, 0)), (1, 20.0, (-1, -1)), (2, 45.0, (1, 3))])
+def test_host_buffer_window_lists_match_oracle(seed, radius, levels):
+    """orbm_window_lists - the facade's device-side gate for host-resident frames (SearchForInitialization on the reference's
+    Frame): grid rebuilt on the device from host keypoints, candidates in GetFeaturesInArea order with their distances;
+    also the ORB_ECAPACITY protocol (needed room reported, second call fits) and windows of radius 0."""
+    import ctypes as C
+    from multiagent_orb_slam2_b200 import _lib
+    from multiagent_orb_slam2_b200.extractor import KP_DTYPE
+    L = _lib.lib()
+    w, h = 640, 480
+    a, b, (dx, dy) = synth.shifted_pair("blocks", w, h, seed + 40)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    ka, da = ex(a)
+    kb, db = ex(b)
+    ka, da, kb, db = ka.copy(), da.copy(), kb.copy(), db.copy()
+    qx, qy = (ka["x"] - np.float32(dx)).astype(np.float32), (ka["y"] - np.float32(dy)).astype(np.float32)
+    r = np.full(len(ka), radius, np.float32)
+    r[::7] = 0.0                                   # empty windows (what the facade passes for keypoints it skips)
+    lo = np.full(len(ka), levels[0], np.int32); hi = np.full(len(ka), levels[1], np.int32)
+    okb = np.stack([kb["x"], kb["y"], kb["size"], kb["angle"], kb["response"], kb["octave"].astype(np.float32)], 1)
+    F = O.OracleFrame(okb, db, w, h)
+    want = [F.features_in_area(qx[i], qy[i], r[i], int(lo[i]), int(hi[i])) if r[i] > 0 else [] for i in range(len(ka))]
+    total_want = sum(len(c) for c in want)
+    assert total_want > 1000
+    kbr = np.ascontiguousarray(kb.astype(KP_DTYPE))
+    bounds = np.array([0, 0, w, h], np.float32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+
+    def call(cap):
+        offs = np.zeros(len(ka) + 1, np.int32); cands = np.zeros(max(cap, 1), np.int32); dist = np.zeros(max(cap, 1), np.int16)
+        total = C.c_int(0)
+        rc = L.orbm_window_lists(0, p(kbr), len(kbr), p(bounds), p(db), p(da), len(ka), p(qx), p(qy), p(r), p(lo), p(hi), p(offs), p(cands), p(dist),
+                                 cap, C.byref(total))
+        return rc, total.value, offs, cands, dist
+
+    rc, total, _, _, _ = call(16)                  # too small: the needed room is reported
+    assert rc == _lib.ORB_ECAPACITY and total == total_want
+    rc, total, offs, cands, dist = call(total_want)
+    assert rc == _lib.ORB_OK and total == total_want and offs[-1] == total_want
+    for i in range(len(ka)):
+        got = cands[offs[i]:offs[i + 1]]
+        assert list(got) == list(want[i]), i
+        for k, j in enumerate(got[:8]):
+            assert dist[offs[i] + k] == O.hamming(da[i], db[j])
