@@ -446,6 +446,80 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
             if (count + 3 * n_expand > N) final_phase = true;
             continue;
         }
+        if (final_phase && before <= kQtThreads) {
+            // The size-ordered phase (676-737) on a list that fits one node per thread: slot of an expandable node = its rank by
+            // (size descending, list position ascending); the children counts are scattered to the slots and scanned there; the
+            // number of slots that get processed is the first at which the list reaches N (730-731); children of processed
+            // nodes go to the front (later slots first), everything else follows in list order. 7 block barriers instead of ~25.
+            const int i = threadIdx.x, lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+            int l = 0, h = 0, d = 0, c = 0, ex = 0, bb[5] = {0, 0, 0, 0, 0};
+            if (i < before) {
+                l = lo[i]; h = hi[i]; d = dep[i];
+                if (h - l >= 2 && d < depth) {
+                    bb[0] = l; bb[1] = q.b1[i]; bb[2] = q.b2[i]; bb[3] = q.b3[i]; bb[4] = h;
+                    ex = 1;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) c += bb[t + 1] > bb[t];
+                }
+            }
+            if (i < before) q.flag[i] = ex ? h - l : 0;                               // sizes of the expandable nodes (>= 2), 0 otherwise
+            if (threadIdx.x == 0) sh.bcast[1] = 0x7fffffff;
+            const int m = __syncthreads_count(ex);                                    // also publishes the sizes
+            int rank = -1;
+            if (ex) {
+                const int mine = h - l;
+                rank = 0;
+                for (int j = 0; j < before; ++j) { const int sj = q.flag[j]; rank += (sj > mine) || (sj == mine && j < i); }
+                q.inc[rank] = c;                                                      // children count of slot `rank`
+            }
+            __syncthreads();
+            // exclusive scan of the children counts over the slots (thread k = slot k)
+            const int v = i < m ? q.inc[i] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane_ >= o) inc += t; }
+            if (lane_ == 31) sh.warp_tmp[warp_] = inc;
+            __syncthreads();
+            int off = 0, all_children = 0;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) { const int t = sh.warp_tmp[w]; all_children += t; off += w < warp_ ? t : 0; }
+            const int before_k = off + inc - v;                                       // children of the slots before slot i
+            if (i < m) {
+                q.scan[i] = before_k;
+                if (before + before_k + v - (i + 1) >= N) atomicMin(&sh.bcast[1], i + 1);   // list size after processing slots 0..i
+            }
+            __syncthreads();
+            const int processed = min(sh.bcast[1], m);
+            const int children = processed < m ? q.scan[processed] : all_children;
+            // untouched nodes keep their order behind the children: their rank among themselves by one more scan
+            const int untouched = i < before && !(ex && rank < processed);
+            int uinc = untouched;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, uinc, o); if (lane_ >= o) uinc += t; }
+            __syncthreads();                                                          // warp_tmp is free again
+            if (lane_ == 31) sh.warp_tmp[warp_] = uinc;
+            __syncthreads();
+            int uoff = 0;
+#pragma unroll
+            for (int w = 0; w < kQtWarps; ++w) uoff += w < warp_ ? sh.warp_tmp[w] : 0;
+            if (i < before) {
+                if (!untouched) {
+                    int pos = children - q.scan[rank] - c;
+#pragma unroll
+                    for (int t = 3; t >= 0; --t)
+                        if (bb[t + 1] > bb[t]) { nlo[pos] = bb[t]; nhi[pos] = bb[t + 1]; ndep[pos] = d + 1; ++pos; }
+                } else {
+                    const int p = children + uoff + uinc - 1;
+                    nlo[p] = l; nhi[p] = h; ndep[p] = d;
+                }
+            }
+            __syncthreads();  // the new list is complete; warp_tmp, flag, inc, scan may be reused
+            count = children + (before - processed);
+            cur ^= 1;
+            QT_MARK(100000 + before);
+            if (count >= N || count == before) break;
+            continue;
+        }
         for (int i = threadIdx.x; i < before; i += kQtThreads) {
             const int l = lo[i], h = hi[i];
             int c = 0;
