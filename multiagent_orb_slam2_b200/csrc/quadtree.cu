@@ -661,14 +661,19 @@ quadtree_kernel(const Geometry* __restrict__ g, const uint32_t* __restrict__ slo
     for (int c = threadIdx.x; c < L.cell_count; c += kQtThreads) cnt_s[c] = counts[c];
     const int total = block_exclusive_scan(cnt_s, offs, L.cell_count, sh);
     __syncthreads();
-    // 8 lanes per cell (a cell holds ~10 candidates): the slot loads of 4 cells per warp are in flight together
-    for (int c0 = warp * 4; c0 < L.cell_count; c0 += kQtWarps * 4) {
-        const int c = c0 + (lane >> 3);
-        if (c < L.cell_count) {
-            const int n = cnt_s[c], o = offs[c];
-            const uint32_t* s = lslots + (size_t)c * L.slot_cap;
-            for (int k = lane & 7; k < n; k += 8) cand[o + k] = s[k];
-        }
+    // 8 lanes per cell (a cell holds ~4 candidates, rarely more than 8), two cell groups per step: the slot loads of 8 cells per
+    // warp are in flight together
+    for (int c0 = warp * 4; c0 < L.cell_count; c0 += 2 * kQtWarps * 4) {
+        const int ca = c0 + (lane >> 3), cb = ca + kQtWarps * 4, k0 = lane & 7;
+        const int na = ca < L.cell_count ? cnt_s[ca] : 0, nb = cb < L.cell_count ? cnt_s[cb] : 0;
+        const int oa = ca < L.cell_count ? offs[ca] : 0, ob = cb < L.cell_count ? offs[cb] : 0;
+        const uint32_t* sa = lslots + (size_t)ca * L.slot_cap;
+        const uint32_t* sb = lslots + (size_t)cb * L.slot_cap;
+        const uint32_t pa = k0 < na ? sa[k0] : 0u, pb = k0 < nb ? sb[k0] : 0u;   // both loads before either store
+        if (k0 < na) cand[oa + k0] = pa;
+        if (k0 < nb) cand[ob + k0] = pb;
+        for (int k = k0 + 8; k < na; k += 8) cand[oa + k] = sa[k];
+        for (int k = k0 + 8; k < nb; k += 8) cand[ob + k] = sb[k];
     }
     __syncthreads();
     const int H = L.h - 2 * kMinBorder;
