@@ -62,6 +62,22 @@ __device__ int block_exclusive_scan(const int* in, int* out, int len, QtShared& 
         __syncthreads();  // out[] visible; warp_tmp free for the next scan
         return total;
     }
+    if (len <= 2 * kQtThreads) {  // two consecutive elements per thread (the cell lists of the largest level)
+        const int i0 = 2 * (int)threadIdx.x;
+        const int v0 = i0 < len ? in[i0] : 0, v1 = i0 + 1 < len ? in[i0 + 1] : 0, v = v0 + v1;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sh.warp_tmp[warp] = inc;
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kQtWarps; ++w) { const int t = sh.warp_tmp[w]; total += t; off += w < warp ? t : 0; }
+        if (i0 < len) out[i0] = off + inc - v;
+        if (i0 + 1 < len) out[i0 + 1] = off + inc - v + v0;
+        __syncthreads();  // out[] visible; warp_tmp free for the next scan
+        return total;
+    }
     if (len <= 32 * 32) {
         if (warp == 0) {
             const int per = (len + 31) >> 5, lo = lane * per, hi = min(lo + per, len);
