@@ -156,15 +156,8 @@ __device__ int block_radix_sort(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32
         uint32_t* ko = flip ? kA : kB;       uint32_t* vo = flip ? vA : vB;
         for (int i = threadIdx.x; i < kQtWarps * 256; i += kQtThreads) (&sh.wcount[0][0])[i] = 0;
         __syncthreads();
-        // digit counts of this warp's chunk
-        for (int base = lo; base < hi; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < hi;
-            const uint32_t digit = valid ? (ki[i] >> shift) & 255u : 0x100u + lane;  // invalid lanes never group
-            const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-            if (valid && (peers & lt) == 0) sh.wcount[warp][digit] += __popc(peers);
-            __syncwarp();
-        }
+        // digit counts of this warp's chunk (no order needed: one shared-memory atomic per element)
+        for (int i = lo + lane; i < hi; i += 32) atomicAdd(&sh.wcount[warp][(ki[i] >> shift) & 255u], 1);
         __syncthreads();
         // thread d: total of digit d, exclusive scan over the digits, then the start of every warp's run
         {
@@ -235,15 +228,11 @@ __device__ int block_radix_sort_small(uint32_t* kA, uint32_t* vA, uint32_t* kB, 
                 peers[j] = __match_any_sync(0xffffffffu, valid ? (k[j] >> shift) & 255u : 0x100u + lane);  // invalid lanes never group
             }
         }
+        // (counting needs no order: one shared-memory atomic per element; the matches are only used by the scatter sweep and
+        // are in flight meanwhile)
 #pragma unroll
-        for (int j = 0; j < kQtRegSteps; ++j) {
-            if (lo + 32 * j < hi) {
-                const bool valid = lo + 32 * j + lane < hi;
-                const uint32_t digit = (k[j] >> shift) & 255u;
-                if (valid && (peers[j] & lt) == 0) sh.wcount[warp][digit] += __popc(peers[j]);
-                __syncwarp();
-            }
-        }
+        for (int j = 0; j < kQtRegSteps; ++j)
+            if (lo + 32 * j + lane < hi) atomicAdd(&sh.wcount[warp][(k[j] >> shift) & 255u], 1);
         __syncthreads();
         {
             int c[kQtWarps], t = 0;
