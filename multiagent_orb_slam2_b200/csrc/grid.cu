@@ -23,6 +23,8 @@ struct orbm_grid {
     int n = 0;                    // keypoints of the last build (host copy not needed by the kernels)
     const orbx_keypoint* d_kps = nullptr;
     const int* d_count = nullptr;
+    int* d_qcounts = nullptr;     // per-query candidate counts of orbm_window_lists_device, kept between calls: a stream-ordered
+    int qcounts_cap = 0;          // allocation per call is given back at the call's own synchronisation and costs ~1 ms to get again
 };
 
 namespace orb {
@@ -251,6 +253,7 @@ void orbm_grid_destroy(orbm_grid_handle g) {
     cudaSetDevice(g->device);
     if (g->d_cell_start) cudaFree(g->d_cell_start);
     if (g->d_items) cudaFree(g->d_items);
+    if (g->d_qcounts) cudaFree(g->d_qcounts);
     delete g;
 }
 
@@ -295,8 +298,12 @@ int orbm_window_lists_device(orbm_grid_handle g, const uint8_t* d_desc_frame, co
     ORB_REQUIRE(g->d_kps && d_desc_frame && d_queries && d_x && d_y && d_r && d_min_level && d_max_level && d_offsets, "null pointer / grid not built");
     ORB_CUDA_TRY(cudaSetDevice(g->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int* d_counts = nullptr;
-    ORB_CUDA_TRY(cudaMallocAsync(&d_counts, (size_t)nq * sizeof(int), st));
+    if (nq > g->qcounts_cap) {
+        if (g->d_qcounts) { ORB_CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(g->d_qcounts); g->d_qcounts = nullptr; g->qcounts_cap = 0; }
+        ORB_CUDA_TRY(cudaMalloc(&g->d_qcounts, (size_t)(nq + nq / 2 + 256) * sizeof(int)));
+        g->qcounts_cap = nq + nq / 2 + 256;
+    }
+    int* d_counts = g->d_qcounts;
     const int blocks = ceil_div(nq * 32, 256);
     window_lists_kernel<false><<<blocks, 256, 0, st>>>((const uint4*)d_queries, nq, d_x, d_y, d_r, d_min_level, d_max_level, g->d_kps,
                                                        (const uint4*)d_desc_frame, g->d_cell_start, g->d_items, g->min_x, g->min_y, g->w_inv,
@@ -307,7 +314,6 @@ int orbm_window_lists_device(orbm_grid_handle g, const uint8_t* d_desc_frame, co
     int total = 0;
     ORB_CUDA_TRY(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(int), cudaMemcpyDeviceToHost, st));
     ORB_CUDA_TRY(cudaStreamSynchronize(st));  // the caller needs the total to size / check its buffers
-    ORB_CUDA_TRY(cudaFreeAsync(d_counts, st));
     *total_out = total;
     if (total > cap) { set_error("window lists hold %d candidates, buffer has room for %d", total, cap); return ORB_ECAPACITY; }
     if (total == 0) return ORB_OK;
