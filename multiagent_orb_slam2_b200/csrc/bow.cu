@@ -13,6 +13,8 @@
 #include <new>
 #include <vector>
 
+#include <cstring>
+
 #include "common.cuh"
 
 struct orbv_vocabulary {
@@ -133,22 +135,25 @@ int orbv_descend(orbv_handle v, const uint8_t* desc, int n, int levelsup, int32_
     ORB_REQUIRE(v && n >= 0, "bad arguments");
     if (n == 0) return ORB_OK;
     ORB_REQUIRE(desc && word && node && weight, "null pointer");
-    ORB_CUDA_TRY(cudaSetDevice(v->device));
-    uint8_t* d = nullptr;
-    ORB_CUDA_TRY(cudaMalloc(&d, (size_t)n * (32 + 4 + 4 + 8)));
-    int32_t* dw = (int32_t*)(d + (size_t)n * 32 + (size_t)n * 8);
-    double* dwt = (double*)(d + (size_t)n * 32);
-    cudaError_t e = cudaMemcpyAsync(d, desc, (size_t)n * 32, cudaMemcpyHostToDevice, 0);
-    int rc = e == cudaSuccess ? orbv_descend_device(v, d, n, levelsup, dw, dw + n, dwt, 0) : ORB_ECUDA;
-    if (rc == ORB_OK) {
-        e = cudaMemcpyAsync(word, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(node, dw + n, (size_t)n * 4, cudaMemcpyDeviceToHost, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(weight, dwt, (size_t)n * 8, cudaMemcpyDeviceToHost, 0);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-    }
-    if (e != cudaSuccess) { set_error("bow descend failed: %s", cudaGetErrorString(e)); rc = ORB_ECUDA; }
-    cudaFree(d);
-    return rc;
+    // the vocabulary is shared by every thread of a SLAM system (ComputeBoW): the calling thread's own arena, stream and pinned
+    // staging (common.cuh) - descriptors up, one copy of weight | word | node back, one synchronisation
+    HostCallWorkspace& ws = host_call_workspace();
+    int rc;
+    if ((rc = ws.begin(v->device, ws.need((size_t)n * 32) + ws.need((size_t)n * 16)))) return rc;
+    uint8_t* d_desc = ws.take<uint8_t>((size_t)n * 32);
+    uint8_t* d_out = ws.take<uint8_t>((size_t)n * 16);
+    double* dwt = reinterpret_cast<double*>(d_out);
+    int32_t* dw = reinterpret_cast<int32_t*>(d_out + (size_t)n * 8);
+    ORB_CUDA_TRY(cudaMemcpyAsync(d_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, ws.st));
+    if ((rc = orbv_descend_device(v, d_desc, n, levelsup, dw, dw + n, dwt, ws.st))) return rc;
+    uint8_t* p = nullptr;
+    if ((rc = ws.pinned((size_t)n * 16, &p))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(p, d_out, (size_t)n * 16, cudaMemcpyDeviceToHost, ws.st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(ws.st));
+    memcpy(weight, p, (size_t)n * 8);
+    memcpy(word, p + (size_t)n * 8, (size_t)n * 4);
+    memcpy(node, p + (size_t)n * 12, (size_t)n * 4);
+    return ORB_OK;
 }
 
 }  // extern "C"

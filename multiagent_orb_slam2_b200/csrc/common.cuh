@@ -62,6 +62,67 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
+// ---- host-buffer wrappers: H2D, kernel, D2H, synchronise --------------------------------------
+// ORBmatcher is constructed on the stack at 13 call sites and called from the Tracking, LocalMapping, LoopClosing and
+// MapFusion threads concurrently, the vocabulary is shared by all of them: every calling thread keeps
+// its own device arena (grow-only), pinned staging and stream, so a host-buffer call costs copies + launches, not a
+// cudaMalloc / cudaFree pair per array on the default stream.
+int release_mma_scratch(int device, cudaStream_t st);   // hamming_mma.cu: operand scratch keyed by (device, stream)
+struct HostCallWorkspace {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    uint8_t* base = nullptr;
+    size_t cap = 0, used = 0;
+    uint8_t* pin = nullptr;   // pinned staging for the results: ONE device -> host copy per call instead of one blocking
+    size_t pin_cap = 0;       // copy into pageable memory per output array (~15 us each)
+    ~HostCallWorkspace() { release(); }
+    int pinned(size_t bytes, uint8_t** out) {
+        if (bytes > pin_cap) {
+            if (pin) { cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
+            ORB_CUDA_TRY(cudaMallocHost(&pin, bytes + bytes / 2 + 4096));
+            pin_cap = bytes + bytes / 2 + 4096;
+        }
+        *out = pin;
+        return ORB_OK;
+    }
+    void release() {
+        if (pin) { cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
+        if (device >= 0) {
+            cudaSetDevice(device);
+            if (st) release_mma_scratch(device, st);
+            if (base) cudaFree(base);
+            if (st) cudaStreamDestroy(st);
+        }
+        base = nullptr; st = nullptr; cap = 0; device = -1;
+    }
+    // make room for `bytes` on `dev`; pointers handed out before are invalid afterwards
+    int begin(int dev, size_t bytes) {
+        if (dev != device) {
+            release();
+            ORB_CUDA_TRY(cudaSetDevice(dev));
+            ORB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            device = dev;
+        } else {
+            ORB_CUDA_TRY(cudaSetDevice(dev));
+        }
+        if (bytes > cap) {
+            if (base) { cudaStreamSynchronize(st); cudaFree(base); base = nullptr; cap = 0; }
+            const size_t want = bytes + bytes / 2 + 4096;
+            ORB_CUDA_TRY(cudaMalloc(&base, want));
+            cap = want;
+        }
+        used = 0;
+        return ORB_OK;
+    }
+    template <class T> T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used += align_up(count * sizeof(T) + 1, 256);
+        return p;
+    }
+    static size_t need(size_t bytes) { return align_up(bytes + 1, 256); }
+};
+HostCallWorkspace& host_call_workspace();   // the calling thread's (runtime.cu)
+
 // Launch `kernel` as a programmatic dependent of the previous kernel in `st`: it may be scheduled while that kernel's last
 // blocks still run and must execute griddepcontrol.wait before it touches anything the predecessor writes.
 template <class... KArgs, class... Args>

@@ -238,7 +238,6 @@ __global__ void distance_matrix_kernel(const uint4* __restrict__ A, int nA, cons
 int launch_knn2_mma(const uint8_t* dA, const int* d_nA, int nA_max, int strideA_rows, const uint8_t* dB, const int* d_nB, int nB_max,
                     int strideB_rows, const int* d_pairs, int pairs, int out_stride, int* d_idx, int* d_b1, int* d_b2, cudaStream_t st,
                     int variant);
-int release_mma_scratch(int device, cudaStream_t st);
 static thread_local int t_knn2_backend = 0;        // per calling thread: 0 = by problem size, 1 = POPC kernel, 2 / 3 = tensor-core kernel, one CTA / a CTA pair per query tile
 constexpr long long kMmaMinWork = 1ll << 19;      // comparisons per call from which the tensor-core path is used (measured break-even: ~700 x 700)
 
@@ -357,67 +356,9 @@ int orbm_distance_matrix_device(const uint8_t* dA, int nA, const uint8_t* dB, in
     return ORB_OK;
 }
 
-// ---- host-buffer wrappers: H2D, kernel, D2H, synchronise --------------------------------------
-// ORBmatcher is constructed on the stack at 13 call sites and called from the Tracking, LocalMapping, LoopClosing and
-// MapFusion threads concurrently: every calling thread keeps its own device arena (grow-only) and
-// its own stream, so a search costs copies + one launch, not five cudaMalloc / cudaFree pairs on the default stream.
+// ---- host-buffer wrappers: H2D, kernel, D2H, synchronise (per-thread arena + stream: common.cuh) ------------------
 extern "C++" {
 namespace {
-struct HostCallWorkspace {
-    int device = -1;
-    cudaStream_t st = nullptr;
-    uint8_t* base = nullptr;
-    size_t cap = 0, used = 0;
-    uint8_t* pin = nullptr;   // pinned staging for the results: ONE device -> host copy per call instead of one blocking
-    size_t pin_cap = 0;       // copy into pageable memory per output array (~15 us each)
-    ~HostCallWorkspace() { release(); }
-    int pinned(size_t bytes, uint8_t** out) {
-        if (bytes > pin_cap) {
-            if (pin) { cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
-            ORB_CUDA_TRY(cudaMallocHost(&pin, bytes + bytes / 2 + 4096));
-            pin_cap = bytes + bytes / 2 + 4096;
-        }
-        *out = pin;
-        return ORB_OK;
-    }
-    void release() {
-        if (pin) { cudaFreeHost(pin); pin = nullptr; pin_cap = 0; }
-        if (device >= 0) {
-            cudaSetDevice(device);
-            if (st) release_mma_scratch(device, st);  // the tensor-core matcher's operand scratch is keyed by this stream
-            if (base) cudaFree(base);
-            if (st) cudaStreamDestroy(st);
-        }
-        base = nullptr; st = nullptr; cap = 0; device = -1;
-    }
-    // make room for `bytes` on `dev`; pointers handed out before are invalid afterwards
-    int begin(int dev, size_t bytes) {
-        if (dev != device) {
-            release();
-            ORB_CUDA_TRY(cudaSetDevice(dev));
-            ORB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            device = dev;
-        } else {
-            ORB_CUDA_TRY(cudaSetDevice(dev));
-        }
-        if (bytes > cap) {
-            if (base) { cudaStreamSynchronize(st); cudaFree(base); base = nullptr; cap = 0; }
-            const size_t want = bytes + bytes / 2 + 4096;
-            ORB_CUDA_TRY(cudaMalloc(&base, want));
-            cap = want;
-        }
-        used = 0;
-        return ORB_OK;
-    }
-    template <class T> T* take(size_t count) {
-        T* p = reinterpret_cast<T*>(base + used);
-        used += align_up(count * sizeof(T) + 1, 256);
-        return p;
-    }
-    static size_t need(size_t bytes) { return align_up(bytes + 1, 256); }
-};
-thread_local HostCallWorkspace tls_ws;
-
 // the three result arrays of a search lie back to back on the device: one copy into pinned staging, one synchronisation
 static int download_three(HostCallWorkspace& ws, const int* d_o, size_t n, int32_t* idx, int32_t* best, int32_t* second) {
     uint8_t* p = nullptr;
@@ -437,7 +378,7 @@ int orbm_knn2(int device, const uint8_t* A, int nA, const uint8_t* B, int nB, in
     ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
     if (nA == 0) return ORB_OK;
     ORB_REQUIRE(A && idx && best && second && (nB == 0 || B), "null pointer");
-    HostCallWorkspace& ws = tls_ws;
+    HostCallWorkspace& ws = host_call_workspace();
     int rc;
     if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)nA * 12)))) return rc;
     uint8_t* dA = ws.take<uint8_t>((size_t)nA * 32);
@@ -456,7 +397,7 @@ int orbm_knn2_lists(int device, const uint8_t* A, int nA, const uint8_t* B, int 
     ORB_REQUIRE(A && B && offsets && cands && idx && best && second, "null pointer");
     const int total = offsets[nA];
     ORB_REQUIRE(total >= 0, "bad offsets");
-    HostCallWorkspace& ws = tls_ws;
+    HostCallWorkspace& ws = host_call_workspace();
     int rc;
     if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)(nA + 1) * 4) + ws.need((size_t)total * 4) +
                                    ws.need((size_t)nA * 12))))
@@ -482,7 +423,7 @@ int orbm_list_distances(int device, const uint8_t* A, int nA, const uint8_t* B, 
     const int total = offsets[nA];
     ORB_REQUIRE(total >= 0, "bad offsets");
     if (total == 0) return ORB_OK;
-    HostCallWorkspace& ws = tls_ws;
+    HostCallWorkspace& ws = host_call_workspace();
     int rc;
     if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)(nA + 1) * 4) + ws.need((size_t)total * 4) +
                                    ws.need((size_t)total * 2))))
@@ -506,7 +447,7 @@ int orbm_distance_matrix(int device, const uint8_t* A, int nA, const uint8_t* B,
     ORB_REQUIRE(nA >= 0 && nB >= 0, "negative row count");
     if (nA == 0 || nB == 0) return ORB_OK;
     ORB_REQUIRE(A && B && out, "null pointer");
-    HostCallWorkspace& ws = tls_ws;
+    HostCallWorkspace& ws = host_call_workspace();
     int rc;
     if ((rc = ws.begin(device, ws.need((size_t)nA * 32) + ws.need((size_t)nB * 32) + ws.need((size_t)nA * nB * 2)))) return rc;
     uint8_t* dA = ws.take<uint8_t>((size_t)nA * 32);

@@ -11,6 +11,8 @@
 // added in ascending word order - the order of the reference's merge walk - so the double sum is bit-identical.
 #include <vector>
 
+#include <cstring>
+
 #include "common.cuh"
 
 struct orbdb_database {
@@ -200,20 +202,23 @@ int orbdb_query(orbdb_handle db, const int32_t* q_word_ids, const double* q_weig
     ORB_REQUIRE(cap >= n_kf, "output arrays smaller than the database");
     if (n_kf == 0) return ORB_OK;
     ORB_CUDA_TRY(cudaSetDevice(db->device));
-    void* d = nullptr;
-    ORB_CUDA_TRY(cudaMalloc(&d, (size_t)n_kf * 16));
-    double* d_score = (double*)d;
-    int32_t* d_common = (int32_t*)(d_score + n_kf);
+    // scores | common words | first word: the calling thread's arena (common.cuh), one copy back through pinned staging
+    HostCallWorkspace& ws = host_call_workspace();
+    int rc;
+    if ((rc = ws.begin(db->device, ws.need((size_t)n_kf * 16)))) return rc;
+    uint8_t* d = ws.take<uint8_t>((size_t)n_kf * 16);
+    double* d_score = reinterpret_cast<double*>(d);
+    int32_t* d_common = reinterpret_cast<int32_t*>(d_score + n_kf);
     int32_t* d_first = d_common + n_kf;
-    int rc = orbdb_query_device(db, q_word_ids, q_weights, nq, d_common, d_first, d_score, nullptr);
-    if (rc == ORB_OK) {
-        cudaError_t e = cudaMemcpy(score, d_score, (size_t)n_kf * 8, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(common, d_common, (size_t)n_kf * 4, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(first_word, d_first, (size_t)n_kf * 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { set_error("orbdb_query copy failed: %s", cudaGetErrorString(e)); rc = ORB_ECUDA; }
-    }
-    cudaFree(d);
-    return rc;
+    if ((rc = orbdb_query_device(db, q_word_ids, q_weights, nq, d_common, d_first, d_score, nullptr))) return rc;   // default stream
+    uint8_t* p = nullptr;
+    if ((rc = ws.pinned((size_t)n_kf * 16, &p))) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(p, d, (size_t)n_kf * 16, cudaMemcpyDeviceToHost, nullptr));
+    ORB_CUDA_TRY(cudaStreamSynchronize(nullptr));
+    memcpy(score, p, (size_t)n_kf * 8);
+    memcpy(common, p + (size_t)n_kf * 8, (size_t)n_kf * 4);
+    memcpy(first_word, p + (size_t)n_kf * 12, (size_t)n_kf * 4);
+    return ORB_OK;
 }
 
 }  // extern "C"

@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+HostCallWorkspace& host_call_workspace() {
+    static thread_local HostCallWorkspace ws;
+    return ws;
+}
 }  // namespace orb
 
 extern "C" {
