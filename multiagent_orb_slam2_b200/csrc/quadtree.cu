@@ -376,16 +376,33 @@ __device__ void quadtree_select(const uint32_t* cand, int n, int N, int nRoots, 
 
     // roots (539-585): non-empty ones, in order
     int cur = 0;
-    for (int r = threadIdx.x; r < nRoots; r += kQtThreads) {
-        const int lo = lower_bound_key((uint32_t)r << (2 * depth));
-        const int hi = r + 1 == nRoots ? n : lower_bound_key((uint32_t)(r + 1) << (2 * depth));
-        q.b1[r] = lo; q.b2[r] = hi; q.flag[r] = hi > lo;
+    int count;
+    if (nRoots <= 32) {  // the usual 1 - 2 roots: one warp, one vote, one block barrier
+        if (threadIdx.x < 32) {
+            const int r = threadIdx.x;
+            int lo = 0, hi = 0;
+            if (r < nRoots) {
+                lo = lower_bound_key((uint32_t)r << (2 * depth));
+                hi = r + 1 == nRoots ? n : lower_bound_key((uint32_t)(r + 1) << (2 * depth));
+            }
+            const uint32_t nonempty = __ballot_sync(0xffffffffu, hi > lo);
+            if (hi > lo) { const int p = __popc(nonempty & ((1u << r) - 1u)); q.lo[0][p] = lo; q.hi[0][p] = hi; q.dep[0][p] = 0; }
+            if (r == 0) sh.bcast[0] = __popc(nonempty);
+        }
+        __syncthreads();
+        count = sh.bcast[0];
+    } else {
+        for (int r = threadIdx.x; r < nRoots; r += kQtThreads) {
+            const int lo = lower_bound_key((uint32_t)r << (2 * depth));
+            const int hi = r + 1 == nRoots ? n : lower_bound_key((uint32_t)(r + 1) << (2 * depth));
+            q.b1[r] = lo; q.b2[r] = hi; q.flag[r] = hi > lo;
+        }
+        __syncthreads();
+        count = block_exclusive_scan(q.flag, q.scan, nRoots, sh);
+        for (int r = threadIdx.x; r < nRoots; r += kQtThreads)
+            if (q.flag[r]) { const int p = q.scan[r]; q.lo[0][p] = q.b1[r]; q.hi[0][p] = q.b2[r]; q.dep[0][p] = 0; }
+        __syncthreads();
     }
-    __syncthreads();
-    int count = block_exclusive_scan(q.flag, q.scan, nRoots, sh);
-    for (int r = threadIdx.x; r < nRoots; r += kQtThreads)
-        if (q.flag[r]) { const int p = q.scan[r]; q.lo[0][p] = q.b1[r]; q.hi[0][p] = q.b2[r]; q.dep[0][p] = 0; }
-    __syncthreads();
 
     bool final_phase = false;
     QT_MARK(4);
