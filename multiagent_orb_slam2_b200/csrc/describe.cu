@@ -38,7 +38,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 constexpr int kDescWarps = 8;
-constexpr int kDescSlots = 32;  // keypoint slots per block
+constexpr int kDescSlotsMax = 32;  // keypoint slots per block: 8 warps x SPW (4 for batches, 1 for one or two frames: four
+                                   // times the blocks, a warp's keypoints no longer queue behind each other)
 // blurred window of a keypoint in shared memory: rows y-18..y+18, 40 bytes from the word at or left of x-18
 // (64-bit loads of a 48-byte window were tried: 43 KB of shared memory per block pushes the SM to its largest
 // carve-out and the kernel, which also lives on L1 hits, from 0.49 to 0.64 ms; cudaFuncAttributePreferredSharedMemoryCarveout
@@ -54,6 +55,7 @@ struct SlotInfo { int valid, level, x, y, response, dst; };
 //      after the table fill no block barrier separates the phases
 //   C. every warp: rotated BRIEF of 4 slots, two at a time, sampled from a shared-memory copy of the
 //      blurred 37 x 40 window (lane = output byte), keypoint record
+template <int SPW>
 __global__ void __launch_bounds__(kDescWarps * 32, 5)
 orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_t* __restrict__ pyr,
                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ selected,
@@ -62,10 +64,12 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     // Shared memory is kept below 31.8 KB per block on purpose: five blocks then fit the 164 KB carve-out and leave 92 KB of L1
     // to the window gathers (37.7 KB per block = 196 KB carve-out measured 0.469 ms, this layout 0.36 ms at B=512).
     __shared__ uint32_t pat8[kPatternWords];  // x0 | y0 << 8 | x1 << 16 | y1 << 24 (int8) of test t of byte `lane` at [t * 32 + lane]
-    __shared__ SlotInfo info[kDescSlots];
-    __shared__ float s_angle[kDescSlots], s_cos[kDescSlots], s_sin[kDescSlots];
+    constexpr int kDescSlots = kDescWarps * SPW;
+    __shared__ SlotInfo info[kDescSlots + 1];   // + 1: the pair partner of the last slot when SPW is odd (always invalid)
+    __shared__ float s_angle[kDescSlots + 1], s_cos[kDescSlots + 1], s_sin[kDescSlots + 1];
     __shared__ __align__(16) uint32_t patch[kDescWarps * 2 * kPatchWords];  // per warp: blurred windows of two keypoints
     __shared__ int s_m10[kDescSlots], s_m01[kDescSlots];
+    if (threadIdx.x == 0) info[kDescSlots] = SlotInfo{0, 0, 0, 0, 0, 0};
     __shared__ uint32_t ictab[kIcTableWords];  // [phase][item]: u + 16 per byte, 0 outside the patch
     for (int i = threadIdx.x; i < kPatternWords; i += blockDim.x) pat8[i] = pattern[i];
     for (int i = threadIdx.x; i < kIcTableWords; i += blockDim.x) ictab[i] = ic_table[i];
@@ -172,7 +176,7 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
     const int pt_lr = lane / kPatchRowWords, pt_lj = lane - pt_lr * kPatchRowWords;
     for (int kk = 0; kk < kDescSlots / kDescWarps; kk += 2) {
         const int sidx0 = warp * (kDescSlots / kDescWarps) + kk;
-        const SlotInfo si0 = info[sidx0], si1 = info[sidx0 + 1];
+        const SlotInfo si0 = info[sidx0], si1 = info[kk + 1 < SPW ? sidx0 + 1 : kDescSlots];
         if (!si0.valid && !si1.valid) continue;
         // (an invalid slot of the pair samples stale data around the window centre and stores nothing)
         int off[2] = {kPatchReach * kPatchRowWords * 4 + kPatchReach, kPatchReach * kPatchRowWords * 4 + kPatchReach};
@@ -201,7 +205,7 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
         const uint8_t* p0 = reinterpret_cast<const uint8_t*>(mypatch) + off[0];
         const uint8_t* p1 = reinterpret_cast<const uint8_t*>(mypatch + kPatchWords) + off[1];
         const float a0 = si0.valid ? s_cos[sidx0] : 0.f, b0 = si0.valid ? s_sin[sidx0] : 0.f;  // s_cos / s_sin are unset for invalid slots
-        const float a1 = si1.valid ? s_cos[sidx0 + 1] : 0.f, b1 = si1.valid ? s_sin[sidx0 + 1] : 0.f;
+        const float a1 = si1.valid ? s_cos[sidx0 + 1] : 0.f, b1 = si1.valid ? s_sin[sidx0 + 1] : 0.f;  // (valid only when kk + 1 < SPW)
         const uint32_t* pp = pat8 + lane;
         uint32_t val0 = 0, val1 = 0;  // bits enter at the bottom, test 7 first: sign of I(p0) - I(p1) by one funnel shift
         constexpr int kRow = kPatchRowWords * 4;
@@ -248,13 +252,15 @@ orient_describe_kernel(const Geometry* __restrict__ g, FrameSet fs, const uint8_
 }
 
 int launch_describe(const Geometry& hg, const DeviceBuffers& db, const FrameSet& fs, int n, cudaStream_t st, bool pdl) {
-    const dim3 grid(ceil_div(hg.sel_words, kDescSlots), n);
+    const bool spread = n <= 2;   // one keypoint per warp: the GPU is far from full, latency is what counts
+    const dim3 grid(ceil_div(hg.sel_words, kDescWarps * (spread ? 1 : 4)), n);
+    auto kernel = spread ? orient_describe_kernel<1> : orient_describe_kernel<4>;
     if (pdl)
-        ORB_CUDA_TRY(launch_pdl(orient_describe_kernel, grid, dim3(kDescWarps * 32), 0, st, db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts,
-                                db.pattern, db.ic_table, db.kps, db.desc, db.counts));
+        ORB_CUDA_TRY(launch_pdl(kernel, grid, dim3(kDescWarps * 32), 0, st, db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern,
+                                db.ic_table, db.kps, db.desc, db.counts));
     else
-        orient_describe_kernel<<<grid, kDescWarps * 32, 0, st>>>(db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.ic_table,
-                                                                 db.kps, db.desc, db.counts);
+        kernel<<<grid, kDescWarps * 32, 0, st>>>(db.geom, fs, db.pyr, db.blur, db.selected, db.sel_counts, db.pattern, db.ic_table, db.kps, db.desc,
+                                                 db.counts);
     count_launch();
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
